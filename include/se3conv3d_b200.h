@@ -1,0 +1,189 @@
+/*
+ * se3conv3d_b200 -- C ABI of the B200-native (sm_100a) SE(3) group-convolution hot path.
+ *
+ * This header is the drop-in boundary.  It replaces the pybind11 module `point_cloud_lib_ops`
+ * of the reference (point_cloud_lib/custom_ops/ops_list.cpp:19-26) and adds the fused entry
+ * points the rewritten internals use.  Every function:
+ *   - is `extern "C"`, takes plain device pointers + sizes + a CUDA stream (cudaStream_t passed
+ *     as void*), never a torch type;
+ *   - borrows its inputs, writes only into caller-provided outputs / workspace (the caller --
+ *     the Python host side -- owns all device memory);
+ *   - is asynchronous on `stream` and never synchronises the host;
+ *   - returns 0 on success, a negative SE3_E* code otherwise; se3_last_error() gives the text.
+ *     (The reference silently returns zeros on unsupported K / D,
+ *      custom_ops/feature_aggregation/feat_basis_utils.cuh:35-41.)
+ *
+ * Index conventions (identical to the reference):
+ *   neighbour list   int64 [E,2], column 0 = sample (output) index, column 1 = source (input)
+ *                    index, rows grouped by sample in increasing sample order
+ *                    (custom_ops/ball_query/ball_query.cu:94-103)
+ *   row_ends         int32 [M], INCLUSIVE running end offsets ("start_ids_" in the reference,
+ *                    custom_ops/ball_query/store_neighbors.cu:263-286)
+ *   features         float32 [N*F, C], row = point*F + frame
+ *                    (layers/PNEConvLayerRotEquiv.py:94-104)
+ *   frames           float32 [N, F, 9], row-major 3x3 whose COLUMNS are the axes
+ *                    (pc/RotationFunctions.py:307-406)
+ */
+#ifndef SE3CONV3D_B200_H_
+#define SE3CONV3D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SE3_OK 0
+#define SE3_EINVAL (-1)    /* bad argument / unsupported shape */
+#define SE3_ECUDA (-2)     /* CUDA runtime error (text in se3_last_error) */
+#define SE3_EWORKSPACE (-3)/* workspace too small */
+
+typedef void* se3_stream_t; /* cudaStream_t */
+
+int se3_abi_version(void);
+const char* se3_last_error(void);
+/* number of kernels launched by this library since load (all entry points); for gpu_launches */
+int64_t se3_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Grid keys.  Replaces compute_keys (custom_ops/ball_query/compute_keys.cu:76-125, cell/key
+ * math custom_ops/ball_query/grid_utils.cuh:56-93; caller custom_ops/ComputeKeys.py:35-40).
+ *   cell = clamp(floor((p - aabb_min[b]) * (1/cell_size)), 0, num_cells-1)
+ *   key  = ((b*nx + x)*ny + y)*nz + z
+ * aabb_min [B,3], num_cells [3], cell_size [3] are DEVICE arrays, as in the reference. */
+int se3_compute_keys(const float* pts, const int32_t* batch_ids, int64_t n,
+                     const float* aabb_min, const int32_t* num_cells, const float* cell_size,
+                     int64_t* keys_out, se3_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Ball query.  Replaces ball_query (custom_ops/ball_query/ball_query.cu:22-104 and its five
+ * kernels; caller custom_ops/BallQuery.py:44-52).  Two phases because E is data dependent and
+ * the caller owns the output allocation:
+ *   _count : keys -> sort -> 9 tube ranges per sample -> strict (|s-p|/r < 1) count
+ *            -> inclusive row_ends [M] and the total E (device int64 scalar)
+ *   _fill  : re-scans the cached ranges and writes neighbours [E,2] int64 in a DETERMINISTIC
+ *            order (tube offset, then sorted-key position), unlike the reference's atomic order.
+ * `radius` [3] and `num_cells` [3], `min_pt` [B,3] are DEVICE arrays as in the reference. */
+size_t se3_ball_query_workspace_bytes(int64_t n_src, int64_t n_dst);
+int se3_ball_query_count(const float* pts_src, const float* pts_dst,
+                         const int32_t* batch_src, const int32_t* batch_dst,
+                         int64_t n_src, int64_t n_dst,
+                         const float* min_pt, const int32_t* num_cells, const float* radius,
+                         void* workspace, size_t workspace_bytes,
+                         int32_t* row_ends_out, int64_t* total_out, se3_stream_t stream);
+int se3_ball_query_fill(const float* pts_dst, int64_t n_src, int64_t n_dst, const float* radius,
+                        const void* workspace, size_t workspace_bytes,
+                        const int32_t* row_ends, int64_t n_edges,
+                        int64_t* neighbors_out, se3_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * CSR helpers for the conv kernels: int32 source column + transposed CSR (edges grouped by
+ * SOURCE point, stable in edge id) used by the atomic-free data gradient.
+ *   col_src [E] int32; t_row_ends [n_src] int32 inclusive; t_edge [E] int32 (edge id);
+ *   t_dst [E] int32 (sample index of that edge). */
+size_t se3_csr_transpose_workspace_bytes(int64_t n_edges, int64_t n_src);
+int se3_csr_transpose(const int64_t* neighbors, int64_t n_edges, int64_t n_src, int64_t n_dst,
+                      void* workspace, size_t workspace_bytes,
+                      int32_t* col_src, int32_t* t_row_ends, int32_t* t_edge, int32_t* t_dst,
+                      se3_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * k-NN (self included, within batch, k <= 32).  Replaces knn_query
+ * (custom_ops/knn_query/knn_query.cu:18-197; caller custom_ops/KNNQuery.py:30-33).
+ * out [N,k] int32, ascending distance, -1 padded. */
+size_t se3_knn_workspace_bytes(int64_t n);
+int se3_knn_query(const float* pts, const int32_t* batch_ids, int64_t n, int32_t k,
+                  void* workspace, size_t workspace_bytes, int32_t* out, se3_stream_t stream);
+
+/* PCA reference frames from a k-NN table (pc/RotationFunctions.py:307-406).
+ * knn [N,k] int32 (-1 => self loop).  fixed_axis: -1 none (4 frames) | 0,1,2 (2 frames; 0 behaves
+ * as "none" in the reference because of `not axis_fixed`, pc/RotationFunctions.py:323).
+ * frames_out [N, 4 or 2, 9]. */
+int se3_pca_frames(const float* pts, const int32_t* knn, int64_t n, int32_t k, int32_t fixed_axis,
+                   float* frames_out, se3_stream_t stream);
+
+/* SO(3) frames from normal-distributed quaternions (pc/RotationFunctions.py:176-216, 53-82):
+ * q [n,4] (torch.randn output, so RNG parity is kept) -> frames [n,9]. */
+int se3_quat_frames(const float* q, int64_t n, float* frames_out, se3_stream_t stream);
+
+/* Segment mean / max over dense cell ids (GridSubSample.__subsample_tensor__,
+ * pc/GridSubSample.py:59-72).  sorted_ids [N] = argsort(cell_ids) (stable), seg_ends [M]
+ * inclusive ends of each cell in that order.  mode 0 = mean (float32 [N,C]), 1 = max. */
+int se3_segment_pool_f32(const float* x, int64_t n, int32_t c, const int64_t* sorted_ids,
+                         const int32_t* seg_ends, int64_t m, int32_t mode, float* out,
+                         se3_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Legacy aggregation ops (custom_ops/feature_aggregation/feat_basis_proj.cuh:27-31 and
+ * feat_basis_proj_grads.cuh:29-34; callers custom_ops/FeatBasisProj.py:36-40, 59-66).
+ *   T[m,c,k] = sum_{e in row m} feats[nbr[e,1], c] * basis[e,k]
+ * neighbors int32 [E,2]; ends int32 [M] inclusive; K in {8,16,32,64}; any C >= 1.
+ * The gradient is atomic-free when `t_*` (transposed CSR over column 1) is given, else uses
+ * fp32 atomics like the reference. */
+int se3_feat_basis_proj(const float* basis, const float* feats, const int32_t* neighbors,
+                        const int32_t* ends, int64_t n_edges, int64_t m, int32_t c, int32_t k,
+                        float* out, se3_stream_t stream);
+int se3_feat_basis_proj_grad(const float* basis, const float* feats, const int32_t* neighbors,
+                             const int32_t* ends, const float* grads, int64_t n_edges, int64_t m,
+                             int64_t n_feat_rows, int32_t c, int32_t k, float* feat_grads,
+                             float* basis_grads, se3_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused PNEConvLayerRotEquiv (layers/PNEConvLayerRotEquiv.py:61-128, 160-216).
+ * The relative geometry g[e,a,b] (9 values), the basis h = gelu(g.W9 + b) and the expanded
+ * neighbour list never reach HBM.
+ *
+ * precision: 0 = fp32 CUDA-core path (exactness mode, <=1e-4 rel vs the reference)
+ *            1 = bf16 tensor-core path (mma.sync aggregation + tcgen05/TMEM projection),
+ *                fp32 accumulation everywhere.
+ */
+typedef struct se3_conv_desc {
+  int64_t n_in;        /* input points N */
+  int64_t n_out;       /* output points M */
+  int64_t n_edges;     /* E */
+  int32_t f_in;        /* frames per input point  (1..4) */
+  int32_t f_out;       /* frames per output point (1..4) */
+  int32_t c_in;        /* input channels */
+  int32_t c_out;       /* output channels */
+  int32_t k;           /* basis functions (32) */
+  int32_t act;         /* 0 linear, 1 relu, 2 gelu(erf), 3 sin */
+  int32_t precision;   /* see above */
+  int32_t reserved;
+  float norm_neigh_dist;   /* buffer norm_neigh_dist_ (layers/IConvLayer.py:33-36) */
+  float out_scale;         /* norm_num_neighs_ / f_in (PNEConvLayerRotEquiv.py:213-216) */
+  /* geometry (device) */
+  const float* pts_in;     /* [N,3] */
+  const float* pts_out;    /* [M,3] */
+  const float* frames_in;  /* [N,f_in,9] */
+  const float* frames_out; /* [M,f_out,9] */
+  /* forward CSR (device) */
+  const int32_t* row_ends; /* [M] inclusive */
+  const int32_t* col_src;  /* [E] */
+  /* transposed CSR (device; needed by backward) */
+  const int32_t* t_row_ends; /* [N] inclusive */
+  const int32_t* t_edge;     /* [E] */
+  const int32_t* t_dst;      /* [E] */
+  /* parameters (device) */
+  const float* proj_axes;    /* [9,K]   */
+  const float* proj_biases;  /* [K]     */
+  const float* conv_weights; /* [c_in,K,c_out] */
+} se3_conv_desc;
+
+size_t se3_conv_fwd_workspace_bytes(const se3_conv_desc* d);
+size_t se3_conv_bwd_workspace_bytes(const se3_conv_desc* d);
+/* bytes of the per-call "saved" buffer written by fwd and consumed by bwd (may be 0) */
+size_t se3_conv_saved_bytes(const se3_conv_desc* d);
+
+/* y [M*f_out, c_out] = conv(x [N*f_in, c_in]) */
+int se3_conv_fwd(const se3_conv_desc* d, const float* x, float* y, void* saved,
+                 void* workspace, size_t workspace_bytes, se3_stream_t stream);
+/* gradients of y wrt x, conv_weights, proj_axes, proj_biases; any output may be NULL */
+int se3_conv_bwd(const se3_conv_desc* d, const float* x, const float* dy, const void* saved,
+                 float* dx, float* d_conv_weights, float* d_proj_axes, float* d_proj_biases,
+                 void* workspace, size_t workspace_bytes, se3_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SE3CONV3D_B200_H_ */

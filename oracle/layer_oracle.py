@@ -1,0 +1,108 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement (torch tensors on the host, any float dtype) of the
+floating-point part of the reference hot path.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / reference legs may import this; se3conv3d_b200/ never does.
+
+Follows (paths relative to /root/reference/point_cloud_lib/point_cloud_lib):
+  rot_tensors        layers/PNEConvLayerRotEquiv.py:61-128 with pc/RotationFunctions.py:16-21 (pair
+                     order a*F_in+b), :637-665 (u = d^T R_out), :549-600 + :236-252 (rows 0-1 of
+                     R_out^T R_in)
+  conv_forward       layers/PNEConvLayerRotEquiv.py:199-216; aggregation semantics of
+                     custom_ops/feature_aggregation/feat_basis_proj.cu:55-118 written as the scatter
+                     formulation  T[r,c,k] = sum_e x[src(e),c] h[e,k]
+  pca_frames         pc/RotationFunctions.py:307-406
+  quat_frames        pc/RotationFunctions.py:176-216, 53-82
+Backward comes from torch.autograd over conv_forward (the reference's backward is autograd over the
+same graph plus feat_basis_proj_grads.cu, which computes exactly these sums).
+
+Pinning: tests/golden/layer_*.npz, frames_*.npz are produced by tests/golden/gen_layer_golden.py by
+running the reference's own Python (get_rot_tenors, __compute_convolution__,
+sample_reference_frames_pca, sample_reference_frames) in this container; tests/test_oracle.py
+checks this file against them.
+"""
+import math
+
+import torch
+
+
+def act_fn(name):
+    return {"mlp_linear": lambda t: t, "mlp_relu": torch.relu,
+            "mlp_gelu": lambda t: 0.5 * t * (1.0 + torch.erf(t / math.sqrt(2.0))), "mlp_sin": torch.sin}[name]
+
+
+def rot_tensors(pts_in, pts_out, frames_in, frames_out, neighbors, norm):
+    """g [E,F_out,F_in,9], expanded rows [E,F_out,F_in] (= i*F_out+a), cols (= j*F_in+b)."""
+    i, j = neighbors[:, 0].long(), neighbors[:, 1].long()
+    e = i.shape[0]
+    fo, fi = frames_out.shape[1], frames_in.shape[1]
+    d = (pts_in[j] - pts_out[i]) * norm
+    Ro = frames_out[i].reshape(e, fo, 3, 3)
+    Ri = frames_in[j].reshape(e, fi, 3, 3)
+    u = torch.einsum("er,earc->eac", d, Ro)
+    rel = torch.einsum("earm,ebrn->eabmn", Ro, Ri)
+    r6 = rel[:, :, :, :2, :].reshape(e, fo, fi, 6)
+    g = torch.cat((u[:, :, None, :].expand(e, fo, fi, 3), r6), dim=-1)
+    a = torch.arange(fo)[None, :, None]
+    b = torch.arange(fi)[None, None, :]
+    rows = (i[:, None, None] * fo + a).expand(e, fo, fi)
+    cols = (j[:, None, None] * fi + b).expand(e, fo, fi)
+    return g, rows, cols
+
+
+def conv_forward(x, proj_axes, proj_biases, conv_weights, pts_in, pts_out, frames_in, frames_out, neighbors,
+                 norm_neigh_dist, norm_num_neighs, pne_type="mlp_gelu", chunk=1 << 15):
+    """y [M*F_out, Cout]; differentiable wrt x and the three parameters."""
+    fo, fi = frames_out.shape[1], frames_in.shape[1]
+    m = pts_out.shape[0]
+    cin, k, cout = conv_weights.shape
+    act = act_fn(pne_type)
+    T = torch.zeros((m * fo, cin, k), dtype=x.dtype)
+    for s in range(0, neighbors.shape[0], chunk):
+        g, rows, cols = rot_tensors(pts_in, pts_out, frames_in, frames_out, neighbors[s:s + chunk], norm_neigh_dist)
+        h = act(g.reshape(-1, 9) @ proj_axes + proj_biases)
+        contrib = x[cols.reshape(-1)][:, :, None] * h[:, None, :]
+        T = T.index_add(0, rows.reshape(-1), contrib)
+    y = torch.einsum("nik,iko->no", T, conv_weights)
+    return y / fi * norm_num_neighs
+
+
+def pca_frames(points, knn, fixed_axis=None):
+    """[N, 4 or 2, 9] candidate frames; knn [N,k] (negative -> self)."""
+    n, k = knn.shape
+    idx = torch.where(knn < 0, torch.arange(n)[:, None].expand(n, k), knn.long())
+    X = points[idx].clone()
+    fixed = bool(fixed_axis)
+    if fixed:
+        X[:, :, int(fixed_axis)] = 0
+    Xc = X - X.mean(dim=1, keepdim=True)
+    C = Xc.transpose(1, 2) @ Xc
+    _, vec = torch.linalg.eigh(C)
+    if fixed:
+        vec = torch.flip(vec, dims=[-1])
+    vec = vec * torch.where(torch.linalg.det(vec) < 0, -1.0, 1.0)[:, None, None].to(vec.dtype)
+    signs = [(1, 1, 1), (-1, -1, 1)] if fixed else [(1, 1, 1), (1, -1, -1), (-1, 1, -1), (-1, -1, 1)]
+    S = torch.tensor(signs, dtype=vec.dtype)
+    fr = vec[:, None, :, :] * S[None, :, None, :]
+    if fixed and int(fixed_axis) == 1:
+        fr = fr[:, :, :, [0, 2, 1]]
+    if fixed:
+        fr = torch.where(fr.abs() < 1e-6, torch.zeros_like(fr), fr)
+    return fr.reshape(n, len(signs), 9)
+
+
+def quat_frames(o):
+    """[n,4] normal samples -> [n,9] rotation matrices."""
+    s = (o * o).sum(1)
+    nrm = torch.sqrt(s)
+    nrm = torch.where((nrm < 0) != (o[:, 0] < 0), -nrm, nrm)
+    q = o / nrm[:, None]
+    r, i, j, k = q.unbind(-1)
+    two_s = 2.0 / (q * q).sum(-1)
+    return torch.stack((1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r),
+                        two_s * (i * j + k * r), 1 - two_s * (i * i + k * k), two_s * (j * k - i * r),
+                        two_s * (i * k - j * r), two_s * (j * k + i * r), 1 - two_s * (i * i + j * j)), -1)
+
+
+def frame_set_distance(a, b):
+    """Max over points of the set distance between two frame sets [N,F,9] (order-free)."""
+    d = (a[:, :, None, :] - b[:, None, :, :]).abs().amax(-1)   # [N,F,F]
+    return torch.maximum(d.amin(2).amax(1), d.amin(1).amax(1))

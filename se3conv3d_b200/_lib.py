@@ -1,0 +1,119 @@
+"""ctypes binding of libse3conv3d_b200.so (the C ABI declared in include/se3conv3d_b200.h).
+
+There is deliberately no fallback: if the library is missing or a call fails, an exception is
+raised.  Nothing in this package ever routes a product call through `oracle/` or a CPU path.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libse3conv3d_b200.so")
+
+# every symbol include/se3conv3d_b200.h declares (tests check the .so exports exactly these)
+ABI_SYMBOLS = [
+    "se3_abi_version", "se3_last_error", "se3_launch_count",
+    "se3_compute_keys",
+    "se3_ball_query_workspace_bytes", "se3_ball_query_count", "se3_ball_query_fill",
+    "se3_csr_transpose_workspace_bytes", "se3_csr_transpose",
+    "se3_knn_workspace_bytes", "se3_knn_query", "se3_pca_frames", "se3_quat_frames",
+    "se3_segment_pool_f32",
+    "se3_feat_basis_proj", "se3_feat_basis_proj_grad",
+    "se3_conv_fwd_workspace_bytes", "se3_conv_bwd_workspace_bytes", "se3_conv_saved_bytes",
+    "se3_conv_fwd", "se3_conv_bwd",
+]
+
+
+class ConvDesc(C.Structure):
+    """Mirror of `struct se3_conv_desc`."""
+    _fields_ = [
+        ("n_in", C.c_int64), ("n_out", C.c_int64), ("n_edges", C.c_int64),
+        ("f_in", C.c_int32), ("f_out", C.c_int32), ("c_in", C.c_int32), ("c_out", C.c_int32),
+        ("k", C.c_int32), ("act", C.c_int32), ("precision", C.c_int32), ("reserved", C.c_int32),
+        ("norm_neigh_dist", C.c_float), ("out_scale", C.c_float),
+        ("pts_in", C.c_void_p), ("pts_out", C.c_void_p), ("frames_in", C.c_void_p), ("frames_out", C.c_void_p),
+        ("row_ends", C.c_void_p), ("col_src", C.c_void_p),
+        ("t_row_ends", C.c_void_p), ("t_edge", C.c_void_p), ("t_dst", C.c_void_p),
+        ("proj_axes", C.c_void_p), ("proj_biases", C.c_void_p), ("conv_weights", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+class Se3Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Returns the loaded library; raises if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Se3Error(
+            "libse3conv3d_b200.so is missing (%s). Build it with `python -m se3conv3d_b200.build`; "
+            "this package has no CPU / PyTorch fallback by design." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32, sz, f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_size_t, C.c_float
+    L.se3_abi_version.restype = C.c_int
+    L.se3_last_error.restype = C.c_char_p
+    L.se3_launch_count.restype = i64
+    L.se3_compute_keys.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp]
+    L.se3_ball_query_workspace_bytes.argtypes = [i64, i64]
+    L.se3_ball_query_workspace_bytes.restype = sz
+    L.se3_ball_query_count.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, sz, vp, vp, vp]
+    L.se3_ball_query_fill.argtypes = [vp, i64, i64, vp, vp, sz, vp, i64, vp, vp]
+    L.se3_csr_transpose_workspace_bytes.argtypes = [i64, i64]
+    L.se3_csr_transpose_workspace_bytes.restype = sz
+    L.se3_csr_transpose.argtypes = [vp, i64, i64, i64, vp, sz, vp, vp, vp, vp, vp]
+    L.se3_knn_workspace_bytes.argtypes = [i64]
+    L.se3_knn_workspace_bytes.restype = sz
+    L.se3_knn_query.argtypes = [vp, vp, i64, i32, vp, sz, vp, vp]
+    L.se3_pca_frames.argtypes = [vp, vp, i64, i32, i32, vp, vp]
+    L.se3_quat_frames.argtypes = [vp, i64, vp, vp]
+    L.se3_segment_pool_f32.argtypes = [vp, i64, i32, vp, vp, i64, i32, vp, vp]
+    L.se3_feat_basis_proj.argtypes = [vp, vp, vp, vp, i64, i64, i32, i32, vp, vp]
+    L.se3_feat_basis_proj_grad.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, vp, vp, vp]
+    dp = C.POINTER(ConvDesc)
+    for n in ("se3_conv_fwd_workspace_bytes", "se3_conv_bwd_workspace_bytes", "se3_conv_saved_bytes"):
+        getattr(L, n).argtypes = [dp]
+        getattr(L, n).restype = sz
+    L.se3_conv_fwd.argtypes = [dp, vp, vp, vp, vp, sz, vp]
+    L.se3_conv_bwd.argtypes = [dp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    for n in ABI_SYMBOLS:
+        f = getattr(L, n)
+        if n not in ("se3_last_error", "se3_launch_count") and not n.endswith("_bytes"):
+            f.restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().se3_last_error().decode("utf-8", "replace")
+        raise Se3Error("%s failed (%d): %s" % (what or "se3 call", rc, msg))
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise Se3Error("se3conv3d_b200 kernels need CUDA tensors (got %s); there is no CPU fallback" % t.device)
+    if not t.is_contiguous():
+        raise Se3Error("tensor must be contiguous")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def launch_count():
+    return int(lib().se3_launch_count())

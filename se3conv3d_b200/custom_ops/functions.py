@@ -1,0 +1,142 @@
+import ctypes as C
+
+import torch
+
+from .. import point_cloud_lib_ops as ops
+from .._lib import lib, check, ptr, stream, workspace, ConvDesc, Se3Error
+from ..scatter import scatter_max, scatter_min
+
+ACT_CODES = {"mlp_linear": 0, "mlp_relu": 1, "mlp_gelu": 2, "mlp_sin": 3}
+
+
+class FeatBasisProj(torch.autograd.Function):
+    """T[m,c,k] = sum_e feats[src(e),c] * basis[e,k]   (custom_ops/FeatBasisProj.py:10-66)."""
+
+    @staticmethod
+    def forward(ctx, p_pt_basis, p_pt_features, p_neighbors, p_start_ids):
+        ctx.save_for_backward(p_pt_basis, p_pt_features, p_neighbors, p_start_ids)
+        return ops.feat_basis_proj(p_pt_basis, p_pt_features, p_neighbors, p_start_ids)
+
+    @staticmethod
+    def backward(ctx, p_grads):
+        basis, feats, neighbors, start_ids = ctx.saved_tensors
+        feat_grads, basis_grads = ops.feat_basis_proj_grad(basis, feats, neighbors, start_ids, p_grads.contiguous())
+        return basis_grads.to(basis.dtype), feat_grads.to(feats.dtype), None, None
+
+
+class BallQuery(torch.autograd.Function):
+    """Radius neighbours of every sample among same-batch sources (custom_ops/BallQuery.py:11-54).
+
+    The grid set-up reproduces the reference wrapper exactly, including its quirk of subtracting
+    1e-6 from the per-batch maximum as well as the minimum (custom_ops/BallQuery.py:36-37)."""
+
+    @staticmethod
+    def forward(ctx, p_pt_src, p_pt_sample, p_batch_id_src, p_batch_id_sample, radius, max_neighbors):
+        min_pt = scatter_min(p_pt_src, p_batch_id_src.to(torch.int64), dim=0)[0] - 1e-6
+        max_pt = scatter_max(p_pt_src, p_batch_id_src.to(torch.int64), dim=0)[0] - 1e-6
+        num_cells = (max_pt - min_pt) / radius
+        num_cells = torch.max(num_cells.to(torch.int32) + 1, dim=0)[0]
+        radius_tensor = torch.full((p_pt_src.shape[1],), float(radius), dtype=torch.float32, device=p_pt_src.device)
+        neighbors, start_ids = ops.ball_query(p_pt_src, p_pt_sample, p_batch_id_src, p_batch_id_sample, min_pt,
+                                              num_cells, radius_tensor, max_neighbors)
+        ctx.mark_non_differentiable(neighbors, start_ids)
+        return neighbors, start_ids
+
+    @staticmethod
+    def backward(ctx, *grads):
+        return None, None, None, None, None, None
+
+
+class KNNQuery(torch.autograd.Function):
+    """k nearest neighbours inside a batch, self included (custom_ops/KNNQuery.py:11-35)."""
+
+    @staticmethod
+    def forward(ctx, p_pt_src, p_batch_id_src, p_k):
+        out = ops.knn_query(p_pt_src, p_batch_id_src, p_k)
+        ctx.mark_non_differentiable(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, *grads):
+        return None, None, None
+
+
+class ComputeKeys(torch.autograd.Function):
+    """Voxel key per point (custom_ops/ComputeKeys.py:11-40)."""
+
+    @staticmethod
+    def forward(ctx, p_pts, p_batch_ids, p_aabb_min, p_grid_size, p_cell_size):
+        out = ops.compute_keys(p_pts, p_batch_ids, p_aabb_min, p_grid_size, p_cell_size)
+        ctx.mark_non_differentiable(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, *grads):
+        return None, None, None, None, None
+
+
+def make_conv_desc(geom, c_in, c_out, k, act, precision, norm_neigh_dist, out_scale, proj_axes, proj_biases,
+                   conv_weights):
+    """Fills a `se3_conv_desc` from a neighbourhood geometry record (see pc/ConvGeometry)."""
+    d = ConvDesc()
+    d.n_in, d.n_out, d.n_edges = geom.n_in, geom.n_out, geom.n_edges
+    d.f_in, d.f_out, d.c_in, d.c_out, d.k = geom.f_in, geom.f_out, int(c_in), int(c_out), int(k)
+    d.act, d.precision, d.reserved = int(act), int(precision), 0
+    d.norm_neigh_dist, d.out_scale = float(norm_neigh_dist), float(out_scale)
+    d.pts_in, d.pts_out = ptr(geom.pts_in), ptr(geom.pts_out)
+    d.frames_in, d.frames_out = ptr(geom.frames_in), ptr(geom.frames_out)
+    d.row_ends, d.col_src = ptr(geom.row_ends), ptr(geom.col_src)
+    d.t_row_ends, d.t_edge, d.t_dst = ptr(geom.t_row_ends), ptr(geom.t_edge), ptr(geom.t_dst)
+    d.proj_axes, d.proj_biases, d.conv_weights = ptr(proj_axes), ptr(proj_biases), ptr(conv_weights)
+    return d
+
+
+class RotEquivConv(torch.autograd.Function):
+    """Fused forward/backward of PNEConvLayerRotEquiv.__compute_convolution__
+    (layers/PNEConvLayerRotEquiv.py:160-216) through se3_conv_fwd / se3_conv_bwd."""
+
+    @staticmethod
+    def forward(ctx, x, proj_axes, proj_biases, conv_weights, geom, act, precision, norm_neigh_dist, out_scale):
+        if not x.is_cuda:
+            raise Se3Error("RotEquivConv needs CUDA tensors; there is no CPU fallback")
+        x32 = x.to(torch.float32).contiguous()
+        pa = proj_axes.detach().to(torch.float32).contiguous()
+        pb = proj_biases.detach().to(torch.float32).contiguous()
+        cw = conv_weights.detach().to(torch.float32).contiguous()
+        c_in, k, c_out = cw.shape
+        if x32.shape[0] != geom.n_in * geom.f_in or x32.shape[1] != c_in:
+            raise Se3Error("RotEquivConv: features must be [N*F_in, C_in] = [%d, %d], got %s" %
+                           (geom.n_in * geom.f_in, c_in, tuple(x32.shape)))
+        if pa.shape[0] != 9:
+            raise Se3Error("RotEquivConv: proj_axes_ must be [9, K] (p_dims=9, '6D' relative rotation)")
+        L = lib()
+        d = make_conv_desc(geom, c_in, c_out, k, act, precision, norm_neigh_dist, out_scale, pa, pb, cw)
+        y = torch.empty((geom.n_out * geom.f_out, c_out), dtype=torch.float32, device=x.device)
+        saved_bytes = L.se3_conv_saved_bytes(C.byref(d))
+        saved = workspace(saved_bytes, x.device) if saved_bytes else None
+        ws = workspace(L.se3_conv_fwd_workspace_bytes(C.byref(d)), x.device)
+        check(L.se3_conv_fwd(C.byref(d), ptr(x32), ptr(y), ptr(saved), ptr(ws), ws.numel(), stream()), "se3_conv_fwd")
+        ctx.geom = geom
+        ctx.meta = (act, precision, float(norm_neigh_dist), float(out_scale), x.dtype)
+        ctx.save_for_backward(x32, pa, pb, cw, saved if saved is not None else x32.new_empty(0))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x32, pa, pb, cw, saved = ctx.saved_tensors
+        act, precision, nnd, osc, x_dtype = ctx.meta
+        geom = ctx.geom
+        c_in, k, c_out = cw.shape
+        dy = dy.to(torch.float32).contiguous()
+        L = lib()
+        d = make_conv_desc(geom, c_in, c_out, k, act, precision, nnd, osc, pa, pb, cw)
+        need = ctx.needs_input_grad
+        dx = torch.empty_like(x32) if need[0] else None
+        dA = torch.empty_like(pa) if (need[1] or need[2]) else None
+        dB = torch.empty_like(pb) if (need[1] or need[2]) else None
+        dW = torch.empty_like(cw) if need[3] else None
+        ws = workspace(L.se3_conv_bwd_workspace_bytes(C.byref(d)), x32.device)
+        check(L.se3_conv_bwd(C.byref(d), ptr(x32), ptr(dy), ptr(saved) if saved.numel() else None, ptr(dx), ptr(dW),
+                             ptr(dA), ptr(dB), ptr(ws), ws.numel(), stream()), "se3_conv_bwd")
+        return (dx.to(x_dtype) if dx is not None else None, dA if need[1] else None, dB if need[2] else None, dW,
+                None, None, None, None, None)

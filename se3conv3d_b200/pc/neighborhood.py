@@ -1,0 +1,119 @@
+from abc import ABC, abstractmethod
+
+import torch
+
+from .._lib import lib, check, ptr, stream, workspace, Se3Error
+from ..custom_ops import BallQuery, KNNQuery
+
+
+class ConvGeometry(object):
+    """Device-resident record a conv call needs: forward CSR (int32), transposed CSR, coordinates
+    and frames.  Built once per (neighbourhood, pc_in, pc_out) and cached on the neighbourhood; it
+    replaces the reference's per-call sha256-keyed rot-tensor cache
+    (layers/PNEConvLayerRotEquiv.py:71-128) -- the expanded [E*C,9] geometry is never materialised."""
+
+    def __init__(self, p_pc_in, p_pc_out, p_neighborhood):
+        nb = p_neighborhood.neighbors_
+        if nb.dtype != torch.int64:
+            nb = nb.to(torch.int64)
+        nb = nb.contiguous()
+        dev = nb.device
+        self.n_in = int(p_pc_in.pts_.shape[0])
+        self.n_out = int(p_pc_out.pts_.shape[0])
+        self.n_edges = int(nb.shape[0])
+        self.f_in = int(getattr(p_pc_in, "n_frames_", 1))
+        self.f_out = int(getattr(p_pc_out, "n_frames_", 1))
+        self.pts_in = p_pc_in.pts_.detach().to(torch.float32).contiguous()
+        self.pts_out = p_pc_out.pts_.detach().to(torch.float32).contiguous()
+        self.frames_in = p_pc_in.local_frames_.detach().to(torch.float32).contiguous()
+        self.frames_out = p_pc_out.local_frames_.detach().to(torch.float32).contiguous()
+        self.row_ends = p_neighborhood.start_ids_.to(torch.int32).contiguous()
+        if self.row_ends.shape[0] != self.n_out:
+            raise Se3Error("neighbourhood has %d rows but the output cloud has %d points" %
+                           (self.row_ends.shape[0], self.n_out))
+        L = lib()
+        e = max(self.n_edges, 1)
+        self.col_src = torch.empty(e, dtype=torch.int32, device=dev)
+        self.t_row_ends = torch.empty(max(self.n_in, 1), dtype=torch.int32, device=dev)
+        self.t_edge = torch.empty(e, dtype=torch.int32, device=dev)
+        self.t_dst = torch.empty(e, dtype=torch.int32, device=dev)
+        ws = workspace(L.se3_csr_transpose_workspace_bytes(self.n_edges, self.n_in), dev)
+        check(L.se3_csr_transpose(ptr(nb), self.n_edges, self.n_in, self.n_out, ptr(ws), ws.numel(),
+                                  ptr(self.col_src), ptr(self.t_row_ends), ptr(self.t_edge), ptr(self.t_dst),
+                                  stream()), "se3_csr_transpose")
+
+
+class Neighborhood(ABC):
+    """Neighbourhood interface: `neighbors_` [E,2] (sample, source), `start_ids_` [M] inclusive
+    row ends (pc/Neighborhood.py:7-37)."""
+
+    def __init__(self, p_pc_src, p_samples):
+        self.pc_src_ = p_pc_src
+        self.samples_ = p_samples
+        self.neighbors_ = None
+        self.start_ids_ = None
+        self.conv_geometry_cache_ = {}
+        self.__compute_neighborhood__()
+
+    @abstractmethod
+    def __compute_neighborhood__(self):
+        pass
+
+    def conv_geometry(self, p_pc_in, p_pc_out):
+        """Cached ConvGeometry; keyed on the identity of the clouds and their frame tensors, so a
+        cloud whose frames were re-sampled gets a fresh record."""
+        key = (id(p_pc_in), id(p_pc_out), id(getattr(p_pc_in, "local_frames_", None)),
+               id(getattr(p_pc_out, "local_frames_", None)), id(self.neighbors_))
+        geom = self.conv_geometry_cache_.get(key)
+        if geom is None:
+            geom = ConvGeometry(p_pc_in, p_pc_out, self)
+            self.conv_geometry_cache_ = {key: geom}
+        return geom
+
+    def __repr__(self):
+        return "### Neighbors:\n{}\n### Start indices:\n{}".format(self.neighbors_, self.start_ids_)
+
+
+class BQNeighborhood(Neighborhood):
+    """Ball-query neighbourhood (pc/BQNeighborhood.py:12-64)."""
+
+    def __init__(self, p_pc_src, p_samples, p_radius, p_max_neighbors=0):
+        self.radius_ = p_radius
+        self.max_neighbors_ = p_max_neighbors
+        super(BQNeighborhood, self).__init__(p_pc_src, p_samples)
+
+    def __compute_neighborhood__(self):
+        self.neighbors_, self.start_ids_ = BallQuery.apply(
+            self.pc_src_.pts_, self.samples_.pts_, self.pc_src_.batch_ids_, self.samples_.batch_ids_, self.radius_,
+            self.max_neighbors_)
+
+
+class KnnNeighborhood(Neighborhood):
+    """k-NN neighbourhood (pc/KnnNeighborhood.py:14-135).  The self-query branch (k <= 32) runs on
+    the sweep kernel; the cross-cloud / standard_knn branch of the reference delegates to
+    torch_cluster.knn, which is outside this path -- it raises here."""
+
+    def __init__(self, p_pc_src, p_samples, p_k, p_keep_empty=False, p_standard_knn=False):
+        self.k_ = p_k
+        self.keep_empty_ = p_keep_empty
+        self.standard_knn_ = p_standard_knn
+        super(KnnNeighborhood, self).__init__(p_pc_src, p_samples)
+
+    def __compute_neighborhood__(self):
+        if self.pc_src_ is not self.samples_:
+            raise Se3Error("KnnNeighborhood between two different clouds (torch_cluster.knn branch, "
+                           "pc/KnnNeighborhood.py:78-84) is not part of the B200 hot path")
+        if self.k_ > 32:
+            raise Se3Error("KnnNeighborhood: k <= 32 (all shipped configs use k = 16)")
+        pts = self.pc_src_.pts_
+        n, dev = pts.shape[0], pts.device
+        cur = KNNQuery.apply(pts, self.pc_src_.batch_ids_, self.k_)
+        centers = torch.arange(n, dtype=torch.int32, device=dev).unsqueeze(1).expand(n, self.k_)
+        self.neighbors_ = torch.stack((centers.reshape(-1), cur.reshape(-1)), dim=-1)
+        if self.keep_empty_:
+            self.start_ids_ = (torch.arange(n, dtype=torch.int32, device=dev) + 1) * self.k_
+        else:
+            valid = self.neighbors_[:, 1] >= 0
+            self.neighbors_ = self.neighbors_[valid]
+            counts = torch.bincount(self.neighbors_[:, 0].to(torch.int64), minlength=n)
+            self.start_ids_ = torch.cumsum(counts, 0).to(torch.int32)

@@ -1,0 +1,107 @@
+import torch
+
+from .pointcloud import Pointcloud, pool_by_index
+from .rotation_functions import (sample_reference_frames, sample_reference_frames_pca,
+                                 sample_global_reference_frames_pca)
+from .neighborhood import KnnNeighborhood, BQNeighborhood
+
+
+def _shuffle_and_take(all_frames, n_keep):
+    """Random per-point permutation of the candidate frames, keep the first n_keep
+    (pc/PointcloudRotEquiv.py:148-168; the same torch.multinomial call, so RNG use matches)."""
+    n_points, n_frames = all_frames.shape[0], all_frames.shape[1]
+    weights = torch.ones(n_frames, device=all_frames.device).expand(n_points, -1)
+    perm = torch.multinomial(weights, num_samples=n_frames, replacement=False)
+    shuffled = torch.gather(all_frames, 1, perm[:, :, None].expand(-1, -1, all_frames.shape[-1]))
+    return shuffled[:, :n_keep, :]
+
+
+class PointcloudRotEquiv(Pointcloud):
+    """Point cloud with `n_frames_` local reference frames per point, `local_frames_` [N,F,9]
+    (same constructor / attributes as pc/PointcloudRotEquiv.py:13-52).
+
+    p_ref_frames_config keys: pca, neigh_method, neigh_kwargs, fixed_axis, n_frames."""
+
+    def __init__(self, p_pts, p_batch_ids, p_ref_frames_config, ref_frames_pts=None, standard_knn=False, **kwargs):
+        super(PointcloudRotEquiv, self).__init__(p_pts, p_batch_ids, **kwargs)
+        self.neigh_cache_ = {}
+        self.local_frames_pca_cache_ = {}
+        self.local_frames_config_ = p_ref_frames_config
+        self.standard_knn_ = standard_knn
+        self.ref_frames_pts = ref_frames_pts
+        frames = self.get_local_ref_frames()
+        self.n_frames_ = frames.shape[1]
+        self.local_frames_ = torch.as_tensor(frames, **kwargs).contiguous()
+        self.batch_ids_considering_frames_ = torch.repeat_interleave(self.batch_ids_, self.n_frames_)
+        if self.pts_with_grads_:
+            self.local_frames_.requires_grad = True
+
+    def get_ref_frame_neighborhood(self, p_neigh_method, **kwargs):
+        key = str(p_neigh_method)
+        if p_neigh_method == "knn":
+            key += str(kwargs["neigh_k"])
+        elif p_neigh_method == "ball_query":
+            key += str(kwargs["bq_radius"])
+        if key not in self.neigh_cache_:
+            if p_neigh_method == "knn":
+                # keep_empty: every point gets exactly k entries even in tiny clouds
+                self.neigh_cache_[key] = KnnNeighborhood(self, self, kwargs["neigh_k"], p_keep_empty=True,
+                                                         p_standard_knn=self.standard_knn_)
+            elif p_neigh_method == "ball_query":
+                self.neigh_cache_[key] = BQNeighborhood(self, self, kwargs["bq_radius"])
+            else:
+                raise ValueError("unknown neighbourhood method " + str(p_neigh_method))
+        return self.neigh_cache_[key]
+
+    def get_local_ref_frames(self):
+        cfg = self.local_frames_config_
+        dev = self.pts_.device
+        if cfg["pca"]:
+            if "se3-all" not in self.local_frames_pca_cache_:
+                if self.ref_frames_pts is not None:
+                    b = self.pts_.shape[0]  # one point per batch item
+                    pts = self.ref_frames_pts.reshape(b, -1, self.ref_frames_pts.shape[-1])
+                    cand = sample_global_reference_frames_pca(pts, axis_fixed=cfg["fixed_axis"], device=dev)
+                else:
+                    neigh = self.get_ref_frame_neighborhood(cfg["neigh_method"], **cfg["neigh_kwargs"])
+                    cand = sample_reference_frames_pca(self.pts_, neigh, axis_fixed=cfg["fixed_axis"], device=dev)
+                self.local_frames_pca_cache_["se3-all"] = cand
+            return _shuffle_and_take(self.local_frames_pca_cache_["se3-all"], cfg["n_frames"])
+        n_origins = 1 if self.ref_frames_pts is not None else self.pts_.shape[0]
+        return sample_reference_frames(n_origins=n_origins, n_frames=cfg["n_frames"], axis_fixed=cfg["fixed_axis"],
+                                       device=dev)
+
+    def to_device(self, p_device):
+        super(PointcloudRotEquiv, self).to_device(p_device)
+        self.local_frames_ = self.local_frames_.to(p_device)
+        self.batch_ids_considering_frames_ = self.batch_ids_considering_frames_.to(p_device)
+
+    def feature_pooling(self, p_in_tensor, p_pooling_method="avg"):
+        """Pools the F per-frame feature rows of every point (pc/PointcloudRotEquiv.py:224-251)."""
+        f = self.local_frames_config_["n_frames"]
+        n = self.pts_.shape[0]
+        x = p_in_tensor.reshape(n, f, *p_in_tensor.shape[1:])
+        if p_pooling_method == "avg":
+            return x.mean(dim=1)
+        if p_pooling_method == "sum":
+            return x.sum(dim=1)
+        if p_pooling_method == "max":
+            return x.max(dim=1)[0]
+        if p_pooling_method == "min":
+            return x.min(dim=1)[0]
+        raise ValueError("unknown pooling method " + str(p_pooling_method))
+
+    def global_pooling_specific_feature_pooling(self, p_in_tensor, p_global_pooling_method="avg",
+                                                p_feature_pooling_method="avg"):
+        pooled = self.feature_pooling(p_in_tensor, p_pooling_method=p_feature_pooling_method)
+        return pool_by_index(pooled, self.batch_ids_.to(torch.int64), p_global_pooling_method)
+
+    def global_pooling(self, p_in_tensor, p_pooling_method="avg"):
+        return pool_by_index(p_in_tensor, self.batch_ids_considering_frames_.to(torch.int64), p_pooling_method)
+
+    def global_upsample(self, p_in_tensor):
+        return torch.index_select(p_in_tensor, 0, self.batch_ids_considering_frames_.to(torch.int64))
+
+    def __repr__(self):
+        return "### Points:\n{}\n### Local Ref Frames:\n{}\n### Batch Ids:\n{}\n### Batch Size:\n{}".format(
+            self.pts_, self.local_frames_, self.batch_ids_, self.batch_size_)
