@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py -- points/sec of the PNEConvLayerRotEquiv hot path (hierarchy + frames + neighbourhoods +
+21 fused convolutions, forward and backward) on the dfaust_I_rot_pca_2F shapes (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU port of the reference path
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the definition of every key.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_CLOUDS, N_POINTS = 32, 6890
+METRIC = "points/sec PNEConvLayerRotEquiv fwd+bwd (dfaust_I_rot_pca_2F hot path, F=2)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", type=int, default=int(os.environ.get("SE3_PRECISION", "0")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler(object):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_bytes(spec_sizes):
+    """SURVEY 8(d) gather model, fp32 features: bytes one conv forward / backward must move."""
+    fwd = bwd = 0.0
+    for (m, e, f, cin, cout) in spec_sizes:
+        kbar = e / max(m, 1)
+        w = (cin * 32 * cout + 9 * 32 + 32) * 4
+        fwd += m * (kbar * (4 + 12 + 36 * f + f * cin * 4) + (12 + 36 * f + 4) + f * cout * 4) + w
+        bwd += m * (kbar * (2 * (4 + 12 + 36 * f) + f * cin * 4 + f * cout * 4) + f * cout * 4 + f * cin * 4) + 2 * w
+    return fwd, bwd
+
+
+def run_reference(args, rank, world):
+    """CPU port of the reference path (oracle/), all host threads, bounded sample: ONE cloud per step."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import hierarchy_oracle as ho
+    from se3conv3d_b200 import workloads as wl
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pts, batch = wl.synthetic_bodies(1, N_POINTS, seed=0)
+    specs = wl.dfaust_conv_specs()
+    torch.manual_seed(0)
+    params = []
+    for (_, _, _, _, cin, cout) in specs:
+        params.append((torch.empty(9, 32).uniform_(-1 / 3, 1 / 3), torch.zeros(32),
+                       torch.empty(cin, 32, cout).uniform_(-1, 1) / (cin * 32) ** 0.5))
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        ho.dfaust_step_cpu(pts.numpy(), batch.numpy(), specs, params, wl.DFAUST_CFG)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = N_POINTS * len(times) / total
+    sample = "1 of %d clouds (%d points) per step through the full hot path, oracle port (torch CPU + C)" % (
+        N_CLOUDS, N_POINTS)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "dfaust_I_rot_pca_2F conv stack (21 convs) + hierarchy, 6890-point clouds, F=2",
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import torch
+    import torch.distributed as dist
+    from se3conv3d_b200 import _lib, workloads as wl
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+
+    # ---- workload: 32 clouds x 6890 points per GPU (weak scaling: clouds are independent, no collective)
+    pts_h, batch_h = wl.synthetic_bodies(N_CLOUDS, N_POINTS, seed=rank)
+    pts_h, batch_h = pts_h.pin_memory(), batch_h.pin_memory()
+    step = wl.DfaustStep(dev, precision=args.precision, seed=0)
+    pts_d, batch_d = pts_h.to(dev), batch_h.to(dev)
+    pcs, neighs = step.build_hierarchy(pts_d, batch_d)
+    step.calibrate(pcs, neighs)
+    step.make_inputs(pcs)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def hot_step(p, b):
+        pcs_, neighs_ = step.build_hierarchy(p, b)
+        return step.conv_fwd_bwd(pcs_, neighs_)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+            step.zero_grad()
+        barrier()
+        tot = 0.0
+        for _ in range(steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            tot += e0.elapsed_time(e1)
+            step.zero_grad()
+        barrier()
+        t = torch.tensor([tot], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = _lib.launch_count()
+    # (1) device-resident: hierarchy + neighbourhoods + conv stack fwd+bwd
+    ms_total = timed(lambda: hot_step(pts_d, batch_d), args.steps, args.warmup)
+    launches = (_lib.launch_count() - launches0) // max(args.steps + args.warmup, 1) * args.steps
+
+    # (2) end to end: pinned host buffers -> H2D -> hot path -> D2H of the checksum
+    def e2e_step():
+        p = pts_h.to(dev, non_blocking=True)
+        b = batch_h.to(dev, non_blocking=True)
+        return float(hot_step(p, b).item())
+
+    ms_e2e = timed(e2e_step, args.steps, max(args.warmup, 3))
+    # (3) convolutions only (hierarchy cached), and the dominant layer alone for the roofline
+    ms_conv = timed(lambda: step.conv_fwd_bwd(pcs, neighs), args.steps, args.warmup)
+    clk = clocks.stop()
+
+    sizes = [(pcs[lo].pts_.shape[0], nb.neighbors_.shape[0], 2, cin, cout)
+             for (_, li, lo, _, cin, cout), nb in zip(step.specs, neighs)]
+    fwd_b, bwd_b = algorithmic_bytes(sizes)
+    # dominant kernel(s): time every conv's forward and backward separately through the C ABI call
+    per_layer = []
+    xs, dys = step.inputs
+    for layer, nb, (name, li, lo, _, cin, cout), x, dy, sz in zip(step.layers, neighs, step.specs, xs, dys, sizes):
+        def one():
+            y = layer(pcs[li], pcs[lo], x, nb)
+            y.backward(dy)
+        t = timed(one, max(args.steps // 2, 3), 2)
+        fb, bb = algorithmic_bytes([sz])
+        per_layer.append({"name": name, "ms": t / max(args.steps // 2, 3), "alg_bytes": fb + bb,
+                          "m": sz[0], "e": sz[1], "c_in": cin, "c_out": cout})
+    dom = max(per_layer, key=lambda d: d["ms"])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = dom["alg_bytes"] / (dom["ms"] * 1e-3) / 1e9
+
+    n_pts_global = N_CLOUDS * N_POINTS * world
+    value = n_pts_global * args.steps / (ms_total * 1e-3)
+    e2e_value = n_pts_global * args.steps / (ms_e2e * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32" if args.precision == 0 else "bf16", "data": "synthetic",
+        "config": {"workload": "dfaust_I_rot_pca_2F hot path: grid hierarchy (0.04;0.05,0.1,0.2,0.4) + kNN16/PCA frames "
+                               "+ ball-query CSRs + 21 PNEConvLayerRotEquiv fwd+bwd, 32 clouds x 6890 points per GPU, F=2",
+                   "points_per_gpu": N_CLOUDS * N_POINTS, "precision": args.precision,
+                   "l2": "256 MB flush write between timed iterations",
+                   "level_points": [int(p.pts_.shape[0]) for p in pcs], "edges_total": int(sum(s[1] for s in sizes))},
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(pts_h.numel() * 4 + batch_h.numel() * 4), "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "breakdown_ms": {"hierarchy_frames_neighbourhoods": (ms_total - ms_conv) / args.steps,
+                         "conv_fwd_bwd_x21": ms_conv / args.steps},
+        "conv_only_points_per_s": n_pts_global * args.steps / (ms_conv * 1e-3),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "se3_conv_fwd+bwd of layer %s (M=%d E=%d %d->%d)" % (
+                         dom["name"], dom["m"], dom["e"], dom["c_in"], dom["c_out"]),
+                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
+                     "stack_alg_gb_per_step": (fwd_b + bwd_b) / 1e9,
+                     "stack_achieved_gbs": (fwd_b + bwd_b) / (ms_conv / args.steps * 1e-3) / 1e9},
+        "per_layer_ms": {d["name"]: round(d["ms"], 4) for d in per_layer},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # CPU port of the same hot path on a bounded sample (one cloud), all host threads
+        from oracle import hierarchy_oracle as ho
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        p1, b1 = wl.synthetic_bodies(1, N_POINTS, seed=0)
+        params = [(l.proj_axes_.detach().cpu(), l.proj_biases_.detach().cpu(), l.conv_weights_.detach().cpu())
+                  for l in step.layers]
+        ho.dfaust_step_cpu(p1.numpy(), b1.numpy(), step.specs, params, wl.DFAUST_CFG)
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 3 or (time.perf_counter() - t0 < 10 and reps < 20):
+            ho.dfaust_step_cpu(p1.numpy(), b1.numpy(), step.specs, params, wl.DFAUST_CFG)
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        line["cpu_baseline"] = {"value": N_POINTS / dt, "unit": "points/s", "cores": cores, "kind": "port",
+                                "sample": "1 of 32 clouds (6890 points) per step, oracle port (torch CPU + C), %d reps" % reps}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

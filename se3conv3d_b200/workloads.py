@@ -1,0 +1,148 @@
+"""Synthetic workloads of the named shapes (BASELINE.json configs) built on the public API.
+
+dfaust_conv_stack: the 21 PNEConvLayerRotEquiv calls one forward of FPNSegUNetMLPGeluRotEqFAUST issues
+(tasks/SemSeg/seg_models.py:16-36 with models/PatchEncoder.py:95-106, Encoder.py:134-171,
+Decoder.py:72-96, FPNDecoder.py:104-132, PatchDecoder.py:62-82, FPNSegUNet.py:166-182), with their
+levels, radii (2.0 x level cell size) and channel widths, on the hierarchy create_hierarchy builds
+(tasks/SemSeg/train_dfaust_rot.py:108-158; confs/dfaust/dfaust_I_rot_pca_2F.yaml).
+"""
+import math
+
+import torch
+
+DFAUST_CFG = {
+    "init_subsample": 0.04,
+    "grid_subsamples": [0.05, 0.1, 0.2, 0.4],
+    "RefFrames": {"pca": True, "neigh_method": "knn", "neigh_kwargs": {"neigh_k": 16}, "fixed_axis": False,
+                  "n_frames": 2},
+}
+
+
+def synthetic_bodies(n_clouds=32, n_points=6890, seed=0):
+    """SMPL-sized synthetic clouds: points on a union of capsules (torso, head, 2 arms, 2 legs) inside a
+    0.6 x 0.3 x 1.8 m box, N(0, 0.005) noise.  Returns pts [B*n,3] f32, batch ids i32."""
+    g = torch.Generator().manual_seed(seed)
+    # (centre a, centre b, radius, weight)
+    caps = [((0.0, 0.0, 0.95), (0.0, 0.0, 1.45), 0.13, 0.30), ((0.0, 0.0, 1.62), (0.0, 0.0, 1.70), 0.09, 0.08),
+            ((-0.20, 0.0, 1.40), (-0.28, 0.0, 0.85), 0.045, 0.12), ((0.20, 0.0, 1.40), (0.28, 0.0, 0.85), 0.045, 0.12),
+            ((-0.09, 0.0, 0.90), (-0.11, 0.0, 0.08), 0.07, 0.19), ((0.09, 0.0, 0.90), (0.11, 0.0, 0.08), 0.07, 0.19)]
+    w = torch.tensor([c[3] for c in caps])
+    total = n_clouds * n_points
+    which = torch.multinomial(w, total, replacement=True, generator=g)
+    a = torch.tensor([c[0] for c in caps])[which]
+    b = torch.tensor([c[1] for c in caps])[which]
+    r = torch.tensor([c[2] for c in caps])[which]
+    t = torch.rand(total, generator=g)
+    d = torch.randn(total, 3, generator=g)
+    axis = (b - a) / (b - a).norm(dim=1, keepdim=True)
+    d = d - (d * axis).sum(1, keepdim=True) * axis          # direction orthogonal to the capsule axis
+    d = d / d.norm(dim=1, keepdim=True).clamp_min(1e-9)
+    pts = a + (b - a) * t[:, None] + d * r[:, None] + 0.005 * torch.randn(total, 3, generator=g)
+    # small per-cloud pose jitter so the clouds differ
+    ang = (torch.rand(n_clouds, generator=g) - 0.5) * 0.6
+    c, s = torch.cos(ang), torch.sin(ang)
+    batch = torch.arange(n_clouds).repeat_interleave(n_points)
+    x = pts[:, 0] * c[batch] - pts[:, 1] * s[batch]
+    y = pts[:, 0] * s[batch] + pts[:, 1] * c[batch]
+    pts = torch.stack((x, y, pts[:, 2]), 1).to(torch.float32).contiguous()
+    return pts, batch.to(torch.int32)
+
+
+def uniform_cloud(n, seed=0):
+    """BASELINE config 1: torch.rand(n,3) with manual_seed(seed), one batch item."""
+    pts = torch.rand(n, 3, generator=torch.Generator().manual_seed(seed))
+    return pts, torch.zeros(n, dtype=torch.int32)
+
+
+# (name, level_in, level_out, radius_level, c_in, c_out); level 5 = the output cloud of the seg head
+def dfaust_conv_specs():
+    feats, lv = [32, 64, 128, 256], [1, 2, 3, 4]
+    specs = [("patch_enc0", 0, 1, 0, 1, 32), ("patch_enc1", 1, 1, 1, 32, 32)]
+    for i, (f, l) in enumerate(zip(feats, lv)):
+        specs += [("enc%d_block%d" % (i, j), l, l, l, f, f) for j in range(2)]
+        if i < 3:
+            specs.append(("enc%d_down" % i, l, l + 1, l, f, feats[i + 1]))
+    specs += [("dec%d" % i, 4 - i, 3 - i, 4 - i, feats[3 - i], feats[2 - i]) for i in range(3)]
+    specs += [("fpn%d" % i, 4 - i, 1, 4 - i, 32, 32) for i in range(3)]
+    specs += [("patch_dec0", 1, 0, 1, 32, 32), ("seg_head", 0, 5, 0, 32, 32)]
+    assert len(specs) == 21
+    return specs
+
+
+class DfaustStep(object):
+    """One 'step' of the dfaust_I_rot_pca_2F hot path: hierarchy + frames + neighbourhoods + the 21
+    convolutions forward and backward.  Layers and their inputs are independent (no BN / MLP glue --
+    that is SURVEY 8 row f2), each conv gets a fixed random input and output gradient."""
+
+    def __init__(self, device, precision=0, seed=0):
+        from .layers import PNEConvLayerRotEquiv
+        self.device = device
+        self.specs = dfaust_conv_specs()
+        torch.manual_seed(seed)
+        self.layers = []
+        for (_, _, _, _, cin, cout) in self.specs:
+            layer = PNEConvLayerRotEquiv(9, cin, cout, 32, "mlp_gelu").to(device)
+            layer.precision = precision
+            self.layers.append(layer)
+        self.inputs = None
+
+    def build_hierarchy(self, pts, batch_ids):
+        from .pc import Pointcloud, GridSubSample, PointcloudRotEquiv, PointHierarchyRotEquiv
+        cfg = DFAUST_CFG
+        with torch.no_grad():
+            pc = Pointcloud(pts, batch_ids)
+            samp = GridSubSample(pc, cfg["init_subsample"])
+            new_pts = samp.__subsample_tensor__(pc.pts_, "avg")
+            new_b = samp.__subsample_tensor__(pc.batch_ids_, "max")
+            new_pc = PointcloudRotEquiv(new_pts, new_b, cfg["RefFrames"])
+            h = PointHierarchyRotEquiv(new_pc, len(cfg["grid_subsamples"]), "grid_avg", grid_radii=cfg["grid_subsamples"])
+            # output cloud of the seg head: one random point per 0.04 cell (output_subsample)
+            osamp = GridSubSample(pc, cfg["init_subsample"], p_rnd_sample=True)
+            out_pc = PointcloudRotEquiv(osamp.__subsample_tensor__(pc.pts_, "avg"),
+                                        osamp.__subsample_tensor__(pc.batch_ids_, "max"), cfg["RefFrames"])
+            radii = [cfg["init_subsample"]] + cfg["grid_subsamples"]
+            pcs = list(h.pcs_) + [out_pc]
+            neighs = []
+            for (_, li, lo, lr, _, _) in self.specs:
+                r = 2.0 * radii[lr]
+                if lo == 5:
+                    from .pc import BQNeighborhood
+                    nb = BQNeighborhood(pcs[li], out_pc, r)
+                else:
+                    nb = h.create_neighborhood(li, lo, "ball_query", bq_radius=r)
+                neighs.append(nb)
+        return pcs, neighs
+
+    def calibrate(self, pcs, neighs):
+        """What the pre-process epoch converges to: norm_neigh_dist_ = 1/r, norm_num_neighs_ = M/E."""
+        for layer, nb in zip(self.layers, neighs):
+            layer.norm_neigh_dist_.fill_(1.0 / nb.radius_)
+            layer.norm_num_neighs_.fill_(nb.start_ids_.shape[0] / max(nb.neighbors_.shape[0], 1))
+
+    def make_inputs(self, pcs, seed=1):
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        xs, dys = [], []
+        for (_, li, lo, _, cin, cout) in self.specs:
+            xs.append(torch.randn(pcs[li].pts_.shape[0] * 2, cin, generator=g).to(self.device).requires_grad_(True))
+            dys.append(torch.randn(pcs[lo].pts_.shape[0] * 2, cout, generator=g).to(self.device) / math.sqrt(cout))
+        self.inputs = (xs, dys)
+        return xs, dys
+
+    def conv_fwd_bwd(self, pcs, neighs, xs=None, dys=None):
+        if xs is None:
+            xs, dys = self.inputs
+        checksum = None
+        for layer, nb, (_, li, lo, _, _, _), x, dy in zip(self.layers, neighs, self.specs, xs, dys):
+            y = layer(pcs[li], pcs[lo], x, nb)
+            y.backward(dy)
+            s = y.detach().sum()
+            checksum = s if checksum is None else checksum + s
+        return checksum
+
+    def zero_grad(self):
+        for layer in self.layers:
+            for p in layer.parameters():
+                p.grad = None
+        if self.inputs is not None:
+            for x in self.inputs[0]:
+                x.grad = None

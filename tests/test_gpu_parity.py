@@ -163,8 +163,18 @@ def test_pca_frames_match_oracle_and_golden():
         got = sample_reference_frames_pca(pts.to(DEV), neigh, axis_fixed=axis).cpu().double()
         ref = torch.from_numpy(g["frames64_" + tag])
         assert got.shape == ref.shape
-        # frames compared as sets (eigenvector sign is backend-defined); all eigengaps are healthy in this fixture
-        assert float(lo.frame_set_distance(got, ref).max()) < 2e-4
+        # Frames are compared as SETS up to the backend-defined eigenvector signs: on the 4-frame branch the set
+        # is invariant; on the fixed-axis branch the sign of the (v0, fixed) column pair follows LAPACK's arbitrary
+        # choice (RotationFunctions.py:374-383), so the admissible alternatives are the proper column-sign flips.
+        # All eigengaps are healthy in this fixture.
+        dist = None
+        for sg in ((1, 1, 1), (-1, 1, -1), (1, -1, -1), (-1, -1, 1)):
+            alt = (got.reshape(n, -1, 3, 3) * torch.tensor(sg, dtype=got.dtype)).reshape(got.shape)
+            d = lo.frame_set_distance(alt, ref)
+            dist = d if dist is None else torch.minimum(dist, d)
+        assert float(dist.max()) < 2e-4
+        R = got.reshape(-1, 3, 3)
+        assert torch.allclose(R.transpose(1, 2) @ R, torch.eye(3, dtype=R.dtype).expand_as(R), atol=1e-5)
 
 
 def test_mc_frames_match_golden():
