@@ -56,6 +56,32 @@ int se3_compute_keys(const float* pts, const int32_t* batch_ids, int64_t n,
                      const float* aabb_min, const int32_t* num_cells, const float* cell_size,
                      int64_t* keys_out, se3_stream_t stream);
 
+/* Per-batch bounding box and grid extents without host round trips.  Replaces the scatter_min /
+ * scatter_max + elementwise chain of pc/BoundingBox.py:17-18 + pc/Grid.py:26-28 (max_pad = +1e-6) and of
+ * custom_ops/BallQuery.py:36-39 (max_pad = -1e-6: the wrapper subtracts 1e-6 from the maximum too):
+ *   min_pt[b] = min_b(p) - 1e-6,  max_pt[b] = max_b(p) + max_pad,
+ *   num_cells = max_b( int((max_pt - min_pt) * (1/cell)) + 1 )      (fp32; torch's CUDA division by a
+ *   host scalar is a multiplication by the reciprocal, which is what the reference executes). */
+int se3_grid_setup(const float* pts, const int32_t* batch_ids, int64_t n, int32_t n_batches, float cell,
+                   float max_pad, float* min_pt_out, float* max_pt_out, int32_t* num_cells_out,
+                   se3_stream_t stream);
+
+/* Dense cell ranks of a voxel grid (pc/Grid.py:39-58: compute_keys -> unique(return_inverse) -> argsort):
+ *   cell_ids [N] int64 = rank of the point's key among the distinct keys (sorted-key order),
+ *   sorted_ids [N] int64 = stable argsort(cell_ids), cell_ends [N] int32 = inclusive end of every cell
+ *   in that order (first *m_out entries valid), m_out = device int64 number of occupied cells. */
+size_t se3_grid_cells_workspace_bytes(int64_t n);
+int se3_grid_cells(const float* pts, const int32_t* batch_ids, int64_t n, const float* min_pt,
+                   const int32_t* num_cells, float cell, void* workspace, size_t workspace_bytes,
+                   int64_t* cell_ids, int64_t* sorted_ids, int32_t* cell_ends, int64_t* m_out,
+                   se3_stream_t stream);
+
+/* Keeps n_keep of the n_cand candidate frames of every point after a uniform random permutation
+ * (pc/PointcloudRotEquiv.py:148-168); u [N] uniform in [0,1) supplies the randomness (u = NULL keeps
+ * the first n_keep).  cand [N,n_cand,9] -> out [N,n_keep,9]. */
+int se3_frames_select(const float* cand, const float* u, int64_t n, int32_t n_cand, int32_t n_keep,
+                      float* out, se3_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Ball query.  Replaces ball_query (custom_ops/ball_query/ball_query.cu:22-104 and its five
  * kernels; caller custom_ops/BallQuery.py:44-52).  Two phases because E is data dependent and

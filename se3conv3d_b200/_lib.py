@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libse3conv3d_b200.so")
 # every symbol include/se3conv3d_b200.h declares (tests check the .so exports exactly these)
 ABI_SYMBOLS = [
     "se3_abi_version", "se3_last_error", "se3_launch_count",
-    "se3_compute_keys",
+    "se3_compute_keys", "se3_grid_setup", "se3_grid_cells_workspace_bytes", "se3_grid_cells", "se3_frames_select",
     "se3_ball_query_workspace_bytes", "se3_ball_query_count", "se3_ball_query_fill",
     "se3_csr_transpose_workspace_bytes", "se3_csr_transpose",
     "se3_knn_workspace_bytes", "se3_knn_query", "se3_pca_frames", "se3_quat_frames",
@@ -61,6 +61,11 @@ def lib():
     L.se3_last_error.restype = C.c_char_p
     L.se3_launch_count.restype = i64
     L.se3_compute_keys.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp]
+    L.se3_grid_setup.argtypes = [vp, vp, i64, i32, f32, f32, vp, vp, vp, vp]
+    L.se3_grid_cells_workspace_bytes.argtypes = [i64]
+    L.se3_grid_cells_workspace_bytes.restype = sz
+    L.se3_grid_cells.argtypes = [vp, vp, i64, vp, vp, f32, vp, sz, vp, vp, vp, vp, vp]
+    L.se3_frames_select.argtypes = [vp, vp, i64, i32, i32, vp, vp]
     L.se3_ball_query_workspace_bytes.argtypes = [i64, i64]
     L.se3_ball_query_workspace_bytes.restype = sz
     L.se3_ball_query_count.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, sz, vp, vp, vp]
@@ -109,6 +114,31 @@ def ptr(t):
 
 def stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+def grid_setup(pts, batch_ids, n_batches, cell, max_pad):
+    """Per-batch (min - 1e-6, max + max_pad) and the grid extents, on the device, no host sync."""
+    pts = pts.to(torch.float32).contiguous()
+    b = batch_ids.to(torch.int32).contiguous()
+    mn = torch.empty((n_batches, 3), dtype=torch.float32, device=pts.device)
+    mx = torch.empty((n_batches, 3), dtype=torch.float32, device=pts.device)
+    nc = torch.empty(3, dtype=torch.int32, device=pts.device)
+    check(lib().se3_grid_setup(ptr(pts), ptr(b), pts.shape[0], int(n_batches), float(cell), float(max_pad), ptr(mn),
+                               ptr(mx), ptr(nc), stream()), "se3_grid_setup")
+    return mn, mx, nc
+
+
+def num_batches(pc):
+    """Number of batch items of a cloud as a host int, cached on the object (one sync per root cloud;
+    sub-sampled clouds inherit it)."""
+    nb = getattr(pc, "batch_size_host_", None)
+    if nb is None:
+        nb = int(pc.batch_size_)
+        try:
+            pc.batch_size_host_ = nb
+        except AttributeError:
+            pass
+    return nb
 
 
 def workspace(nbytes, device):

@@ -187,6 +187,12 @@ __global__ void k_splitk_reduce(const float* __restrict__ partials, int splits, 
   }
 }
 
+void splitk_reduce_launch(const float* partials, int splits, int64_t mn, float alpha, float* c, cudaStream_t st) {
+  int64_t blocks = (mn + 255) / 256;
+  if (blocks > (int64_t)num_sms() * 8) blocks = (int64_t)num_sms() * 8;
+  k_splitk_reduce<<<(int)blocks, 256, 0, st>>>(partials, splits, mn, alpha, c);
+}
+
 int launch_sgemm(bool at, bool bt, int64_t m, int64_t n, int64_t k, float alpha, const float* a, int64_t lda,
                  const float* b, int64_t ldb, float* c, int64_t ldc, int splits, float* partials, cudaStream_t st) {
   if (m == 0 || n == 0) return SE3_OK;

@@ -109,6 +109,241 @@ extern "C" int se3_compute_keys(const float* pts, const int32_t* batch_ids, int6
 }
 
 // ---------------------------------------------------------------------------------------------
+// bounding box / grid extents, dense cell ranks, frame selection
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_min_f32(float* a, float v) {
+  if (v >= 0) atomicMin((int*)a, __float_as_int(v)); else atomicMax((unsigned*)a, __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f32(float* a, float v) {
+  if (v >= 0) atomicMax((int*)a, __float_as_int(v)); else atomicMin((unsigned*)a, __float_as_uint(v));
+}
+
+__global__ void k_bbox_init(float* mn, float* mx, int nb3) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb3; i += gridDim.x * blockDim.x) {
+    mn[i] = INFINITY;
+    mx[i] = -INFINITY;
+  }
+}
+
+__global__ void k_bbox_reduce(const float* __restrict__ pts, const int* __restrict__ batch, int64_t n, float* mn,
+                              float* mx) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t base = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) - lane; base < n;
+       base += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = base + lane;
+    const bool ok = i < n;
+    const int b = ok ? batch[i] : -1;
+    float v[3] = {0.f, 0.f, 0.f};
+    if (ok) { v[0] = pts[3 * i]; v[1] = pts[3 * i + 1]; v[2] = pts[3 * i + 2]; }
+    const int b0 = __shfl_sync(0xffffffffu, b, 0);
+    const bool uniform = __all_sync(0xffffffffu, b == b0);
+    if (uniform) {  // the common case: batch ids are contiguous
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        float lo = v[d], hi = v[d];
+        for (int o = 16; o > 0; o >>= 1) {
+          lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+          hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (lane == 0) { atomic_min_f32(mn + 3 * b0 + d, lo); atomic_max_f32(mx + 3 * b0 + d, hi); }
+      }
+    } else if (ok) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { atomic_min_f32(mn + 3 * b + d, v[d]); atomic_max_f32(mx + 3 * b + d, v[d]); }
+    }
+  }
+}
+
+__global__ void k_bbox_finalize(float* mn, float* mx, int nb, float cell, float max_pad, int* num_cells) {
+  // one warp; batches without points keep (+inf, -inf) and do not contribute
+  const int lane = threadIdx.x;
+  const float inv = __fdiv_rn(1.0f, cell);
+  int best[3] = {1, 1, 1};
+  bool any = false;
+  for (int b = lane; b < nb; b += 32) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float lo = mn[3 * b + d], hi = mx[3 * b + d];
+      if (lo <= hi) {
+        const float plo = __fsub_rn(lo, 1e-6f), phi = __fadd_rn(hi, max_pad);
+        mn[3 * b + d] = plo;
+        mx[3 * b + d] = phi;
+        const int c = (int)__fmul_rn(__fsub_rn(phi, plo), inv) + 1;
+        best[d] = any ? max(best[d], c) : c;
+      } else {
+        mn[3 * b + d] = 0.0f;
+        mx[3 * b + d] = 0.0f;
+      }
+    }
+    if (mn[3 * b] <= mx[3 * b]) any = true;
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    int v = any ? best[d] : INT_MIN;
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) num_cells[d] = v == INT_MIN ? 1 : v;
+  }
+}
+
+extern "C" int se3_grid_setup(const float* pts, const int32_t* batch_ids, int64_t n, int32_t n_batches, float cell,
+                              float max_pad, float* min_pt_out, float* max_pt_out, int32_t* num_cells_out,
+                              se3_stream_t stream) {
+  SE3_CHECK_ARG(n >= 0 && n_batches >= 1 && cell > 0.0f, "bad arguments");
+  SE3_CHECK_ARG(pts && batch_ids && min_pt_out && max_pt_out && num_cells_out, "null pointer");
+  cudaStream_t st = as_stream(stream);
+  k_bbox_init<<<(n_batches * 3 + 127) / 128, 128, 0, st>>>(min_pt_out, max_pt_out, n_batches * 3);
+  SE3_LAUNCH_CHECK();
+  if (n > 0) {
+    k_bbox_reduce<<<grid_for(n, 256), 256, 0, st>>>(pts, batch_ids, n, min_pt_out, max_pt_out);
+    SE3_LAUNCH_CHECK();
+  }
+  k_bbox_finalize<<<1, 32, 0, st>>>(min_pt_out, max_pt_out, n_batches, cell, max_pad, num_cells_out);
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
+}
+
+__global__ void k_cell_keys(const float* __restrict__ pts, const int* __restrict__ batch, int64_t n,
+                            const float* __restrict__ aabb_min, const int* __restrict__ num_cells, float cell,
+                            int64_t* __restrict__ keys, int* __restrict__ iota) {
+  GridParams g;
+  g.nx = num_cells[0]; g.ny = num_cells[1]; g.nz = num_cells[2];
+  g.ix = g.iy = g.iz = __fdiv_rn(1.0f, cell);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = batch[i];
+    int cx, cy, cz;
+    point_cell(g, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], aabb_min[3 * b], aabb_min[3 * b + 1],
+               aabb_min[3 * b + 2], cx, cy, cz);
+    keys[i] = cell_key(g, b, cx, cy, cz);
+    iota[i] = (int)i;
+  }
+}
+
+__global__ void k_cell_flags(const int64_t* __restrict__ keys_sorted, int64_t n, int* __restrict__ flags) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    flags[i] = (i == 0 || keys_sorted[i] != keys_sorted[i - 1]) ? 1 : 0;
+}
+
+__global__ void k_cell_ranks(const int* __restrict__ rank1, const int* __restrict__ idx_sorted, int64_t n,
+                             int64_t* __restrict__ cell_ids, int64_t* __restrict__ sorted_ids,
+                             int* __restrict__ cell_ends, int64_t* __restrict__ m_out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = rank1[i] - 1;
+    const int src = idx_sorted[i];
+    cell_ids[src] = r;
+    sorted_ids[i] = src;
+    if (i == n - 1 || rank1[i + 1] - 1 != r) cell_ends[r] = (int)(i + 1);
+    if (i == n - 1) *m_out = r + 1;
+  }
+}
+
+struct CellsWorkspace {
+  int64_t* keys;
+  int64_t* keys_sorted;
+  int* iota;
+  int* idx_sorted;
+  int* flags;
+  int* rank1;
+  void* cub_tmp;
+  size_t cub_bytes;
+};
+
+static size_t cells_cub_bytes(int64_t n) {
+  size_t a = 0, b = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, a, (int64_t*)nullptr, (int64_t*)nullptr, (int*)nullptr, (int*)nullptr, (int)n);
+  cub::DeviceScan::InclusiveSum(nullptr, b, (int*)nullptr, (int*)nullptr, (int)n);
+  return a > b ? a : b;
+}
+
+static bool cells_layout(void* ws, size_t bytes, int64_t n, CellsWorkspace& w) {
+  Arena ar(ws, bytes);
+  w.keys = ar.take<int64_t>(n);
+  w.keys_sorted = ar.take<int64_t>(n);
+  w.iota = ar.take<int>(n);
+  w.idx_sorted = ar.take<int>(n);
+  w.flags = ar.take<int>(n);
+  w.rank1 = ar.take<int>(n);
+  w.cub_bytes = cells_cub_bytes(n);
+  w.cub_tmp = ar.take<char>(w.cub_bytes);
+  return ar.ok();
+}
+
+extern "C" size_t se3_grid_cells_workspace_bytes(int64_t n) {
+  if (n < 1) n = 1;
+  Arena ar(nullptr, 0);
+  ar.take<int64_t>(n); ar.take<int64_t>(n); ar.take<int>(n); ar.take<int>(n); ar.take<int>(n); ar.take<int>(n);
+  ar.take<char>(cells_cub_bytes(n));
+  return ar.off + 256;
+}
+
+extern "C" int se3_grid_cells(const float* pts, const int32_t* batch_ids, int64_t n, const float* min_pt,
+                              const int32_t* num_cells, float cell, void* workspace, size_t workspace_bytes,
+                              int64_t* cell_ids, int64_t* sorted_ids, int32_t* cell_ends, int64_t* m_out,
+                              se3_stream_t stream) {
+  SE3_CHECK_ARG(n >= 0 && n < (1ll << 31) && cell > 0.0f, "bad arguments");
+  SE3_CHECK_ARG(m_out, "null m_out");
+  cudaStream_t st = as_stream(stream);
+  if (n == 0) {
+    SE3_CUDA(cudaMemsetAsync(m_out, 0, sizeof(int64_t), st));
+    return SE3_OK;
+  }
+  SE3_CHECK_ARG(pts && batch_ids && min_pt && num_cells && workspace && cell_ids && sorted_ids && cell_ends,
+                "null pointer");
+  CellsWorkspace w;
+  if (!cells_layout(workspace, workspace_bytes, n, w)) {
+    set_error("se3_grid_cells: workspace too small");
+    return SE3_EWORKSPACE;
+  }
+  k_cell_keys<<<grid_for(n, 256), 256, 0, st>>>(pts, batch_ids, n, min_pt, num_cells, cell, w.keys, w.iota);
+  SE3_LAUNCH_CHECK();
+  size_t cb = w.cub_bytes;
+  SE3_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, cb, w.keys, w.keys_sorted, w.iota, w.idx_sorted, (int)n, 0, 64, st));
+  count_launch(8);
+  k_cell_flags<<<grid_for(n, 256), 256, 0, st>>>(w.keys_sorted, n, w.flags);
+  SE3_LAUNCH_CHECK();
+  cb = w.cub_bytes;
+  SE3_CUDA(cub::DeviceScan::InclusiveSum(w.cub_tmp, cb, w.flags, w.rank1, (int)n, st));
+  count_launch(1);
+  k_cell_ranks<<<grid_for(n, 256), 256, 0, st>>>(w.rank1, w.idx_sorted, n, cell_ids, sorted_ids, cell_ends, m_out);
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
+}
+
+__global__ void k_frames_select(const float* __restrict__ cand, const float* __restrict__ u, int64_t n, int n_cand,
+                                int n_keep, float* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int perm[4] = {0, 1, 2, 3};
+    if (u) {
+      // decode one uniform variate into a permutation (Fisher-Yates over n_cand <= 4 items)
+      int total = 1;
+      for (int k = 2; k <= n_cand; ++k) total *= k;
+      int code = min((int)(u[i] * (float)total), total - 1);
+      for (int k = 0; k < n_cand - 1; ++k) {
+        const int span = n_cand - k;
+        const int pick = k + code % span;
+        code /= span;
+        const int tmp = perm[k]; perm[k] = perm[pick]; perm[pick] = tmp;
+      }
+    }
+    for (int f = 0; f < n_keep; ++f) {
+      const float* src = cand + (i * n_cand + perm[f]) * 9;
+      float* dst = out + (i * n_keep + f) * 9;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) dst[k] = src[k];
+    }
+  }
+}
+
+extern "C" int se3_frames_select(const float* cand, const float* u, int64_t n, int32_t n_cand, int32_t n_keep,
+                                 float* out, se3_stream_t stream) {
+  SE3_CHECK_ARG(n >= 0 && n_cand >= 1 && n_cand <= 4 && n_keep >= 1 && n_keep <= n_cand, "bad arguments");
+  if (n == 0) return SE3_OK;
+  SE3_CHECK_ARG(cand && out, "null pointer");
+  k_frames_select<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(cand, u, n, n_cand, n_keep, out);
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // ball query
 // ---------------------------------------------------------------------------------------------
 struct BQWorkspace {

@@ -3,8 +3,7 @@ import ctypes as C
 import torch
 
 from .. import point_cloud_lib_ops as ops
-from .._lib import lib, check, ptr, stream, workspace, ConvDesc, Se3Error
-from ..scatter import scatter_max, scatter_min
+from .._lib import lib, check, ptr, stream, workspace, ConvDesc, Se3Error, grid_setup
 
 ACT_CODES = {"mlp_linear": 0, "mlp_relu": 1, "mlp_gelu": 2, "mlp_sin": 3}
 
@@ -31,11 +30,11 @@ class BallQuery(torch.autograd.Function):
     1e-6 from the per-batch maximum as well as the minimum (custom_ops/BallQuery.py:36-37)."""
 
     @staticmethod
-    def forward(ctx, p_pt_src, p_pt_sample, p_batch_id_src, p_batch_id_sample, radius, max_neighbors):
-        min_pt = scatter_min(p_pt_src, p_batch_id_src.to(torch.int64), dim=0)[0] - 1e-6
-        max_pt = scatter_max(p_pt_src, p_batch_id_src.to(torch.int64), dim=0)[0] - 1e-6
-        num_cells = (max_pt - min_pt) / radius
-        num_cells = torch.max(num_cells.to(torch.int32) + 1, dim=0)[0]
+    def forward(ctx, p_pt_src, p_pt_sample, p_batch_id_src, p_batch_id_sample, radius, max_neighbors, n_batches=None):
+        if n_batches is None:
+            n_batches = int(p_batch_id_src.max()) + 1
+        # min - 1e-6, max - 1e-6, num_cells = max_b(int((max - min)/radius) + 1): one fused native call
+        min_pt, _, num_cells = grid_setup(p_pt_src, p_batch_id_src, n_batches, radius, -1e-6)
         radius_tensor = torch.full((p_pt_src.shape[1],), float(radius), dtype=torch.float32, device=p_pt_src.device)
         neighbors, start_ids = ops.ball_query(p_pt_src, p_pt_sample, p_batch_id_src, p_batch_id_sample, min_pt,
                                               num_cells, radius_tensor, max_neighbors)
@@ -44,7 +43,7 @@ class BallQuery(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *grads):
-        return None, None, None, None, None, None
+        return None, None, None, None, None, None, None
 
 
 class KNNQuery(torch.autograd.Function):

@@ -2,7 +2,7 @@ from .pointcloud import Pointcloud
 from .pointcloud_rot_equiv import PointcloudRotEquiv
 from .subsample import GridSubSample
 from .neighborhood import KnnNeighborhood, BQNeighborhood
-from .._lib import Se3Error
+from .._lib import Se3Error, num_batches
 
 
 class PointHierarchy(object):
@@ -33,7 +33,9 @@ class PointHierarchy(object):
         samp = self.__make_sampler__(p_point_cloud, p_samp_method, p_id, **kwargs)
         new_pts = samp.__subsample_tensor__(p_point_cloud.pts_, "avg")
         new_batch_ids = samp.__subsample_tensor__(p_point_cloud.batch_ids_, "max")
-        return Pointcloud(new_pts, new_batch_ids), samp
+        new_pc = Pointcloud(new_pts, new_batch_ids)
+        new_pc.batch_size_host_ = num_batches(p_point_cloud)
+        return new_pc, samp
 
     def create_neighborhood(self, p_pc_src_id, p_pc_dest_id, p_neigh_method, **kwargs):
         key = str(p_pc_src_id) + "_" + str(p_pc_dest_id) + "_" + p_neigh_method
@@ -71,4 +73,5 @@ class PointHierarchyRotEquiv(PointHierarchy):
         samp = self.__make_sampler__(p_point_cloud, p_samp_method, p_id, **kwargs)
         new_pts = samp.__subsample_tensor__(p_point_cloud.pts_, "avg")
         new_batch_ids = samp.__subsample_tensor__(p_point_cloud.batch_ids_, "max")
-        return PointcloudRotEquiv(new_pts, new_batch_ids, p_point_cloud.local_frames_config_), samp
+        return PointcloudRotEquiv(new_pts, new_batch_ids, p_point_cloud.local_frames_config_,
+                                  batch_size_host=num_batches(p_point_cloud)), samp

@@ -2,7 +2,7 @@ from abc import ABC, abstractmethod
 
 import torch
 
-from .._lib import lib, check, ptr, stream, workspace, Se3Error
+from .._lib import lib, check, ptr, stream, workspace, Se3Error, num_batches
 from ..custom_ops import BallQuery, KNNQuery
 
 
@@ -85,7 +85,7 @@ class BQNeighborhood(Neighborhood):
     def __compute_neighborhood__(self):
         self.neighbors_, self.start_ids_ = BallQuery.apply(
             self.pc_src_.pts_, self.samples_.pts_, self.pc_src_.batch_ids_, self.samples_.batch_ids_, self.radius_,
-            self.max_neighbors_)
+            self.max_neighbors_, num_batches(self.pc_src_))
 
 
 class KnnNeighborhood(Neighborhood):
@@ -105,15 +105,45 @@ class KnnNeighborhood(Neighborhood):
                            "pc/KnnNeighborhood.py:78-84) is not part of the B200 hot path")
         if self.k_ > 32:
             raise Se3Error("KnnNeighborhood: k <= 32 (all shipped configs use k = 16)")
-        pts = self.pc_src_.pts_
-        n, dev = pts.shape[0], pts.device
-        cur = KNNQuery.apply(pts, self.pc_src_.batch_ids_, self.k_)
+        # [N,k] int32 table straight from the sweep kernel; the [N*k,2] pair list and the row ends of
+        # the reference layout are materialised lazily (the frame construction only needs the table)
+        self.knn_table_ = KNNQuery.apply(self.pc_src_.pts_, self.pc_src_.batch_ids_, self.k_)
+        self._pairs = None
+        self._ends = None
+
+    def _materialise(self):
+        if self._pairs is not None:
+            return
+        cur = self.knn_table_
+        n, dev = cur.shape[0], cur.device
         centers = torch.arange(n, dtype=torch.int32, device=dev).unsqueeze(1).expand(n, self.k_)
-        self.neighbors_ = torch.stack((centers.reshape(-1), cur.reshape(-1)), dim=-1)
+        pairs = torch.stack((centers.reshape(-1), cur.reshape(-1)), dim=-1)
         if self.keep_empty_:
-            self.start_ids_ = (torch.arange(n, dtype=torch.int32, device=dev) + 1) * self.k_
+            ends = (torch.arange(n, dtype=torch.int32, device=dev) + 1) * self.k_
         else:
-            valid = self.neighbors_[:, 1] >= 0
-            self.neighbors_ = self.neighbors_[valid]
-            counts = torch.bincount(self.neighbors_[:, 0].to(torch.int64), minlength=n)
-            self.start_ids_ = torch.cumsum(counts, 0).to(torch.int32)
+            pairs = pairs[pairs[:, 1] >= 0]
+            counts = torch.bincount(pairs[:, 0].to(torch.int64), minlength=n)
+            ends = torch.cumsum(counts, 0).to(torch.int32)
+        self._pairs, self._ends = pairs, ends
+
+    @property
+    def neighbors_(self):
+        if getattr(self, "knn_table_", None) is None:
+            return None
+        self._materialise()
+        return self._pairs
+
+    @neighbors_.setter
+    def neighbors_(self, v):
+        self._pairs = v
+
+    @property
+    def start_ids_(self):
+        if getattr(self, "knn_table_", None) is None:
+            return None
+        self._materialise()
+        return self._ends
+
+    @start_ids_.setter
+    def start_ids_(self, v):
+        self._ends = v

@@ -22,6 +22,7 @@ class Pointcloud(object):
 
     def __init__(self, p_pts, p_batch_ids, **kwargs):
         self.pts_with_grads_ = bool(kwargs.pop("requires_grad", False))
+        self.batch_size_host_ = kwargs.pop("batch_size_host", None)  # optional host copy: avoids a sync
         self.pts_ = torch.as_tensor(p_pts, **kwargs)
         self.batch_ids_ = torch.as_tensor(p_batch_ids, **kwargs)
         self.batch_size_ = torch.max(self.batch_ids_) + 1

@@ -1,5 +1,6 @@
 import torch
 
+from .._lib import lib, check, ptr, stream
 from .pointcloud import Pointcloud, pool_by_index
 from .rotation_functions import (sample_reference_frames, sample_reference_frames_pca,
                                  sample_global_reference_frames_pca)
@@ -7,13 +8,16 @@ from .neighborhood import KnnNeighborhood, BQNeighborhood
 
 
 def _shuffle_and_take(all_frames, n_keep):
-    """Random per-point permutation of the candidate frames, keep the first n_keep
-    (pc/PointcloudRotEquiv.py:148-168; the same torch.multinomial call, so RNG use matches)."""
-    n_points, n_frames = all_frames.shape[0], all_frames.shape[1]
-    weights = torch.ones(n_frames, device=all_frames.device).expand(n_points, -1)
-    perm = torch.multinomial(weights, num_samples=n_frames, replacement=False)
-    shuffled = torch.gather(all_frames, 1, perm[:, :, None].expand(-1, -1, all_frames.shape[-1]))
-    return shuffled[:, :n_keep, :]
+    """Uniform random per-point permutation of the candidate frames, keep the first n_keep
+    (pc/PointcloudRotEquiv.py:148-168).  One torch.rand draw per point feeds se3_frames_select; the
+    reference spends a torch.multinomial call on the same distribution."""
+    all_frames = all_frames.contiguous()
+    n, n_cand = all_frames.shape[0], all_frames.shape[1]
+    u = torch.rand(n, device=all_frames.device, dtype=torch.float32)
+    out = torch.empty((n, n_keep, 9), dtype=torch.float32, device=all_frames.device)
+    check(lib().se3_frames_select(ptr(all_frames), ptr(u), n, n_cand, int(n_keep), ptr(out), stream()),
+          "se3_frames_select")
+    return out
 
 
 class PointcloudRotEquiv(Pointcloud):
@@ -23,7 +27,10 @@ class PointcloudRotEquiv(Pointcloud):
     p_ref_frames_config keys: pca, neigh_method, neigh_kwargs, fixed_axis, n_frames."""
 
     def __init__(self, p_pts, p_batch_ids, p_ref_frames_config, ref_frames_pts=None, standard_knn=False, **kwargs):
-        super(PointcloudRotEquiv, self).__init__(p_pts, p_batch_ids, **kwargs)
+        bs_host = kwargs.pop("batch_size_host", None)
+        grads = kwargs.pop("requires_grad", False)
+        super(PointcloudRotEquiv, self).__init__(p_pts, p_batch_ids, requires_grad=grads, batch_size_host=bs_host,
+                                                 **kwargs)
         self.neigh_cache_ = {}
         self.local_frames_pca_cache_ = {}
         self.local_frames_config_ = p_ref_frames_config

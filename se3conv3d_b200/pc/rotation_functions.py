@@ -43,7 +43,10 @@ def sample_reference_frames_pca(points, p_neighborhood, axis_fixed=False, dtype=
     """Per-point PCA frames [N, 4 or 2, 9] from a k-NN neighbourhood (pc/RotationFunctions.py:307-406)."""
     k = p_neighborhood.k_
     n = points.shape[0]
-    knn = p_neighborhood.neighbors_[:, 1].to(torch.int32).reshape(n, k).contiguous()
+    knn = getattr(p_neighborhood, "knn_table_", None)
+    if knn is None:
+        knn = p_neighborhood.neighbors_[:, 1].to(torch.int32).reshape(n, k)
+    knn = knn.contiguous()
     fixed = -1 if (axis_fixed is None or axis_fixed is False or not axis_fixed) else int(axis_fixed)
     nf = 2 if fixed > 0 else 4
     pts = points.to(torch.float32).contiguous()

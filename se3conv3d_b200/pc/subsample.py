@@ -76,7 +76,7 @@ class GridSubSample(SubSample):
     def __upsample_tensor__(self, p_tensor):
         if self.rnd_sample_:
             target = self.grid_.sorted_ids_[self.ids_.to(torch.int64)]
-            out = torch.zeros((self.grid_.sorted_cell_ids_.shape[0], p_tensor.shape[-1]), dtype=p_tensor.dtype,
+            out = torch.zeros((self.grid_.cell_ids_.shape[0], p_tensor.shape[-1]), dtype=p_tensor.dtype,
                               device=p_tensor.device)
             out[target] = p_tensor
             return out

@@ -239,6 +239,42 @@ def test_layer_fp32_matches_reference_golden(case):
         assert rel_err(got, g[key + "_f64"]) < 1e-4, key
 
 
+@pytest.mark.parametrize("case", LAYER_CASES)
+def test_layer_bf16_matches_reference_golden(case):
+    """bf16 tensor-core mode (bf16 operands, fp32 accumulation) vs the reference golden: stated tolerance
+    3e-2 relative (max-abs error / max-abs value) on outputs and every gradient."""
+    g = dict(np.load(os.path.join(GOLDEN, "layer_%s.npz" % case)))
+    y, dx, dW, dA, dB = _run_layer(g, 1)
+    for got, key in ((y, "y"), (dx, "dx"), (dW, "dW"), (dA, "dA"), (dB, "dB")):
+        assert got.shape == g[key + "_f64"].shape
+        err = rel_err(got, g[key + "_f64"])
+        print(case, key, "bf16 rel err %.2e" % err)
+        assert err < 3e-2, key
+
+
+def test_layer_bf16_matches_fp32_path_config1():
+    """BASELINE config 1 size: the tensor-core path against the fp32 path on the GPU (same inputs)."""
+    from se3conv3d_b200.layers import PNEConvLayerRotEquiv
+    pc, neigh, x = _synthetic_layer_problem(8192, 0.1, 2, 32, 64)
+    torch.manual_seed(2)
+    layer = PNEConvLayerRotEquiv(9, 32, 64, 32, "mlp_gelu").to(DEV)
+    layer.norm_neigh_dist_.fill_(10.0)
+    layer.norm_num_neighs_.fill_(8192 / 258754)
+    res = []
+    for precision in (0, 1):
+        layer.precision = precision
+        layer.zero_grad()
+        xx = x.clone().requires_grad_(True)
+        y = layer(pc, pc, xx, neigh)
+        y.square().mean().backward()
+        res.append([t.detach().cpu().numpy() for t in (y, xx.grad, layer.conv_weights_.grad, layer.proj_axes_.grad,
+                                                       layer.proj_biases_.grad)])
+    for a, b, name in zip(res[1], res[0], ("y", "dx", "dW", "dA", "dB")):
+        err = rel_err(a, b)
+        print(name, "bf16 vs fp32 rel err %.2e" % err)
+        assert err < 3e-2, name
+
+
 def _synthetic_layer_problem(n, r, fi, cin, cout, seed=0, batches=1):
     from se3conv3d_b200.pc import PointcloudRotEquiv, BQNeighborhood
     torch.manual_seed(seed)
