@@ -209,6 +209,13 @@ int se3_conv_bwd(const se3_conv_desc* d, const float* x, const float* dy, const 
                  float* dx, float* d_conv_weights, float* d_proj_axes, float* d_proj_biases,
                  void* workspace, size_t workspace_bytes, se3_stream_t stream);
 
+/* The projection GEMM on its own: C[M,N] = alpha * A[M,K] . B[N,K]^T, bf16 operands stored K-major
+ * (row-major [rows][K]), fp32 accumulation, C fp32 or bf16 row-major.  This is the [K*Cin] x Cout
+ * contraction of the layer (layers/PNEConvLayerRotEquiv.py:210) and its data-gradient twins.
+ * impl: 0 = auto (tcgen05/TMEM when N % 16 == 0, else mma.sync), 1 = mma.sync, 2 = tcgen05. */
+int se3_gemm_bf16_tn(const void* a_bf16, const void* b_bf16, int64_t m, int64_t n, int64_t k, float alpha,
+                     void* c, int32_t c_is_bf16, int32_t impl, se3_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "se3_segment_pool_f32",
     "se3_feat_basis_proj", "se3_feat_basis_proj_grad",
     "se3_conv_fwd_workspace_bytes", "se3_conv_bwd_workspace_bytes", "se3_conv_saved_bytes",
-    "se3_conv_fwd", "se3_conv_bwd",
+    "se3_conv_fwd", "se3_conv_bwd", "se3_gemm_bf16_tn",
 ]
 
 
@@ -86,6 +86,7 @@ def lib():
         getattr(L, n).argtypes = [dp]
         getattr(L, n).restype = sz
     L.se3_conv_fwd.argtypes = [dp, vp, vp, vp, vp, sz, vp]
+    L.se3_gemm_bf16_tn.argtypes = [vp, vp, i64, i64, i64, f32, vp, i32, i32, vp]
     L.se3_conv_bwd.argtypes = [dp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     for n in ABI_SYMBOLS:
         f = getattr(L, n)
@@ -141,8 +142,24 @@ def num_batches(pc):
     return nb
 
 
-def workspace(nbytes, device):
-    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+_ws_pool = {}
+
+
+def workspace(nbytes, device, tag=None):
+    """Scratch memory for one C-ABI call.  With a `tag` the buffer is pooled per (device, stream, tag) and
+    only grows: scratch of calls issued in order on one stream can be reused without a fresh allocation.
+    Buffers that must outlive the call (saved-for-backward, cached CSR state) are allocated untagged."""
+    nbytes = max(int(nbytes), 256)
+    if torch.device(device).type != "cuda":
+        raise Se3Error("se3conv3d_b200 kernels need CUDA tensors (got %s); there is no CPU fallback" % device)
+    if tag is None:
+        return torch.empty(nbytes, dtype=torch.uint8, device=device)
+    key = (str(device), stream(), tag)
+    buf = _ws_pool.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+        _ws_pool[key] = buf
+    return buf
 
 
 def launch_count():

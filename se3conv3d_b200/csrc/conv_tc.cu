@@ -15,12 +15,17 @@
 //                projection and its three backward products; deterministic split-K.
 // The tcgen05/TMEM projection kernel lives in proj_tcgen05.cu and replaces k_gemm_bf16 for the
 // K-major x K-major products when it is enabled.
+#include <stdlib.h>
 #include "conv_simt.cuh"
 #include "tc_common.cuh"
 
 namespace se3 {
 
 void splitk_reduce_launch(const float* partials, int splits, int64_t mn, float alpha, float* c, cudaStream_t st);
+// proj_tcgen05.cu
+bool tcgen05_gemm_supported(int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb);
+int launch_gemm_tcgen05(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16* a, int64_t lda,
+                        const __nv_bfloat16* b, int64_t ldb, void* c, int64_t ldc, bool out_bf16, cudaStream_t st);
 
 struct TcAggArgs {
   const int* row_ends;
@@ -484,16 +489,21 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, 3) k_edge_tc(const TcEdgeArgs 
     }
 }
 
+// one warp per output element: lanes stride over the per-warp partials, fixed-order shuffle reduce
 __global__ void k_edge_tc_reduce(const float* __restrict__ partials, int n_partials, float* __restrict__ d_axes,
                                  float* __restrict__ d_bias) {
-  const int tix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tix >= 320) return;
+  const int lane = threadIdx.x & 31;
+  const int out = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (out >= 320) return;
   float s = 0.0f;
-  for (int p = 0; p < n_partials; ++p) s += partials[(int64_t)p * 512 + tix];
-  if (tix < 288) {
-    if (d_axes) d_axes[tix] = s;
-  } else if (d_bias) {
-    d_bias[tix - 288] = s;
+  for (int p = lane; p < n_partials; p += 32) s += partials[(int64_t)p * 512 + out];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    if (out < 288) {
+      if (d_axes) d_axes[out] = s;
+    } else if (d_bias) {
+      d_bias[out - 288] = s;
+    }
   }
 }
 
@@ -533,7 +543,7 @@ static int launch_edge_tc(const TcEdgeArgs& a, int f_out, int n_warps, float* dA
     default: set_error("launch_edge_tc: unsupported frame count"); return SE3_EINVAL;
   }
   if (rc) return rc;
-  k_edge_tc_reduce<<<2, 160, 0, st>>>(a.partials, n_warps, dA, dB);
+  k_edge_tc_reduce<<<40, 256, 0, st>>>(a.partials, n_warps, dA, dB);
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }
@@ -692,9 +702,42 @@ static int launch_gemm_cfg(int64_t m, int64_t n, int64_t k, float alpha, const _
   return SE3_OK;
 }
 
+// C = alpha * A[M,K] . B[N,K]^T (both K-major): tcgen05/TMEM kernel when the shape allows, else mma.sync.
+// SE3_GEMM_IMPL=mma forces the mma.sync kernel (A/B testing); impl: 0 auto, 1 mma.sync, 2 tcgen05.
+static int gemm_impl_env() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SE3_GEMM_IMPL");
+    v = (e && e[0] == 'm') ? 1 : 0;
+  }
+  return v;
+}
+
+int gemm_tn(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16* a, int64_t lda, const __nv_bfloat16* b,
+            int64_t ldb, void* c, int64_t ldc, bool out_bf16, int impl, cudaStream_t st) {
+  if (impl == 0) impl = gemm_impl_env();
+  const bool can = tcgen05_gemm_supported(m, n, k, lda, ldb);
+  if (impl == 2 && !can) {
+    set_error("gemm_tn: shape not supported by the tcgen05 kernel");
+    return SE3_EINVAL;
+  }
+  if (impl != 1 && can) return launch_gemm_tcgen05(m, n, k, alpha, a, lda, b, ldb, c, ldc, out_bf16, st);
+  if (out_bf16) return launch_gemm_cfg<true, true, true>(m, n, k, alpha, a, lda, b, ldb, c, ldc, 1, nullptr, st);
+  return launch_gemm_cfg<true, true, false>(m, n, k, alpha, a, lda, b, ldb, c, ldc, 1, nullptr, st);
+}
+
 // --------------------------------------------------------------------------------------------
 // conversions
 // --------------------------------------------------------------------------------------------
+// wt[o][ck] = w[ck][o]  (bf16): K-major B operand of the forward projection
+__global__ void k_transpose_w_bf16(const float* __restrict__ w, int64_t ck, int c_out, __nv_bfloat16* __restrict__ wt) {
+  const int64_t total = ck * c_out;
+  for (int64_t tix = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; tix < total; tix += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t o = tix / ck, r = tix - o * ck;
+    wt[tix] = __float2bfloat16(w[r * c_out + o]);
+  }
+}
+
 __global__ void k_f32_to_bf16(const float* __restrict__ in, int64_t n, __nv_bfloat16* __restrict__ out) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16(in[i]);
@@ -766,7 +809,7 @@ int conv_tc_fwd(const se3_conv_desc* d, const float* x, float* y, void* saved, v
   __nv_bfloat16* Wb = ar.take<__nv_bfloat16>(ck * d->c_out);
   if (!ar.ok()) { set_error("conv_tc_fwd: workspace too small"); return SE3_EWORKSPACE; }
   __nv_bfloat16* T = reinterpret_cast<__nv_bfloat16*>(saved);
-  k_f32_to_bf16<<<blocks_for(ck * d->c_out), 256, 0, st>>>(d->conv_weights, ck * d->c_out, Wb);
+  k_transpose_w_bf16<<<blocks_for(ck * d->c_out), 256, 0, st>>>(d->conv_weights, ck, d->c_out, Wb);
   SE3_LAUNCH_CHECK();
   TcAggArgs a;
   a.row_ends = d->row_ends; a.nbr = d->col_src;
@@ -775,8 +818,8 @@ int conv_tc_fwd(const se3_conv_desc* d, const float* x, float* y, void* saved, v
   a.feat = x; a.c = d->c_in; a.w9 = d->proj_axes; a.bias = d->proj_biases; a.norm = d->norm_neigh_dist;
   a.act = d->act; a.out = T; a.n_rows = d->n_out;
   if (int rc = launch_agg_tc<false>(a, d->f_out, st)) return rc;
-  return launch_gemm_cfg<true, false, false>(R, d->c_out, ck, d->out_scale, T, ck, Wb, d->c_out, y, d->c_out, 1,
-                                             nullptr, st);
+  // y[r,o] = s * sum_(c,k) T[r,(c,k)] Wt[o,(c,k)]   (tcgen05 / TMEM)
+  return gemm_tn(R, d->c_out, ck, d->out_scale, T, ck, Wb, ck, y, d->c_out, false, 0, st);
 }
 
 int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const void* saved, float* dx, float* dW,
@@ -810,9 +853,7 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
     k_f32_to_bf16<<<blocks_for(ck * d->c_out), 256, 0, st>>>(d->conv_weights, ck * d->c_out, Wb);
     SE3_LAUNCH_CHECK();
     // dT[r,(c,k)] = s * sum_o dy[r,o] W[(c,k),o]
-    if (int rc = launch_gemm_cfg<true, true, true>(R, ck, d->c_out, d->out_scale, dyb, d->c_out, Wb, d->c_out, dTb, ck, 1,
-                                                   nullptr, st))
-      return rc;
+    if (int rc = gemm_tn(R, ck, d->c_out, d->out_scale, dyb, d->c_out, Wb, d->c_out, dTb, ck, true, 0, st)) return rc;
     TcEdgeArgs g;
     g.row_ends = d->row_ends; g.col_src = d->col_src;
     g.pts_out = d->pts_out; g.frm_out = d->frames_out;
@@ -832,11 +873,21 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
     k_permute_w_bf16<<<blocks_for(ck * d->c_out), 256, 0, st>>>(d->conv_weights, d->c_in, d->k, d->c_out, Wpb);
     SE3_LAUNCH_CHECK();
     // dx[n,c] = s * sum_(o,k) U[n,(o,k)] Wp[c,(o,k)]
-    if (int rc = launch_gemm_cfg<true, true, false>(Nf, d->c_in, ok, d->out_scale, U, ok, Wpb, ok, dx, d->c_in, 1, nullptr,
-                                                    st))
-      return rc;
+    if (int rc = gemm_tn(Nf, d->c_in, ok, d->out_scale, U, ok, Wpb, ok, dx, d->c_in, false, 0, st)) return rc;
   }
   return SE3_OK;
 }
 
 }  // namespace se3
+
+// C = alpha * A[M,K] . B[N,K]^T, bf16 operands (K-major), fp32 or bf16 output.  impl: 0 auto, 1 mma.sync, 2 tcgen05.
+extern "C" int se3_gemm_bf16_tn(const void* a, const void* b, int64_t m, int64_t n, int64_t k, float alpha, void* c,
+                                int32_t c_is_bf16, int32_t impl, se3_stream_t stream) {
+  using namespace se3;
+  SE3_CHECK_ARG(m >= 0 && n >= 1 && k >= 8 && (k % 8) == 0, "bad sizes (k must be a multiple of 8)");
+  SE3_CHECK_ARG(impl >= 0 && impl <= 2, "impl must be 0, 1 or 2");
+  if (m == 0) return SE3_OK;
+  SE3_CHECK_ARG(a && b && c, "null pointer");
+  return gemm_tn(m, n, k, alpha, reinterpret_cast<const __nv_bfloat16*>(a), k, reinterpret_cast<const __nv_bfloat16*>(b), k,
+                 c, n, c_is_bf16 != 0, impl, as_stream(stream));
+}

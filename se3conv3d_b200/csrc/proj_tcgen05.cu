@@ -1,0 +1,262 @@
+// tcgen05 / TMEM projection GEMM (sm_100a):  C[M,N] = alpha * A[M,K] * B[N,K]^T
+//   A, B bf16, K-major (row-major [rows][K]);  C fp32 or bf16;  fp32 accumulation in tensor memory.
+//
+// Used for the three K-major x K-major products of the layer:
+//   y  = s * T  . W        (A = T  [R, Cin*K],     B = W^T  [Cout, Cin*K])
+//   dT = s * dy . W^T      (A = dy [R, Cout],      B = W    [Cin*K, Cout])
+//   dx = s * U  . Wp^T     (A = U  [N*F, Cout*K],  B = Wp   [Cin, Cout*K])
+//
+// Structure (one CTA = one 128 x BN output tile, 128 threads):
+//   * operands are streamed with 16-byte cp.async into a 4-stage ring of 128B-swizzled K-major tiles
+//     (the canonical UMMA "SW128 K-major" layout: 128-byte rows, 16-byte chunk index XOR row%8,
+//     8-row groups 1024 bytes apart), zero-filled outside the matrix;
+//   * after a stage has landed (cp.async.wait_group + fence.proxy.async + barrier) ONE thread issues
+//     four tcgen05.mma (kind::f16, M=128, N=BN, K=16) whose accumulator lives in TMEM, then
+//     tcgen05.commit arrives on the stage's mbarrier so the ring slot can be refilled;
+//   * the epilogue reads the accumulator with tcgen05.ld (32 lanes x 32 bit, 8 columns at a time),
+//     scales it and stores rows straight to global memory.
+// SASS evidence: UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld), UTCBAR (commit), LDGSTS (cp.async).
+#include <cuda_bf16.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace se3 {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;       // 64 bf16 = 128 bytes = one swizzle span
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * 128;
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4, [16,30) LBO >> 4 (ignored for swizzled K-major, set to 1),
+//   [32,46) SBO >> 4 (1024 B between 8-row groups), [46,48) version = 1, [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int BN, bool OUT_BF16>
+__global__ void __launch_bounds__(128) k_gemm_tcgen05(int M, int N, int K, float alpha, const __nv_bfloat16* __restrict__ A,
+                                                      int64_t lda, const __nv_bfloat16* __restrict__ B, int64_t ldb,
+                                                      void* __restrict__ Cout, int64_t ldc) {
+  constexpr int B_STAGE_BYTES = BN * 128;
+  constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ __align__(8) uint64_t bars[STAGES + 1];
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // 1024-byte aligned operand ring
+  const uint32_t raw = smem_u32(smem_dyn);
+  const uint32_t ring = (raw + 1023u) & ~1023u;
+  const uint32_t a_ring = ring, b_ring = ring + STAGES * A_STAGE_BYTES;
+  const int bm = blockIdx.y * BM, bn = blockIdx.x * BN;
+  const int nkb = (K + BK - 1) / BK;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i <= STAGES; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_slot;
+  constexpr uint32_t IDESC = make_idesc(BM, BN);
+
+  auto load_stage = [&](int stage, int kb) {
+    const int k0 = kb * BK;
+    const uint32_t as = a_ring + stage * A_STAGE_BYTES;
+    const uint32_t bs = b_ring + stage * B_STAGE_BYTES;
+#pragma unroll
+    for (int i = 0; i < BM * 8 / 128; ++i) {
+      const int id = tid + i * 128;
+      const int r = id >> 3, c = id & 7;
+      const bool p = (bm + r < M) && (k0 + c * 8 < K);
+      const __nv_bfloat16* src = p ? A + (int64_t)(bm + r) * lda + k0 + c * 8 : A;
+      cp_async16(as + r * 128 + ((c ^ (r & 7)) << 4), src, p);
+    }
+#pragma unroll
+    for (int i = 0; i < BN * 8 / 128; ++i) {
+      const int id = tid + i * 128;
+      const int r = id >> 3, c = id & 7;
+      const bool p = (bn + r < N) && (k0 + c * 8 < K);
+      const __nv_bfloat16* src = p ? B + (int64_t)(bn + r) * ldb + k0 + c * 8 : B;
+      cp_async16(bs + r * 128 + ((c ^ (r & 7)) << 4), src, p);
+    }
+  };
+
+  for (int it = 0; it < nkb + STAGES - 1; ++it) {
+    if (it < nkb) {
+      const int s = it % STAGES;
+      if (it >= STAGES) mbar_wait(smem_u32(&bars[s]), (uint32_t)((it / STAGES - 1) & 1));  // slot consumed by the MMA
+      load_stage(s, it);
+    }
+    cp_async_commit();
+    const int c = it - (STAGES - 1);
+    if (c >= 0) {
+      cp_async_wait<STAGES - 1>();  // k-block c has landed (for this thread's copies)
+      fence_proxy_async();          // make them visible to the tensor-core (async) proxy
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const int s = c % STAGES;
+        const uint32_t as = a_ring + s * A_STAGE_BYTES;
+        const uint32_t bs = b_ring + s * B_STAGE_BYTES;
+#pragma unroll
+        for (int k4 = 0; k4 < BK / 16; ++k4) {
+          // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle span
+          umma_f16(tmem_d, make_desc_sw128(as + k4 * 32), make_desc_sw128(bs + k4 * 32), IDESC, (c > 0 || k4 > 0) ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&bars[s]));
+        if (c == nkb - 1) umma_commit(smem_u32(&bars[STAGES]));
+      }
+    }
+  }
+  // accumulator complete
+  mbar_wait(smem_u32(&bars[STAGES]), 0u);
+  tc_fence_after();
+  const int row = bm + warp * 32 + lane;
+#pragma unroll
+  for (int c0 = 0; c0 < BN; c0 += 8) {
+    float v[8];
+    tmem_ld8(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+    const int col = bn + c0;
+    if (row < M && col < N) {
+      if (OUT_BF16) {
+        __nv_bfloat16* C = reinterpret_cast<__nv_bfloat16*>(Cout) + (int64_t)row * ldc + col;
+        if (col + 8 <= N && ((reinterpret_cast<uintptr_t>(C) & 15) == 0)) {
+          uint4 p;
+          p.x = pack_bf16(alpha * v[0], alpha * v[1]);
+          p.y = pack_bf16(alpha * v[2], alpha * v[3]);
+          p.z = pack_bf16(alpha * v[4], alpha * v[5]);
+          p.w = pack_bf16(alpha * v[6], alpha * v[7]);
+          *reinterpret_cast<uint4*>(C) = p;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (col + i < N) C[i] = __float2bfloat16(alpha * v[i]);
+        }
+      } else {
+        float* C = reinterpret_cast<float*>(Cout) + (int64_t)row * ldc + col;
+        if (col + 8 <= N && ((reinterpret_cast<uintptr_t>(C) & 15) == 0)) {
+          *reinterpret_cast<float4*>(C) = make_float4(alpha * v[0], alpha * v[1], alpha * v[2], alpha * v[3]);
+          *reinterpret_cast<float4*>(C + 4) = make_float4(alpha * v[4], alpha * v[5], alpha * v[6], alpha * v[7]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (col + i < N) C[i] = alpha * v[i];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+template <int BN, bool OB>
+int launch_cfg(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16* a, int64_t lda, const __nv_bfloat16* b,
+               int64_t ldb, void* c, int64_t ldc, cudaStream_t st) {
+  const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BN * 128) + 1024;
+  auto kern = k_gemm_tcgen05<BN, OB>;
+  SE3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((n + BN - 1) / BN), (unsigned)((m + BM - 1) / BM), 1);
+  kern<<<grid, 128, smem, st>>>((int)m, (int)n, (int)k, alpha, a, lda, b, ldb, c, ldc);
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
+}
+
+}  // namespace
+
+bool tcgen05_gemm_supported(int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb) {
+  return m >= 1 && n >= 16 && (n % 16) == 0 && (k % 8) == 0 && (lda % 8) == 0 && (ldb % 8) == 0;
+}
+
+// C = alpha * A[M,K] . B[N,K]^T ; out_bf16 selects the output type
+int launch_gemm_tcgen05(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16* a, int64_t lda,
+                        const __nv_bfloat16* b, int64_t ldb, void* c, int64_t ldc, bool out_bf16, cudaStream_t st) {
+  if (!tcgen05_gemm_supported(m, n, k, lda, ldb)) {
+    set_error("launch_gemm_tcgen05: unsupported shape m=%lld n=%lld k=%lld", (long long)m, (long long)n, (long long)k);
+    return SE3_EINVAL;
+  }
+  // one N tile when N <= 256, else 256/128-wide tiles (N % 16 == 0 is guaranteed)
+  const int bn = n <= 16 ? 16 : (n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : 256)));
+#define SE3_TC_CASE(BN_)                                                                                           \
+  case BN_:                                                                                                         \
+    return out_bf16 ? launch_cfg<BN_, true>(m, n, k, alpha, a, lda, b, ldb, c, ldc, st)                             \
+                    : launch_cfg<BN_, false>(m, n, k, alpha, a, lda, b, ldb, c, ldc, st);
+  switch (bn) {
+    SE3_TC_CASE(16)
+    SE3_TC_CASE(32)
+    SE3_TC_CASE(64)
+    SE3_TC_CASE(128)
+    SE3_TC_CASE(256)
+  }
+#undef SE3_TC_CASE
+  return SE3_EINVAL;
+}
+
+}  // namespace se3

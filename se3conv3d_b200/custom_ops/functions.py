@@ -113,7 +113,7 @@ class RotEquivConv(torch.autograd.Function):
         y = torch.empty((geom.n_out * geom.f_out, c_out), dtype=torch.float32, device=x.device)
         saved_bytes = L.se3_conv_saved_bytes(C.byref(d))
         saved = workspace(saved_bytes, x.device) if saved_bytes else None
-        ws = workspace(L.se3_conv_fwd_workspace_bytes(C.byref(d)), x.device)
+        ws = workspace(L.se3_conv_fwd_workspace_bytes(C.byref(d)), x.device, 'conv')
         check(L.se3_conv_fwd(C.byref(d), ptr(x32), ptr(y), ptr(saved), ptr(ws), ws.numel(), stream()), "se3_conv_fwd")
         ctx.geom = geom
         ctx.meta = (act, precision, float(norm_neigh_dist), float(out_scale), x.dtype)
@@ -134,7 +134,7 @@ class RotEquivConv(torch.autograd.Function):
         dA = torch.empty_like(pa) if (need[1] or need[2]) else None
         dB = torch.empty_like(pb) if (need[1] or need[2]) else None
         dW = torch.empty_like(cw) if need[3] else None
-        ws = workspace(L.se3_conv_bwd_workspace_bytes(C.byref(d)), x32.device)
+        ws = workspace(L.se3_conv_bwd_workspace_bytes(C.byref(d)), x32.device, 'conv')
         check(L.se3_conv_bwd(C.byref(d), ptr(x32), ptr(dy), ptr(saved) if saved.numel() else None, ptr(dx), ptr(dW),
                              ptr(dA), ptr(dB), ptr(ws), ws.numel(), stream()), "se3_conv_bwd")
         return (dx.to(x_dtype) if dx is not None else None, dA if need[1] else None, dB if need[2] else None, dW,

@@ -39,7 +39,7 @@ class Grid(object):
         b = pc.batch_ids_.to(torch.int32).contiguous()
         n, dev = pts.shape[0], pts.device
         L = lib()
-        ws = workspace(L.se3_grid_cells_workspace_bytes(n), dev)
+        ws = workspace(L.se3_grid_cells_workspace_bytes(n), dev, 'grid')
         self.cell_ids_ = torch.empty(n, dtype=torch.int64, device=dev)
         self.sorted_ids_ = torch.empty(n, dtype=torch.int64, device=dev)
         ends = torch.empty(max(n, 1), dtype=torch.int32, device=dev)

@@ -37,7 +37,7 @@ class ConvGeometry(object):
         self.t_row_ends = torch.empty(max(self.n_in, 1), dtype=torch.int32, device=dev)
         self.t_edge = torch.empty(e, dtype=torch.int32, device=dev)
         self.t_dst = torch.empty(e, dtype=torch.int32, device=dev)
-        ws = workspace(L.se3_csr_transpose_workspace_bytes(self.n_edges, self.n_in), dev)
+        ws = workspace(L.se3_csr_transpose_workspace_bytes(self.n_edges, self.n_in), dev, 'csr')
         check(L.se3_csr_transpose(ptr(nb), self.n_edges, self.n_in, self.n_out, ptr(ws), ws.numel(),
                                   ptr(self.col_src), ptr(self.t_row_ends), ptr(self.t_edge), ptr(self.t_dst),
                                   stream()), "se3_csr_transpose")

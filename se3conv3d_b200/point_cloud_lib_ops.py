@@ -49,7 +49,7 @@ def ball_query(p_pt_src, p_pt_dest, p_batch_ids_src, p_batch_ids_dest, p_min_pt,
     n, m = src.shape[0], dst.shape[0]
     L = lib()
     ws_bytes = L.se3_ball_query_workspace_bytes(n, m)
-    ws = workspace(ws_bytes, src.device)
+    ws = workspace(ws_bytes, src.device, 'bq')
     ends = torch.empty(m, dtype=torch.int32, device=src.device)
     total = torch.empty(1, dtype=torch.int64, device=src.device)
     check(L.se3_ball_query_count(ptr(src), ptr(dst), ptr(bs), ptr(bd), n, m, ptr(mn), ptr(nc), ptr(rad), ptr(ws),
@@ -67,7 +67,7 @@ def knn_query(p_pt_src, p_batch_ids_src, p_k):
     pts, b = _f32(p_pt_src), _i32(p_batch_ids_src)
     n = pts.shape[0]
     L = lib()
-    ws = workspace(L.se3_knn_workspace_bytes(n), pts.device)
+    ws = workspace(L.se3_knn_workspace_bytes(n), pts.device, 'knn')
     out = torch.empty((n, int(p_k)), dtype=torch.int32, device=pts.device)
     check(L.se3_knn_query(ptr(pts), ptr(b), n, int(p_k), ptr(ws), ws.numel(), ptr(out), stream()), "se3_knn_query")
     return out

@@ -398,3 +398,24 @@ def test_grid_subsample_and_hierarchy():
     assert nb.start_ids_.shape[0] == sizes[1]
     R = h.pcs_[2].local_frames_.reshape(-1, 3, 3)
     assert torch.allclose(R.transpose(1, 2) @ R, torch.eye(3, device=DEV).expand_as(R), atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("m,n,k", [(128, 64, 64), (300, 32, 1024), (1000, 16, 8), (257, 256, 2048), (5000, 48, 520),
+                                   (4096, 1024, 64)])
+def test_projection_gemm_matches_fp64(impl, m, n, k):
+    """The [K*Cin] x Cout projection on its own (tcgen05/TMEM = impl 2, mma.sync = impl 1): bf16 operands,
+    fp32 accumulation; tolerance 2e-5 relative for fp32 output (accumulation order only), 1.5e-2 for bf16 output."""
+    from se3conv3d_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device=DEV).manual_seed(m + n + k)
+    a = torch.randn(m, k, device=DEV, generator=g).to(torch.bfloat16)
+    b = torch.randn(n, k, device=DEV, generator=g).to(torch.bfloat16)
+    ref = 0.25 * (a.double() @ b.double().t())
+    for out_bf16, tol in ((0, 2e-5), (1, 1.5e-2)):
+        c = torch.full((m, n), float("nan"), device=DEV, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+        _lib.check(L.se3_gemm_bf16_tn(_lib.ptr(a), _lib.ptr(b), m, n, k, 0.25, _lib.ptr(c), out_bf16, impl,
+                                      _lib.stream()), "se3_gemm_bf16_tn")
+        torch.cuda.synchronize()
+        assert rel_err(c.double().cpu(), ref.cpu()) < tol
