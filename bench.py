@@ -29,7 +29,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", type=int, default=int(os.environ.get("SE3_PRECISION", "0")))
+    ap.add_argument("--precision", type=int, default=int(os.environ.get("SE3_PRECISION", "1")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
