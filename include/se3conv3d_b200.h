@@ -190,11 +190,20 @@ typedef struct se3_conv_desc {
   const int32_t* t_row_ends; /* [N] inclusive */
   const int32_t* t_edge;     /* [E] */
   const int32_t* t_dst;      /* [E] */
+  /* packed gather records (device; se3_pack_records): [N*f_in,12] / [M*f_out,12] float32 =
+   * (px,py,pz, R[0..8]) per (point, frame), 48 B, 16-byte aligned.  Required by precision 1 (one
+   * record = three 128-bit loads per gathered neighbour); ignored by precision 0. */
+  const float* rec_in;
+  const float* rec_out;
   /* parameters (device) */
   const float* proj_axes;    /* [9,K]   */
   const float* proj_biases;  /* [K]     */
   const float* conv_weights; /* [c_in,K,c_out] */
 } se3_conv_desc;
+
+/* rec [n*f,12] = (pts[i,0..2], frames[i,a,0..8]) -- the gather record of the tensor-core path. */
+int se3_pack_records(const float* pts, const float* frames, int64_t n, int32_t f, float* rec,
+                     se3_stream_t stream);
 
 size_t se3_conv_fwd_workspace_bytes(const se3_conv_desc* d);
 size_t se3_conv_bwd_workspace_bytes(const se3_conv_desc* d);

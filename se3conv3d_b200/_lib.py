@@ -9,7 +9,8 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libse3conv3d_b200.so")
+# SE3CONV3D_LIB selects an alternative build of the same library (kernel-tuning A/B runs); default = in-tree build
+LIB_PATH = os.environ.get("SE3CONV3D_LIB") or os.path.join(_PKG, "lib", "libse3conv3d_b200.so")
 
 # every symbol include/se3conv3d_b200.h declares (tests check the .so exports exactly these)
 ABI_SYMBOLS = [
@@ -21,7 +22,7 @@ ABI_SYMBOLS = [
     "se3_segment_pool_f32",
     "se3_feat_basis_proj", "se3_feat_basis_proj_grad",
     "se3_conv_fwd_workspace_bytes", "se3_conv_bwd_workspace_bytes", "se3_conv_saved_bytes",
-    "se3_conv_fwd", "se3_conv_bwd", "se3_gemm_bf16_tn",
+    "se3_conv_fwd", "se3_conv_bwd", "se3_gemm_bf16_tn", "se3_pack_records",
 ]
 
 
@@ -35,6 +36,7 @@ class ConvDesc(C.Structure):
         ("pts_in", C.c_void_p), ("pts_out", C.c_void_p), ("frames_in", C.c_void_p), ("frames_out", C.c_void_p),
         ("row_ends", C.c_void_p), ("col_src", C.c_void_p),
         ("t_row_ends", C.c_void_p), ("t_edge", C.c_void_p), ("t_dst", C.c_void_p),
+        ("rec_in", C.c_void_p), ("rec_out", C.c_void_p),
         ("proj_axes", C.c_void_p), ("proj_biases", C.c_void_p), ("conv_weights", C.c_void_p),
     ]
 
@@ -87,6 +89,7 @@ def lib():
         getattr(L, n).restype = sz
     L.se3_conv_fwd.argtypes = [dp, vp, vp, vp, vp, sz, vp]
     L.se3_gemm_bf16_tn.argtypes = [vp, vp, i64, i64, i64, f32, vp, i32, i32, vp]
+    L.se3_pack_records.argtypes = [vp, vp, i64, i32, vp, vp]
     L.se3_conv_bwd.argtypes = [dp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     for n in ABI_SYMBOLS:
         f = getattr(L, n)

@@ -31,6 +31,28 @@ def _digest():
     return h.hexdigest()
 
 
+def build_variant(name, defines):
+    """Builds lib/libse3conv3d_b200.<name>.so with extra -D flags (kernel-tuning A/B runs; load it with
+    SE3CONV3D_LIB=<path>)."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    out = os.path.join(LIBDIR, "libse3conv3d_b200.%s.so" % name)
+    objs = []
+    procs = []
+    for s in SOURCES:
+        o = os.path.join(LIBDIR, "%s.%s.o" % (s, name))
+        objs.append(o)
+        cmd = ["nvcc", "-c", os.path.join(CSRC, s), "-o", o] + [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")] + \
+              ["-D" + d for d in defines]
+        procs.append(subprocess.Popen(cmd))
+    for p in procs:
+        if p.wait() != 0:
+            raise RuntimeError("nvcc failed")
+    subprocess.check_call(["nvcc", "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"])
+    for o in objs:
+        os.remove(o)
+    return out
+
+
 def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     stamp = os.path.join(LIBDIR, "build.sha256")

@@ -30,10 +30,8 @@ int launch_gemm_tcgen05(int64_t m, int64_t n, int64_t k, float alpha, const __nv
 struct TcAggArgs {
   const int* row_ends;
   const int* nbr;
-  const float* pts_row;
-  const float* frm_row;
-  const float* pts_g;
-  const float* frm_g;
+  const float* rec_row;  // [n_rows * FR, 12] records of the row side
+  const float* rec_g;    // [n_g * f_g, 12] records of the gathered side
   int f_g;
   const float* feat;
   int c;
@@ -80,7 +78,33 @@ __device__ __forceinline__ float act_grad_rt(float x, int act) {
   }
 }
 
-// Stage the gathered feature rows of a 32-neighbour chunk into Xs[32][CB+8] (bf16).
+// n -> (edge, frame) for f frames per gathered point (f in 1..4, warp-uniform)
+__device__ __forceinline__ void split_nf(int n, int f, int& e, int& fg) {
+  if (f == 1) {
+    e = n; fg = 0;
+  } else if (f == 2) {
+    e = n >> 1; fg = n & 1;
+  } else if (f == 4) {
+    e = n >> 2; fg = n & 3;
+  } else {
+    e = n / 3; fg = n - 3 * e;
+  }
+}
+
+// 128-bit read-only load that leaves the (pre-zeroed) destination untouched when pred is false
+__device__ __forceinline__ void ldg128_if(float4& v, const float* p, bool pred) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ne.b32 q, %4, 0;\n"
+      "@q ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%5];\n"
+      "}\n"
+      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+      : "r"((int)pred), "l"(p));
+}
+
+// Stage the gathered feature rows of a 32-neighbour chunk into Xs[32][CB+8] (bf16).  Row offsets are
+// 32-bit (the launchers check rows * C < 2^31).
 template <int CB>
 __device__ __forceinline__ void stage_features(const float* __restrict__ feat, int C, int c0, int fidx, int lane,
                                                __nv_bfloat16* Xs) {
@@ -88,25 +112,29 @@ __device__ __forceinline__ void stage_features(const float* __restrict__ feat, i
   if ((C & 3) == 0) {
     constexpr int LPR = CB / 4;    // lanes per row (float4 each)
     constexpr int RPI = 32 / LPR;  // rows per iteration
+    const int col4 = lane % LPR, r0 = lane / LPR;
+    const int ch = c0 + col4 * 4;
+    const bool chok = ch < C;
+    float4 v[LPR];
 #pragma unroll
     for (int it = 0; it < LPR; ++it) {
-      const int row = it * RPI + lane / LPR;
-      const int col4 = lane % LPR;
-      const int src = __shfl_sync(0xffffffffu, fidx, row);
-      const int ch = c0 + col4 * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (src >= 0 && ch < C) v = __ldg(reinterpret_cast<const float4*>(feat + (int64_t)src * C + ch));
+      const int src = __shfl_sync(0xffffffffu, fidx, it * RPI + r0);
+      v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      ldg128_if(v[it], feat + (uint32_t)(src * C + ch), src >= 0 && chok);
+    }
+#pragma unroll
+    for (int it = 0; it < LPR; ++it) {
       uint2 p;
-      p.x = pack_bf16(v.x, v.y);
-      p.y = pack_bf16(v.z, v.w);
-      *reinterpret_cast<uint2*>(Xs + row * XS + col4 * 4) = p;
+      p.x = pack_bf16(v[it].x, v[it].y);
+      p.y = pack_bf16(v[it].z, v[it].w);
+      *reinterpret_cast<uint2*>(Xs + (it * RPI + r0) * XS + col4 * 4) = p;
     }
   } else {
     for (int row = 0; row < 32; ++row) {
       const int src = __shfl_sync(0xffffffffu, fidx, row);
       for (int ch = lane; ch < CB; ch += 32) {
         float v = 0.f;
-        if (src >= 0 && c0 + ch < C) v = __ldg(feat + (int64_t)src * C + c0 + ch);
+        if (src >= 0 && c0 + ch < C) v = __ldg(feat + (uint32_t)(src * C + c0 + ch));
         Xs[row * XS + ch] = __float2bfloat16(v);
       }
     }
@@ -114,34 +142,115 @@ __device__ __forceinline__ void stage_features(const float* __restrict__ feat, i
 }
 
 constexpr int AGG_WARPS = 4;  // warps per CTA of the aggregation / edge kernels
+constexpr int GSTR = 20;      // floats between geometry rows in shared memory (80 B: conflict-free 128-bit rows)
 
-template <int CB, int FR, bool TR, int ACT>
-__global__ void __launch_bounds__(AGG_WARPS * 32, 3) k_agg_tc(const TcAggArgs a, const int ncb) {
-  constexpr int XS = CB + 8;
-  constexpr int MT = CB / 16;
-  constexpr int WARP_BYTES = 32 * XS * 2 + FR * 32 * 12 * 4;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* W9s = reinterpret_cast<float*>(smem_raw);  // [32][12]: w0..w8, bias, 0, 0
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  unsigned char* wbase = smem_raw + 32 * 12 * 4 + wib * WARP_BYTES;
-  __nv_bfloat16* Xs = reinterpret_cast<__nv_bfloat16*>(wbase);
-  float* Gs = reinterpret_cast<float*>(wbase + 32 * XS * 2);  // [FR][32][12]
-  for (int i = threadIdx.x; i < 32 * 12; i += blockDim.x) {
-    const int k = i / 12, d = i % 12;
-    W9s[i] = d < 9 ? a.w9[d * 32 + k] : (d == 9 ? a.bias[k] : 0.0f);
+// A fragments of the basis affine on the tensor cores (tf32 m16n8k8): pre^T[k, n] = sum_d Wext[d, k] G[n, d]
+// with Wext = [proj_axes_ (9 rows); proj_biases_ (row 9); 0].  The 16 d-slots are permuted so that lane (g, t)
+// needs the four CONSECUTIVE components 4t..4t+3 of a geometry row (one 128-bit shared load):
+//   k-step s in {0,1}: slot t <-> component 4t + 2s, slot t+4 <-> component 4t + 2s + 1.
+// Components 12..15 are zero, so lanes t = 3 carry zero fragments and never touch shared memory.
+__device__ __forceinline__ void load_w9_frags(const float* __restrict__ w9, const float* __restrict__ bias, int g, int t,
+                                              uint32_t (&aw)[2][2][4]) {
+  auto wext = [&](int d, int k) -> float { return d < 9 ? __ldg(w9 + d * 32 + k) : (d == 9 ? __ldg(bias + k) : 0.0f); };
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int d0 = 4 * t + 2 * s, k0 = 16 * m + g;
+      aw[m][s][0] = to_tf32(wext(d0, k0));
+      aw[m][s][1] = to_tf32(wext(d0, k0 + 8));
+      aw[m][s][2] = to_tf32(wext(d0 + 1, k0));
+      aw[m][s][3] = to_tf32(wext(d0 + 1, k0 + 8));
+    }
+}
+
+// pre^T tile of one 8-neighbour group: d[m][0..3] = pre[k = 16m+g (+8 for 2,3)][n = 2t (+1 for 1,3)]
+// (the geometry operand is fp32 whose low 13 mantissa bits the tf32 tensor core ignores)
+__device__ __forceinline__ void basis_pre(const uint32_t (&aw)[2][2][4], const float* grow, int t, float (&d)[2][4]) {
+  float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t < 3) gv = *reinterpret_cast<const float4*>(grow + 4 * t);
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    d[m][0] = d[m][1] = d[m][2] = d[m][3] = 0.0f;
+    mma_tf32(d[m], aw[m][0], __float_as_uint(gv.x), __float_as_uint(gv.y));
+    mma_tf32(d[m], aw[m][1], __float_as_uint(gv.z), __float_as_uint(gv.w));
   }
-  __syncthreads();
+}
+
+__device__ __forceinline__ void store_geometry_row(float* row, const float (&gg)[9], float one) {
+  float4* gs = reinterpret_cast<float4*>(row);
+  gs[0] = make_float4(gg[0], gg[1], gg[2], gg[3]);
+  gs[1] = make_float4(gg[4], gg[5], gg[6], gg[7]);
+  gs[2] = make_float4(gg[8], one, 0.f, 0.f);
+}
+
+// This lane's gathered neighbour of a chunk: record (3 x 128-bit), scaled offset and frame.
+template <bool TR>
+__device__ __forceinline__ void gather_neighbour(const float* __restrict__ rec_g, int gidx, float prx, float pry,
+                                                 float prz, float norm, float& dx, float& dy, float& dz,
+                                                 float (&Fq)[9]) {
+  const float4* rp = reinterpret_cast<const float4*>(rec_g) + (int64_t)gidx * 3;
+  const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
+  dx = (TR ? (prx - r0.x) : (r0.x - prx)) * norm;
+  dy = (TR ? (pry - r0.y) : (r0.y - pry)) * norm;
+  dz = (TR ? (prz - r0.z) : (r0.z - prz)) * norm;
+  Fq[0] = r0.w; Fq[1] = r1.x; Fq[2] = r1.y; Fq[3] = r1.z; Fq[4] = r1.w;
+  Fq[5] = r2.x; Fq[6] = r2.y; Fq[7] = r2.z; Fq[8] = r2.w;
+}
+
+__device__ __forceinline__ void load_row_frame(const float* Rs, int f, float (&Frow)[9]) {
+  const float4* r = reinterpret_cast<const float4*>(Rs + f * 12);
+  const float4 r0 = r[0], r1 = r[1], r2 = r[2];
+  Frow[0] = r0.w; Frow[1] = r1.x; Frow[2] = r1.y; Frow[3] = r1.z; Frow[4] = r1.w;
+  Frow[5] = r2.x; Frow[6] = r2.y; Frow[7] = r2.z; Frow[8] = r2.w;
+}
+
+template <int CB, int FR>
+struct AggSmem {
+  static constexpr int XS = CB + 8;
+  static constexpr int X_BYTES = 32 * XS * 2;
+  static constexpr int G_BYTES = FR * 32 * GSTR * 4;  // geometry rows; reused as the T staging tiles (2 KB per frame)
+  static constexpr int R_BYTES = FR * 48;
+  static constexpr int WARP_BYTES = X_BYTES + G_BYTES + ((R_BYTES + 15) / 16) * 16;
+};
+
+#ifndef SE3_AGG_MIN_BLOCKS
+#define SE3_AGG_MIN_BLOCKS 3
+#endif
+
+// One warp per (row point, channel block): the FR row frames share the gathered records and the staged
+// feature rows; their [CB x 32] accumulators live in registers.
+template <int CB, int FR, bool TR, int ACT>
+__global__ void __launch_bounds__(AGG_WARPS * 32, SE3_AGG_MIN_BLOCKS) k_agg_tc(const TcAggArgs a, const int ncb) {
+  using SM = AggSmem<CB, FR>;
+  constexpr int XS = SM::XS;
+  constexpr int MT = CB / 16;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  unsigned char* wbase = smem_raw + wib * SM::WARP_BYTES;
+  __nv_bfloat16* Xs = reinterpret_cast<__nv_bfloat16*>(wbase);
+  float* Gs = reinterpret_cast<float*>(wbase + SM::X_BYTES);               // [FR][32][GSTR]
+  float* Rs = reinterpret_cast<float*>(wbase + SM::X_BYTES + SM::G_BYTES);  // [FR][12] row records
   const int g = lane >> 2, t = lane & 3;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t total = a.n_rows * ncb;
+  uint32_t aw[2][2][4];
+  load_w9_frags(a.w9, a.bias, g, t, aw);
+  const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+  const int total = (int)a.n_rows * ncb;
   const int mid = lane >> 3, mr = lane & 7;  // ldmatrix: matrix id, row inside the matrix
-  for (int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < total; item += nwarps) {
-    const int64_t rp = item / ncb;
-    const int c0 = (int)(item - rp * ncb) * CB;
-    const int lo = rp > 0 ? a.row_ends[rp - 1] : 0;
-    const int hi = a.row_ends[rp];
+  for (int item = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); item < total; item += nwarps) {
+    int rp = item, c0 = 0;
+    if (ncb > 1) {
+      rp = item / ncb;
+      c0 = (item - rp * ncb) * CB;
+    }
+    const int lo = rp > 0 ? __ldg(a.row_ends + rp - 1) : 0;
+    const int hi = __ldg(a.row_ends + rp);
     const int n_total = (hi - lo) * a.f_g;
-    const float prx = a.pts_row[3 * rp], pry = a.pts_row[3 * rp + 1], prz = a.pts_row[3 * rp + 2];
+    __syncwarp();
+    if (lane < FR * 3)
+      reinterpret_cast<float4*>(Rs)[lane] = __ldg(reinterpret_cast<const float4*>(a.rec_row) + (int64_t)rp * (FR * 3) + lane);
+    __syncwarp();
+    const float prx = Rs[0], pry = Rs[1], prz = Rs[2];
     float acc[FR][MT][4][4];
 #pragma unroll
     for (int f = 0; f < FR; ++f)
@@ -154,104 +263,100 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, 3) k_agg_tc(const TcAggArgs a,
     for (int base = 0; base < n_total; base += 32) {
       const int n = base + lane;
       const bool valid = n < n_total;
-      const int e = valid ? n / a.f_g : 0;
-      const int fg = valid ? n - e * a.f_g : 0;
-      const int q = __ldg(a.nbr + lo + e);
-      const int fidx = valid ? q * a.f_g + fg : -1;
-      const float pgx = __ldg(a.pts_g + 3 * (int64_t)q), pgy = __ldg(a.pts_g + 3 * (int64_t)q + 1),
-                  pgz = __ldg(a.pts_g + 3 * (int64_t)q + 2);
-      float Fq[9];
+      int e, fg;
+      split_nf(valid ? n : 0, a.f_g, e, fg);
+      const int gidx = __ldg(a.nbr + lo + e) * a.f_g + fg;
       {
-        const float* fp = a.frm_g + ((int64_t)q * a.f_g + fg) * 9;
+        float dx, dy, dz, Fq[9];
+        gather_neighbour<TR>(a.rec_g, gidx, prx, pry, prz, a.norm, dx, dy, dz, Fq);
 #pragma unroll
-        for (int i = 0; i < 9; ++i) Fq[i] = __ldg(fp + i);
+        for (int f = 0; f < FR; ++f) {
+          float Frow[9], gg[9];
+          load_row_frame(Rs, f, Frow);
+          geometry9<TR>(Frow, Fq, dx, dy, dz, gg);
+          store_geometry_row(Gs + (f * 32 + lane) * GSTR, gg, 1.0f);
+        }
       }
-      const float dx = (TR ? (prx - pgx) : (pgx - prx)) * a.norm;
-      const float dy = (TR ? (pry - pgy) : (pgy - pry)) * a.norm;
-      const float dz = (TR ? (prz - pgz) : (pgz - prz)) * a.norm;
-#pragma unroll
-      for (int f = 0; f < FR; ++f) {
-        float Frow[9];
-        const float* fp = a.frm_row + (rp * FR + f) * 9;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) Frow[i] = __ldg(fp + i);
-        float gg[9];
-        geometry9<TR>(Frow, Fq, dx, dy, dz, gg);
-        float4* gs = reinterpret_cast<float4*>(Gs + (f * 32 + lane) * 12);
-        gs[0] = make_float4(gg[0], gg[1], gg[2], gg[3]);
-        gs[1] = make_float4(gg[4], gg[5], gg[6], gg[7]);
-        gs[2] = make_float4(gg[8], 0.f, 0.f, 0.f);
-      }
-      stage_features<CB>(a.feat, a.c, c0, fidx, lane, Xs);
+      stage_features<CB>(a.feat, a.c, c0, valid ? gidx : -1, lane, Xs);
       __syncwarp();
+      const int n_here = min(32, n_total - base);  // warp-uniform: 8-neighbour groups beyond it are skipped
 #pragma unroll 1
       for (int ks = 0; ks < 2; ++ks) {
+        if (ks * 16 >= n_here) break;
         // A fragments (x^T): [m = channel][k = neighbour], from Xs[n][c] through ldmatrix.trans
         uint32_t af[MT][4];
 #pragma unroll
         for (int m = 0; m < MT; ++m)
           ldmatrix_x4_trans(af[m][0], af[m][1], af[m][2], af[m][3],
                             smem_u32(Xs + (ks * 16 + (mid >> 1) * 8 + mr) * XS + m * 16 + (mid & 1) * 8));
+        const bool second = ks * 16 + 8 < n_here;
 #pragma unroll
         for (int f = 0; f < FR; ++f) {
-          // this lane's 4 neighbours of the k-step: 2t, 2t+1, 2t+8, 2t+9
-          float gv[4][9];
+          // basis h = act(pre) of the 16 neighbours of this k-step, produced directly as the B fragments
+          // of the aggregation mma: n-tile j (k = 8j + g), b0 = neighbours 2t,2t+1, b1 = neighbours 2t+8,2t+9
+          uint32_t hb[4][2];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int nn = ks * 16 + 2 * t + (u & 1) + (u >> 1) * 8;
-            const float4* gs = reinterpret_cast<const float4*>(Gs + (f * 32 + nn) * 12);
-            const float4 v0 = gs[0], v1 = gs[1], v2 = gs[2];
-            gv[u][0] = v0.x; gv[u][1] = v0.y; gv[u][2] = v0.z; gv[u][3] = v0.w;
-            gv[u][4] = v1.x; gv[u][5] = v1.y; gv[u][6] = v1.z; gv[u][7] = v1.w;
-            gv[u][8] = v2.x;
-          }
+          for (int hq = 0; hq < 2; ++hq) {
+            if (hq == 1 && !second) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            // basis column k = g + 8 j of this lane: weights from shared memory (w0..w8, bias)
-            const float4* wp = reinterpret_cast<const float4*>(W9s + (g + 8 * j) * 12);
-            const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2];
-            const float wv[9] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x};
-            float h[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              float pre = w2.y;
-#pragma unroll
-              for (int d = 0; d < 9; ++d) pre = fmaf(gv[u][d], wv[d], pre);
-              h[u] = act_rt<ACT>(pre, a.act);
+              for (int j = 0; j < 4; ++j) hb[j][1] = 0u;
+              break;
             }
-            const uint32_t b0 = pack_bf16(h[0], h[1]), b1 = pack_bf16(h[2], h[3]);
+            float d[2][4];
+            basis_pre(aw, Gs + (f * 32 + ks * 16 + hq * 8 + g) * GSTR, t, d);
 #pragma unroll
-            for (int m = 0; m < MT; ++m) mma_bf16(acc[f][m][j], af[m], b0, b1);
+            for (int m = 0; m < 2; ++m) {
+              hb[2 * m][hq] = pack_bf16(act_rt<ACT>(d[m][0], a.act), act_rt<ACT>(d[m][1], a.act));
+              hb[2 * m + 1][hq] = pack_bf16(act_rt<ACT>(d[m][2], a.act), act_rt<ACT>(d[m][3], a.act));
+            }
           }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int m = 0; m < MT; ++m) mma_bf16(acc[f][m][j], af[m], hb[j][0], hb[j][1]);
         }
       }
       __syncwarp();
     }
+    // epilogue: accumulators -> bf16 tile [CB][32] in shared memory (16-byte chunks XOR-swizzled by the row
+    // pair, conflict free both ways) -> 128-bit coalesced stores of the contiguous [CB x 32] block of T
 #pragma unroll
     for (int f = 0; f < FR; ++f) {
-      __nv_bfloat16* o = a.out + (rp * FR + f) * (int64_t)a.c * 32;
+      uint32_t* ts = reinterpret_cast<uint32_t*>(Gs + f * 32 * GSTR);  // [CB][16 words]
 #pragma unroll
       for (int m = 0; m < MT; ++m)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int c = c0 + m * 16 + g;
-          const int k = j * 8 + 2 * t;
-          if (c < a.c) *reinterpret_cast<uint32_t*>(o + c * 32 + k) = pack_bf16(acc[f][m][j][0], acc[f][m][j][1]);
-          if (c + 8 < a.c) *reinterpret_cast<uint32_t*>(o + (c + 8) * 32 + k) = pack_bf16(acc[f][m][j][2], acc[f][m][j][3]);
+          const int r0 = m * 16 + g, r1 = r0 + 8;
+          ts[r0 * 16 + ((j ^ ((r0 >> 1) & 3)) << 2) + t] = pack_bf16(acc[f][m][j][0], acc[f][m][j][1]);
+          ts[r1 * 16 + ((j ^ ((r1 >> 1) & 3)) << 2) + t] = pack_bf16(acc[f][m][j][2], acc[f][m][j][3]);
         }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int f = 0; f < FR; ++f) {
+      const uint4* ts = reinterpret_cast<const uint4*>(Gs + f * 32 * GSTR);
+      __nv_bfloat16* o = a.out + ((int64_t)rp * FR + f) * (int64_t)a.c * 32 + (int64_t)c0 * 32;
+#pragma unroll
+      for (int it = 0; it < CB / 8; ++it) {
+        const int row = it * 8 + (lane >> 2), part = lane & 3;
+        if (c0 + row < a.c) reinterpret_cast<uint4*>(o + row * 32)[part] = ts[row * 4 + (part ^ ((row >> 1) & 3))];
+      }
     }
   }
 }
 
 template <int CB, int FR, bool TR>
-static int launch_agg_cfg(const TcAggArgs& a, cudaStream_t st) {
-  constexpr int XS = CB + 8;
-  constexpr int WARP_BYTES = 32 * XS * 2 + FR * 32 * 12 * 4;
-  const size_t smem = 32 * 12 * 4 + AGG_WARPS * WARP_BYTES;
+static int launch_agg_cfg(const TcAggArgs& a, int64_t n_g, cudaStream_t st) {
+  const size_t smem = AGG_WARPS * AggSmem<CB, FR>::WARP_BYTES;
   const int ncb = (a.c + CB - 1) / CB;
   const int64_t warps = a.n_rows * ncb;
+  if (warps >= (int64_t)1 << 30 || n_g * a.f_g * a.c >= (int64_t)1 << 31) {
+    set_error("launch_agg_tc: problem too large for 32-bit row offsets");
+    return SE3_EINVAL;
+  }
   int64_t blocks = (warps + AGG_WARPS - 1) / AGG_WARPS;
-  const int64_t cap = (int64_t)num_sms() * 3 * 8;
+  const int64_t cap = (int64_t)num_sms() * SE3_AGG_MIN_BLOCKS * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   if (a.act == 2) {
@@ -268,13 +373,13 @@ static int launch_agg_cfg(const TcAggArgs& a, cudaStream_t st) {
 }
 
 template <bool TR>
-static int launch_agg_tc(const TcAggArgs& a, int f_row, cudaStream_t st) {
+static int launch_agg_tc(const TcAggArgs& a, int f_row, int64_t n_g, cudaStream_t st) {
   if (a.n_rows == 0) return SE3_OK;
   switch (f_row) {
-    case 1: return a.c > 32 ? launch_agg_cfg<64, 1, TR>(a, st) : (a.c > 16 ? launch_agg_cfg<32, 1, TR>(a, st) : launch_agg_cfg<16, 1, TR>(a, st));
-    case 2: return a.c > 16 ? launch_agg_cfg<32, 2, TR>(a, st) : launch_agg_cfg<16, 2, TR>(a, st);
-    case 3: return launch_agg_cfg<16, 3, TR>(a, st);
-    case 4: return launch_agg_cfg<16, 4, TR>(a, st);
+    case 1: return a.c > 16 ? launch_agg_cfg<32, 1, TR>(a, n_g, st) : launch_agg_cfg<16, 1, TR>(a, n_g, st);
+    case 2: return a.c > 16 ? launch_agg_cfg<32, 2, TR>(a, n_g, st) : launch_agg_cfg<16, 2, TR>(a, n_g, st);
+    case 3: return launch_agg_cfg<16, 3, TR>(a, n_g, st);
+    case 4: return launch_agg_cfg<16, 4, TR>(a, n_g, st);
   }
   set_error("launch_agg_tc: unsupported frame count");
   return SE3_EINVAL;
@@ -286,10 +391,8 @@ static int launch_agg_tc(const TcAggArgs& a, int f_row, cudaStream_t st) {
 struct TcEdgeArgs {
   const int* row_ends;
   const int* col_src;
-  const float* pts_out;
-  const float* frm_out;
-  const float* pts_in;
-  const float* frm_in;
+  const float* rec_out;  // [n_out * FR, 12]
+  const float* rec_in;   // [n_in * f_in, 12]
   int f_in;
   const float* x;
   int c;
@@ -299,37 +402,43 @@ struct TcEdgeArgs {
   int act;
   const __nv_bfloat16* dT;  // [n_out*FR, c, 32]
   int64_t n_out;
-  float* partials;          // [n_warps, 16, 32]
+  float* partials;          // [n_ctas, 16, 32]
 };
 
-template <int CB, int FR, int ACT>
-__global__ void __launch_bounds__(AGG_WARPS * 32, 3) k_edge_tc(const TcEdgeArgs a) {
-  constexpr int XS = CB + 8;   // Xs row (bf16)
-  constexpr int TS = 32 + 8;   // dTs row (bf16): [c][k]
-  constexpr int GB = 16 + 8;   // Gb row (bf16): [n][16]
-  constexpr int WARP_BYTES = 32 * XS * 2 + CB * TS * 2 + 32 * 12 * 4 + 32 * GB * 2;
+template <int CB>
+struct EdgeSmem {
+  static constexpr int XS = CB + 8;   // Xs row (bf16)
+  static constexpr int TS = 32 + 8;   // dTs row (bf16): [c][k]
+  static constexpr int GB = 16 + 8;   // Gb row (bf16): [n][16]
+  static constexpr int X_BYTES = 32 * XS * 2;
+  static constexpr int T_BYTES = CB * TS * 2;
+  static constexpr int G_BYTES = 32 * GSTR * 4;
+  static constexpr int GB_BYTES = 32 * GB * 2;
+  static constexpr int R_BYTES = 64;
+  static constexpr int WARP_BYTES = X_BYTES + T_BYTES + G_BYTES + GB_BYTES + R_BYTES;
+};
+
+#ifndef SE3_EDGE_MIN_BLOCKS
+#define SE3_EDGE_MIN_BLOCKS 4
+#endif
+
+// One warp per (output point, output frame) item, strided over a persistent grid; per-CTA partial sums.
+template <int CB, int ACT>
+__global__ void __launch_bounds__(AGG_WARPS * 32, SE3_EDGE_MIN_BLOCKS) k_edge_tc(const TcEdgeArgs a, const int f_out) {
+  using SM = EdgeSmem<CB>;
+  constexpr int XS = SM::XS, TS = SM::TS, GB = SM::GB;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* W9s = reinterpret_cast<float*>(smem_raw);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  unsigned char* wbase = smem_raw + 32 * 12 * 4 + wib * WARP_BYTES;
+  unsigned char* wbase = smem_raw + wib * SM::WARP_BYTES;
   __nv_bfloat16* Xs = reinterpret_cast<__nv_bfloat16*>(wbase);
-  __nv_bfloat16* dTs = reinterpret_cast<__nv_bfloat16*>(wbase + 32 * XS * 2);
-  float* Gs = reinterpret_cast<float*>(wbase + 32 * XS * 2 + CB * TS * 2);
-  __nv_bfloat16* Gb = reinterpret_cast<__nv_bfloat16*>(wbase + 32 * XS * 2 + CB * TS * 2 + 32 * 12 * 4);
-  for (int i = threadIdx.x; i < 32 * 12; i += blockDim.x) {
-    const int k = i / 12, d = i % 12;
-    W9s[i] = d < 9 ? a.w9[d * 32 + k] : (d == 9 ? a.bias[k] : 0.0f);
-  }
-  __syncthreads();
+  __nv_bfloat16* dTs = reinterpret_cast<__nv_bfloat16*>(wbase + SM::X_BYTES);
+  float* Gs = reinterpret_cast<float*>(wbase + SM::X_BYTES + SM::T_BYTES);                                   // [32][GSTR]
+  __nv_bfloat16* Gb = reinterpret_cast<__nv_bfloat16*>(wbase + SM::X_BYTES + SM::T_BYTES + SM::G_BYTES);     // [32][GB]
+  float* Rs = reinterpret_cast<float*>(wbase + SM::X_BYTES + SM::T_BYTES + SM::G_BYTES + SM::GB_BYTES);       // [12]
   const int g = lane >> 2, t = lane & 3;
   const int mid = lane >> 3, mr = lane & 7;
-  float wr[4][9], br[4];  // k = g + 8*j  (j = 2*mtile + half)
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-#pragma unroll
-    for (int d = 0; d < 9; ++d) wr[j][d] = W9s[(g + 8 * j) * 12 + d];
-    br[j] = W9s[(g + 8 * j) * 12 + 9];
-  }
+  uint32_t aw[2][2][4];
+  load_w9_frags(a.w9, a.bias, g, t, aw);
   float accA[2][2][4];  // [k m-tile][d n-tile]
 #pragma unroll
   for (int m = 0; m < 2; ++m)
@@ -337,213 +446,213 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, 3) k_edge_tc(const TcEdgeArgs 
     for (int dd = 0; dd < 2; ++dd)
 #pragma unroll
       for (int i = 0; i < 4; ++i) accA[m][dd][i] = 0.0f;
-  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
   const int ncb = (a.c + CB - 1) / CB;
-  for (int64_t rp = gw; rp < a.n_out; rp += nwarps) {
-    const int lo = rp > 0 ? a.row_ends[rp - 1] : 0;
-    const int hi = a.row_ends[rp];
+  const int total = (int)a.n_out * f_out;
+  for (int item = gw; item < total; item += nwarps) {
+    const int rp = item / f_out;
+    const int lo = rp > 0 ? __ldg(a.row_ends + rp - 1) : 0;
+    const int hi = __ldg(a.row_ends + rp);
     const int n_total = (hi - lo) * a.f_in;
-    const float prx = a.pts_out[3 * rp], pry = a.pts_out[3 * rp + 1], prz = a.pts_out[3 * rp + 2];
+    __syncwarp();
+    if (lane < 3) reinterpret_cast<float4*>(Rs)[lane] = __ldg(reinterpret_cast<const float4*>(a.rec_out) + (int64_t)item * 3 + lane);
+    __syncwarp();
+    const float prx = Rs[0], pry = Rs[1], prz = Rs[2];
+    float Frow[9];
+    load_row_frame(Rs, 0, Frow);
+    const __nv_bfloat16* dTrow = a.dT + (int64_t)item * (int64_t)a.c * 32;
     for (int base = 0; base < n_total; base += 32) {
       const int n = base + lane;
       const bool valid = n < n_total;
-      const int e = valid ? n / a.f_in : 0;
-      const int fg = valid ? n - e * a.f_in : 0;
-      const int q = __ldg(a.col_src + lo + e);
-      const int fidx = valid ? q * a.f_in + fg : -1;
-      float Fq[9];
+      int e, fg;
+      split_nf(valid ? n : 0, a.f_in, e, fg);
+      const int gidx = __ldg(a.col_src + lo + e) * a.f_in + fg;
+      const int fidx = valid ? gidx : -1;
+      const int n_here = min(32, n_total - base);
+      const int nq = (n_here + 7) >> 3;  // valid 8-neighbour groups (warp-uniform)
       {
-        const float* fp = a.frm_in + ((int64_t)q * a.f_in + fg) * 9;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) Fq[i] = __ldg(fp + i);
-      }
-      const float dx = (__ldg(a.pts_in + 3 * (int64_t)q) - prx) * a.norm;
-      const float dy = (__ldg(a.pts_in + 3 * (int64_t)q + 1) - pry) * a.norm;
-      const float dz = (__ldg(a.pts_in + 3 * (int64_t)q + 2) - prz) * a.norm;
-#pragma unroll 1
-      for (int f = 0; f < FR; ++f) {
-        float Frow[9];
-        {
-          const float* fp = a.frm_out + (rp * FR + f) * 9;
-#pragma unroll
-          for (int i = 0; i < 9; ++i) Frow[i] = __ldg(fp + i);
-        }
-        float gg[9];
+        float dx, dy, dz, Fq[9], gg[9];
+        gather_neighbour<false>(a.rec_in, gidx, prx, pry, prz, a.norm, dx, dy, dz, Fq);
         geometry9<false>(Frow, Fq, dx, dy, dz, gg);
         if (!valid) {
 #pragma unroll
           for (int i = 0; i < 9; ++i) gg[i] = 0.0f;
         }
-        {
-          float4* gs = reinterpret_cast<float4*>(Gs + lane * 12);
-          gs[0] = make_float4(gg[0], gg[1], gg[2], gg[3]);
-          gs[1] = make_float4(gg[4], gg[5], gg[6], gg[7]);
-          gs[2] = make_float4(gg[8], 0.f, 0.f, 0.f);
-          uint4 p0, p1;
-          p0.x = pack_bf16(gg[0], gg[1]); p0.y = pack_bf16(gg[2], gg[3]);
-          p0.z = pack_bf16(gg[4], gg[5]); p0.w = pack_bf16(gg[6], gg[7]);
-          p1.x = pack_bf16(gg[8], valid ? 1.0f : 0.0f);  // column 9 = 1 -> bias gradient
-          p1.y = 0u; p1.z = 0u; p1.w = 0u;
-          uint4* gb = reinterpret_cast<uint4*>(Gb + lane * GB);
-          gb[0] = p0;
-          gb[1] = p1;
-        }
-        // dH^T[k, n] = sum_c dT[c, k] x[n, c], accumulated over channel blocks
-        float dH[2][4][4];
+        store_geometry_row(Gs + lane * GSTR, gg, 1.0f);
+        uint4 p0, p1;
+        p0.x = pack_bf16(gg[0], gg[1]); p0.y = pack_bf16(gg[2], gg[3]);
+        p0.z = pack_bf16(gg[4], gg[5]); p0.w = pack_bf16(gg[6], gg[7]);
+        p1.x = pack_bf16(gg[8], valid ? 1.0f : 0.0f);  // column 9 = 1 -> bias gradient
+        p1.y = 0u; p1.z = 0u; p1.w = 0u;
+        uint4* gb = reinterpret_cast<uint4*>(Gb + lane * GB);
+        gb[0] = p0;
+        gb[1] = p1;
+      }
+      // dH^T[k, n] = sum_c dT[c, k] x[n, c], accumulated over channel blocks
+      float dH[2][4][4];
 #pragma unroll
-        for (int m = 0; m < 2; ++m)
+      for (int m = 0; m < 2; ++m)
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) dH[m][j][i] = 0.0f;
-        const __nv_bfloat16* dTrow = a.dT + (rp * FR + f) * (int64_t)a.c * 32;
-        for (int cb = 0; cb < ncb; ++cb) {
-          const int c0 = cb * CB;
-          __syncwarp();
-          stage_features<CB>(a.x, a.c, c0, fidx, lane, Xs);
-          // dT rows of this channel block: CB rows of 32 bf16 (64 B) = 4 x 16 B each
-          for (int i = lane; i < CB * 4; i += 32) {
+          for (int i = 0; i < 4; ++i) dH[m][j][i] = 0.0f;
+      for (int cb = 0; cb < ncb; ++cb) {
+        const int c0 = cb * CB;
+        __syncwarp();
+        stage_features<CB>(a.x, a.c, c0, fidx, lane, Xs);
+        // dT rows of this channel block: CB rows of 32 bf16 (64 B) = 4 x 16 B each
+        if (ncb > 1 || base == 0) {
+#pragma unroll
+          for (int i0 = 0; i0 < CB * 4; i0 += 32) {
+            const int i = i0 + lane;
             const int c = i >> 2, part = i & 3;
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (c0 + c < a.c) v = __ldg(reinterpret_cast<const uint4*>(dTrow + (int64_t)(c0 + c) * 32) + part);
+            if (c0 + c < a.c) v = __ldg(reinterpret_cast<const uint4*>(dTrow + (c0 + c) * 32) + part);
             *reinterpret_cast<uint4*>(dTs + c * TS + part * 8) = v;
-          }
-          __syncwarp();
-#pragma unroll
-          for (int ks = 0; ks < CB / 16; ++ks) {
-            // A = dT^T: [m = k][kk = c] from dTs[c][k] (.trans); B = x^T: [kk = c][nn = n] from Xs[n][c]
-            uint32_t af[2][4];
-#pragma unroll
-            for (int m = 0; m < 2; ++m)
-              ldmatrix_x4_trans(af[m][0], af[m][1], af[m][2], af[m][3],
-                                smem_u32(dTs + (ks * 16 + (mid >> 1) * 8 + mr) * TS + m * 16 + (mid & 1) * 8));
-#pragma unroll
-            for (int jp = 0; jp < 2; ++jp) {
-              uint32_t b[4];  // n-tiles 2jp (b0,b1) and 2jp+1 (b0,b1)
-              ldmatrix_x4(b[0], b[1], b[2], b[3], smem_u32(Xs + (jp * 16 + (mid >> 1) * 8 + mr) * XS + ks * 16 + (mid & 1) * 8));
-#pragma unroll
-              for (int m = 0; m < 2; ++m) {
-                mma_bf16(dH[m][2 * jp], af[m], b[0], b[1]);
-                mma_bf16(dH[m][2 * jp + 1], af[m], b[2], b[3]);
-              }
-            }
-          }
-        }
-        // dpre = dH * act'(pre) in the accumulator layout: k in {g, g+8} + 16 m, n = 8 j + 2 t + {0,1}
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float gv[2][9];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const float4* gs = reinterpret_cast<const float4*>(Gs + (8 * j + 2 * t + u) * 12);
-            const float4 v0 = gs[0], v1 = gs[1], v2 = gs[2];
-            gv[u][0] = v0.x; gv[u][1] = v0.y; gv[u][2] = v0.z; gv[u][3] = v0.w;
-            gv[u][4] = v1.x; gv[u][5] = v1.y; gv[u][6] = v1.z; gv[u][7] = v1.w;
-            gv[u][8] = v2.x;
-          }
-#pragma unroll
-          for (int m = 0; m < 2; ++m)
-#pragma unroll
-            for (int half = 0; half < 2; ++half)
-#pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                const int jj = 2 * m + half;
-                float pre = br[jj];
-#pragma unroll
-                for (int d = 0; d < 9; ++d) pre = fmaf(gv[u][d], wr[jj][d], pre);
-                dH[m][j][half * 2 + u] *= act_grad_rt<ACT>(pre, a.act);
-              }
-        }
-        // accA[k, d] += dpre[k, n] G[n, d]: dpre (C layout) -> A fragments, G from Gb[n][16] (.trans)
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          uint32_t gb[4];
-          ldmatrix_x4_trans(gb[0], gb[1], gb[2], gb[3], smem_u32(Gb + (ks * 16 + (mid & 1) * 8 + mr) * GB + (mid >> 1) * 8));
-#pragma unroll
-          for (int m = 0; m < 2; ++m) {
-            uint32_t afr[4];
-            afr[0] = pack_bf16(dH[m][2 * ks][0], dH[m][2 * ks][1]);
-            afr[1] = pack_bf16(dH[m][2 * ks][2], dH[m][2 * ks][3]);
-            afr[2] = pack_bf16(dH[m][2 * ks + 1][0], dH[m][2 * ks + 1][1]);
-            afr[3] = pack_bf16(dH[m][2 * ks + 1][2], dH[m][2 * ks + 1][3]);
-            mma_bf16(accA[m][0], afr, gb[0], gb[1]);
-            mma_bf16(accA[m][1], afr, gb[2], gb[3]);
           }
         }
         __syncwarp();
+#pragma unroll
+        for (int ks = 0; ks < CB / 16; ++ks) {
+          // A = dT^T: [m = k][kk = c] from dTs[c][k] (.trans); B = x^T: [kk = c][nn = n] from Xs[n][c]
+          uint32_t af[2][4];
+#pragma unroll
+          for (int m = 0; m < 2; ++m)
+            ldmatrix_x4_trans(af[m][0], af[m][1], af[m][2], af[m][3],
+                              smem_u32(dTs + (ks * 16 + (mid >> 1) * 8 + mr) * TS + m * 16 + (mid & 1) * 8));
+#pragma unroll
+          for (int jp = 0; jp < 2; ++jp) {
+            if (jp * 2 >= nq) break;
+            uint32_t b[4];  // n-tiles 2jp (b0,b1) and 2jp+1 (b0,b1)
+            ldmatrix_x4(b[0], b[1], b[2], b[3], smem_u32(Xs + (jp * 16 + (mid >> 1) * 8 + mr) * XS + ks * 16 + (mid & 1) * 8));
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+              mma_bf16(dH[m][2 * jp], af[m], b[0], b[1]);
+              mma_bf16(dH[m][2 * jp + 1], af[m], b[2], b[3]);
+            }
+          }
+        }
       }
+      // dpre = dH * act'(pre): pre^T tiles from the tensor cores (tf32) land in the same accumulator
+      // layout as dH: k in {g, g+8} + 16 m, n = 8 j + 2 t + {0,1}
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j >= nq) break;
+        float d[2][4];
+        basis_pre(aw, Gs + (8 * j + g) * GSTR, t, d);
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dH[m][j][i] *= act_grad_rt<ACT>(d[m][i], a.act);
+      }
+      // accA[k, d] += dpre[k, n] G[n, d]: dpre (C layout) -> A fragments, G from Gb[n][16] (.trans)
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        if (ks * 2 >= nq) break;
+        uint32_t gb[4];
+        ldmatrix_x4_trans(gb[0], gb[1], gb[2], gb[3], smem_u32(Gb + (ks * 16 + (mid & 1) * 8 + mr) * GB + (mid >> 1) * 8));
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          uint32_t afr[4];
+          afr[0] = pack_bf16(dH[m][2 * ks][0], dH[m][2 * ks][1]);
+          afr[1] = pack_bf16(dH[m][2 * ks][2], dH[m][2 * ks][3]);
+          afr[2] = pack_bf16(dH[m][2 * ks + 1][0], dH[m][2 * ks + 1][1]);
+          afr[3] = pack_bf16(dH[m][2 * ks + 1][2], dH[m][2 * ks + 1][3]);
+          mma_bf16(accA[m][0], afr, gb[0], gb[1]);
+          mma_bf16(accA[m][1], afr, gb[2], gb[3]);
+        }
+      }
+      __syncwarp();
     }
   }
-  // per-warp partial [d (16)][k (32)]
-  float* p = a.partials + gw * 512;
+  // per-CTA partial [d (16)][k (32)]: warps -> shared memory (the staging area is free now), summed in
+  // warp order (deterministic)
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(smem_raw);  // [AGG_WARPS][512]
+  {
+    float* p = red + wib * 512;
 #pragma unroll
-  for (int m = 0; m < 2; ++m)
+    for (int m = 0; m < 2; ++m)
 #pragma unroll
-    for (int dd = 0; dd < 2; ++dd) {
-      const int k = m * 16 + g, d = dd * 8 + 2 * t;
-      p[d * 32 + k] = accA[m][dd][0];
-      p[(d + 1) * 32 + k] = accA[m][dd][1];
-      p[d * 32 + k + 8] = accA[m][dd][2];
-      p[(d + 1) * 32 + k + 8] = accA[m][dd][3];
-    }
+      for (int dd = 0; dd < 2; ++dd) {
+        const int k = m * 16 + g, d = dd * 8 + 2 * t;
+        p[d * 32 + k] = accA[m][dd][0];
+        p[(d + 1) * 32 + k] = accA[m][dd][1];
+        p[d * 32 + k + 8] = accA[m][dd][2];
+        p[(d + 1) * 32 + k + 8] = accA[m][dd][3];
+      }
+  }
+  __syncthreads();
+  float* out = a.partials + (int64_t)blockIdx.x * 512;
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+    float s = red[i];
+#pragma unroll
+    for (int w = 1; w < AGG_WARPS; ++w) s += red[w * 512 + i];
+    out[i] = s;
+  }
 }
 
-// one warp per output element: lanes stride over the per-warp partials, fixed-order shuffle reduce
-__global__ void k_edge_tc_reduce(const float* __restrict__ partials, int n_partials, float* __restrict__ d_axes,
-                                 float* __restrict__ d_bias) {
-  const int lane = threadIdx.x & 31;
-  const int out = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (out >= 320) return;
+// Ordered reduction of the per-CTA partials: block b owns outputs 32b..32b+31; warp w sums partials w, w+32, ...
+// (lane = output, 128-byte coalesced rows), then the 32 warp sums are added in warp order.
+__global__ void __launch_bounds__(1024) k_edge_tc_reduce(const float* __restrict__ partials, int n_partials,
+                                                         float* __restrict__ d_axes, float* __restrict__ d_bias) {
+  __shared__ float sm[32][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int out = blockIdx.x * 32 + lane;
   float s = 0.0f;
-  for (int p = lane; p < n_partials; p += 32) s += partials[(int64_t)p * 512 + out];
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) {
+  for (int p = w; p < n_partials; p += 32) s += partials[(int64_t)p * 512 + out];
+  sm[w][lane] = s;
+  __syncthreads();
+  if (w == 0) {
+    float tot = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) tot += sm[i][lane];
     if (out < 288) {
-      if (d_axes) d_axes[out] = s;
-    } else if (d_bias) {
-      d_bias[out - 288] = s;
+      if (d_axes) d_axes[out] = tot;
+    } else if (out < 320 && d_bias) {
+      d_bias[out - 288] = tot;
     }
   }
 }
 
-static int edge_tc_warps(int64_t n_out) {
-  int64_t blocks = (n_out + AGG_WARPS - 1) / AGG_WARPS;
-  const int64_t cap = (int64_t)num_sms() * 3;
+static int edge_tc_warps(int64_t n_items) {
+  int64_t blocks = (n_items + AGG_WARPS - 1) / AGG_WARPS;
+  const int64_t cap = (int64_t)num_sms() * SE3_EDGE_MIN_BLOCKS;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks * AGG_WARPS;
 }
 
-template <int CB, int FR>
-static int launch_edge_cfg(const TcEdgeArgs& a, int n_warps, cudaStream_t st) {
-  constexpr int WARP_BYTES = 32 * (CB + 8) * 2 + CB * 40 * 2 + 32 * 12 * 4 + 32 * 24 * 2;
-  const size_t smem = 32 * 12 * 4 + AGG_WARPS * WARP_BYTES;
+template <int CB>
+static int launch_edge_cfg(const TcEdgeArgs& a, int f_out, int n_warps, cudaStream_t st) {
+  static_assert(AGG_WARPS * EdgeSmem<CB>::WARP_BYTES >= AGG_WARPS * 512 * 4, "partials must fit the staging area");
+  const size_t smem = AGG_WARPS * EdgeSmem<CB>::WARP_BYTES;
   if (a.act == 2) {
-    auto kern = k_edge_tc<CB, FR, 2>;
+    auto kern = k_edge_tc<CB, 2>;
     SE3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<n_warps / AGG_WARPS, AGG_WARPS * 32, smem, st>>>(a);
+    kern<<<n_warps / AGG_WARPS, AGG_WARPS * 32, smem, st>>>(a, f_out);
   } else {
-    auto kern = k_edge_tc<CB, FR, -1>;
+    auto kern = k_edge_tc<CB, -1>;
     SE3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<n_warps / AGG_WARPS, AGG_WARPS * 32, smem, st>>>(a);
+    kern<<<n_warps / AGG_WARPS, AGG_WARPS * 32, smem, st>>>(a, f_out);
   }
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }
 
-static int launch_edge_tc(const TcEdgeArgs& a, int f_out, int n_warps, float* dA, float* dB, cudaStream_t st) {
-  int rc = SE3_OK;
-  const bool small = a.c <= 16;
-  switch (f_out) {
-    case 1: rc = small ? launch_edge_cfg<16, 1>(a, n_warps, st) : launch_edge_cfg<32, 1>(a, n_warps, st); break;
-    case 2: rc = small ? launch_edge_cfg<16, 2>(a, n_warps, st) : launch_edge_cfg<32, 2>(a, n_warps, st); break;
-    case 3: rc = small ? launch_edge_cfg<16, 3>(a, n_warps, st) : launch_edge_cfg<32, 3>(a, n_warps, st); break;
-    case 4: rc = small ? launch_edge_cfg<16, 4>(a, n_warps, st) : launch_edge_cfg<32, 4>(a, n_warps, st); break;
-    default: set_error("launch_edge_tc: unsupported frame count"); return SE3_EINVAL;
+static int launch_edge_tc(const TcEdgeArgs& a, int f_out, int64_t n_in, int n_warps, float* dA, float* dB, cudaStream_t st) {
+  if (f_out < 1 || f_out > 4) {
+    set_error("launch_edge_tc: unsupported frame count");
+    return SE3_EINVAL;
   }
+  if (n_in * a.f_in * a.c >= (int64_t)1 << 31 || a.n_out * f_out * (int64_t)a.c * 32 >= (int64_t)1 << 40) {
+    set_error("launch_edge_tc: problem too large for 32-bit row offsets");
+    return SE3_EINVAL;
+  }
+  int rc = a.c <= 16 ? launch_edge_cfg<16>(a, f_out, n_warps, st) : launch_edge_cfg<32>(a, f_out, n_warps, st);
   if (rc) return rc;
-  k_edge_tc_reduce<<<40, 256, 0, st>>>(a.partials, n_warps, dA, dB);
+  k_edge_tc_reduce<<<10, 1024, 0, st>>>(a.partials, n_warps / AGG_WARPS, dA, dB);
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }
@@ -775,6 +884,14 @@ static int splits_for_tc(int64_t m, int64_t n, int64_t k) {
 // orchestration
 // --------------------------------------------------------------------------------------------
 static int check_tc(const se3_conv_desc* d) {
+  if (!d->rec_in || !d->rec_out) {
+    set_error("precision 1 needs the packed gather records rec_in / rec_out (se3_pack_records)");
+    return SE3_EINVAL;
+  }
+  if (d->n_in * d->f_in >= ((int64_t)1 << 30) || d->n_out * d->f_out >= ((int64_t)1 << 30)) {
+    set_error("precision 1: more than 2^30 (point, frame) rows");
+    return SE3_EINVAL;
+  }
   if (d->c_out % 8 != 0) {
     set_error("precision 1 needs c_out to be a multiple of 8 (got %d)", d->c_out);
     return SE3_EINVAL;
@@ -796,7 +913,7 @@ size_t conv_tc_bwd_workspace_bytes(const se3_conv_desc* d) {
   b += align_up((size_t)R * ck * 2);                                              // dT bf16
   b += align_up((size_t)Nf * d->c_out * d->k * 2);                                // U bf16
   b += align_up((size_t)splits_for_tc(ck, d->c_out, R) * ck * d->c_out * 4);      // dW partials
-  b += align_up((size_t)edge_tc_warps(d->n_out) * 512 * 4);                       // basis-gradient partials
+  b += align_up((size_t)edge_tc_warps(d->n_out * d->f_out) * 512 * 4);                       // basis-gradient partials
   return b + 256;
 }
 
@@ -813,11 +930,10 @@ int conv_tc_fwd(const se3_conv_desc* d, const float* x, float* y, void* saved, v
   SE3_LAUNCH_CHECK();
   TcAggArgs a;
   a.row_ends = d->row_ends; a.nbr = d->col_src;
-  a.pts_row = d->pts_out; a.frm_row = d->frames_out;
-  a.pts_g = d->pts_in; a.frm_g = d->frames_in; a.f_g = d->f_in;
+  a.rec_row = d->rec_out; a.rec_g = d->rec_in; a.f_g = d->f_in;
   a.feat = x; a.c = d->c_in; a.w9 = d->proj_axes; a.bias = d->proj_biases; a.norm = d->norm_neigh_dist;
   a.act = d->act; a.out = T; a.n_rows = d->n_out;
-  if (int rc = launch_agg_tc<false>(a, d->f_out, st)) return rc;
+  if (int rc = launch_agg_tc<false>(a, d->f_out, d->n_in, st)) return rc;
   // y[r,o] = s * sum_(c,k) T[r,(c,k)] Wt[o,(c,k)]   (tcgen05 / TMEM)
   return gemm_tn(R, d->c_out, ck, d->out_scale, T, ck, Wb, ck, y, d->c_out, false, 0, st);
 }
@@ -837,7 +953,7 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
   __nv_bfloat16* U = ar.take<__nv_bfloat16>(Nf * ok);
   const int splits = splits_for_tc(ck, d->c_out, R);
   float* dWp = ar.take<float>((size_t)splits * ck * d->c_out);
-  const int n_warps = edge_tc_warps(d->n_out);
+  const int n_warps = edge_tc_warps(d->n_out * d->f_out);
   float* eg = ar.take<float>((size_t)n_warps * 512);
   if (!ar.ok()) { set_error("conv_tc_bwd: workspace too small"); return SE3_EWORKSPACE; }
   const __nv_bfloat16* T = reinterpret_cast<const __nv_bfloat16*>(saved);
@@ -856,20 +972,18 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
     if (int rc = gemm_tn(R, ck, d->c_out, d->out_scale, dyb, d->c_out, Wb, d->c_out, dTb, ck, true, 0, st)) return rc;
     TcEdgeArgs g;
     g.row_ends = d->row_ends; g.col_src = d->col_src;
-    g.pts_out = d->pts_out; g.frm_out = d->frames_out;
-    g.pts_in = d->pts_in; g.frm_in = d->frames_in; g.f_in = d->f_in;
+    g.rec_out = d->rec_out; g.rec_in = d->rec_in; g.f_in = d->f_in;
     g.x = x; g.c = d->c_in; g.w9 = d->proj_axes; g.bias = d->proj_biases; g.norm = d->norm_neigh_dist;
     g.act = d->act; g.dT = dTb; g.n_out = d->n_out; g.partials = eg;
-    if (int rc = launch_edge_tc(g, d->f_out, n_warps, dA, dB, st)) return rc;
+    if (int rc = launch_edge_tc(g, d->f_out, d->n_in, n_warps, dA, dB, st)) return rc;
   }
   if (dx) {
     TcAggArgs a;
     a.row_ends = d->t_row_ends; a.nbr = d->t_dst;
-    a.pts_row = d->pts_in; a.frm_row = d->frames_in;
-    a.pts_g = d->pts_out; a.frm_g = d->frames_out; a.f_g = d->f_out;
+    a.rec_row = d->rec_in; a.rec_g = d->rec_out; a.f_g = d->f_out;
     a.feat = dy; a.c = d->c_out; a.w9 = d->proj_axes; a.bias = d->proj_biases; a.norm = d->norm_neigh_dist;
     a.act = d->act; a.out = U; a.n_rows = d->n_in;
-    if (int rc = launch_agg_tc<true>(a, d->f_in, st)) return rc;
+    if (int rc = launch_agg_tc<true>(a, d->f_in, d->n_out, st)) return rc;
     k_permute_w_bf16<<<blocks_for(ck * d->c_out), 256, 0, st>>>(d->conv_weights, d->c_in, d->k, d->c_out, Wpb);
     SE3_LAUNCH_CHECK();
     // dx[n,c] = s * sum_(o,k) U[n,(o,k)] Wp[c,(o,k)]
@@ -879,6 +993,32 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
 }
 
 }  // namespace se3
+
+namespace se3 {
+__global__ void k_pack_records(const float* __restrict__ pts, const float* __restrict__ frames, int64_t n, int f,
+                               float4* __restrict__ rec) {
+  const int64_t total = n * f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / f;
+    const float* fr = frames + i * 9;
+    rec[3 * i] = make_float4(pts[3 * p], pts[3 * p + 1], pts[3 * p + 2], fr[0]);
+    rec[3 * i + 1] = make_float4(fr[1], fr[2], fr[3], fr[4]);
+    rec[3 * i + 2] = make_float4(fr[5], fr[6], fr[7], fr[8]);
+  }
+}
+}  // namespace se3
+
+extern "C" int se3_pack_records(const float* pts, const float* frames, int64_t n, int32_t f, float* rec,
+                                se3_stream_t stream) {
+  using namespace se3;
+  SE3_CHECK_ARG(n >= 0 && f >= 1 && f <= 4, "bad sizes");
+  if (n == 0) return SE3_OK;
+  SE3_CHECK_ARG(pts && frames && rec, "null pointer");
+  SE3_CHECK_ARG((reinterpret_cast<uintptr_t>(rec) & 15) == 0, "rec must be 16-byte aligned");
+  k_pack_records<<<blocks_for(n * f), 256, 0, as_stream(stream)>>>(pts, frames, n, f, reinterpret_cast<float4*>(rec));
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
+}
 
 // C = alpha * A[M,K] . B[N,K]^T, bf16 operands (K-major), fp32 or bf16 output.  impl: 0 auto, 1 mma.sync, 2 tcgen05.
 extern "C" int se3_gemm_bf16_tn(const void* a, const void* b, int64_t m, int64_t n, int64_t k, float alpha, void* c,

@@ -86,6 +86,7 @@ def make_conv_desc(geom, c_in, c_out, k, act, precision, norm_neigh_dist, out_sc
     d.frames_in, d.frames_out = ptr(geom.frames_in), ptr(geom.frames_out)
     d.row_ends, d.col_src = ptr(geom.row_ends), ptr(geom.col_src)
     d.t_row_ends, d.t_edge, d.t_dst = ptr(geom.t_row_ends), ptr(geom.t_edge), ptr(geom.t_dst)
+    d.rec_in, d.rec_out = ptr(geom.rec_in), ptr(geom.rec_out)
     d.proj_axes, d.proj_biases, d.conv_weights = ptr(proj_axes), ptr(proj_biases), ptr(conv_weights)
     return d
 

@@ -6,6 +6,26 @@ from .._lib import lib, check, ptr, stream, workspace, Se3Error, num_batches
 from ..custom_ops import BallQuery, KNNQuery
 
 
+def gather_records(p_pc):
+    """[N*F,12] float32 records (point, frame) of a cloud for the tensor-core kernels (se3_pack_records),
+    cached on the cloud and rebuilt when its coordinates or frames are replaced."""
+    pts, frames = p_pc.pts_, p_pc.local_frames_
+    key = (id(pts), id(frames), pts._version, frames._version)
+    cached = getattr(p_pc, "_se3_records", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    p32 = pts.detach().to(torch.float32).contiguous()
+    f32 = frames.detach().to(torch.float32).contiguous()
+    n, f = int(p32.shape[0]), int(f32.shape[1])
+    rec = torch.empty((max(n * f, 1), 12), dtype=torch.float32, device=p32.device)
+    check(lib().se3_pack_records(ptr(p32), ptr(f32), n, f, ptr(rec), stream()), "se3_pack_records")
+    try:
+        p_pc._se3_records = (key, rec)
+    except AttributeError:
+        pass
+    return rec
+
+
 class ConvGeometry(object):
     """Device-resident record a conv call needs: forward CSR (int32), transposed CSR, coordinates
     and frames.  Built once per (neighbourhood, pc_in, pc_out) and cached on the neighbourhood; it
@@ -27,6 +47,8 @@ class ConvGeometry(object):
         self.pts_out = p_pc_out.pts_.detach().to(torch.float32).contiguous()
         self.frames_in = p_pc_in.local_frames_.detach().to(torch.float32).contiguous()
         self.frames_out = p_pc_out.local_frames_.detach().to(torch.float32).contiguous()
+        self.rec_in = gather_records(p_pc_in)
+        self.rec_out = self.rec_in if p_pc_out is p_pc_in else gather_records(p_pc_out)
         self.row_ends = p_neighborhood.start_ids_.to(torch.int32).contiguous()
         if self.row_ends.shape[0] != self.n_out:
             raise Se3Error("neighbourhood has %d rows but the output cloud has %d points" %
