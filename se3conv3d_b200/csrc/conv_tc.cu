@@ -33,8 +33,9 @@ struct TcAggArgs {
   const float* rec_row;  // [n_rows * FR, 12] records of the row side
   const float* rec_g;    // [n_g * f_g, 12] records of the gathered side
   int f_g;
-  const float* feat;
-  int c;
+  const __nv_bfloat16* feat;  // [n_g * f_g, cs] bf16 rows
+  int c;                      // channels
+  int cs;                     // row stride of feat (multiple of 8, >= c)
   const float* w9;
   const float* bias;
   float norm;
@@ -91,54 +92,56 @@ __device__ __forceinline__ void split_nf(int n, int f, int& e, int& fg) {
   }
 }
 
-// 128-bit read-only load that leaves the (pre-zeroed) destination untouched when pred is false
-__device__ __forceinline__ void ldg128_if(float4& v, const float* p, bool pred) {
-  asm volatile(
-      "{\n"
-      ".reg .pred q;\n"
-      "setp.ne.b32 q, %4, 0;\n"
-      "@q ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%5];\n"
-      "}\n"
-      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
-      : "r"((int)pred), "l"(p));
+// 16-byte asynchronous copy through L1 (neighbouring rows share gathered lines), zero fill when !pred
+__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void* src, bool pred) {
+  const int sz = pred ? 16 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
 
-// Stage the gathered feature rows of a 32-neighbour chunk into Xs[32][CB+8] (bf16).  Row offsets are
-// 32-bit (the launchers check rows * C < 2^31).
+// Gather of one 32-neighbour chunk, fully asynchronous (no registers in flight):
+//   * this lane's neighbour record (48 B) -> Rg[lane][12]
+//   * the bf16 feature rows of all 32 neighbours, channels [c0, c0+CB) -> Xs[32][CB+8]; CB/8 lanes per row.
+// gidx < 0 marks a padding lane (zero filled).  feat rows are `cs` bf16 apart (cs % 8 == 0).
 template <int CB>
-__device__ __forceinline__ void stage_features(const float* __restrict__ feat, int C, int c0, int fidx, int lane,
-                                               __nv_bfloat16* Xs) {
+__device__ __forceinline__ void gather_chunk_async(const float* __restrict__ rec_g, const __nv_bfloat16* __restrict__ feat,
+                                                   int cs, int c0, int gidx, int lane, uint32_t rg_s, uint32_t xs_s) {
   constexpr int XS = CB + 8;
-  if ((C & 3) == 0) {
-    constexpr int LPR = CB / 4;    // lanes per row (float4 each)
-    constexpr int RPI = 32 / LPR;  // rows per iteration
-    const int col4 = lane % LPR, r0 = lane / LPR;
-    const int ch = c0 + col4 * 4;
-    const bool chok = ch < C;
-    float4 v[LPR];
-#pragma unroll
-    for (int it = 0; it < LPR; ++it) {
-      const int src = __shfl_sync(0xffffffffu, fidx, it * RPI + r0);
-      v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-      ldg128_if(v[it], feat + (uint32_t)(src * C + ch), src >= 0 && chok);
-    }
-#pragma unroll
-    for (int it = 0; it < LPR; ++it) {
-      uint2 p;
-      p.x = pack_bf16(v[it].x, v[it].y);
-      p.y = pack_bf16(v[it].z, v[it].w);
-      *reinterpret_cast<uint2*>(Xs + (it * RPI + r0) * XS + col4 * 4) = p;
-    }
-  } else {
-    for (int row = 0; row < 32; ++row) {
-      const int src = __shfl_sync(0xffffffffu, fidx, row);
-      for (int ch = lane; ch < CB; ch += 32) {
-        float v = 0.f;
-        if (src >= 0 && c0 + ch < C) v = __ldg(feat + (uint32_t)(src * C + c0 + ch));
-        Xs[row * XS + ch] = __float2bfloat16(v);
-      }
-    }
+  {
+    const bool ok = gidx >= 0;
+    const float* src = rec_g + (ok ? (uint32_t)gidx * 12u : 0u);
+    const uint32_t dst = rg_s + lane * 48;
+    cp_async16_ca(dst, src, ok);
+    cp_async16_ca(dst + 16, src + 4, ok);
+    cp_async16_ca(dst + 32, src + 8, ok);
   }
+  constexpr int LPR = CB / 8;    // lanes per row (16 B = 8 bf16 each)
+  constexpr int RPI = 32 / LPR;  // rows per iteration
+  const int col = lane % LPR, r0 = lane / LPR;
+  const int ch = c0 + col * 8;
+  const bool chok = ch < cs;
+#pragma unroll
+  for (int it = 0; it < LPR; ++it) {
+    const int row = it * RPI + r0;
+    const int src = __shfl_sync(0xffffffffu, gidx, row);
+    const bool ok = src >= 0 && chok;
+    cp_async16_ca(xs_s + (row * XS + col * 8) * 2, feat + (ok ? (uint32_t)(src * cs + ch) : 0u), ok);
+  }
+}
+
+// This lane's gathered index of chunk `base` of a row with `nt` (edge x frame) entries: -1 when padding.
+// idx holds the row's first 32 neighbour ids (lane e <-> edge e); longer rows fall back to a direct load.
+__device__ __forceinline__ int chunk_gidx(const int* __restrict__ nbr, int lo, int nt, int idx, int f_g, int base, int lane) {
+  const int n = base + lane;
+  const bool valid = n < nt;
+  int e, fg;
+  split_nf(valid ? n : 0, f_g, e, fg);
+  int q;
+  if (base + 31 < 32 * f_g) {  // warp-uniform: every edge of this chunk is among the preloaded 32
+    q = __shfl_sync(0xffffffffu, idx, e);
+  } else {
+    q = __ldg(nbr + lo + e);
+  }
+  return valid ? q * f_g + fg : -1;
 }
 
 constexpr int AGG_WARPS = 4;  // warps per CTA of the aggregation / edge kernels
@@ -184,13 +187,12 @@ __device__ __forceinline__ void store_geometry_row(float* row, const float (&gg)
   gs[2] = make_float4(gg[8], one, 0.f, 0.f);
 }
 
-// This lane's gathered neighbour of a chunk: record (3 x 128-bit), scaled offset and frame.
+// This lane's gathered neighbour of a chunk from its staged record: scaled offset and frame.
 template <bool TR>
-__device__ __forceinline__ void gather_neighbour(const float* __restrict__ rec_g, int gidx, float prx, float pry,
-                                                 float prz, float norm, float& dx, float& dy, float& dz,
-                                                 float (&Fq)[9]) {
-  const float4* rp = reinterpret_cast<const float4*>(rec_g) + (int64_t)gidx * 3;
-  const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
+__device__ __forceinline__ void unpack_neighbour(const float* rg, float prx, float pry, float prz, float norm, float& dx,
+                                                 float& dy, float& dz, float (&Fq)[9]) {
+  const float4* rp = reinterpret_cast<const float4*>(rg);
+  const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2];
   dx = (TR ? (prx - r0.x) : (r0.x - prx)) * norm;
   dy = (TR ? (pry - r0.y) : (r0.y - pry)) * norm;
   dz = (TR ? (prz - r0.z) : (r0.z - prz)) * norm;
@@ -208,10 +210,14 @@ __device__ __forceinline__ void load_row_frame(const float* Rs, int f, float (&F
 template <int CB, int FR>
 struct AggSmem {
   static constexpr int XS = CB + 8;
-  static constexpr int X_BYTES = 32 * XS * 2;
+  static constexpr int X_BYTES = 32 * XS * 2;         // one feature buffer (bf16)
+  static constexpr int RG_BYTES = 32 * 48;            // one record buffer
   static constexpr int G_BYTES = FR * 32 * GSTR * 4;  // geometry rows; reused as the T staging tiles (2 KB per frame)
-  static constexpr int R_BYTES = FR * 48;
-  static constexpr int WARP_BYTES = X_BYTES + G_BYTES + ((R_BYTES + 15) / 16) * 16;
+  static constexpr int RS_BYTES = ((FR * 48 + 63) / 64) * 64;  // one row-record buffer
+  static constexpr int OFF_RG = 2 * X_BYTES;
+  static constexpr int OFF_G = OFF_RG + 2 * RG_BYTES;
+  static constexpr int OFF_RS = OFF_G + G_BYTES;
+  static constexpr int WARP_BYTES = OFF_RS + 2 * RS_BYTES;
 };
 
 #ifndef SE3_AGG_MIN_BLOCKS
@@ -220,37 +226,75 @@ struct AggSmem {
 
 // One warp per (row point, channel block): the FR row frames share the gathered records and the staged
 // feature rows; their [CB x 32] accumulators live in registers.
+//
+// Software pipeline (per warp, no block-level synchronisation): while chunk i is computed, the records and
+// feature rows of chunk i+1 -- the next chunk of the same row, or the first chunk of the warp's next row --
+// are in flight as cp.async copies into the other shared-memory buffer; the neighbour ids of the next row
+// and the CSR bounds of the row after it are register prefetches issued one row earlier.  No gather latency
+// sits on the critical path after the first chunk.
 template <int CB, int FR, bool TR, int ACT>
 __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_AGG_MIN_BLOCKS) k_agg_tc(const TcAggArgs a, const int ncb) {
   using SM = AggSmem<CB, FR>;
   constexpr int XS = SM::XS;
   constexpr int MT = CB / 16;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   unsigned char* wbase = smem_raw + wib * SM::WARP_BYTES;
-  __nv_bfloat16* Xs = reinterpret_cast<__nv_bfloat16*>(wbase);
-  float* Gs = reinterpret_cast<float*>(wbase + SM::X_BYTES);               // [FR][32][GSTR]
-  float* Rs = reinterpret_cast<float*>(wbase + SM::X_BYTES + SM::G_BYTES);  // [FR][12] row records
+  const uint32_t wbase_s = smem_u32(wbase);
+  float* Gs = reinterpret_cast<float*>(wbase + SM::OFF_G);  // [FR][32][GSTR]
   const int g = lane >> 2, t = lane & 3;
-  uint32_t aw[2][2][4];
-  load_w9_frags(a.w9, a.bias, g, t, aw);
   const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
   const int total = (int)a.n_rows * ncb;
   const int mid = lane >> 3, mr = lane & 7;  // ldmatrix: matrix id, row inside the matrix
-  for (int item = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); item < total; item += nwarps) {
-    int rp = item, c0 = 0;
+  int item0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (item0 >= total) return;
+  uint32_t aw[2][2][4];
+  load_w9_frags(a.w9, a.bias, g, t, aw);
+
+  auto row_of = [&](int item, int& rp, int& c0) {
+    rp = item;
+    c0 = 0;
     if (ncb > 1) {
       rp = item / ncb;
       c0 = (item - rp * ncb) * CB;
     }
-    const int lo = rp > 0 ? __ldg(a.row_ends + rp - 1) : 0;
-    const int hi = __ldg(a.row_ends + rp);
-    const int n_total = (hi - lo) * a.f_g;
-    __syncwarp();
-    if (lane < FR * 3)
-      reinterpret_cast<float4*>(Rs)[lane] = __ldg(reinterpret_cast<const float4*>(a.rec_row) + (int64_t)rp * (FR * 3) + lane);
-    __syncwarp();
-    const float prx = Rs[0], pry = Rs[1], prz = Rs[2];
+  };
+  auto issue = [&](int rp, int c0, int lo, int nt, int idx, int base, int buf, int rb, bool with_row) {
+    const int gidx = chunk_gidx(a.nbr, lo, nt, idx, a.f_g, base, lane);
+    gather_chunk_async<CB>(a.rec_g, a.feat, a.cs, c0, gidx, lane, wbase_s + SM::OFF_RG + buf * SM::RG_BYTES,
+                           wbase_s + buf * SM::X_BYTES);
+    if (with_row && lane < FR * 3)
+      cp_async16_ca(wbase_s + SM::OFF_RS + rb * SM::RS_BYTES + lane * 16,
+                    reinterpret_cast<const float4*>(a.rec_row) + (int64_t)rp * (FR * 3) + lane, true);
+  };
+
+  // ---- prologue: row 0 bounds + ids (synchronous, once), row 1 bounds (synchronous) + ids (in flight),
+  //      row 2 bounds (in flight)
+  int rp0, c00;
+  row_of(item0, rp0, c00);
+  int lo0 = rp0 > 0 ? __ldg(a.row_ends + rp0 - 1) : 0;
+  int ne0 = __ldg(a.row_ends + rp0) - lo0;
+  int idx0 = lane < ne0 ? __ldg(a.nbr + lo0 + lane) : 0;
+  int item1 = item0 + nwarps, rp1 = 0, c01 = 0, lo1 = 0, ne1 = 0, idx1 = 0;
+  if (item1 < total) {
+    row_of(item1, rp1, c01);
+    lo1 = rp1 > 0 ? __ldg(a.row_ends + rp1 - 1) : 0;
+    ne1 = __ldg(a.row_ends + rp1) - lo1;
+    idx1 = lane < ne1 ? __ldg(a.nbr + lo1 + lane) : 0;
+  }
+  int item2 = item1 + nwarps, e2a = 0, e2b = 0;
+  if (item2 < total) {
+    int rp2, c02;
+    row_of(item2, rp2, c02);
+    e2a = rp2 > 0 ? __ldg(a.row_ends + rp2 - 1) : 0;
+    e2b = __ldg(a.row_ends + rp2);
+  }
+  int buf = 0, rb = 0;
+  issue(rp0, c00, lo0, ne0 * a.f_g, idx0, 0, 0, 0, true);
+  cp_async_commit();
+
+  for (;;) {
+    const int nt0 = ne0 * a.f_g;
     float acc[FR][MT][4][4];
 #pragma unroll
     for (int f = 0; f < FR; ++f)
@@ -260,15 +304,22 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_AGG_MIN_BLOCKS) k_agg_tc(c
         for (int j = 0; j < 4; ++j)
 #pragma unroll
           for (int i = 0; i < 4; ++i) acc[f][m][j][i] = 0.0f;
-    for (int base = 0; base < n_total; base += 32) {
-      const int n = base + lane;
-      const bool valid = n < n_total;
-      int e, fg;
-      split_nf(valid ? n : 0, a.f_g, e, fg);
-      const int gidx = __ldg(a.nbr + lo + e) * a.f_g + fg;
+    int base = 0;
+    do {
+      // ---- chunk i+1 in flight
+      if (base + 32 < nt0) {
+        issue(rp0, c00, lo0, nt0, idx0, base + 32, buf ^ 1, rb, false);
+      } else if (item1 < total) {
+        issue(rp1, c01, lo1, ne1 * a.f_g, idx1, 0, buf ^ 1, rb ^ 1, true);
+      }
+      cp_async_commit();
+      cp_async_wait<1>();  // chunk i has landed
+      __syncwarp();
+      const float* Rs = reinterpret_cast<const float*>(wbase + SM::OFF_RS + rb * SM::RS_BYTES);
       {
+        const float* rg = reinterpret_cast<const float*>(wbase + SM::OFF_RG + buf * SM::RG_BYTES) + lane * 12;
         float dx, dy, dz, Fq[9];
-        gather_neighbour<TR>(a.rec_g, gidx, prx, pry, prz, a.norm, dx, dy, dz, Fq);
+        unpack_neighbour<TR>(rg, Rs[0], Rs[1], Rs[2], a.norm, dx, dy, dz, Fq);
 #pragma unroll
         for (int f = 0; f < FR; ++f) {
           float Frow[9], gg[9];
@@ -277,9 +328,9 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_AGG_MIN_BLOCKS) k_agg_tc(c
           store_geometry_row(Gs + (f * 32 + lane) * GSTR, gg, 1.0f);
         }
       }
-      stage_features<CB>(a.feat, a.c, c0, valid ? gidx : -1, lane, Xs);
       __syncwarp();
-      const int n_here = min(32, n_total - base);  // warp-uniform: 8-neighbour groups beyond it are skipped
+      const __nv_bfloat16* Xs = reinterpret_cast<const __nv_bfloat16*>(wbase + buf * SM::X_BYTES);
+      const int n_here = min(32, nt0 - base);  // warp-uniform: 8-neighbour groups beyond it are skipped
 #pragma unroll 1
       for (int ks = 0; ks < 2; ++ks) {
         if (ks * 16 >= n_here) break;
@@ -317,9 +368,11 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_AGG_MIN_BLOCKS) k_agg_tc(c
         }
       }
       __syncwarp();
-    }
-    // epilogue: accumulators -> bf16 tile [CB][32] in shared memory (16-byte chunks XOR-swizzled by the row
-    // pair, conflict free both ways) -> 128-bit coalesced stores of the contiguous [CB x 32] block of T
+      buf ^= 1;
+      base += 32;
+    } while (base < nt0);
+    // ---- epilogue: accumulators -> bf16 tile [CB][32] in shared memory (16-byte chunks XOR-swizzled by the
+    // row pair, conflict free both ways) -> 128-bit coalesced stores of the contiguous [CB x 32] block of T
 #pragma unroll
     for (int f = 0; f < FR; ++f) {
       uint32_t* ts = reinterpret_cast<uint32_t*>(Gs + f * 32 * GSTR);  // [CB][16 words]
@@ -336,14 +389,34 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_AGG_MIN_BLOCKS) k_agg_tc(c
 #pragma unroll
     for (int f = 0; f < FR; ++f) {
       const uint4* ts = reinterpret_cast<const uint4*>(Gs + f * 32 * GSTR);
-      __nv_bfloat16* o = a.out + ((int64_t)rp * FR + f) * (int64_t)a.c * 32 + (int64_t)c0 * 32;
+      __nv_bfloat16* o = a.out + ((int64_t)rp0 * FR + f) * (int64_t)a.c * 32 + (int64_t)c00 * 32;
 #pragma unroll
       for (int it = 0; it < CB / 8; ++it) {
         const int row = it * 8 + (lane >> 2), part = lane & 3;
-        if (c0 + row < a.c) reinterpret_cast<uint4*>(o + row * 32)[part] = ts[row * 4 + (part ^ ((row >> 1) & 3))];
+        if (c00 + row < a.c) reinterpret_cast<uint4*>(o + row * 32)[part] = ts[row * 4 + (part ^ ((row >> 1) & 3))];
       }
     }
+    __syncwarp();
+    // ---- rotate the row pipeline
+    if (item1 >= total) break;
+    item0 = item1; rp0 = rp1; c00 = c01; lo0 = lo1; ne0 = ne1; idx0 = idx1;
+    rb ^= 1;
+    item1 = item2;
+    if (item1 < total) {
+      row_of(item1, rp1, c01);
+      lo1 = e2a;
+      ne1 = e2b - e2a;
+      idx1 = lane < ne1 ? __ldg(a.nbr + lo1 + lane) : 0;
+    }
+    item2 = item1 + nwarps;
+    if (item2 < total) {
+      int rp2, c02;
+      row_of(item2, rp2, c02);
+      e2a = rp2 > 0 ? __ldg(a.row_ends + rp2 - 1) : 0;
+      e2b = __ldg(a.row_ends + rp2);
+    }
   }
+  cp_async_wait<0>();
 }
 
 template <int CB, int FR, bool TR>
@@ -351,7 +424,7 @@ static int launch_agg_cfg(const TcAggArgs& a, int64_t n_g, cudaStream_t st) {
   const size_t smem = AGG_WARPS * AggSmem<CB, FR>::WARP_BYTES;
   const int ncb = (a.c + CB - 1) / CB;
   const int64_t warps = a.n_rows * ncb;
-  if (warps >= (int64_t)1 << 30 || n_g * a.f_g * a.c >= (int64_t)1 << 31) {
+  if (warps >= (int64_t)1 << 30 || n_g * a.f_g * a.cs >= (int64_t)1 << 31 || (a.cs & 7) || a.cs < a.c) {
     set_error("launch_agg_tc: problem too large for 32-bit row offsets");
     return SE3_EINVAL;
   }
@@ -391,16 +464,17 @@ static int launch_agg_tc(const TcAggArgs& a, int f_row, int64_t n_g, cudaStream_
 struct TcEdgeArgs {
   const int* row_ends;
   const int* col_src;
-  const float* rec_out;  // [n_out * FR, 12]
+  const float* rec_out;  // [n_out * f_out, 12]
   const float* rec_in;   // [n_in * f_in, 12]
   int f_in;
-  const float* x;
+  const __nv_bfloat16* x;  // [n_in * f_in, cs] bf16 rows
   int c;
+  int cs;
   const float* w9;
   const float* bias;
   float norm;
   int act;
-  const __nv_bfloat16* dT;  // [n_out*FR, c, 32]
+  const __nv_bfloat16* dT;  // [n_out*f_out, c, 32]
   int64_t n_out;
   float* partials;          // [n_ctas, 16, 32]
 };
@@ -411,34 +485,38 @@ struct EdgeSmem {
   static constexpr int TS = 32 + 8;   // dTs row (bf16): [c][k]
   static constexpr int GB = 16 + 8;   // Gb row (bf16): [n][16]
   static constexpr int X_BYTES = 32 * XS * 2;
+  static constexpr int RG_BYTES = 32 * 48;
   static constexpr int T_BYTES = CB * TS * 2;
   static constexpr int G_BYTES = 32 * GSTR * 4;
   static constexpr int GB_BYTES = 32 * GB * 2;
-  static constexpr int R_BYTES = 64;
-  static constexpr int WARP_BYTES = X_BYTES + T_BYTES + G_BYTES + GB_BYTES + R_BYTES;
+  static constexpr int RS_BYTES = 64;
+  static constexpr int OFF_RG = 2 * X_BYTES;
+  static constexpr int OFF_T = OFF_RG + 2 * RG_BYTES;
+  static constexpr int OFF_G = OFF_T + 2 * T_BYTES;
+  static constexpr int OFF_GB = OFF_G + G_BYTES;
+  static constexpr int OFF_RS = OFF_GB + GB_BYTES;
+  static constexpr int WARP_BYTES = OFF_RS + 2 * RS_BYTES;
 };
 
 #ifndef SE3_EDGE_MIN_BLOCKS
-#define SE3_EDGE_MIN_BLOCKS 4
+#define SE3_EDGE_MIN_BLOCKS 3
 #endif
 
 // One warp per (output point, output frame) item, strided over a persistent grid; per-CTA partial sums.
+// Same cp.async software pipeline as k_agg_tc; a chunk here is (32 neighbours, one channel block) and its
+// in-flight set also holds the [CB x 32] tile of dT.
 template <int CB, int ACT>
 __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_EDGE_MIN_BLOCKS) k_edge_tc(const TcEdgeArgs a, const int f_out) {
   using SM = EdgeSmem<CB>;
   constexpr int XS = SM::XS, TS = SM::TS, GB = SM::GB;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   unsigned char* wbase = smem_raw + wib * SM::WARP_BYTES;
-  __nv_bfloat16* Xs = reinterpret_cast<__nv_bfloat16*>(wbase);
-  __nv_bfloat16* dTs = reinterpret_cast<__nv_bfloat16*>(wbase + SM::X_BYTES);
-  float* Gs = reinterpret_cast<float*>(wbase + SM::X_BYTES + SM::T_BYTES);                                   // [32][GSTR]
-  __nv_bfloat16* Gb = reinterpret_cast<__nv_bfloat16*>(wbase + SM::X_BYTES + SM::T_BYTES + SM::G_BYTES);     // [32][GB]
-  float* Rs = reinterpret_cast<float*>(wbase + SM::X_BYTES + SM::T_BYTES + SM::G_BYTES + SM::GB_BYTES);       // [12]
+  const uint32_t wbase_s = smem_u32(wbase);
+  float* Gs = reinterpret_cast<float*>(wbase + SM::OFF_G);                    // [32][GSTR]
+  __nv_bfloat16* Gb = reinterpret_cast<__nv_bfloat16*>(wbase + SM::OFF_GB);   // [32][GB]
   const int g = lane >> 2, t = lane & 3;
   const int mid = lane >> 3, mr = lane & 7;
-  uint32_t aw[2][2][4];
-  load_w9_frags(a.w9, a.bias, g, t, aw);
   float accA[2][2][4];  // [k m-tile][d n-tile]
 #pragma unroll
   for (int m = 0; m < 2; ++m)
@@ -446,125 +524,177 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_EDGE_MIN_BLOCKS) k_edge_tc
     for (int dd = 0; dd < 2; ++dd)
 #pragma unroll
       for (int i = 0; i < 4; ++i) accA[m][dd][i] = 0.0f;
-  const int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
   const int ncb = (a.c + CB - 1) / CB;
   const int total = (int)a.n_out * f_out;
-  for (int item = gw; item < total; item += nwarps) {
-    const int rp = item / f_out;
-    const int lo = rp > 0 ? __ldg(a.row_ends + rp - 1) : 0;
-    const int hi = __ldg(a.row_ends + rp);
-    const int n_total = (hi - lo) * a.f_in;
-    __syncwarp();
-    if (lane < 3) reinterpret_cast<float4*>(Rs)[lane] = __ldg(reinterpret_cast<const float4*>(a.rec_out) + (int64_t)item * 3 + lane);
-    __syncwarp();
-    const float prx = Rs[0], pry = Rs[1], prz = Rs[2];
-    float Frow[9];
-    load_row_frame(Rs, 0, Frow);
-    const __nv_bfloat16* dTrow = a.dT + (int64_t)item * (int64_t)a.c * 32;
-    for (int base = 0; base < n_total; base += 32) {
-      const int n = base + lane;
-      const bool valid = n < n_total;
-      int e, fg;
-      split_nf(valid ? n : 0, a.f_in, e, fg);
-      const int gidx = __ldg(a.col_src + lo + e) * a.f_in + fg;
-      const int fidx = valid ? gidx : -1;
-      const int n_here = min(32, n_total - base);
-      const int nq = (n_here + 7) >> 3;  // valid 8-neighbour groups (warp-uniform)
-      {
-        float dx, dy, dz, Fq[9], gg[9];
-        gather_neighbour<false>(a.rec_in, gidx, prx, pry, prz, a.norm, dx, dy, dz, Fq);
-        geometry9<false>(Frow, Fq, dx, dy, dz, gg);
-        if (!valid) {
+  int item0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (item0 < total) {
+    uint32_t aw[2][2][4];
+    load_w9_frags(a.w9, a.bias, g, t, aw);
+    auto issue = [&](int item, int lo, int nt, int idx, int j, int buf, int rb, bool with_row) {
+      const int jb = j / ncb, cb = j - jb * ncb;
+      const int gidx = chunk_gidx(a.col_src, lo, nt, idx, a.f_in, jb * 32, lane);
+      gather_chunk_async<CB>(a.rec_in, a.x, a.cs, cb * CB, gidx, lane, wbase_s + SM::OFF_RG + buf * SM::RG_BYTES,
+                             wbase_s + buf * SM::X_BYTES);
+      // [CB x 32] tile of dT of this (item, channel block): CB rows of 64 B = 4 x 16 B
+      const __nv_bfloat16* dTrow = a.dT + (int64_t)item * (int64_t)a.c * 32 + (int64_t)cb * CB * 32;
 #pragma unroll
-          for (int i = 0; i < 9; ++i) gg[i] = 0.0f;
-        }
-        store_geometry_row(Gs + lane * GSTR, gg, 1.0f);
-        uint4 p0, p1;
-        p0.x = pack_bf16(gg[0], gg[1]); p0.y = pack_bf16(gg[2], gg[3]);
-        p0.z = pack_bf16(gg[4], gg[5]); p0.w = pack_bf16(gg[6], gg[7]);
-        p1.x = pack_bf16(gg[8], valid ? 1.0f : 0.0f);  // column 9 = 1 -> bias gradient
-        p1.y = 0u; p1.z = 0u; p1.w = 0u;
-        uint4* gb = reinterpret_cast<uint4*>(Gb + lane * GB);
-        gb[0] = p0;
-        gb[1] = p1;
+      for (int i0 = 0; i0 < CB * 4; i0 += 32) {
+        const int i = i0 + lane;
+        const int c = i >> 2, part = i & 3;
+        const bool ok = cb * CB + c < a.c;
+        cp_async16_ca(wbase_s + SM::OFF_T + buf * SM::T_BYTES + (c * TS + part * 8) * 2, dTrow + (ok ? c * 32 + part * 8 : 0), ok);
       }
-      // dH^T[k, n] = sum_c dT[c, k] x[n, c], accumulated over channel blocks
+      if (with_row && lane < 3)
+        cp_async16_ca(wbase_s + SM::OFF_RS + rb * SM::RS_BYTES + lane * 16,
+                      reinterpret_cast<const float4*>(a.rec_out) + (int64_t)item * 3 + lane, true);
+    };
+    auto chunks_of = [&](int ne) { return max(1, (ne * a.f_in + 31) >> 5) * ncb; };
+
+    int rp0 = item0 / f_out;
+    int lo0 = rp0 > 0 ? __ldg(a.row_ends + rp0 - 1) : 0;
+    int ne0 = __ldg(a.row_ends + rp0) - lo0;
+    int idx0 = lane < ne0 ? __ldg(a.col_src + lo0 + lane) : 0;
+    int item1 = item0 + nwarps, lo1 = 0, ne1 = 0, idx1 = 0;
+    if (item1 < total) {
+      const int rp1 = item1 / f_out;
+      lo1 = rp1 > 0 ? __ldg(a.row_ends + rp1 - 1) : 0;
+      ne1 = __ldg(a.row_ends + rp1) - lo1;
+      idx1 = lane < ne1 ? __ldg(a.col_src + lo1 + lane) : 0;
+    }
+    int item2 = item1 + nwarps, e2a = 0, e2b = 0;
+    if (item2 < total) {
+      const int rp2 = item2 / f_out;
+      e2a = rp2 > 0 ? __ldg(a.row_ends + rp2 - 1) : 0;
+      e2b = __ldg(a.row_ends + rp2);
+    }
+    int buf = 0, rb = 0;
+    issue(item0, lo0, ne0 * a.f_in, idx0, 0, 0, 0, true);
+    cp_async_commit();
+
+    for (;;) {
+      const int nt0 = ne0 * a.f_in;
+      const int nch = chunks_of(ne0);
       float dH[2][4][4];
-#pragma unroll
-      for (int m = 0; m < 2; ++m)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) dH[m][j][i] = 0.0f;
-      for (int cb = 0; cb < ncb; ++cb) {
-        const int c0 = cb * CB;
-        __syncwarp();
-        stage_features<CB>(a.x, a.c, c0, fidx, lane, Xs);
-        // dT rows of this channel block: CB rows of 32 bf16 (64 B) = 4 x 16 B each
-        if (ncb > 1 || base == 0) {
-#pragma unroll
-          for (int i0 = 0; i0 < CB * 4; i0 += 32) {
-            const int i = i0 + lane;
-            const int c = i >> 2, part = i & 3;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (c0 + c < a.c) v = __ldg(reinterpret_cast<const uint4*>(dTrow + (c0 + c) * 32) + part);
-            *reinterpret_cast<uint4*>(dTs + c * TS + part * 8) = v;
-          }
+      int nq = 0;
+      for (int j = 0; j < nch; ++j) {
+        if (j + 1 < nch) {
+          issue(item0, lo0, nt0, idx0, j + 1, buf ^ 1, rb, false);
+        } else if (item1 < total) {
+          issue(item1, lo1, ne1 * a.f_in, idx1, 0, buf ^ 1, rb ^ 1, true);
         }
+        cp_async_commit();
+        cp_async_wait<1>();
         __syncwarp();
+        const int jb = j / ncb, cb = j - jb * ncb;
+        if (cb == 0) {
+          const int base = jb * 32;
+          const bool valid = base + lane < nt0;
+          nq = (min(32, nt0 - base) + 7) >> 3;  // valid 8-neighbour groups (warp-uniform)
+          const float* Rs = reinterpret_cast<const float*>(wbase + SM::OFF_RS + rb * SM::RS_BYTES);
+          const float* rg = reinterpret_cast<const float*>(wbase + SM::OFF_RG + buf * SM::RG_BYTES) + lane * 12;
+          float dx, dy, dz, Fq[9], Frow[9], gg[9];
+          unpack_neighbour<false>(rg, Rs[0], Rs[1], Rs[2], a.norm, dx, dy, dz, Fq);
+          load_row_frame(Rs, 0, Frow);
+          geometry9<false>(Frow, Fq, dx, dy, dz, gg);
+          if (!valid) {
 #pragma unroll
-        for (int ks = 0; ks < CB / 16; ++ks) {
-          // A = dT^T: [m = k][kk = c] from dTs[c][k] (.trans); B = x^T: [kk = c][nn = n] from Xs[n][c]
-          uint32_t af[2][4];
+            for (int i = 0; i < 9; ++i) gg[i] = 0.0f;
+          }
+          store_geometry_row(Gs + lane * GSTR, gg, 1.0f);
+          uint4 p0, p1;
+          p0.x = pack_bf16(gg[0], gg[1]); p0.y = pack_bf16(gg[2], gg[3]);
+          p0.z = pack_bf16(gg[4], gg[5]); p0.w = pack_bf16(gg[6], gg[7]);
+          p1.x = pack_bf16(gg[8], valid ? 1.0f : 0.0f);  // column 9 = 1 -> bias gradient
+          p1.y = 0u; p1.z = 0u; p1.w = 0u;
+          uint4* gb = reinterpret_cast<uint4*>(Gb + lane * GB);
+          gb[0] = p0;
+          gb[1] = p1;
 #pragma unroll
           for (int m = 0; m < 2; ++m)
-            ldmatrix_x4_trans(af[m][0], af[m][1], af[m][2], af[m][3],
-                              smem_u32(dTs + (ks * 16 + (mid >> 1) * 8 + mr) * TS + m * 16 + (mid & 1) * 8));
 #pragma unroll
-          for (int jp = 0; jp < 2; ++jp) {
-            if (jp * 2 >= nq) break;
-            uint32_t b[4];  // n-tiles 2jp (b0,b1) and 2jp+1 (b0,b1)
-            ldmatrix_x4(b[0], b[1], b[2], b[3], smem_u32(Xs + (jp * 16 + (mid >> 1) * 8 + mr) * XS + ks * 16 + (mid & 1) * 8));
+            for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
-              mma_bf16(dH[m][2 * jp], af[m], b[0], b[1]);
-              mma_bf16(dH[m][2 * jp + 1], af[m], b[2], b[3]);
+              for (int i = 0; i < 4; ++i) dH[m][jj][i] = 0.0f;
+          __syncwarp();
+        }
+        // dH^T[k, n] += sum_c dT[c, k] x[n, c] over this channel block
+        {
+          const __nv_bfloat16* Xs = reinterpret_cast<const __nv_bfloat16*>(wbase + buf * SM::X_BYTES);
+          const __nv_bfloat16* dTs = reinterpret_cast<const __nv_bfloat16*>(wbase + SM::OFF_T + buf * SM::T_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < CB / 16; ++ks) {
+            // A = dT^T: [m = k][kk = c] from dTs[c][k] (.trans); B = x^T: [kk = c][nn = n] from Xs[n][c]
+            uint32_t af[2][4];
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+              ldmatrix_x4_trans(af[m][0], af[m][1], af[m][2], af[m][3],
+                                smem_u32(dTs + (ks * 16 + (mid >> 1) * 8 + mr) * TS + m * 16 + (mid & 1) * 8));
+#pragma unroll
+            for (int jp = 0; jp < 2; ++jp) {
+              if (jp * 2 >= nq) break;
+              uint32_t b[4];  // n-tiles 2jp (b0,b1) and 2jp+1 (b0,b1)
+              ldmatrix_x4(b[0], b[1], b[2], b[3], smem_u32(Xs + (jp * 16 + (mid >> 1) * 8 + mr) * XS + ks * 16 + (mid & 1) * 8));
+#pragma unroll
+              for (int m = 0; m < 2; ++m) {
+                mma_bf16(dH[m][2 * jp], af[m], b[0], b[1]);
+                mma_bf16(dH[m][2 * jp + 1], af[m], b[2], b[3]);
+              }
             }
           }
         }
-      }
-      // dpre = dH * act'(pre): pre^T tiles from the tensor cores (tf32) land in the same accumulator
-      // layout as dH: k in {g, g+8} + 16 m, n = 8 j + 2 t + {0,1}
+        if (cb == ncb - 1) {
+          // dpre = dH * act'(pre): pre^T tiles from the tensor cores (tf32) land in the same accumulator
+          // layout as dH: k in {g, g+8} + 16 m, n = 8 j + 2 t + {0,1}
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (j >= nq) break;
-        float d[2][4];
-        basis_pre(aw, Gs + (8 * j + g) * GSTR, t, d);
+          for (int jj = 0; jj < 4; ++jj) {
+            if (jj >= nq) break;
+            float d[2][4];
+            basis_pre(aw, Gs + (8 * jj + g) * GSTR, t, d);
 #pragma unroll
-        for (int m = 0; m < 2; ++m)
+            for (int m = 0; m < 2; ++m)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) dH[m][j][i] *= act_grad_rt<ACT>(d[m][i], a.act);
-      }
-      // accA[k, d] += dpre[k, n] G[n, d]: dpre (C layout) -> A fragments, G from Gb[n][16] (.trans)
+              for (int i = 0; i < 4; ++i) dH[m][jj][i] *= act_grad_rt<ACT>(d[m][i], a.act);
+          }
+          // accA[k, d] += dpre[k, n] G[n, d]: dpre (C layout) -> A fragments, G from Gb[n][16] (.trans)
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        if (ks * 2 >= nq) break;
-        uint32_t gb[4];
-        ldmatrix_x4_trans(gb[0], gb[1], gb[2], gb[3], smem_u32(Gb + (ks * 16 + (mid & 1) * 8 + mr) * GB + (mid >> 1) * 8));
+          for (int ks = 0; ks < 2; ++ks) {
+            if (ks * 2 >= nq) break;
+            uint32_t gb[4];
+            ldmatrix_x4_trans(gb[0], gb[1], gb[2], gb[3], smem_u32(Gb + (ks * 16 + (mid & 1) * 8 + mr) * GB + (mid >> 1) * 8));
 #pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          uint32_t afr[4];
-          afr[0] = pack_bf16(dH[m][2 * ks][0], dH[m][2 * ks][1]);
-          afr[1] = pack_bf16(dH[m][2 * ks][2], dH[m][2 * ks][3]);
-          afr[2] = pack_bf16(dH[m][2 * ks + 1][0], dH[m][2 * ks + 1][1]);
-          afr[3] = pack_bf16(dH[m][2 * ks + 1][2], dH[m][2 * ks + 1][3]);
-          mma_bf16(accA[m][0], afr, gb[0], gb[1]);
-          mma_bf16(accA[m][1], afr, gb[2], gb[3]);
+            for (int m = 0; m < 2; ++m) {
+              uint32_t afr[4];
+              afr[0] = pack_bf16(dH[m][2 * ks][0], dH[m][2 * ks][1]);
+              afr[1] = pack_bf16(dH[m][2 * ks][2], dH[m][2 * ks][3]);
+              afr[2] = pack_bf16(dH[m][2 * ks + 1][0], dH[m][2 * ks + 1][1]);
+              afr[3] = pack_bf16(dH[m][2 * ks + 1][2], dH[m][2 * ks + 1][3]);
+              mma_bf16(accA[m][0], afr, gb[0], gb[1]);
+              mma_bf16(accA[m][1], afr, gb[2], gb[3]);
+            }
+          }
         }
+        __syncwarp();
+        buf ^= 1;
       }
-      __syncwarp();
+      // ---- rotate the row pipeline
+      if (item1 >= total) break;
+      item0 = item1; lo0 = lo1; ne0 = ne1; idx0 = idx1;
+      rb ^= 1;
+      item1 = item2;
+      if (item1 < total) {
+        lo1 = e2a;
+        ne1 = e2b - e2a;
+        idx1 = lane < ne1 ? __ldg(a.col_src + lo1 + lane) : 0;
+      }
+      item2 = item1 + nwarps;
+      if (item2 < total) {
+        const int rp2 = item2 / f_out;
+        e2a = rp2 > 0 ? __ldg(a.row_ends + rp2 - 1) : 0;
+        e2b = __ldg(a.row_ends + rp2);
+      }
     }
+    cp_async_wait<0>();
   }
   // per-CTA partial [d (16)][k (32)]: warps -> shared memory (the staging area is free now), summed in
   // warp order (deterministic)
@@ -646,7 +776,7 @@ static int launch_edge_tc(const TcEdgeArgs& a, int f_out, int64_t n_in, int n_wa
     set_error("launch_edge_tc: unsupported frame count");
     return SE3_EINVAL;
   }
-  if (n_in * a.f_in * a.c >= (int64_t)1 << 31 || a.n_out * f_out * (int64_t)a.c * 32 >= (int64_t)1 << 40) {
+  if (n_in * a.f_in * a.cs >= (int64_t)1 << 31 || a.n_out * f_out >= (int64_t)1 << 30 || (a.cs & 7) || a.cs < a.c) {
     set_error("launch_edge_tc: problem too large for 32-bit row offsets");
     return SE3_EINVAL;
   }
@@ -851,6 +981,15 @@ __global__ void k_f32_to_bf16(const float* __restrict__ in, int64_t n, __nv_bflo
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16(in[i]);
 }
+// out[r][0..cs) = bf16(in[r][0..c)), zero padded: the gathered feature rows of the tensor-core kernels
+__global__ void k_rows_to_bf16(const float* __restrict__ in, int64_t rows, int c, int cs, __nv_bfloat16* __restrict__ out) {
+  const int64_t total = rows * cs;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cs;
+    const int ch = (int)(i - r * cs);
+    out[i] = __float2bfloat16(ch < c ? in[r * c + ch] : 0.0f);
+  }
+}
 // wp[c][o][k] = w[c][k][o]  (bf16)
 __global__ void k_permute_w_bf16(const float* __restrict__ w, int c_in, int k, int c_out, __nv_bfloat16* __restrict__ wp) {
   const int64_t total = (int64_t)c_in * k * c_out;
@@ -899,8 +1038,11 @@ static int check_tc(const se3_conv_desc* d) {
   return SE3_OK;
 }
 
+static inline int pad8(int c) { return (c + 7) & ~7; }
+
 size_t conv_tc_saved_bytes(const se3_conv_desc* d) {
-  return align_up((size_t)d->n_out * d->f_out * d->c_in * d->k * 2) + 256;  // T in bf16
+  return align_up((size_t)d->n_out * d->f_out * d->c_in * d->k * 2) +        // T in bf16
+         align_up((size_t)d->n_in * d->f_in * pad8(d->c_in) * 2) + 256;       // x in bf16 (gather rows)
 }
 size_t conv_tc_fwd_workspace_bytes(const se3_conv_desc* d) {
   return align_up((size_t)d->c_in * d->k * d->c_out * 2) + 256;  // W in bf16
@@ -926,12 +1068,19 @@ int conv_tc_fwd(const se3_conv_desc* d, const float* x, float* y, void* saved, v
   __nv_bfloat16* Wb = ar.take<__nv_bfloat16>(ck * d->c_out);
   if (!ar.ok()) { set_error("conv_tc_fwd: workspace too small"); return SE3_EWORKSPACE; }
   __nv_bfloat16* T = reinterpret_cast<__nv_bfloat16*>(saved);
+  const int cs = pad8(d->c_in);
+  const int64_t Nf = d->n_in * d->f_in;
+  __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(saved) + align_up((size_t)R * ck * 2));
   k_transpose_w_bf16<<<blocks_for(ck * d->c_out), 256, 0, st>>>(d->conv_weights, ck, d->c_out, Wb);
   SE3_LAUNCH_CHECK();
+  if (Nf > 0) {
+    k_rows_to_bf16<<<blocks_for(Nf * cs), 256, 0, st>>>(x, Nf, d->c_in, cs, xb);
+    SE3_LAUNCH_CHECK();
+  }
   TcAggArgs a;
   a.row_ends = d->row_ends; a.nbr = d->col_src;
   a.rec_row = d->rec_out; a.rec_g = d->rec_in; a.f_g = d->f_in;
-  a.feat = x; a.c = d->c_in; a.w9 = d->proj_axes; a.bias = d->proj_biases; a.norm = d->norm_neigh_dist;
+  a.feat = xb; a.c = d->c_in; a.cs = cs; a.w9 = d->proj_axes; a.bias = d->proj_biases; a.norm = d->norm_neigh_dist;
   a.act = d->act; a.out = T; a.n_rows = d->n_out;
   if (int rc = launch_agg_tc<false>(a, d->f_out, d->n_in, st)) return rc;
   // y[r,o] = s * sum_(c,k) T[r,(c,k)] Wt[o,(c,k)]   (tcgen05 / TMEM)
@@ -957,6 +1106,8 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
   float* eg = ar.take<float>((size_t)n_warps * 512);
   if (!ar.ok()) { set_error("conv_tc_bwd: workspace too small"); return SE3_EWORKSPACE; }
   const __nv_bfloat16* T = reinterpret_cast<const __nv_bfloat16*>(saved);
+  const __nv_bfloat16* xb =
+      reinterpret_cast<const __nv_bfloat16*>(reinterpret_cast<const char*>(saved) + align_up((size_t)R * ck * 2));
   k_f32_to_bf16<<<blocks_for(R * d->c_out), 256, 0, st>>>(dy, R * d->c_out, dyb);
   SE3_LAUNCH_CHECK();
   if (dW) {
@@ -973,7 +1124,7 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
     TcEdgeArgs g;
     g.row_ends = d->row_ends; g.col_src = d->col_src;
     g.rec_out = d->rec_out; g.rec_in = d->rec_in; g.f_in = d->f_in;
-    g.x = x; g.c = d->c_in; g.w9 = d->proj_axes; g.bias = d->proj_biases; g.norm = d->norm_neigh_dist;
+    g.x = xb; g.c = d->c_in; g.cs = pad8(d->c_in); g.w9 = d->proj_axes; g.bias = d->proj_biases; g.norm = d->norm_neigh_dist;
     g.act = d->act; g.dT = dTb; g.n_out = d->n_out; g.partials = eg;
     if (int rc = launch_edge_tc(g, d->f_out, d->n_in, n_warps, dA, dB, st)) return rc;
   }
@@ -981,7 +1132,7 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
     TcAggArgs a;
     a.row_ends = d->t_row_ends; a.nbr = d->t_dst;
     a.rec_row = d->rec_in; a.rec_g = d->rec_out; a.f_g = d->f_out;
-    a.feat = dy; a.c = d->c_out; a.w9 = d->proj_axes; a.bias = d->proj_biases; a.norm = d->norm_neigh_dist;
+    a.feat = dyb; a.c = d->c_out; a.cs = d->c_out; a.w9 = d->proj_axes; a.bias = d->proj_biases; a.norm = d->norm_neigh_dist;
     a.act = d->act; a.out = U; a.n_rows = d->n_in;
     if (int rc = launch_agg_tc<true>(a, d->f_in, d->n_out, st)) return rc;
     k_permute_w_bf16<<<blocks_for(ck * d->c_out), 256, 0, st>>>(d->conv_weights, d->c_in, d->k, d->c_out, Wpb);
