@@ -152,9 +152,12 @@ constexpr int GSTR = 20;      // floats between geometry rows in shared memory (
 // needs the four CONSECUTIVE components 4t..4t+3 of a geometry row (one 128-bit shared load):
 //   k-step s in {0,1}: slot t <-> component 4t + 2s, slot t+4 <-> component 4t + 2s + 1.
 // Components 12..15 are zero, so lanes t = 3 carry zero fragments and never touch shared memory.
+// `scale` (act_pre_scale) is folded into the fragments, so the tiles hold z = scale * pre.
 __device__ __forceinline__ void load_w9_frags(const float* __restrict__ w9, const float* __restrict__ bias, int g, int t,
-                                              uint32_t (&aw)[2][2][4]) {
-  auto wext = [&](int d, int k) -> float { return d < 9 ? __ldg(w9 + d * 32 + k) : (d == 9 ? __ldg(bias + k) : 0.0f); };
+                                              float scale, uint32_t (&aw)[2][2][4]) {
+  auto wext = [&](int d, int k) -> float {
+    return scale * (d < 9 ? __ldg(w9 + d * 32 + k) : (d == 9 ? __ldg(bias + k) : 0.0f));
+  };
 #pragma unroll
   for (int m = 0; m < 2; ++m)
 #pragma unroll
@@ -207,6 +210,45 @@ __device__ __forceinline__ void load_row_frame(const float* Rs, int f, float (&F
   Frow[5] = r2.x; Frow[6] = r2.y; Frow[7] = r2.z; Frow[8] = r2.w;
 }
 
+// One aggregation k-step (16 neighbours, NG = 1 or 2 groups of 8) for all FR row frames, straight-line code:
+// basis h = act(pre) is produced directly as the B fragments of the aggregation mma -- n-tile j (k = 8j + g),
+// b0 = neighbours 2t,2t+1, b1 = neighbours 2t+8,2t+9 -- and T[c,k] += x[n,c] h[n,k].
+template <int CB, int FR, int NG, int ACT>
+__device__ __forceinline__ void agg_kstep(float (&acc)[FR][CB / 16][4][4], const uint32_t (&aw)[2][2][4], const float* Gs,
+                                          const __nv_bfloat16* Xs, int ks, int lane, int act) {
+  constexpr int XS = CB + 8, MT = CB / 16;
+  const int g = lane >> 2, t = lane & 3, mid = lane >> 3, mr = lane & 7;
+  // A fragments (x^T): [m = channel][k = neighbour], from Xs[n][c] through ldmatrix.trans
+  uint32_t af[MT][4];
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+    ldmatrix_x4_trans(af[m][0], af[m][1], af[m][2], af[m][3],
+                      smem_u32(Xs + (ks * 16 + (mid >> 1) * 8 + mr) * XS + m * 16 + (mid & 1) * 8));
+#pragma unroll
+  for (int f = 0; f < FR; ++f) {
+    uint32_t hb[4][2];
+#pragma unroll
+    for (int hq = 0; hq < 2; ++hq) {
+      if (hq < NG) {
+        float d[2][4];
+        basis_pre(aw, Gs + (f * 32 + ks * 16 + hq * 8 + g) * GSTR, t, d);
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          hb[2 * m][hq] = pack_bf16(act_rt<ACT>(d[m][0], act), act_rt<ACT>(d[m][1], act));
+          hb[2 * m + 1][hq] = pack_bf16(act_rt<ACT>(d[m][2], act), act_rt<ACT>(d[m][3], act));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hb[j][hq] = 0u;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int m = 0; m < MT; ++m) mma_bf16(acc[f][m][j], af[m], hb[j][0], hb[j][1]);
+  }
+}
+
 template <int CB, int FR>
 struct AggSmem {
   static constexpr int XS = CB + 8;
@@ -222,6 +264,9 @@ struct AggSmem {
 
 #ifndef SE3_AGG_MIN_BLOCKS
 #define SE3_AGG_MIN_BLOCKS 3
+#endif
+#ifndef SE3_AGG_WAVES
+#define SE3_AGG_WAVES 1
 #endif
 
 // One warp per (row point, channel block): the FR row frames share the gathered records and the staged
@@ -249,7 +294,7 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_AGG_MIN_BLOCKS) k_agg_tc(c
   int item0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (item0 >= total) return;
   uint32_t aw[2][2][4];
-  load_w9_frags(a.w9, a.bias, g, t, aw);
+  load_w9_frags(a.w9, a.bias, g, t, act_pre_scale(a.act), aw);
 
   auto row_of = [&](int item, int& rp, int& c0) {
     rp = item;
@@ -334,38 +379,10 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_AGG_MIN_BLOCKS) k_agg_tc(c
 #pragma unroll 1
       for (int ks = 0; ks < 2; ++ks) {
         if (ks * 16 >= n_here) break;
-        // A fragments (x^T): [m = channel][k = neighbour], from Xs[n][c] through ldmatrix.trans
-        uint32_t af[MT][4];
-#pragma unroll
-        for (int m = 0; m < MT; ++m)
-          ldmatrix_x4_trans(af[m][0], af[m][1], af[m][2], af[m][3],
-                            smem_u32(Xs + (ks * 16 + (mid >> 1) * 8 + mr) * XS + m * 16 + (mid & 1) * 8));
-        const bool second = ks * 16 + 8 < n_here;
-#pragma unroll
-        for (int f = 0; f < FR; ++f) {
-          // basis h = act(pre) of the 16 neighbours of this k-step, produced directly as the B fragments
-          // of the aggregation mma: n-tile j (k = 8j + g), b0 = neighbours 2t,2t+1, b1 = neighbours 2t+8,2t+9
-          uint32_t hb[4][2];
-#pragma unroll
-          for (int hq = 0; hq < 2; ++hq) {
-            if (hq == 1 && !second) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) hb[j][1] = 0u;
-              break;
-            }
-            float d[2][4];
-            basis_pre(aw, Gs + (f * 32 + ks * 16 + hq * 8 + g) * GSTR, t, d);
-#pragma unroll
-            for (int m = 0; m < 2; ++m) {
-              hb[2 * m][hq] = pack_bf16(act_rt<ACT>(d[m][0], a.act), act_rt<ACT>(d[m][1], a.act));
-              hb[2 * m + 1][hq] = pack_bf16(act_rt<ACT>(d[m][2], a.act), act_rt<ACT>(d[m][3], a.act));
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int m = 0; m < MT; ++m) mma_bf16(acc[f][m][j], af[m], hb[j][0], hb[j][1]);
-        }
+        if (ks * 16 + 8 < n_here)
+          agg_kstep<CB, FR, 2, ACT>(acc, aw, Gs, Xs, ks, lane, a.act);
+        else
+          agg_kstep<CB, FR, 1, ACT>(acc, aw, Gs, Xs, ks, lane, a.act);
       }
       __syncwarp();
       buf ^= 1;
@@ -429,8 +446,8 @@ static int launch_agg_cfg(const TcAggArgs& a, int64_t n_g, cudaStream_t st) {
     return SE3_EINVAL;
   }
   int64_t blocks = (warps + AGG_WARPS - 1) / AGG_WARPS;
-  const int64_t cap = (int64_t)num_sms() * SE3_AGG_MIN_BLOCKS * 8;
-  if (blocks > cap) blocks = cap;
+  const int64_t cap = (int64_t)num_sms() * SE3_AGG_MIN_BLOCKS * SE3_AGG_WAVES;  // persistent: the row pipeline
+  if (blocks > cap) blocks = cap;                                               // needs many rows per warp
   if (blocks < 1) blocks = 1;
   if (a.act == 2) {
     auto kern = k_agg_tc<CB, FR, TR, 2>;
@@ -478,6 +495,66 @@ struct TcEdgeArgs {
   int64_t n_out;
   float* partials;          // [n_ctas, 16, 32]
 };
+
+// dH^T[k, n] += sum_c dT[c, k] x[n, c] for the first NP pairs of 8-neighbour groups (straight-line code).
+//   A = dT^T: [m = k][kk = c] from dTs[c][k] (.trans); B = x^T: [kk = c][nn = n] from Xs[n][c]
+template <int CB, int NP>
+__device__ __forceinline__ void edge_dh(float (&dH)[2][4][4], const __nv_bfloat16* dTs, const __nv_bfloat16* Xs, int lane) {
+  constexpr int XS = CB + 8, TS = 32 + 8;
+  const int mid = lane >> 3, mr = lane & 7;
+#pragma unroll
+  for (int ks = 0; ks < CB / 16; ++ks) {
+    uint32_t af[2][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+      ldmatrix_x4_trans(af[m][0], af[m][1], af[m][2], af[m][3],
+                        smem_u32(dTs + (ks * 16 + (mid >> 1) * 8 + mr) * TS + m * 16 + (mid & 1) * 8));
+#pragma unroll
+    for (int jp = 0; jp < NP; ++jp) {
+      uint32_t b[4];  // n-tiles 2jp (b0,b1) and 2jp+1 (b0,b1)
+      ldmatrix_x4(b[0], b[1], b[2], b[3], smem_u32(Xs + (jp * 16 + (mid >> 1) * 8 + mr) * XS + ks * 16 + (mid & 1) * 8));
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        mma_bf16(dH[m][2 * jp], af[m], b[0], b[1]);
+        mma_bf16(dH[m][2 * jp + 1], af[m], b[2], b[3]);
+      }
+    }
+  }
+}
+
+// dpre = dH * act'(pre) for 2 NP groups -- the pre^T tiles from the tensor cores (tf32) land in the accumulator
+// layout of dH: k in {g, g+8} + 16 m, n = 8 j + 2 t + {0,1} -- then accA[k, d] += dpre[k, n] G[n, d] with dpre
+// repacked as A fragments and G from Gb[n][16] (.trans).  Groups beyond the valid ones carry dH = 0.
+template <int NP, int ACT>
+__device__ __forceinline__ void edge_finish(float (&dH)[2][4][4], float (&accA)[2][2][4], const uint32_t (&aw)[2][2][4],
+                                            const float* Gs, const __nv_bfloat16* Gb, int lane, int act) {
+  constexpr int GB = 16 + 8;
+  const int g = lane >> 2, t = lane & 3, mid = lane >> 3, mr = lane & 7;
+#pragma unroll
+  for (int jj = 0; jj < 2 * NP; ++jj) {
+    float d[2][4];
+    basis_pre(aw, Gs + (8 * jj + g) * GSTR, t, d);
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dH[m][jj][i] *= act_grad_rt<ACT>(d[m][i], act);
+  }
+#pragma unroll
+  for (int ks = 0; ks < NP; ++ks) {
+    uint32_t gb[4];
+    ldmatrix_x4_trans(gb[0], gb[1], gb[2], gb[3], smem_u32(Gb + (ks * 16 + (mid & 1) * 8 + mr) * GB + (mid >> 1) * 8));
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      uint32_t afr[4];
+      afr[0] = pack_bf16(dH[m][2 * ks][0], dH[m][2 * ks][1]);
+      afr[1] = pack_bf16(dH[m][2 * ks][2], dH[m][2 * ks][3]);
+      afr[2] = pack_bf16(dH[m][2 * ks + 1][0], dH[m][2 * ks + 1][1]);
+      afr[3] = pack_bf16(dH[m][2 * ks + 1][2], dH[m][2 * ks + 1][3]);
+      mma_bf16(accA[m][0], afr, gb[0], gb[1]);
+      mma_bf16(accA[m][1], afr, gb[2], gb[3]);
+    }
+  }
+}
 
 template <int CB>
 struct EdgeSmem {
@@ -530,7 +607,7 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_EDGE_MIN_BLOCKS) k_edge_tc
   int item0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (item0 < total) {
     uint32_t aw[2][2][4];
-    load_w9_frags(a.w9, a.bias, g, t, aw);
+    load_w9_frags(a.w9, a.bias, g, t, act_pre_scale(a.act), aw);
     auto issue = [&](int item, int lo, int nt, int idx, int j, int buf, int rb, bool with_row) {
       const int jb = j / ncb, cb = j - jb * ncb;
       const int gidx = chunk_gidx(a.col_src, lo, nt, idx, a.f_in, jb * 32, lane);
@@ -622,57 +699,16 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_EDGE_MIN_BLOCKS) k_edge_tc
         {
           const __nv_bfloat16* Xs = reinterpret_cast<const __nv_bfloat16*>(wbase + buf * SM::X_BYTES);
           const __nv_bfloat16* dTs = reinterpret_cast<const __nv_bfloat16*>(wbase + SM::OFF_T + buf * SM::T_BYTES);
-#pragma unroll
-          for (int ks = 0; ks < CB / 16; ++ks) {
-            // A = dT^T: [m = k][kk = c] from dTs[c][k] (.trans); B = x^T: [kk = c][nn = n] from Xs[n][c]
-            uint32_t af[2][4];
-#pragma unroll
-            for (int m = 0; m < 2; ++m)
-              ldmatrix_x4_trans(af[m][0], af[m][1], af[m][2], af[m][3],
-                                smem_u32(dTs + (ks * 16 + (mid >> 1) * 8 + mr) * TS + m * 16 + (mid & 1) * 8));
-#pragma unroll
-            for (int jp = 0; jp < 2; ++jp) {
-              if (jp * 2 >= nq) break;
-              uint32_t b[4];  // n-tiles 2jp (b0,b1) and 2jp+1 (b0,b1)
-              ldmatrix_x4(b[0], b[1], b[2], b[3], smem_u32(Xs + (jp * 16 + (mid >> 1) * 8 + mr) * XS + ks * 16 + (mid & 1) * 8));
-#pragma unroll
-              for (int m = 0; m < 2; ++m) {
-                mma_bf16(dH[m][2 * jp], af[m], b[0], b[1]);
-                mma_bf16(dH[m][2 * jp + 1], af[m], b[2], b[3]);
-              }
-            }
-          }
+          if (nq > 2)
+            edge_dh<CB, 2>(dH, dTs, Xs, lane);
+          else if (nq > 0)
+            edge_dh<CB, 1>(dH, dTs, Xs, lane);
         }
         if (cb == ncb - 1) {
-          // dpre = dH * act'(pre): pre^T tiles from the tensor cores (tf32) land in the same accumulator
-          // layout as dH: k in {g, g+8} + 16 m, n = 8 j + 2 t + {0,1}
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            if (jj >= nq) break;
-            float d[2][4];
-            basis_pre(aw, Gs + (8 * jj + g) * GSTR, t, d);
-#pragma unroll
-            for (int m = 0; m < 2; ++m)
-#pragma unroll
-              for (int i = 0; i < 4; ++i) dH[m][jj][i] *= act_grad_rt<ACT>(d[m][i], a.act);
-          }
-          // accA[k, d] += dpre[k, n] G[n, d]: dpre (C layout) -> A fragments, G from Gb[n][16] (.trans)
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            if (ks * 2 >= nq) break;
-            uint32_t gb[4];
-            ldmatrix_x4_trans(gb[0], gb[1], gb[2], gb[3], smem_u32(Gb + (ks * 16 + (mid & 1) * 8 + mr) * GB + (mid >> 1) * 8));
-#pragma unroll
-            for (int m = 0; m < 2; ++m) {
-              uint32_t afr[4];
-              afr[0] = pack_bf16(dH[m][2 * ks][0], dH[m][2 * ks][1]);
-              afr[1] = pack_bf16(dH[m][2 * ks][2], dH[m][2 * ks][3]);
-              afr[2] = pack_bf16(dH[m][2 * ks + 1][0], dH[m][2 * ks + 1][1]);
-              afr[3] = pack_bf16(dH[m][2 * ks + 1][2], dH[m][2 * ks + 1][3]);
-              mma_bf16(accA[m][0], afr, gb[0], gb[1]);
-              mma_bf16(accA[m][1], afr, gb[2], gb[3]);
-            }
-          }
+          if (nq > 2)
+            edge_finish<2, ACT>(dH, accA, aw, Gs, Gb, lane, a.act);
+          else if (nq > 0)
+            edge_finish<1, ACT>(dH, accA, aw, Gs, Gb, lane, a.act);
         }
         __syncwarp();
         buf ^= 1;
@@ -799,7 +835,7 @@ __global__ void __launch_bounds__(256) k_gemm_bf16(int M, int N, int K, float al
   constexpr int BM = 128, BN = 64, BK = 32, ST = 3;
   constexpr int A_ROWS = A_KMAJOR ? BM : BK, A_LD = (A_KMAJOR ? BK : BM) + 8;
   constexpr int B_ROWS = B_KMAJOR ? BN : BK, B_LD = (B_KMAJOR ? BK : BN) + 8;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   __nv_bfloat16* As = reinterpret_cast<__nv_bfloat16*>(smem_raw);
   __nv_bfloat16* Bs = As + ST * A_ROWS * A_LD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
