@@ -1,4 +1,4 @@
-"""Host-side profile of one hierarchy build (cProfile) + per-stage device timings."""
+"""Host-side profile of one hierarchy build (cProfile, steady state) + wall/GPU split."""
 import cProfile
 import os
 import pstats
@@ -14,41 +14,21 @@ dev = torch.device("cuda:0")
 pts, b = wl.synthetic_bodies(32, 6890, 0)
 pts, b = pts.to(dev), b.to(dev)
 step = wl.DfaustStep(dev, precision=1)
-for _ in range(3):
+for _ in range(10):
     pcs, neighs = step.build_hierarchy(pts, b)
 torch.cuda.synchronize()
 t0 = time.perf_counter()
-for _ in range(5):
+for _ in range(10):
     pcs, neighs = step.build_hierarchy(pts, b)
+th = time.perf_counter() - t0
 torch.cuda.synchronize()
-print("hierarchy build: %.2f ms" % ((time.perf_counter() - t0) / 5 * 1e3))
+print("hierarchy build: host %.2f ms, total %.2f ms" % (th / 10 * 1e3, (time.perf_counter() - t0) / 10 * 1e3))
 pr = cProfile.Profile()
 pr.enable()
-for _ in range(5):
+for _ in range(10):
     pcs, neighs = step.build_hierarchy(pts, b)
 torch.cuda.synchronize()
 pr.disable()
 st = pstats.Stats(pr)
-st.sort_stats("cumulative").print_stats(45)
-
-step.calibrate(pcs, neighs)
-step.make_inputs(pcs)
-for _ in range(3):
-    step.conv_fwd_bwd(pcs, neighs)
-    step.zero_grad()
-torch.cuda.synchronize()
-t0 = time.perf_counter()
-for _ in range(5):
-    step.conv_fwd_bwd(pcs, neighs)
-    step.zero_grad()
-th = time.perf_counter() - t0
-torch.cuda.synchronize()
-print("conv stack: host %.2f ms, total %.2f ms" % (th / 5 * 1e3, (time.perf_counter() - t0) / 5 * 1e3))
-pr = cProfile.Profile()
-pr.enable()
-for _ in range(5):
-    step.conv_fwd_bwd(pcs, neighs)
-    step.zero_grad()
-torch.cuda.synchronize()
-pr.disable()
-pstats.Stats(pr).sort_stats("tottime").print_stats(25)
+st.sort_stats("tottime").print_stats(30)
+st.sort_stats("cumulative").print_stats(40)
