@@ -114,6 +114,17 @@ int se3_csr_transpose(const int64_t* neighbors, int64_t n_edges, int64_t n_src, 
                       int32_t* col_src, int32_t* t_row_ends, int32_t* t_edge, int32_t* t_dst,
                       se3_stream_t stream);
 
+/* int32-CSR variants used by the fused hierarchy builder: the fill writes the source column and the
+ * sample of every edge as int32 (the [E,2] int64 pair list of the reference contract is then only
+ * materialised on demand), and the transposed CSR is built from those two columns. */
+int se3_ball_query_fill_csr(const float* pts_dst, int64_t n_src, int64_t n_dst, const float* radius,
+                            const void* workspace, size_t workspace_bytes,
+                            const int32_t* row_ends, int64_t n_edges,
+                            int32_t* col_src_out, int32_t* edge_dst_out, se3_stream_t stream);
+int se3_csr_transpose_i32(const int32_t* col_src, const int32_t* edge_dst, int64_t n_edges, int64_t n_src,
+                          void* workspace, size_t workspace_bytes,
+                          int32_t* t_row_ends, int32_t* t_edge, int32_t* t_dst, se3_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * k-NN (self included, within batch, k <= 32).  Replaces knn_query
  * (custom_ops/knn_query/knn_query.cu:18-197; caller custom_ops/KNNQuery.py:30-33).
@@ -139,6 +150,68 @@ int se3_quat_frames(const float* q, int64_t n, float* frames_out, se3_stream_t s
 int se3_segment_pool_f32(const float* x, int64_t n, int32_t c, const int64_t* sorted_ids,
                          const int32_t* seg_ends, int64_t m, int32_t mode, float* out,
                          se3_stream_t stream);
+
+/* out[s] = x[first point of cell s] (int32; the batch id of a voxel -- the reference pools batch ids
+ * with scatter_max, pc/GridSubSample.py:72, and all points of a voxel share one id). */
+int se3_segment_first_i32(const int32_t* x, const int64_t* sorted_ids, const int32_t* seg_ends, int64_t m,
+                          int32_t* out, se3_stream_t stream);
+/* One uniformly random point per cell (GridSubSample with p_rnd_sample, pc/GridSubSample.py:36-57):
+ * picks sorted_ids[start + floor(u[s] * count)]; u [m] uniform in [0,1).  picked_out (optional) [m] int64. */
+int se3_segment_pick(const float* pts, const int32_t* batch, const int64_t* sorted_ids,
+                     const int32_t* seg_ends, int64_t m, const float* u, float* pts_out,
+                     int32_t* batch_out, int64_t* picked_out, se3_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused hierarchy construction: everything `create_hierarchy`
+ * (tasks/SemSeg/train_dfaust_rot.py:108-158) and the model's neighbourhood requests
+ * (models/Encoder.py:134-154, Decoder.py:72-80, FPNDecoder.py:104-113) build per step --
+ *   level 0 = grid average of the raw cloud (init_cell), n_pool further grid-average levels,
+ *   k-NN + PCA frames + random frame selection + gather records for every cloud,
+ *   the optional output cloud (one random raw point per init_cell voxel) with its frames,
+ *   every requested ball-query neighbourhood as int32 CSR + transposed CSR
+ * -- in ONE native call over a caller-provided device arena: (n_pool + 2) blocking size reads instead
+ * of one per object, no per-object host allocation.  Same kernels as the per-object entry points.
+ * Offsets in the result are BYTE offsets into the arena; 0-sized objects have offset 0. */
+#define SE3_HIER_MAX_CLOUDS 10
+#define SE3_HIER_MAX_NEIGH 32
+typedef struct se3_hier_desc {
+  int64_t n;             /* raw input points */
+  int32_t n_batches;
+  int32_t n_pool;        /* grid-average levels below level 0 */
+  float init_cell;       /* level 0 = grid average of the raw cloud with this voxel size (> 0) */
+  float cells[SE3_HIER_MAX_CLOUDS]; /* voxel size of pooling step l -> l+1 */
+  int32_t knn_k;         /* PCA frames: k nearest neighbours (<= 32) */
+  int32_t n_frames;      /* frames kept per point (1..4) */
+  int32_t fixed_axis;    /* -1 none */
+  int32_t out_cloud;     /* 1: also build the output cloud (index n_pool + 1) */
+  int32_t n_neigh;
+  int32_t neigh_src[SE3_HIER_MAX_NEIGH]; /* cloud indices */
+  int32_t neigh_dst[SE3_HIER_MAX_NEIGH];
+  float neigh_radius[SE3_HIER_MAX_NEIGH];
+} se3_hier_desc;
+typedef struct se3_hier_cloud {
+  int64_t n;
+  int64_t pts, batch, frames, rec;         /* f32 [n,3], i32 [n], f32 [n,F,9], f32 [n*F,12] */
+  int64_t m;                                /* occupied cells of the grid built on this cloud (0: none) */
+  int64_t cell_ids, sorted_ids, cell_ends;  /* i64 [n], i64 [n], i32 [m] */
+} se3_hier_cloud;
+typedef struct se3_hier_neigh {
+  int64_t e;
+  int64_t row_ends, col_src, edge_dst, t_row_ends, t_edge, t_dst; /* i32 [n_dst], [e], [e], [n_src], [e], [e] */
+} se3_hier_neigh;
+typedef struct se3_hier_result {
+  int64_t arena_used;       /* bytes consumed (on SE3_EWORKSPACE: bytes wanted by the failing allocation) */
+  int32_t n_clouds;
+  int32_t reserved;
+  se3_hier_cloud raw;       /* the raw cloud's init_cell grid (pts/batch/frames/rec unused) */
+  int64_t out_picked;       /* i64 [clouds[out].n]: raw index of every output-cloud point (0 if no out cloud) */
+  se3_hier_cloud clouds[SE3_HIER_MAX_CLOUDS];
+  se3_hier_neigh neigh[SE3_HIER_MAX_NEIGH];
+} se3_hier_result;
+/* u_frames: >= (n_pool + 2) * n uniforms (device); u_cells: >= n uniforms (device, only with out_cloud). */
+int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, const int32_t* batch_ids,
+                        const float* u_frames, const float* u_cells, void* arena, size_t arena_bytes,
+                        se3_hier_result* out, se3_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Legacy aggregation ops (custom_ops/feature_aggregation/feat_basis_proj.cuh:27-31 and

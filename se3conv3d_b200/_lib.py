@@ -23,6 +23,8 @@ ABI_SYMBOLS = [
     "se3_feat_basis_proj", "se3_feat_basis_proj_grad",
     "se3_conv_fwd_workspace_bytes", "se3_conv_bwd_workspace_bytes", "se3_conv_saved_bytes",
     "se3_conv_fwd", "se3_conv_bwd", "se3_gemm_bf16_tn", "se3_pack_records",
+    "se3_ball_query_fill_csr", "se3_csr_transpose_i32", "se3_segment_first_i32", "se3_segment_pick",
+    "se3_hierarchy_build",
 ]
 
 
@@ -38,6 +40,36 @@ class ConvDesc(C.Structure):
         ("t_row_ends", C.c_void_p), ("t_edge", C.c_void_p), ("t_dst", C.c_void_p),
         ("rec_in", C.c_void_p), ("rec_out", C.c_void_p),
         ("proj_axes", C.c_void_p), ("proj_biases", C.c_void_p), ("conv_weights", C.c_void_p),
+    ]
+
+
+HIER_MAX_CLOUDS, HIER_MAX_NEIGH = 10, 32
+
+
+class HierDesc(C.Structure):
+    """Mirror of `struct se3_hier_desc`."""
+    _fields_ = [
+        ("n", C.c_int64), ("n_batches", C.c_int32), ("n_pool", C.c_int32), ("init_cell", C.c_float),
+        ("cells", C.c_float * HIER_MAX_CLOUDS), ("knn_k", C.c_int32), ("n_frames", C.c_int32),
+        ("fixed_axis", C.c_int32), ("out_cloud", C.c_int32), ("n_neigh", C.c_int32),
+        ("neigh_src", C.c_int32 * HIER_MAX_NEIGH), ("neigh_dst", C.c_int32 * HIER_MAX_NEIGH),
+        ("neigh_radius", C.c_float * HIER_MAX_NEIGH),
+    ]
+
+
+class HierCloud(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in ("n", "pts", "batch", "frames", "rec", "m", "cell_ids", "sorted_ids", "cell_ends")]
+
+
+class HierNeigh(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in ("e", "row_ends", "col_src", "edge_dst", "t_row_ends", "t_edge", "t_dst")]
+
+
+class HierResult(C.Structure):
+    """Mirror of `struct se3_hier_result`."""
+    _fields_ = [
+        ("arena_used", C.c_int64), ("n_clouds", C.c_int32), ("reserved", C.c_int32), ("raw", HierCloud),
+        ("out_picked", C.c_int64), ("clouds", HierCloud * HIER_MAX_CLOUDS), ("neigh", HierNeigh * HIER_MAX_NEIGH),
     ]
 
 
@@ -90,6 +122,11 @@ def lib():
     L.se3_conv_fwd.argtypes = [dp, vp, vp, vp, vp, sz, vp]
     L.se3_gemm_bf16_tn.argtypes = [vp, vp, i64, i64, i64, f32, vp, i32, i32, vp]
     L.se3_pack_records.argtypes = [vp, vp, i64, i32, vp, vp]
+    L.se3_ball_query_fill_csr.argtypes = [vp, i64, i64, vp, vp, sz, vp, i64, vp, vp, vp]
+    L.se3_csr_transpose_i32.argtypes = [vp, vp, i64, i64, vp, sz, vp, vp, vp, vp]
+    L.se3_segment_first_i32.argtypes = [vp, vp, vp, i64, vp, vp]
+    L.se3_segment_pick.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
+    L.se3_hierarchy_build.argtypes = [C.POINTER(HierDesc), vp, vp, vp, vp, vp, sz, C.POINTER(HierResult), vp]
     L.se3_conv_bwd.argtypes = [dp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     for n in ABI_SYMBOLS:
         f = getattr(L, n)

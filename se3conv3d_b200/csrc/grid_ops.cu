@@ -434,7 +434,8 @@ __global__ void __launch_bounds__(256) k_bq_scan(const float* __restrict__ pts_d
                                                  const float4* __restrict__ pts_sorted,
                                                  const int* __restrict__ idx_sorted, int2* __restrict__ ranges,
                                                  int* __restrict__ counts, const int* __restrict__ row_ends,
-                                                 int64_t* __restrict__ neighbors) {
+                                                 int64_t* __restrict__ neighbors, int* __restrict__ col_src,
+                                                 int* __restrict__ edge_dst) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -474,8 +475,13 @@ __global__ void __launch_bounds__(256) k_bq_scan(const float* __restrict__ pts_d
         const unsigned m = __ballot_sync(0xffffffffu, hit);
         if (FILL && hit) {
           const int64_t slot = out_base + total + __popc(m & ((1u << lane) - 1u));
-          neighbors[2 * slot] = s;
-          neighbors[2 * slot + 1] = (int64_t)idx_sorted[p];
+          if (neighbors) {
+            neighbors[2 * slot] = s;
+            neighbors[2 * slot + 1] = (int64_t)idx_sorted[p];
+          } else {
+            col_src[slot] = idx_sorted[p];
+            edge_dst[slot] = (int)s;
+          }
         }
         total += __popc(m);
       }
@@ -520,7 +526,7 @@ extern "C" int se3_ball_query_count(const float* pts_src, const float* pts_dst, 
   const int blocks = grid_for(n_dst * 32, 256);
   k_bq_scan<false><<<blocks, 256, 0, st>>>(pts_dst, batch_dst, n_dst, (int)n_src, min_pt, num_cells, radius,
                                            w.keys_sorted, w.pts_sorted, w.idx_sorted, w.ranges, w.counts, nullptr,
-                                           nullptr);
+                                           nullptr, nullptr, nullptr);
   SE3_LAUNCH_CHECK();
   cb = w.cub_bytes;
   SE3_CUDA(cub::DeviceScan::InclusiveSum(w.cub_tmp, cb, w.counts, row_ends_out, (int)n_dst, st));
@@ -543,7 +549,26 @@ extern "C" int se3_ball_query_fill(const float* pts_dst, int64_t n_src, int64_t 
   const int blocks = grid_for(n_dst * 32, 256);
   k_bq_scan<true><<<blocks, 256, 0, as_stream(stream)>>>(pts_dst, nullptr, n_dst, (int)n_src, nullptr, nullptr,
                                                          radius, w.keys_sorted, w.pts_sorted, w.idx_sorted, w.ranges,
-                                                         w.counts, row_ends, neighbors_out);
+                                                         w.counts, row_ends, neighbors_out, nullptr, nullptr);
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
+}
+
+extern "C" int se3_ball_query_fill_csr(const float* pts_dst, int64_t n_src, int64_t n_dst, const float* radius,
+                                       const void* workspace, size_t workspace_bytes, const int32_t* row_ends,
+                                       int64_t n_edges, int32_t* col_src_out, int32_t* edge_dst_out,
+                                       se3_stream_t stream) {
+  if (n_edges == 0 || n_dst == 0 || n_src == 0) return SE3_OK;
+  SE3_CHECK_ARG(pts_dst && radius && workspace && row_ends && col_src_out && edge_dst_out, "null pointer");
+  BQWorkspace w;
+  if (!bq_layout(const_cast<void*>(workspace), workspace_bytes, n_src, n_dst, w)) {
+    set_error("se3_ball_query_fill_csr: workspace too small");
+    return SE3_EWORKSPACE;
+  }
+  const int blocks = grid_for(n_dst * 32, 256);
+  k_bq_scan<true><<<blocks, 256, 0, as_stream(stream)>>>(pts_dst, nullptr, n_dst, (int)n_src, nullptr, nullptr,
+                                                         radius, w.keys_sorted, w.pts_sorted, w.idx_sorted, w.ranges,
+                                                         w.counts, row_ends, nullptr, col_src_out, edge_dst_out);
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }
@@ -618,6 +643,106 @@ extern "C" int se3_csr_transpose(const int64_t* neighbors, int64_t n_edges, int6
   const int64_t work = n_edges > n_src ? n_edges : n_src;
   k_transposed_rows<<<grid_for(work, 256), 256, 0, st>>>(src_sorted, t_edge, neighbors, n_edges, n_src, t_row_ends,
                                                         t_dst);
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
+}
+
+__global__ void k_iota(int* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (int)i;
+}
+
+__global__ void k_transposed_rows_i32(const int* __restrict__ src_sorted, const int* __restrict__ t_edge,
+                                      const int* __restrict__ edge_dst, int64_t e, int64_t n_src,
+                                      int* __restrict__ t_row_ends, int* __restrict__ t_dst) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < e; i += stride) t_dst[i] = edge_dst[t_edge[i]];
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n_src; j += stride) {
+    int lo = 0, hi = (int)e;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (src_sorted[mid] <= (int)j) lo = mid + 1; else hi = mid;
+    }
+    t_row_ends[j] = lo;
+  }
+}
+
+// Transposed CSR straight from the int32 CSR columns (col_src [E], edge_dst [E] = sample of every edge).
+extern "C" int se3_csr_transpose_i32(const int32_t* col_src, const int32_t* edge_dst, int64_t n_edges, int64_t n_src,
+                                     void* workspace, size_t workspace_bytes, int32_t* t_row_ends, int32_t* t_edge,
+                                     int32_t* t_dst, se3_stream_t stream) {
+  SE3_CHECK_ARG(n_edges >= 0 && n_edges < (1ll << 31) && n_src >= 0, "bad sizes");
+  cudaStream_t st = as_stream(stream);
+  if (n_edges == 0) {
+    if (n_src > 0 && t_row_ends) SE3_CUDA(cudaMemsetAsync(t_row_ends, 0, n_src * sizeof(int), st));
+    return SE3_OK;
+  }
+  SE3_CHECK_ARG(col_src && edge_dst && workspace && t_row_ends && t_edge && t_dst, "null pointer");
+  Arena ar(workspace, workspace_bytes);
+  int* iota = ar.take<int>(n_edges);
+  int* src_sorted = ar.take<int>(n_edges);
+  size_t cb = tr_cub_bytes(n_edges);
+  void* tmp = ar.take<char>(cb);
+  if (!ar.ok()) {
+    set_error("se3_csr_transpose_i32: workspace too small");
+    return SE3_EWORKSPACE;
+  }
+  k_iota<<<grid_for(n_edges, 256), 256, 0, st>>>(iota, n_edges);
+  SE3_LAUNCH_CHECK();
+  int bits = 1;
+  while ((1ll << bits) < n_src && bits < 31) ++bits;
+  SE3_CUDA(cub::DeviceRadixSort::SortPairs(tmp, cb, col_src, src_sorted, iota, t_edge, (int)n_edges, 0, bits, st));
+  count_launch(4);
+  const int64_t work = n_edges > n_src ? n_edges : n_src;
+  k_transposed_rows_i32<<<grid_for(work, 256), 256, 0, st>>>(src_sorted, t_edge, edge_dst, n_edges, n_src, t_row_ends,
+                                                            t_dst);
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
+}
+
+// first element of every segment of an int32 array (batch id of a voxel: all its points share it)
+__global__ void k_segment_first_i32(const int* __restrict__ x, const int64_t* __restrict__ sorted_ids,
+                                    const int* __restrict__ seg_ends, int64_t m, int* __restrict__ out) {
+  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < m; s += (int64_t)gridDim.x * blockDim.x) {
+    const int lo = s > 0 ? seg_ends[s - 1] : 0;
+    out[s] = x[sorted_ids[lo]];
+  }
+}
+extern "C" int se3_segment_first_i32(const int32_t* x, const int64_t* sorted_ids, const int32_t* seg_ends, int64_t m,
+                                     int32_t* out, se3_stream_t stream) {
+  if (m <= 0) return SE3_OK;
+  SE3_CHECK_ARG(x && sorted_ids && seg_ends && out, "null pointer");
+  k_segment_first_i32<<<grid_for(m, 256), 256, 0, as_stream(stream)>>>(x, sorted_ids, seg_ends, m, out);
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
+}
+
+// one uniformly random member of every segment: pts / batch id of point sorted_ids[start + floor(u * count)]
+// (GridSubSample with rnd sampling, pc/GridSubSample.py:36-57)
+__global__ void k_segment_pick(const float* __restrict__ pts, const int* __restrict__ batch,
+                               const int64_t* __restrict__ sorted_ids, const int* __restrict__ seg_ends, int64_t m,
+                               const float* __restrict__ u, float* __restrict__ pts_out, int* __restrict__ batch_out,
+                               int64_t* __restrict__ picked) {
+  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < m; s += (int64_t)gridDim.x * blockDim.x) {
+    const int lo = s > 0 ? seg_ends[s - 1] : 0;
+    const int cnt = seg_ends[s] - lo;
+    int off = (int)floorf(u[s] * (float)cnt);
+    off = min(max(off, 0), cnt - 1);
+    const int64_t src = sorted_ids[lo + off];
+    pts_out[3 * s] = pts[3 * src];
+    pts_out[3 * s + 1] = pts[3 * src + 1];
+    pts_out[3 * s + 2] = pts[3 * src + 2];
+    batch_out[s] = batch[src];
+    if (picked) picked[s] = src;
+  }
+}
+extern "C" int se3_segment_pick(const float* pts, const int32_t* batch, const int64_t* sorted_ids,
+                                const int32_t* seg_ends, int64_t m, const float* u, float* pts_out,
+                                int32_t* batch_out, int64_t* picked_out, se3_stream_t stream) {
+  if (m <= 0) return SE3_OK;
+  SE3_CHECK_ARG(pts && batch && sorted_ids && seg_ends && u && pts_out && batch_out, "null pointer");
+  k_segment_pick<<<grid_for(m, 256), 256, 0, as_stream(stream)>>>(pts, batch, sorted_ids, seg_ends, m, u, pts_out,
+                                                                  batch_out, picked_out);
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }

@@ -1,0 +1,227 @@
+// Fused hierarchy construction: one native call builds every cloud, frame set, gather record and
+// ball-query CSR a training step needs (see include/se3conv3d_b200.h, se3_hierarchy_build).  It drives the
+// same kernels as the per-object entry points; what it removes is the host work between them: one Python
+// object, several tensor allocations and one blocking size read per grid / neighbourhood become
+// (n_pool + 2) size reads in total and a bump allocator over a caller-provided arena.
+#include <string.h>
+#include "common.cuh"
+
+namespace se3 {
+namespace {
+
+struct Bump {
+  char* base;
+  size_t cap, off, want;
+  bool ok;
+  Bump(void* p, size_t c) : base(reinterpret_cast<char*>(p)), cap(c), off(0), want(0), ok(true) {}
+  // returns the byte offset of a fresh block (0-sized requests still get a valid aligned offset)
+  int64_t take(size_t bytes) {
+    const size_t b = align_up(bytes ? bytes : 1);
+    const size_t at = off;
+    off += b;
+    if (off > cap) {
+      ok = false;
+      want = off;
+      return 0;
+    }
+    return (int64_t)at;
+  }
+  template <typename T>
+  T* at(int64_t o) const { return reinterpret_cast<T*>(base + o); }
+};
+
+int64_t* pinned_scalars() {
+  static int64_t* p = nullptr;
+  if (!p) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&p), 64 * sizeof(int64_t), cudaHostAllocDefault) != cudaSuccess) p = nullptr;
+  }
+  return p;
+}
+
+}  // namespace
+}  // namespace se3
+
+using namespace se3;
+
+#define HB_TRY(expr)            \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc != SE3_OK) return _rc; \
+  } while (0)
+#define HB_CHECK_ARENA(what)                                        \
+  do {                                                              \
+    if (!ar.ok) {                                                   \
+      out->arena_used = (int64_t)ar.want;                           \
+      set_error("se3_hierarchy_build: arena too small (%s)", what); \
+      return SE3_EWORKSPACE;                                        \
+    }                                                               \
+  } while (0)
+
+extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, const int32_t* batch_ids,
+                                   const float* u_frames, const float* u_cells, void* arena, size_t arena_bytes,
+                                   se3_hier_result* out, se3_stream_t stream) {
+  SE3_CHECK_ARG(d && out && arena, "null pointer");
+  SE3_CHECK_ARG(d->n >= 1 && d->n < (1ll << 31) && d->n_batches >= 1, "bad sizes");
+  SE3_CHECK_ARG(d->n_pool >= 0 && d->n_pool + 2 <= SE3_HIER_MAX_CLOUDS, "too many levels");
+  SE3_CHECK_ARG(d->init_cell > 0.0f, "init_cell must be positive");
+  SE3_CHECK_ARG(d->knn_k >= 1 && d->knn_k <= 32 && d->n_frames >= 1 && d->n_frames <= 4, "bad frame configuration");
+  SE3_CHECK_ARG(d->n_neigh >= 0 && d->n_neigh <= SE3_HIER_MAX_NEIGH, "too many neighbourhoods");
+  SE3_CHECK_ARG(pts && batch_ids && u_frames, "null input");
+  SE3_CHECK_ARG(!d->out_cloud || u_cells, "the output cloud needs u_cells");
+  cudaStream_t st = as_stream(stream);
+  int64_t* host = pinned_scalars();
+  if (!host) {
+    set_error("se3_hierarchy_build: cannot allocate pinned host scalars");
+    return SE3_ECUDA;
+  }
+  memset(out, 0, sizeof(*out));
+  Bump ar(arena, arena_bytes);
+  const int n_cand = d->fixed_axis > 0 ? 2 : 4;
+  const int F = d->n_frames;
+  SE3_CHECK_ARG(F <= n_cand, "n_frames exceeds the PCA candidates");
+  const int n_clouds = d->n_pool + 1 + (d->out_cloud ? 1 : 0);
+  out->n_clouds = n_clouds;
+
+  // small device scalars shared by every grid: min/max [B,3], num_cells [3], a count
+  const int64_t o_min = ar.take((size_t)d->n_batches * 3 * 4), o_max = ar.take((size_t)d->n_batches * 3 * 4);
+  const int64_t o_nc = ar.take(16), o_cnt = ar.take(8 * (SE3_HIER_MAX_NEIGH + 2)), o_rad = ar.take(16 * SE3_HIER_MAX_NEIGH);
+  HB_CHECK_ARENA("scalars");
+  float* min_pt = ar.at<float>(o_min);
+  float* max_pt = ar.at<float>(o_max);
+  int32_t* num_cells = ar.at<int32_t>(o_nc);
+  int64_t* d_cnt = ar.at<int64_t>(o_cnt);
+
+  // grid on (p, b, n) with voxel `cell`; fills g.cell_ids / sorted_ids / cell_ends / m (blocking read of m)
+  auto build_grid = [&](const float* p, const int32_t* b, int64_t n, float cell, se3_hier_cloud& g) -> int {
+    g.cell_ids = ar.take((size_t)n * 8);
+    g.sorted_ids = ar.take((size_t)n * 8);
+    g.cell_ends = ar.take((size_t)n * 4);
+    const size_t wsb = se3_grid_cells_workspace_bytes(n);
+    const int64_t o_ws = ar.take(wsb);
+    HB_CHECK_ARENA("grid");
+    HB_TRY(se3_grid_setup(p, b, n, d->n_batches, cell, 1e-6f, min_pt, max_pt, num_cells, stream));
+    HB_TRY(se3_grid_cells(p, b, n, min_pt, num_cells, cell, ar.at<char>(o_ws), wsb, ar.at<int64_t>(g.cell_ids),
+                          ar.at<int64_t>(g.sorted_ids), ar.at<int32_t>(g.cell_ends), d_cnt, stream));
+    SE3_CUDA(cudaMemcpyAsync(host, d_cnt, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    SE3_CUDA(cudaStreamSynchronize(st));
+    g.m = host[0];
+    return SE3_OK;
+  };
+  // frames + records of cloud c (pts / batch already in place)
+  int64_t u_off = 0;
+  auto build_frames = [&](se3_hier_cloud& c) -> int {
+    const int64_t n = c.n;
+    c.frames = ar.take((size_t)n * F * 36);
+    c.rec = ar.take((size_t)n * F * 48);
+    const int64_t o_knn = ar.take((size_t)n * d->knn_k * 4);
+    const int64_t o_cand = ar.take((size_t)n * n_cand * 36);
+    const size_t wsb = se3_knn_workspace_bytes(n);
+    const int64_t o_ws = ar.take(wsb);
+    HB_CHECK_ARENA("frames");
+    if (n == 0) return SE3_OK;
+    HB_TRY(se3_knn_query(ar.at<float>(c.pts), ar.at<int32_t>(c.batch), n, d->knn_k, ar.at<char>(o_ws), wsb,
+                         ar.at<int32_t>(o_knn), stream));
+    HB_TRY(se3_pca_frames(ar.at<float>(c.pts), ar.at<int32_t>(o_knn), n, d->knn_k, d->fixed_axis, ar.at<float>(o_cand),
+                          stream));
+    HB_TRY(se3_frames_select(ar.at<float>(o_cand), u_frames + u_off, n, n_cand, F, ar.at<float>(c.frames), stream));
+    u_off += n;
+    HB_TRY(se3_pack_records(ar.at<float>(c.pts), ar.at<float>(c.frames), n, F, ar.at<float>(c.rec), stream));
+    return SE3_OK;
+  };
+  // cloud `dst` = grid-average pooling of (p, b) over grid g
+  auto pool_cloud = [&](const float* p, const int32_t* b, int64_t n, const se3_hier_cloud& g, se3_hier_cloud& dst) -> int {
+    dst.n = g.m;
+    dst.pts = ar.take((size_t)g.m * 12);
+    dst.batch = ar.take((size_t)g.m * 4);
+    HB_CHECK_ARENA("pooled cloud");
+    HB_TRY(se3_segment_pool_f32(p, n, 3, ar.at<int64_t>(g.sorted_ids), ar.at<int32_t>(g.cell_ends), g.m, 0,
+                                ar.at<float>(dst.pts), stream));
+    HB_TRY(se3_segment_first_i32(b, ar.at<int64_t>(g.sorted_ids), ar.at<int32_t>(g.cell_ends), g.m,
+                                 ar.at<int32_t>(dst.batch), stream));
+    return SE3_OK;
+  };
+
+  // ---- level 0 and the output cloud share the raw cloud's init_cell grid
+  out->raw.n = d->n;
+  HB_TRY(build_grid(pts, batch_ids, d->n, d->init_cell, out->raw));
+  HB_TRY(pool_cloud(pts, batch_ids, d->n, out->raw, out->clouds[0]));
+  HB_TRY(build_frames(out->clouds[0]));
+  // ---- pooled levels
+  for (int l = 0; l < d->n_pool; ++l) {
+    se3_hier_cloud& src = out->clouds[l];
+    SE3_CHECK_ARG(d->cells[l] > 0.0f, "cell sizes must be positive");
+    HB_TRY(build_grid(ar.at<float>(src.pts), ar.at<int32_t>(src.batch), src.n, d->cells[l], src));
+    HB_TRY(pool_cloud(ar.at<float>(src.pts), ar.at<int32_t>(src.batch), src.n, src, out->clouds[l + 1]));
+    HB_TRY(build_frames(out->clouds[l + 1]));
+  }
+  if (d->out_cloud) {
+    se3_hier_cloud& oc = out->clouds[d->n_pool + 1];
+    oc.n = out->raw.m;
+    oc.pts = ar.take((size_t)oc.n * 12);
+    oc.batch = ar.take((size_t)oc.n * 4);
+    out->out_picked = ar.take((size_t)oc.n * 8);
+    HB_CHECK_ARENA("output cloud");
+    HB_TRY(se3_segment_pick(pts, batch_ids, ar.at<int64_t>(out->raw.sorted_ids), ar.at<int32_t>(out->raw.cell_ends),
+                            oc.n, u_cells, ar.at<float>(oc.pts), ar.at<int32_t>(oc.batch),
+                            ar.at<int64_t>(out->out_picked), stream));
+    HB_TRY(build_frames(oc));
+  }
+
+  // ---- neighbourhoods: all count passes, ONE blocking read of the edge totals, then fills + transposes
+  int64_t ws_off[SE3_HIER_MAX_NEIGH];
+  size_t ws_bytes[SE3_HIER_MAX_NEIGH];
+  float h_rad[SE3_HIER_MAX_NEIGH * 4];
+  for (int i = 0; i < d->n_neigh; ++i) {
+    SE3_CHECK_ARG(d->neigh_src[i] >= 0 && d->neigh_src[i] < n_clouds && d->neigh_dst[i] >= 0 && d->neigh_dst[i] < n_clouds,
+                  "neighbourhood refers to a cloud that does not exist");
+    SE3_CHECK_ARG(d->neigh_radius[i] > 0.0f, "radius must be positive");
+    h_rad[4 * i] = h_rad[4 * i + 1] = h_rad[4 * i + 2] = d->neigh_radius[i];
+    h_rad[4 * i + 3] = 0.0f;
+  }
+  float* d_rad = ar.at<float>(o_rad);
+  if (d->n_neigh > 0) {
+    // pageable source: the copy is staged before the call returns, so the stack buffer is safe
+    SE3_CUDA(cudaMemcpyAsync(d_rad, h_rad, sizeof(float) * 4 * d->n_neigh, cudaMemcpyHostToDevice, st));
+  }
+  for (int i = 0; i < d->n_neigh; ++i) {
+    const se3_hier_cloud& s = out->clouds[d->neigh_src[i]];
+    const se3_hier_cloud& t = out->clouds[d->neigh_dst[i]];
+    se3_hier_neigh& nb = out->neigh[i];
+    nb.row_ends = ar.take((size_t)t.n * 4);
+    nb.t_row_ends = ar.take((size_t)s.n * 4);
+    ws_bytes[i] = se3_ball_query_workspace_bytes(s.n, t.n);
+    ws_off[i] = ar.take(ws_bytes[i]);
+    // per-neighbourhood grid scalars (they must survive until the fill pass)
+    const int64_t o_mn = ar.take((size_t)d->n_batches * 3 * 4), o_mx = ar.take((size_t)d->n_batches * 3 * 4), o_n3 = ar.take(16);
+    HB_CHECK_ARENA("ball-query workspace");
+    HB_TRY(se3_grid_setup(ar.at<float>(s.pts), ar.at<int32_t>(s.batch), s.n, d->n_batches, d->neigh_radius[i], -1e-6f,
+                          ar.at<float>(o_mn), ar.at<float>(o_mx), ar.at<int32_t>(o_n3), stream));
+    HB_TRY(se3_ball_query_count(ar.at<float>(s.pts), ar.at<float>(t.pts), ar.at<int32_t>(s.batch), ar.at<int32_t>(t.batch),
+                                s.n, t.n, ar.at<float>(o_mn), ar.at<int32_t>(o_n3), d_rad + 4 * i, ar.at<char>(ws_off[i]),
+                                ws_bytes[i], ar.at<int32_t>(nb.row_ends), d_cnt + 1 + i, stream));
+  }
+  if (d->n_neigh > 0) {
+    SE3_CUDA(cudaMemcpyAsync(host, d_cnt + 1, sizeof(int64_t) * d->n_neigh, cudaMemcpyDeviceToHost, st));
+    SE3_CUDA(cudaStreamSynchronize(st));
+  }
+  for (int i = 0; i < d->n_neigh; ++i) {
+    const se3_hier_cloud& s = out->clouds[d->neigh_src[i]];
+    const se3_hier_cloud& t = out->clouds[d->neigh_dst[i]];
+    se3_hier_neigh& nb = out->neigh[i];
+    nb.e = host[i];
+    nb.col_src = ar.take((size_t)nb.e * 4);
+    nb.edge_dst = ar.take((size_t)nb.e * 4);
+    nb.t_edge = ar.take((size_t)nb.e * 4);
+    nb.t_dst = ar.take((size_t)nb.e * 4);
+    const size_t twb = se3_csr_transpose_workspace_bytes(nb.e, s.n);
+    const int64_t o_tw = ar.take(twb);
+    HB_CHECK_ARENA("neighbourhood");
+    HB_TRY(se3_ball_query_fill_csr(ar.at<float>(t.pts), s.n, t.n, d_rad + 4 * i, ar.at<char>(ws_off[i]), ws_bytes[i],
+                                   ar.at<int32_t>(nb.row_ends), nb.e, ar.at<int32_t>(nb.col_src),
+                                   ar.at<int32_t>(nb.edge_dst), stream));
+    HB_TRY(se3_csr_transpose_i32(ar.at<int32_t>(nb.col_src), ar.at<int32_t>(nb.edge_dst), nb.e, s.n, ar.at<char>(o_tw), twb,
+                                 ar.at<int32_t>(nb.t_row_ends), ar.at<int32_t>(nb.t_edge), ar.at<int32_t>(nb.t_dst), stream));
+  }
+  out->arena_used = (int64_t)ar.off;
+  return SE3_OK;
+}

@@ -10,3 +10,4 @@ from .neighborhood import Neighborhood, BQNeighborhood, KnnNeighborhood, ConvGeo
 from .subsample import SubSample, GridSubSample
 from .pointcloud_rot_equiv import PointcloudRotEquiv
 from .hierarchy import PointHierarchy, PointHierarchyRotEquiv
+from .fused import build_point_hierarchy

@@ -85,12 +85,15 @@ class Neighborhood(ABC):
         """Cached ConvGeometry; keyed on the identity of the clouds and their frame tensors, so a
         cloud whose frames were re-sampled gets a fresh record."""
         key = (id(p_pc_in), id(p_pc_out), id(getattr(p_pc_in, "local_frames_", None)),
-               id(getattr(p_pc_out, "local_frames_", None)), id(self.neighbors_))
+               id(getattr(p_pc_out, "local_frames_", None)), self._neighbors_token())
         geom = self.conv_geometry_cache_.get(key)
         if geom is None:
             geom = ConvGeometry(p_pc_in, p_pc_out, self)
             self.conv_geometry_cache_ = {key: geom}
         return geom
+
+    def _neighbors_token(self):
+        return id(self.neighbors_)
 
     def __repr__(self):
         return "### Neighbors:\n{}\n### Start indices:\n{}".format(self.neighbors_, self.start_ids_)
@@ -108,6 +111,24 @@ class BQNeighborhood(Neighborhood):
         self.neighbors_, self.start_ids_ = BallQuery.apply(
             self.pc_src_.pts_, self.samples_.pts_, self.pc_src_.batch_ids_, self.samples_.batch_ids_, self.radius_,
             self.max_neighbors_, num_batches(self.pc_src_))
+
+    # `neighbors_` [E,2] int64 (sample, source) is the reference contract.  A neighbourhood that came out of
+    # the fused hierarchy builder carries the int32 CSR columns instead and materialises the pair list on
+    # first access (the conv kernels never need it).
+    @property
+    def neighbors_(self):
+        if self._neighbors is None and getattr(self, "_csr_columns", None) is not None:
+            edge_dst, col_src = self._csr_columns
+            self._neighbors = torch.stack((edge_dst.to(torch.int64), col_src.to(torch.int64)), dim=1)
+        return self._neighbors
+
+    @neighbors_.setter
+    def neighbors_(self, v):
+        self._neighbors = v
+
+    def _neighbors_token(self):
+        cols = getattr(self, "_csr_columns", None)
+        return id(cols[1]) if (self._neighbors is None and cols is not None) else id(self._neighbors)
 
 
 class KnnNeighborhood(Neighborhood):

@@ -25,9 +25,23 @@ class Pointcloud(object):
         self.batch_size_host_ = kwargs.pop("batch_size_host", None)  # optional host copy: avoids a sync
         self.pts_ = torch.as_tensor(p_pts, **kwargs)
         self.batch_ids_ = torch.as_tensor(p_batch_ids, **kwargs)
-        self.batch_size_ = torch.max(self.batch_ids_) + 1
+        self._batch_size = None  # device scalar max(batch_ids_) + 1, built on first use
         if self.pts_with_grads_:
             self.pts_.requires_grad = True
+
+    @property
+    def batch_size_(self):
+        if self._batch_size is None:
+            if self.batch_size_host_ is not None:
+                self._batch_size = torch.tensor(self.batch_size_host_, dtype=self.batch_ids_.dtype,
+                                                device=self.batch_ids_.device)
+            else:
+                self._batch_size = torch.max(self.batch_ids_) + 1
+        return self._batch_size
+
+    @batch_size_.setter
+    def batch_size_(self, v):
+        self._batch_size = v
 
     def to_device(self, p_device):
         self.pts_ = self.pts_.to(p_device)

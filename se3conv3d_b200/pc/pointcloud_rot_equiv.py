@@ -39,9 +39,20 @@ class PointcloudRotEquiv(Pointcloud):
         frames = self.get_local_ref_frames()
         self.n_frames_ = frames.shape[1]
         self.local_frames_ = torch.as_tensor(frames, **kwargs).contiguous()
-        self.batch_ids_considering_frames_ = torch.repeat_interleave(self.batch_ids_, self.n_frames_)
+        self._batch_ids_frames = None  # built on first use (only the pooling helpers read it)
         if self.pts_with_grads_:
             self.local_frames_.requires_grad = True
+
+    @property
+    def batch_ids_considering_frames_(self):
+        """batch id of every (point, frame) feature row (pc/PointcloudRotEquiv.py:50)."""
+        if self._batch_ids_frames is None:
+            self._batch_ids_frames = torch.repeat_interleave(self.batch_ids_, self.n_frames_)
+        return self._batch_ids_frames
+
+    @batch_ids_considering_frames_.setter
+    def batch_ids_considering_frames_(self, v):
+        self._batch_ids_frames = v
 
     def get_ref_frame_neighborhood(self, p_neigh_method, **kwargs):
         key = str(p_neigh_method)

@@ -86,7 +86,11 @@ class DfaustStep(object):
             self.layers.append(layer)
         self.inputs = None
 
-    def build_hierarchy(self, pts, batch_ids):
+    def build_hierarchy(self, pts, batch_ids, fused=True, n_batches=None):
+        """Clouds [level 0..4, output cloud] and one neighbourhood per conv.  fused=True: one native call
+        (pc.build_point_hierarchy); fused=False: the per-object chain with the reference's API."""
+        if fused:
+            return self.build_hierarchy_fused(pts, batch_ids, n_batches)
         from .pc import Pointcloud, GridSubSample, PointcloudRotEquiv, PointHierarchyRotEquiv
         cfg = DFAUST_CFG
         with torch.no_grad():
@@ -113,11 +117,31 @@ class DfaustStep(object):
                 neighs.append(nb)
         return pcs, neighs
 
+    def build_hierarchy_fused(self, pts, batch_ids, n_batches=None):
+        from .pc import build_point_hierarchy
+        cfg = DFAUST_CFG
+        radii = [cfg["init_subsample"]] + cfg["grid_subsamples"]
+        wanted, index = [], {}
+        for (_, li, lo, lr, _, _) in self.specs:
+            key = (li, lo, 2.0 * radii[lr])
+            if key not in index:
+                index[key] = len(wanted)
+                wanted.append(key)
+        with torch.no_grad():
+            h, out_pc = build_point_hierarchy(pts, batch_ids, cfg["RefFrames"], cfg["init_subsample"],
+                                              cfg["grid_subsamples"], neighborhoods=wanted, output_cloud=True,
+                                              n_batches=n_batches)
+        pcs = list(h.pcs_) + [out_pc]
+        neighs = [h.fused_neighborhoods_[index[(li, lo, 2.0 * radii[lr])]] for (_, li, lo, lr, _, _) in self.specs]
+        self.hierarchy = h
+        return pcs, neighs
+
     def calibrate(self, pcs, neighs):
         """What the pre-process epoch converges to: norm_neigh_dist_ = 1/r, norm_num_neighs_ = M/E."""
         for layer, nb in zip(self.layers, neighs):
             layer.norm_neigh_dist_.fill_(1.0 / nb.radius_)
-            layer.norm_num_neighs_.fill_(nb.start_ids_.shape[0] / max(nb.neighbors_.shape[0], 1))
+            n_edges = nb._csr_columns[1].shape[0] if getattr(nb, "_csr_columns", None) is not None else nb.neighbors_.shape[0]
+            layer.norm_num_neighs_.fill_(nb.start_ids_.shape[0] / max(n_edges, 1))
 
     def make_inputs(self, pcs, seed=1):
         g = torch.Generator(device="cpu").manual_seed(seed)

@@ -419,3 +419,58 @@ def test_projection_gemm_matches_fp64(impl, m, n, k):
                                       _lib.stream()), "se3_gemm_bf16_tn")
         torch.cuda.synchronize()
         assert rel_err(c.double().cpu(), ref.cpu()) < tol
+
+
+def test_fused_hierarchy_matches_per_object_path():
+    """se3_hierarchy_build (one native call) against the per-object chain with the reference's API on the
+    same synthetic bodies: level clouds, grids and every CSR bit-exact; frames drawn from the same PCA
+    candidates; the output cloud picks one raw point of every init voxel."""
+    from se3conv3d_b200 import workloads as wl
+    from se3conv3d_b200.pc import BQNeighborhood
+    pts, b = wl.synthetic_bodies(4, 3000, seed=3)
+    pts, b = pts.to(DEV), b.to(DEV)
+    step = wl.DfaustStep(DEV, precision=1)
+    pcs_u, neighs_u = step.build_hierarchy(pts, b, fused=False)
+    pcs_f, neighs_f = step.build_hierarchy(pts, b, fused=True, n_batches=4)
+    h = step.hierarchy
+    assert len(pcs_u) == len(pcs_f) == 6
+    for lvl in range(5):
+        assert torch.equal(pcs_u[lvl].pts_, pcs_f[lvl].pts_), lvl
+        assert torch.equal(pcs_u[lvl].batch_ids_.to(torch.int32), pcs_f[lvl].batch_ids_), lvl
+        cand = pcs_u[lvl].local_frames_pca_cache_["se3-all"]                       # [N,4,9]
+        fr = pcs_f[lvl].local_frames_                                              # [N,2,9]
+        match = (fr[:, :, None, :] == cand[:, None, :, :]).all(-1)                 # [N,2,4]
+        assert bool(match.any(-1).all()), "fused frames must come from the PCA candidates"
+        assert bool((match[:, 0].float().argmax(-1) != match[:, 1].float().argmax(-1)).all())
+    # pooling / upsampling indices of every level
+    hu = None
+    for lvl in range(4):
+        gu = wl_grid_of(pcs_u, lvl, step)
+        gf = h.sub_sampled_objs_[lvl].grid_
+        assert torch.equal(gu.cell_ids_, gf.cell_ids_) and torch.equal(gu.sorted_ids_, gf.sorted_ids_)
+        assert torch.equal(gu.cell_ends_, gf.cell_ends_) and gu.num_used_cells_ == gf.num_used_cells_
+    # output cloud: one raw point per init voxel, in voxel order
+    out = pcs_f[5]
+    assert out.pts_.shape[0] == pcs_f[0].pts_.shape[0]
+    assert torch.equal(h.init_cell_ids_[out.picked_ids_], torch.arange(out.pts_.shape[0], device=DEV))
+    assert torch.equal(out.pts_, pts[out.picked_ids_])
+    # neighbourhoods on the fused clouds: CSR and transposed CSR equal the per-object ops
+    for nb in {id(n): n for n in neighs_f}.values():
+        ref = BQNeighborhood(nb.pc_src_, nb.samples_, nb.radius_)
+        assert torch.equal(ref.start_ids_, nb.start_ids_)
+        assert torch.equal(ref.neighbors_, nb.neighbors_)
+        g_ref = ref.conv_geometry(nb.pc_src_, nb.samples_)
+        g = list(nb.conv_geometry_cache_.values())[0]
+        e = g.n_edges
+        assert e == g_ref.n_edges
+        for k in ("col_src", "t_edge", "t_dst"):
+            assert torch.equal(getattr(g_ref, k)[:e], getattr(g, k)[:e]), k
+        assert torch.equal(g_ref.t_row_ends[:g.n_in], g.t_row_ends[:g.n_in])
+        assert torch.equal(g_ref.rec_in, g.rec_in) and torch.equal(g_ref.rec_out, g.rec_out)
+
+
+def wl_grid_of(pcs, lvl, step):
+    """Grid of level `lvl` -> `lvl + 1` rebuilt with the per-object API (for comparison)."""
+    from se3conv3d_b200 import workloads as wl
+    from se3conv3d_b200.pc import Grid
+    return Grid(pcs[lvl], wl.DFAUST_CFG["grid_subsamples"][lvl])

@@ -1,4 +1,3 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python tools/dfaust_layer_run.py seg_head 6 1; python tools/dfaust_layer_run.py enc1_block0 6 1; python tools/dfaust_layer_run.py dec2 6 1
-python tools/dfaust_layer_run.py seg_head 4 1 > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_seghead_v9.csv python tools/dfaust_layer_run.py seg_head 4 1 > gpurun_out/ncu_l.log 2>&1
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_v9.log 2>&1; tail -c 1800 gpurun_out/bench_v9.log
+python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+python tools/profile_hierarchy.py > gpurun_out/host_prof.log 2>&1; head -3 gpurun_out/host_prof.log
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_v10.log 2>&1; tail -c 1500 gpurun_out/bench_v10.log

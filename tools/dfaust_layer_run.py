@@ -35,5 +35,5 @@ for it in range(iters):
     ev[2].record()
     torch.cuda.synchronize()
     step.zero_grad()
-print("%s: M=%d E=%d %d->%d  fwd %.3f ms  bwd %.3f ms" % (name, pcs[lo].pts_.shape[0], nb.neighbors_.shape[0], cin, cout,
+print("%s: M=%d E=%d %d->%d  fwd %.3f ms  bwd %.3f ms" % (name, pcs[lo].pts_.shape[0], nb.conv_geometry(pcs[li], pcs[lo]).n_edges, cin, cout,
                                                       ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])))
