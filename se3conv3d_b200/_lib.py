@@ -154,7 +154,12 @@ def ptr(t):
 
 
 def stream():
-    return torch.cuda.current_stream().cuda_stream
+    """Raw handle of torch's current CUDA stream (the private fast accessor when available: the public
+    torch.cuda.current_stream() builds a Stream object per call, ~10 us on the hot path)."""
+    try:
+        return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
+    except AttributeError:
+        return torch.cuda.current_stream().cuda_stream
 
 
 def grid_setup(pts, batch_ids, n_batches, cell, max_pad):

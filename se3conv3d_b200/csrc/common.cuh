@@ -35,6 +35,17 @@ inline cudaStream_t as_stream(se3_stream_t s) { return reinterpret_cast<cudaStre
     SE3_CUDA(cudaGetLastError());             \
   } while (0)
 
+// Opt a kernel instantiation into its dynamic shared-memory size once per process (the attribute call costs
+// several microseconds; `kern` must name ONE instantiation at the call site, the flag is per call site).
+#define SE3_SMEM_ONCE(kern, bytes)                                                                       \
+  do {                                                                                                   \
+    static size_t _se3_smem_set = 0;                                                                     \
+    if ((size_t)(bytes) > _se3_smem_set) {                                                               \
+      SE3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));   \
+      _se3_smem_set = (size_t)(bytes);                                                                   \
+    }                                                                                                    \
+  } while (0)
+
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 // Bump allocator over a caller-provided workspace.

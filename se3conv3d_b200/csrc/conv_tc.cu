@@ -451,11 +451,11 @@ static int launch_agg_cfg(const TcAggArgs& a, int64_t n_g, cudaStream_t st) {
   if (blocks < 1) blocks = 1;
   if (a.act == 2) {
     auto kern = k_agg_tc<CB, FR, TR, 2>;
-    SE3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SE3_SMEM_ONCE(kern, smem);
     kern<<<(int)blocks, AGG_WARPS * 32, smem, st>>>(a, ncb);
   } else {
     auto kern = k_agg_tc<CB, FR, TR, -1>;
-    SE3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SE3_SMEM_ONCE(kern, smem);
     kern<<<(int)blocks, AGG_WARPS * 32, smem, st>>>(a, ncb);
   }
   SE3_LAUNCH_CHECK();
@@ -796,11 +796,11 @@ static int launch_edge_cfg(const TcEdgeArgs& a, int f_out, int n_warps, cudaStre
   const size_t smem = AGG_WARPS * EdgeSmem<CB>::WARP_BYTES;
   if (a.act == 2) {
     auto kern = k_edge_tc<CB, 2>;
-    SE3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SE3_SMEM_ONCE(kern, smem);
     kern<<<n_warps / AGG_WARPS, AGG_WARPS * 32, smem, st>>>(a, f_out);
   } else {
     auto kern = k_edge_tc<CB, -1>;
-    SE3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SE3_SMEM_ONCE(kern, smem);
     kern<<<n_warps / AGG_WARPS, AGG_WARPS * 32, smem, st>>>(a, f_out);
   }
   SE3_LAUNCH_CHECK();
@@ -964,7 +964,7 @@ static int launch_gemm_cfg(int64_t m, int64_t n, int64_t k, float alpha, const _
   if (splits < 1) splits = 1;
   dim3 grid((unsigned)((n + BN - 1) / BN), (unsigned)((m + BM - 1) / BM), (unsigned)splits);
   auto kern = k_gemm_bf16<AK, BK_, OB>;
-  SE3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SE3_SMEM_ONCE(kern, smem);
   if (splits > 1) {
     kern<<<grid, 256, smem, st>>>((int)m, (int)n, (int)k, alpha, a, lda, b, ldb, partials, n, kchunk, m * n);
     SE3_LAUNCH_CHECK();
@@ -1014,10 +1014,23 @@ __global__ void k_transpose_w_bf16(const float* __restrict__ w, int64_t ck, int 
 }
 
 __global__ void k_f32_to_bf16(const float* __restrict__ in, int64_t n, __nv_bfloat16* __restrict__ out) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = __float2bfloat16(in[i]);
+  const int64_t n8 = n >> 3;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if ((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += stride) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(in) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(in) + 2 * i + 1);
+      uint4 p;
+      p.x = pack_bf16(a.x, a.y); p.y = pack_bf16(a.z, a.w); p.z = pack_bf16(b.x, b.y); p.w = pack_bf16(b.z, b.w);
+      reinterpret_cast<uint4*>(out)[i] = p;
+    }
+    for (int64_t i = (n8 << 3) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride)
+      out[i] = __float2bfloat16(in[i]);
+  } else {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) out[i] = __float2bfloat16(in[i]);
+  }
 }
 // out[r][0..cs) = bf16(in[r][0..c)), zero padded: the gathered feature rows of the tensor-core kernels
+// (cs = c when c % 8 == 0, handled by the vectorised plain conversion)
 __global__ void k_rows_to_bf16(const float* __restrict__ in, int64_t rows, int c, int cs, __nv_bfloat16* __restrict__ out) {
   const int64_t total = rows * cs;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1035,6 +1048,22 @@ __global__ void k_permute_w_bf16(const float* __restrict__ w, int c_in, int k, i
     const int o = (int)(co % c_out);
     const int64_t c = co / c_out;
     wp[tix] = __float2bfloat16(w[(c * k + kk) * c_out + o]);
+  }
+}
+
+// the three bf16 operand layouts of conv_weights_ [c_in][k][c_out] in one pass:
+//   wt[o][(c,k)] (forward projection), wb[(c,k)][o] (dT = dy . W^T), wp[c][(o,k)] (dx = U . Wp^T)
+__global__ void k_prep_weights(const float* __restrict__ w, int c_in, int k, int c_out, __nv_bfloat16* __restrict__ wt,
+                               __nv_bfloat16* __restrict__ wb, __nv_bfloat16* __restrict__ wp) {
+  const int64_t ck = (int64_t)c_in * k, total = ck * c_out;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / c_out;            // (c,k)
+    const int o = (int)(i - r * c_out);
+    const int c = (int)(r / k), kk = (int)(r - (int64_t)c * k);
+    const __nv_bfloat16 v = __float2bfloat16(w[i]);
+    wb[i] = v;
+    wt[(int64_t)o * ck + r] = v;
+    wp[((int64_t)c * c_out + o) * k + kk] = v;
   }
 }
 
@@ -1076,17 +1105,29 @@ static int check_tc(const se3_conv_desc* d) {
 
 static inline int pad8(int c) { return (c + 7) & ~7; }
 
-size_t conv_tc_saved_bytes(const se3_conv_desc* d) {
-  return align_up((size_t)d->n_out * d->f_out * d->c_in * d->k * 2) +        // T in bf16
-         align_up((size_t)d->n_in * d->f_in * pad8(d->c_in) * 2) + 256;       // x in bf16 (gather rows)
+// saved-for-backward buffer of precision 1: [T bf16][x bf16 rows][Wt][Wb][Wp]
+struct TcSaved {
+  __nv_bfloat16 *T, *xb, *Wt, *Wb, *Wp;
+  size_t bytes;
+};
+static TcSaved tc_saved_layout(const se3_conv_desc* d, void* base) {
+  const size_t wbytes = align_up((size_t)d->c_in * d->k * d->c_out * 2);
+  char* p = reinterpret_cast<char*>(base);
+  size_t off = 0;
+  TcSaved s;
+  s.T = reinterpret_cast<__nv_bfloat16*>(p + off); off += align_up((size_t)d->n_out * d->f_out * d->c_in * d->k * 2);
+  s.xb = reinterpret_cast<__nv_bfloat16*>(p + off); off += align_up((size_t)d->n_in * d->f_in * pad8(d->c_in) * 2);
+  s.Wt = reinterpret_cast<__nv_bfloat16*>(p + off); off += wbytes;
+  s.Wb = reinterpret_cast<__nv_bfloat16*>(p + off); off += wbytes;
+  s.Wp = reinterpret_cast<__nv_bfloat16*>(p + off); off += wbytes;
+  s.bytes = off + 256;
+  return s;
 }
-size_t conv_tc_fwd_workspace_bytes(const se3_conv_desc* d) {
-  return align_up((size_t)d->c_in * d->k * d->c_out * 2) + 256;  // W in bf16
-}
+size_t conv_tc_saved_bytes(const se3_conv_desc* d) { return tc_saved_layout(d, nullptr).bytes; }
+size_t conv_tc_fwd_workspace_bytes(const se3_conv_desc*) { return 256; }
 size_t conv_tc_bwd_workspace_bytes(const se3_conv_desc* d) {
   const int64_t R = d->n_out * d->f_out, ck = (int64_t)d->c_in * d->k, Nf = d->n_in * d->f_in;
   size_t b = 0;
-  b += align_up((size_t)ck * d->c_out * 2) * 2;                                   // Wb, Wpb
   b += align_up((size_t)R * d->c_out * 2);                                        // dy bf16
   b += align_up((size_t)R * ck * 2);                                              // dT bf16
   b += align_up((size_t)Nf * d->c_out * d->k * 2);                                // U bf16
@@ -1097,30 +1138,30 @@ size_t conv_tc_bwd_workspace_bytes(const se3_conv_desc* d) {
 
 int conv_tc_fwd(const se3_conv_desc* d, const float* x, float* y, void* saved, void* ws, size_t ws_bytes,
                 cudaStream_t st) {
+  (void)ws; (void)ws_bytes;
   if (int rc = check_tc(d)) return rc;
-  SE3_CHECK_ARG(saved && ws, "precision 1 needs the saved buffer and a workspace");
+  SE3_CHECK_ARG(saved, "precision 1 needs the saved buffer");
   const int64_t R = d->n_out * d->f_out, ck = (int64_t)d->c_in * d->k;
-  Arena ar(ws, ws_bytes);
-  __nv_bfloat16* Wb = ar.take<__nv_bfloat16>(ck * d->c_out);
-  if (!ar.ok()) { set_error("conv_tc_fwd: workspace too small"); return SE3_EWORKSPACE; }
-  __nv_bfloat16* T = reinterpret_cast<__nv_bfloat16*>(saved);
+  const TcSaved sv = tc_saved_layout(d, saved);
   const int cs = pad8(d->c_in);
   const int64_t Nf = d->n_in * d->f_in;
-  __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(saved) + align_up((size_t)R * ck * 2));
-  k_transpose_w_bf16<<<blocks_for(ck * d->c_out), 256, 0, st>>>(d->conv_weights, ck, d->c_out, Wb);
+  k_prep_weights<<<blocks_for(ck * d->c_out), 256, 0, st>>>(d->conv_weights, d->c_in, d->k, d->c_out, sv.Wt, sv.Wb, sv.Wp);
   SE3_LAUNCH_CHECK();
   if (Nf > 0) {
-    k_rows_to_bf16<<<blocks_for(Nf * cs), 256, 0, st>>>(x, Nf, d->c_in, cs, xb);
+    if (cs == d->c_in)
+      k_f32_to_bf16<<<blocks_for(Nf * cs / 8), 256, 0, st>>>(x, Nf * cs, sv.xb);
+    else
+      k_rows_to_bf16<<<blocks_for(Nf * cs), 256, 0, st>>>(x, Nf, d->c_in, cs, sv.xb);
     SE3_LAUNCH_CHECK();
   }
   TcAggArgs a;
   a.row_ends = d->row_ends; a.nbr = d->col_src;
   a.rec_row = d->rec_out; a.rec_g = d->rec_in; a.f_g = d->f_in;
-  a.feat = xb; a.c = d->c_in; a.cs = cs; a.w9 = d->proj_axes; a.bias = d->proj_biases; a.norm = d->norm_neigh_dist;
-  a.act = d->act; a.out = T; a.n_rows = d->n_out;
+  a.feat = sv.xb; a.c = d->c_in; a.cs = cs; a.w9 = d->proj_axes; a.bias = d->proj_biases; a.norm = d->norm_neigh_dist;
+  a.act = d->act; a.out = sv.T; a.n_rows = d->n_out;
   if (int rc = launch_agg_tc<false>(a, d->f_out, d->n_in, st)) return rc;
   // y[r,o] = s * sum_(c,k) T[r,(c,k)] Wt[o,(c,k)]   (tcgen05 / TMEM)
-  return gemm_tn(R, d->c_out, ck, d->out_scale, T, ck, Wb, ck, y, d->c_out, false, 0, st);
+  return gemm_tn(R, d->c_out, ck, d->out_scale, sv.T, ck, sv.Wt, ck, y, d->c_out, false, 0, st);
 }
 
 int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const void* saved, float* dx, float* dW,
@@ -1131,8 +1172,6 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
   const int64_t R = d->n_out * d->f_out, ck = (int64_t)d->c_in * d->k, Nf = d->n_in * d->f_in;
   const int64_t ok = (int64_t)d->c_out * d->k;
   Arena ar(ws, ws_bytes);
-  __nv_bfloat16* Wb = ar.take<__nv_bfloat16>(ck * d->c_out);
-  __nv_bfloat16* Wpb = ar.take<__nv_bfloat16>(ck * d->c_out);
   __nv_bfloat16* dyb = ar.take<__nv_bfloat16>(R * d->c_out);
   __nv_bfloat16* dTb = ar.take<__nv_bfloat16>(R * ck);
   __nv_bfloat16* U = ar.take<__nv_bfloat16>(Nf * ok);
@@ -1141,10 +1180,9 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
   const int n_warps = edge_tc_warps(d->n_out * d->f_out);
   float* eg = ar.take<float>((size_t)n_warps * 512);
   if (!ar.ok()) { set_error("conv_tc_bwd: workspace too small"); return SE3_EWORKSPACE; }
-  const __nv_bfloat16* T = reinterpret_cast<const __nv_bfloat16*>(saved);
-  const __nv_bfloat16* xb =
-      reinterpret_cast<const __nv_bfloat16*>(reinterpret_cast<const char*>(saved) + align_up((size_t)R * ck * 2));
-  k_f32_to_bf16<<<blocks_for(R * d->c_out), 256, 0, st>>>(dy, R * d->c_out, dyb);
+  const TcSaved sv = tc_saved_layout(d, const_cast<void*>(saved));
+  const __nv_bfloat16 *T = sv.T, *xb = sv.xb, *Wb = sv.Wb, *Wpb = sv.Wp;
+  k_f32_to_bf16<<<blocks_for(R * d->c_out / 8), 256, 0, st>>>(dy, R * d->c_out, dyb);
   SE3_LAUNCH_CHECK();
   if (dW) {
     // dW[(c,k), o] = s * sum_r T[r,(c,k)] dy[r,o]
@@ -1153,8 +1191,6 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
       return rc;
   }
   if (dA || dB) {
-    k_f32_to_bf16<<<blocks_for(ck * d->c_out), 256, 0, st>>>(d->conv_weights, ck * d->c_out, Wb);
-    SE3_LAUNCH_CHECK();
     // dT[r,(c,k)] = s * sum_o dy[r,o] W[(c,k),o]
     if (int rc = gemm_tn(R, ck, d->c_out, d->out_scale, dyb, d->c_out, Wb, d->c_out, dTb, ck, true, 0, st)) return rc;
     TcEdgeArgs g;
@@ -1171,8 +1207,6 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
     a.feat = dyb; a.c = d->c_out; a.cs = d->c_out; a.w9 = d->proj_axes; a.bias = d->proj_biases; a.norm = d->norm_neigh_dist;
     a.act = d->act; a.out = U; a.n_rows = d->n_in;
     if (int rc = launch_agg_tc<true>(a, d->f_in, d->n_out, st)) return rc;
-    k_permute_w_bf16<<<blocks_for(ck * d->c_out), 256, 0, st>>>(d->conv_weights, d->c_in, d->k, d->c_out, Wpb);
-    SE3_LAUNCH_CHECK();
     // dx[n,c] = s * sum_(o,k) U[n,(o,k)] Wp[c,(o,k)]
     if (int rc = gemm_tn(Nf, d->c_in, ok, d->out_scale, U, ok, Wpb, ok, dx, d->c_in, false, 0, st)) return rc;
   }

@@ -90,6 +90,20 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 consecutive accumulator columns of this thread's TMEM lane (no wait: pair with tmem_ld_wait)
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 template <int BN, bool OUT_BF16>
 __global__ void __launch_bounds__(128) k_gemm_tcgen05(int M, int N, int K, float alpha, const __nv_bfloat16* __restrict__ A,
                                                       int64_t lda, const __nv_bfloat16* __restrict__ B, int64_t ldb,
@@ -177,6 +191,40 @@ __global__ void __launch_bounds__(128) k_gemm_tcgen05(int M, int N, int K, float
   mbar_wait(smem_u32(&bars[STAGES]), 0u);
   tc_fence_after();
   const int row = bm + warp * 32 + lane;
+  if (OUT_BF16 && BN >= 64) {
+    // bf16 output, wide tiles: 64 columns at a time through a warp-private, XOR-swizzled staging tile in the
+    // (now idle) operand ring, so that every global store instruction writes four full 128-byte lines
+    // instead of 32 scattered 16-byte pieces.
+    unsigned char* stage = smem_dyn + (ring - raw) + warp * 4096;  // [32 rows][128 B]
+    __nv_bfloat16* Cb = reinterpret_cast<__nv_bfloat16*>(Cout);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 64) {
+      uint32_t r0[32], r1[32];
+      tmem_ld32_nowait(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r0);
+      tmem_ld32_nowait(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c0 + 32), r1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const uint32_t* src = ch < 4 ? r0 + ch * 8 : r1 + (ch - 4) * 8;
+        uint4 p;
+        p.x = pack_bf16(alpha * __uint_as_float(src[0]), alpha * __uint_as_float(src[1]));
+        p.y = pack_bf16(alpha * __uint_as_float(src[2]), alpha * __uint_as_float(src[3]));
+        p.z = pack_bf16(alpha * __uint_as_float(src[4]), alpha * __uint_as_float(src[5]));
+        p.w = pack_bf16(alpha * __uint_as_float(src[6]), alpha * __uint_as_float(src[7]));
+        *reinterpret_cast<uint4*>(stage + lane * 128 + ((ch ^ (lane & 7)) << 4)) = p;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3), ch = lane & 7;
+        const int grow = bm + warp * 32 + r, gcol = bn + c0 + ch * 8;
+        if (grow < M && gcol < N)
+          *reinterpret_cast<uint4*>(Cb + (int64_t)grow * ldc + gcol) =
+              *reinterpret_cast<const uint4*>(stage + r * 128 + ((ch ^ (r & 7)) << 4));
+      }
+      __syncwarp();
+    }
+  } else
 #pragma unroll
   for (int c0 = 0; c0 < BN; c0 += 8) {
     float v[8];
@@ -222,7 +270,7 @@ int launch_cfg(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16
                int64_t ldb, void* c, int64_t ldc, cudaStream_t st) {
   const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BN * 128) + 1024;
   auto kern = k_gemm_tcgen05<BN, OB>;
-  SE3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SE3_SMEM_ONCE(kern, smem);
   dim3 grid((unsigned)((n + BN - 1) / BN), (unsigned)((m + BM - 1) / BM), 1);
   kern<<<grid, 128, smem, st>>>((int)m, (int)n, (int)k, alpha, a, lda, b, ldb, c, ldc);
   SE3_LAUNCH_CHECK();

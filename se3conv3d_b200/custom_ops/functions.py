@@ -76,19 +76,35 @@ class ComputeKeys(torch.autograd.Function):
 
 def make_conv_desc(geom, c_in, c_out, k, act, precision, norm_neigh_dist, out_scale, proj_axes, proj_biases,
                    conv_weights):
-    """Fills a `se3_conv_desc` from a neighbourhood geometry record (see pc/ConvGeometry)."""
-    d = ConvDesc()
-    d.n_in, d.n_out, d.n_edges = geom.n_in, geom.n_out, geom.n_edges
-    d.f_in, d.f_out, d.c_in, d.c_out, d.k = geom.f_in, geom.f_out, int(c_in), int(c_out), int(k)
-    d.act, d.precision, d.reserved = int(act), int(precision), 0
+    """`se3_conv_desc` of one conv call.  The geometry half (sizes, CSR, records) and the byte counts that
+    depend on it are cached on the neighbourhood geometry record per (channels, activation, precision);
+    a call only refreshes the parameter pointers and the two scalars."""
+    key = (int(c_in), int(c_out), int(k), int(act), int(precision))
+    cache = geom.__dict__.setdefault("_desc_cache", {})
+    entry = cache.get(key)
+    if entry is None:
+        d = ConvDesc()
+        d.n_in, d.n_out, d.n_edges = geom.n_in, geom.n_out, geom.n_edges
+        d.f_in, d.f_out, d.c_in, d.c_out, d.k = geom.f_in, geom.f_out, key[0], key[1], key[2]
+        d.act, d.precision, d.reserved = key[3], key[4], 0
+        d.pts_in, d.pts_out = ptr(geom.pts_in), ptr(geom.pts_out)
+        d.frames_in, d.frames_out = ptr(geom.frames_in), ptr(geom.frames_out)
+        d.row_ends, d.col_src = ptr(geom.row_ends), ptr(geom.col_src)
+        d.t_row_ends, d.t_edge, d.t_dst = ptr(geom.t_row_ends), ptr(geom.t_edge), ptr(geom.t_dst)
+        d.rec_in, d.rec_out = ptr(geom.rec_in), ptr(geom.rec_out)
+        L = lib()
+        ref = C.byref(d)
+        entry = (d, ref, int(L.se3_conv_saved_bytes(ref)), int(L.se3_conv_fwd_workspace_bytes(ref)),
+                 int(L.se3_conv_bwd_workspace_bytes(ref)))
+        cache[key] = entry
+    d = entry[0]
     d.norm_neigh_dist, d.out_scale = float(norm_neigh_dist), float(out_scale)
-    d.pts_in, d.pts_out = ptr(geom.pts_in), ptr(geom.pts_out)
-    d.frames_in, d.frames_out = ptr(geom.frames_in), ptr(geom.frames_out)
-    d.row_ends, d.col_src = ptr(geom.row_ends), ptr(geom.col_src)
-    d.t_row_ends, d.t_edge, d.t_dst = ptr(geom.t_row_ends), ptr(geom.t_edge), ptr(geom.t_dst)
-    d.rec_in, d.rec_out = ptr(geom.rec_in), ptr(geom.rec_out)
     d.proj_axes, d.proj_biases, d.conv_weights = ptr(proj_axes), ptr(proj_biases), ptr(conv_weights)
-    return d
+    return entry
+
+
+def _f32c(t):
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous()
 
 
 class RotEquivConv(torch.autograd.Function):
@@ -99,10 +115,8 @@ class RotEquivConv(torch.autograd.Function):
     def forward(ctx, x, proj_axes, proj_biases, conv_weights, geom, act, precision, norm_neigh_dist, out_scale):
         if not x.is_cuda:
             raise Se3Error("RotEquivConv needs CUDA tensors; there is no CPU fallback")
-        x32 = x.to(torch.float32).contiguous()
-        pa = proj_axes.detach().to(torch.float32).contiguous()
-        pb = proj_biases.detach().to(torch.float32).contiguous()
-        cw = conv_weights.detach().to(torch.float32).contiguous()
+        x32 = _f32c(x)
+        pa, pb, cw = _f32c(proj_axes.detach()), _f32c(proj_biases.detach()), _f32c(conv_weights.detach())
         c_in, k, c_out = cw.shape
         if x32.shape[0] != geom.n_in * geom.f_in or x32.shape[1] != c_in:
             raise Se3Error("RotEquivConv: features must be [N*F_in, C_in] = [%d, %d], got %s" %
@@ -110,15 +124,16 @@ class RotEquivConv(torch.autograd.Function):
         if pa.shape[0] != 9:
             raise Se3Error("RotEquivConv: proj_axes_ must be [9, K] (p_dims=9, '6D' relative rotation)")
         L = lib()
-        d = make_conv_desc(geom, c_in, c_out, k, act, precision, norm_neigh_dist, out_scale, pa, pb, cw)
+        d, dref, saved_bytes, fwd_ws, _ = make_conv_desc(geom, c_in, c_out, k, act, precision, norm_neigh_dist, out_scale,
+                                                        pa, pb, cw)
         y = torch.empty((geom.n_out * geom.f_out, c_out), dtype=torch.float32, device=x.device)
-        saved_bytes = L.se3_conv_saved_bytes(C.byref(d))
-        saved = workspace(saved_bytes, x.device) if saved_bytes else None
-        ws = workspace(L.se3_conv_fwd_workspace_bytes(C.byref(d)), x.device, 'conv')
-        check(L.se3_conv_fwd(C.byref(d), ptr(x32), ptr(y), ptr(saved), ptr(ws), ws.numel(), stream()), "se3_conv_fwd")
+        saved = torch.empty(max(saved_bytes, 256), dtype=torch.uint8, device=x.device)
+        ws = workspace(fwd_ws, x.device, 'conv')
+        check(L.se3_conv_fwd(dref, x32.data_ptr(), y.data_ptr(), saved.data_ptr(), ws.data_ptr(), ws.numel(), stream()),
+              "se3_conv_fwd")
         ctx.geom = geom
         ctx.meta = (act, precision, float(norm_neigh_dist), float(out_scale), x.dtype)
-        ctx.save_for_backward(x32, pa, pb, cw, saved if saved is not None else x32.new_empty(0))
+        ctx.save_for_backward(x32, pa, pb, cw, saved)
         return y
 
     @staticmethod
@@ -127,16 +142,16 @@ class RotEquivConv(torch.autograd.Function):
         act, precision, nnd, osc, x_dtype = ctx.meta
         geom = ctx.geom
         c_in, k, c_out = cw.shape
-        dy = dy.to(torch.float32).contiguous()
+        dy = _f32c(dy)
         L = lib()
-        d = make_conv_desc(geom, c_in, c_out, k, act, precision, nnd, osc, pa, pb, cw)
+        d, dref, _, _, bwd_ws = make_conv_desc(geom, c_in, c_out, k, act, precision, nnd, osc, pa, pb, cw)
         need = ctx.needs_input_grad
         dx = torch.empty_like(x32) if need[0] else None
         dA = torch.empty_like(pa) if (need[1] or need[2]) else None
         dB = torch.empty_like(pb) if (need[1] or need[2]) else None
         dW = torch.empty_like(cw) if need[3] else None
-        ws = workspace(L.se3_conv_bwd_workspace_bytes(C.byref(d)), x32.device, 'conv')
-        check(L.se3_conv_bwd(C.byref(d), ptr(x32), ptr(dy), ptr(saved) if saved.numel() else None, ptr(dx), ptr(dW),
-                             ptr(dA), ptr(dB), ptr(ws), ws.numel(), stream()), "se3_conv_bwd")
+        ws = workspace(bwd_ws, x32.device, 'conv')
+        check(L.se3_conv_bwd(dref, x32.data_ptr(), dy.data_ptr(), saved.data_ptr(), ptr(dx), ptr(dW), ptr(dA), ptr(dB),
+                             ws.data_ptr(), ws.numel(), stream()), "se3_conv_bwd")
         return (dx.to(x_dtype) if dx is not None else None, dA if need[1] else None, dB if need[2] else None, dW,
                 None, None, None, None, None)

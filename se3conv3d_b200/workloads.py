@@ -153,15 +153,14 @@ class DfaustStep(object):
         return xs, dys
 
     def conv_fwd_bwd(self, pcs, neighs, xs=None, dys=None):
+        """Forward of the 21 convolutions, then ONE backward pass over all of them (as a training step does:
+        every forward first, a single autograd sweep after), returns the checksum of the outputs."""
         if xs is None:
             xs, dys = self.inputs
-        checksum = None
-        for layer, nb, (_, li, lo, _, _, _), x, dy in zip(self.layers, neighs, self.specs, xs, dys):
-            y = layer(pcs[li], pcs[lo], x, nb)
-            y.backward(dy)
-            s = y.detach().sum()
-            checksum = s if checksum is None else checksum + s
-        return checksum
+        ys = [layer(pcs[li], pcs[lo], x, nb)
+              for layer, nb, (_, li, lo, _, _, _), x in zip(self.layers, neighs, self.specs, xs)]
+        torch.autograd.backward(ys, list(dys))
+        return torch.stack([y.detach().sum() for y in ys]).sum()
 
     def zero_grad(self):
         for layer in self.layers:

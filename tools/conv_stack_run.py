@@ -12,7 +12,7 @@ precision = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 dev = torch.device("cuda:0")
 pts, b = wl.synthetic_bodies(32, 6890, 0)
 step = wl.DfaustStep(dev, precision=precision)
-pcs, neighs = step.build_hierarchy(pts.to(dev), b.to(dev))
+pcs, neighs = step.build_hierarchy(pts.to(dev), b.to(dev), n_batches=32)
 step.calibrate(pcs, neighs)
 step.make_inputs(pcs)
 torch.cuda.synchronize()
