@@ -24,8 +24,10 @@ namespace se3 {
 void splitk_reduce_launch(const float* partials, int splits, int64_t mn, float alpha, float* c, cudaStream_t st);
 // proj_tcgen05.cu
 bool tcgen05_gemm_supported(int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb);
+int tcgen05_gemm_splits(int64_t m, int64_t n, int64_t k);
 int launch_gemm_tcgen05(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16* a, int64_t lda,
-                        const __nv_bfloat16* b, int64_t ldb, void* c, int64_t ldc, bool out_bf16, cudaStream_t st);
+                        const __nv_bfloat16* b, int64_t ldb, void* c, int64_t ldc, bool out_bf16, int splits,
+                        float* partials, cudaStream_t st);
 
 struct TcAggArgs {
   const int* row_ends;
@@ -988,15 +990,24 @@ static int gemm_impl_env() {
   return v;
 }
 
+// bytes of split-K partials gemm_tn may use for an fp32-output product of this shape
+size_t gemm_tn_partial_bytes(int64_t m, int64_t n, int64_t k) {
+  const int s = tcgen05_gemm_splits(m, n, k);
+  return s > 1 ? align_up((size_t)s * m * n * 4) : 0;
+}
+
 int gemm_tn(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16* a, int64_t lda, const __nv_bfloat16* b,
-            int64_t ldb, void* c, int64_t ldc, bool out_bf16, int impl, cudaStream_t st) {
+            int64_t ldb, void* c, int64_t ldc, bool out_bf16, int impl, cudaStream_t st, float* partials = nullptr) {
   if (impl == 0) impl = gemm_impl_env();
   const bool can = tcgen05_gemm_supported(m, n, k, lda, ldb);
   if (impl == 2 && !can) {
     set_error("gemm_tn: shape not supported by the tcgen05 kernel");
     return SE3_EINVAL;
   }
-  if (impl != 1 && can) return launch_gemm_tcgen05(m, n, k, alpha, a, lda, b, ldb, c, ldc, out_bf16, st);
+  if (impl != 1 && can) {
+    const int splits = (partials && !out_bf16) ? tcgen05_gemm_splits(m, n, k) : 1;
+    return launch_gemm_tcgen05(m, n, k, alpha, a, lda, b, ldb, c, ldc, out_bf16, splits, partials, st);
+  }
   if (out_bf16) return launch_gemm_cfg<true, true, true>(m, n, k, alpha, a, lda, b, ldb, c, ldc, 1, nullptr, st);
   return launch_gemm_cfg<true, true, false>(m, n, k, alpha, a, lda, b, ldb, c, ldc, 1, nullptr, st);
 }
@@ -1124,7 +1135,9 @@ static TcSaved tc_saved_layout(const se3_conv_desc* d, void* base) {
   return s;
 }
 size_t conv_tc_saved_bytes(const se3_conv_desc* d) { return tc_saved_layout(d, nullptr).bytes; }
-size_t conv_tc_fwd_workspace_bytes(const se3_conv_desc*) { return 256; }
+size_t conv_tc_fwd_workspace_bytes(const se3_conv_desc* d) {
+  return gemm_tn_partial_bytes(d->n_out * d->f_out, d->c_out, (int64_t)d->c_in * d->k) + 256;
+}
 size_t conv_tc_bwd_workspace_bytes(const se3_conv_desc* d) {
   const int64_t R = d->n_out * d->f_out, ck = (int64_t)d->c_in * d->k, Nf = d->n_in * d->f_in;
   size_t b = 0;
@@ -1133,15 +1146,21 @@ size_t conv_tc_bwd_workspace_bytes(const se3_conv_desc* d) {
   b += align_up((size_t)Nf * d->c_out * d->k * 2);                                // U bf16
   b += align_up((size_t)splits_for_tc(ck, d->c_out, R) * ck * d->c_out * 4);      // dW partials
   b += align_up((size_t)edge_tc_warps(d->n_out * d->f_out) * 512 * 4);                       // basis-gradient partials
+  b += gemm_tn_partial_bytes(Nf, d->c_in, (int64_t)d->c_out * d->k);                         // dx split-K partials
   return b + 256;
 }
 
 int conv_tc_fwd(const se3_conv_desc* d, const float* x, float* y, void* saved, void* ws, size_t ws_bytes,
                 cudaStream_t st) {
-  (void)ws; (void)ws_bytes;
   if (int rc = check_tc(d)) return rc;
   SE3_CHECK_ARG(saved, "precision 1 needs the saved buffer");
   const int64_t R = d->n_out * d->f_out, ck = (int64_t)d->c_in * d->k;
+  const size_t pbytes = gemm_tn_partial_bytes(R, d->c_out, ck);
+  if (pbytes && (!ws || ws_bytes < pbytes)) {
+    set_error("conv_tc_fwd: workspace too small");
+    return SE3_EWORKSPACE;
+  }
+  float* partials = pbytes ? reinterpret_cast<float*>(ws) : nullptr;
   const TcSaved sv = tc_saved_layout(d, saved);
   const int cs = pad8(d->c_in);
   const int64_t Nf = d->n_in * d->f_in;
@@ -1161,7 +1180,7 @@ int conv_tc_fwd(const se3_conv_desc* d, const float* x, float* y, void* saved, v
   a.act = d->act; a.out = sv.T; a.n_rows = d->n_out;
   if (int rc = launch_agg_tc<false>(a, d->f_out, d->n_in, st)) return rc;
   // y[r,o] = s * sum_(c,k) T[r,(c,k)] Wt[o,(c,k)]   (tcgen05 / TMEM)
-  return gemm_tn(R, d->c_out, ck, d->out_scale, sv.T, ck, sv.Wt, ck, y, d->c_out, false, 0, st);
+  return gemm_tn(R, d->c_out, ck, d->out_scale, sv.T, ck, sv.Wt, ck, y, d->c_out, false, 0, st, partials);
 }
 
 int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const void* saved, float* dx, float* dW,
@@ -1179,6 +1198,8 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
   float* dWp = ar.take<float>((size_t)splits * ck * d->c_out);
   const int n_warps = edge_tc_warps(d->n_out * d->f_out);
   float* eg = ar.take<float>((size_t)n_warps * 512);
+  const size_t dx_pbytes = gemm_tn_partial_bytes(Nf, d->c_in, ok);
+  float* dx_partials = dx_pbytes ? ar.take<float>(dx_pbytes / 4) : nullptr;
   if (!ar.ok()) { set_error("conv_tc_bwd: workspace too small"); return SE3_EWORKSPACE; }
   const TcSaved sv = tc_saved_layout(d, const_cast<void*>(saved));
   const __nv_bfloat16 *T = sv.T, *xb = sv.xb, *Wb = sv.Wb, *Wpb = sv.Wp;
@@ -1208,7 +1229,7 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
     a.act = d->act; a.out = U; a.n_rows = d->n_in;
     if (int rc = launch_agg_tc<true>(a, d->f_in, d->n_out, st)) return rc;
     // dx[n,c] = s * sum_(o,k) U[n,(o,k)] Wp[c,(o,k)]
-    if (int rc = gemm_tn(Nf, d->c_in, ok, d->out_scale, U, ok, Wpb, ok, dx, d->c_in, false, 0, st)) return rc;
+    if (int rc = gemm_tn(Nf, d->c_in, ok, d->out_scale, U, ok, Wpb, ok, dx, d->c_in, false, 0, st, dx_partials)) return rc;
   }
   return SE3_OK;
 }

@@ -22,6 +22,8 @@
 
 namespace se3 {
 
+void splitk_reduce_launch(const float* partials, int splits, int64_t mn, float alpha, float* c, cudaStream_t st);
+
 namespace {
 
 constexpr int BM = 128;
@@ -107,7 +109,8 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 template <int BN, bool OUT_BF16>
 __global__ void __launch_bounds__(128) k_gemm_tcgen05(int M, int N, int K, float alpha, const __nv_bfloat16* __restrict__ A,
                                                       int64_t lda, const __nv_bfloat16* __restrict__ B, int64_t ldb,
-                                                      void* __restrict__ Cout, int64_t ldc) {
+                                                      void* __restrict__ Cout, int64_t ldc, int kb_per_split,
+                                                      int64_t split_stride) {
   constexpr int B_STAGE_BYTES = BN * 128;
   constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   extern __shared__ unsigned char smem_dyn[];
@@ -119,7 +122,11 @@ __global__ void __launch_bounds__(128) k_gemm_tcgen05(int M, int N, int K, float
   const uint32_t ring = (raw + 1023u) & ~1023u;
   const uint32_t a_ring = ring, b_ring = ring + STAGES * A_STAGE_BYTES;
   const int bm = blockIdx.y * BM, bn = blockIdx.x * BN;
-  const int nkb = (K + BK - 1) / BK;
+  // split-K: blockIdx.z owns k-blocks [kb0, kb0 + nkb) and writes its partial tile to Cout + z * split_stride
+  const int nkb_all = (K + BK - 1) / BK;
+  const int kb0 = blockIdx.z * kb_per_split;
+  const int nkb = min(kb_per_split, nkb_all - kb0);
+  if (split_stride) Cout = reinterpret_cast<float*>(Cout) + (int64_t)blockIdx.z * split_stride;
 
   if (tid == 0) {
 #pragma unroll
@@ -164,7 +171,7 @@ __global__ void __launch_bounds__(128) k_gemm_tcgen05(int M, int N, int K, float
     if (it < nkb) {
       const int s = it % STAGES;
       if (it >= STAGES) mbar_wait(smem_u32(&bars[s]), (uint32_t)((it / STAGES - 1) & 1));  // slot consumed by the MMA
-      load_stage(s, it);
+      load_stage(s, kb0 + it);
     }
     cp_async_commit();
     const int c = it - (STAGES - 1);
@@ -267,13 +274,24 @@ __global__ void __launch_bounds__(128) k_gemm_tcgen05(int M, int N, int K, float
 
 template <int BN, bool OB>
 int launch_cfg(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16* a, int64_t lda, const __nv_bfloat16* b,
-               int64_t ldb, void* c, int64_t ldc, cudaStream_t st) {
+               int64_t ldb, void* c, int64_t ldc, int splits, float* partials, cudaStream_t st) {
   const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BN * 128) + 1024;
   auto kern = k_gemm_tcgen05<BN, OB>;
   SE3_SMEM_ONCE(kern, smem);
-  dim3 grid((unsigned)((n + BN - 1) / BN), (unsigned)((m + BM - 1) / BM), 1);
-  kern<<<grid, 128, smem, st>>>((int)m, (int)n, (int)k, alpha, a, lda, b, ldb, c, ldc);
-  SE3_LAUNCH_CHECK();
+  const int nkb = (int)((k + BK - 1) / BK);
+  if (OB || partials == nullptr || splits < 1) splits = 1;
+  int per = (nkb + splits - 1) / splits;
+  splits = (nkb + per - 1) / per;
+  dim3 grid((unsigned)((n + BN - 1) / BN), (unsigned)((m + BM - 1) / BM), (unsigned)splits);
+  if (splits > 1) {
+    kern<<<grid, 128, smem, st>>>((int)m, (int)n, (int)k, 1.0f, a, lda, b, ldb, partials, n, per, m * n);
+    SE3_LAUNCH_CHECK();
+    splitk_reduce_launch(partials, splits, m * n, alpha, reinterpret_cast<float*>(c), st);
+    SE3_LAUNCH_CHECK();
+  } else {
+    kern<<<grid, 128, smem, st>>>((int)m, (int)n, (int)k, alpha, a, lda, b, ldb, c, ldc, nkb, (int64_t)0);
+    SE3_LAUNCH_CHECK();
+  }
   return SE3_OK;
 }
 
@@ -283,9 +301,25 @@ bool tcgen05_gemm_supported(int64_t m, int64_t n, int64_t k, int64_t lda, int64_
   return m >= 1 && n >= 16 && (n % 16) == 0 && (k % 8) == 0 && (lda % 8) == 0 && (ldb % 8) == 0;
 }
 
-// C = alpha * A[M,K] . B[N,K]^T ; out_bf16 selects the output type
+// Split-K factor for a (fp32-output, ldc == n) product whose output tiles cannot fill the GPU: the k-blocks are
+// spread over enough CTAs for ~2 per SM, at least 4 k-blocks each.
+int tcgen05_gemm_splits(int64_t m, int64_t n, int64_t k) {
+  const int bn = n <= 16 ? 16 : (n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : 256)));
+  const int64_t tiles = ((m + BM - 1) / BM) * ((n + bn - 1) / bn);
+  const int64_t nkb = (k + BK - 1) / BK;
+  if (tiles >= num_sms() || nkb < 8) return 1;
+  int64_t s = (2 * (int64_t)num_sms() + tiles - 1) / tiles;
+  if (s > nkb / 4) s = nkb / 4;
+  if (s > 64) s = 64;
+  return s < 1 ? 1 : (int)s;
+}
+
+// C = alpha * A[M,K] . B[N,K]^T ; out_bf16 selects the output type.  splits > 1 (fp32 output with ldc == n only)
+// runs split-K through `partials` (splits * m * n floats) and an ordered reduction.
 int launch_gemm_tcgen05(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16* a, int64_t lda,
-                        const __nv_bfloat16* b, int64_t ldb, void* c, int64_t ldc, bool out_bf16, cudaStream_t st) {
+                        const __nv_bfloat16* b, int64_t ldb, void* c, int64_t ldc, bool out_bf16, int splits,
+                        float* partials, cudaStream_t st) {
+  if (ldc != n) splits = 1;
   if (!tcgen05_gemm_supported(m, n, k, lda, ldb)) {
     set_error("launch_gemm_tcgen05: unsupported shape m=%lld n=%lld k=%lld", (long long)m, (long long)n, (long long)k);
     return SE3_EINVAL;
@@ -294,8 +328,8 @@ int launch_gemm_tcgen05(int64_t m, int64_t n, int64_t k, float alpha, const __nv
   const int bn = n <= 16 ? 16 : (n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : 256)));
 #define SE3_TC_CASE(BN_)                                                                                           \
   case BN_:                                                                                                         \
-    return out_bf16 ? launch_cfg<BN_, true>(m, n, k, alpha, a, lda, b, ldb, c, ldc, st)                             \
-                    : launch_cfg<BN_, false>(m, n, k, alpha, a, lda, b, ldb, c, ldc, st);
+    return out_bf16 ? launch_cfg<BN_, true>(m, n, k, alpha, a, lda, b, ldb, c, ldc, 1, nullptr, st)                 \
+                    : launch_cfg<BN_, false>(m, n, k, alpha, a, lda, b, ldb, c, ldc, splits, partials, st);
   switch (bn) {
     SE3_TC_CASE(16)
     SE3_TC_CASE(32)

@@ -154,13 +154,13 @@ class DfaustStep(object):
 
     def conv_fwd_bwd(self, pcs, neighs, xs=None, dys=None):
         """Forward of the 21 convolutions, then ONE backward pass over all of them (as a training step does:
-        every forward first, a single autograd sweep after), returns the checksum of the outputs."""
+        every forward first, a single autograd sweep after), returns the checksum of the last output."""
         if xs is None:
             xs, dys = self.inputs
         ys = [layer(pcs[li], pcs[lo], x, nb)
               for layer, nb, (_, li, lo, _, _, _), x in zip(self.layers, neighs, self.specs, xs)]
         torch.autograd.backward(ys, list(dys))
-        return torch.stack([y.detach().sum() for y in ys]).sum()
+        return ys[-1].detach().sum()  # the seg-head output is the model's result: its checksum is read back
 
     def zero_grad(self):
         for layer in self.layers:
