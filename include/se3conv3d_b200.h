@@ -66,15 +66,23 @@ int se3_grid_setup(const float* pts, const int32_t* batch_ids, int64_t n, int32_
                    float max_pad, float* min_pt_out, float* max_pt_out, int32_t* num_cells_out,
                    se3_stream_t stream);
 
+/* The two halves of se3_grid_setup for callers that build several grids on one cloud: the raw per-batch box
+ * (no padding; empty batches keep (+inf, -inf)), and the padded box + extents for one cell size. */
+int se3_bbox(const float* pts, const int32_t* batch_ids, int64_t n, int32_t n_batches, float* min_out,
+             float* max_out, se3_stream_t stream);
+int se3_grid_extents(const float* raw_min, const float* raw_max, int32_t n_batches, float cell, float max_pad,
+                     float* min_pt_out, float* max_pt_out, int32_t* num_cells_out, se3_stream_t stream);
+
 /* Dense cell ranks of a voxel grid (pc/Grid.py:39-58: compute_keys -> unique(return_inverse) -> argsort):
  *   cell_ids [N] int64 = rank of the point's key among the distinct keys (sorted-key order),
  *   sorted_ids [N] int64 = stable argsort(cell_ids), cell_ends [N] int32 = inclusive end of every cell
- *   in that order (first *m_out entries valid), m_out = device int64 number of occupied cells. */
+ *   in that order (first *m_out entries valid), m_out = device int64 number of occupied cells.
+ *   key_bits: upper bound on the significant bits of the keys (bounds the radix sort), 0 = unknown (64). */
 size_t se3_grid_cells_workspace_bytes(int64_t n);
 int se3_grid_cells(const float* pts, const int32_t* batch_ids, int64_t n, const float* min_pt,
                    const int32_t* num_cells, float cell, void* workspace, size_t workspace_bytes,
                    int64_t* cell_ids, int64_t* sorted_ids, int32_t* cell_ends, int64_t* m_out,
-                   se3_stream_t stream);
+                   int32_t key_bits, se3_stream_t stream);
 
 /* Keeps n_keep of the n_cand candidate frames of every point after a uniform random permutation
  * (pc/PointcloudRotEquiv.py:148-168); u [N] uniform in [0,1) supplies the randomness (u = NULL keeps
@@ -121,6 +129,22 @@ int se3_ball_query_fill_csr(const float* pts_dst, int64_t n_src, int64_t n_dst, 
                             const void* workspace, size_t workspace_bytes,
                             const int32_t* row_ends, int64_t n_edges,
                             int32_t* col_src_out, int32_t* edge_dst_out, se3_stream_t stream);
+/* Prepared variants: one sorted source structure (se3_ball_query_prepare) per (source cloud, radius) serves
+ * every query against it; the workspace is split into a source part and a per-query part. */
+size_t se3_ball_query_src_workspace_bytes(int64_t n_src, int64_t n_dst_max);
+size_t se3_ball_query_dst_workspace_bytes(int64_t n_dst);
+int se3_ball_query_prepare(const float* pts_src, const int32_t* batch_src, int64_t n_src, int64_t n_dst_max,
+                           const float* min_pt, const int32_t* num_cells, const float* radius,
+                           void* ws_src, size_t ws_src_bytes, int32_t key_bits, se3_stream_t stream);
+int se3_ball_query_count_prepared(const float* pts_dst, const int32_t* batch_dst, int64_t n_src, int64_t n_dst,
+                                  int64_t n_dst_max, const float* min_pt, const int32_t* num_cells,
+                                  const float* radius, void* ws_src, size_t ws_src_bytes, void* ws_dst,
+                                  size_t ws_dst_bytes, int32_t* row_ends_out, int64_t* total_out,
+                                  se3_stream_t stream);
+int se3_ball_query_fill_csr_prepared(const float* pts_dst, int64_t n_src, int64_t n_dst, int64_t n_dst_max,
+                                     const float* radius, void* ws_src, size_t ws_src_bytes, void* ws_dst,
+                                     size_t ws_dst_bytes, const int32_t* row_ends, int64_t n_edges,
+                                     int32_t* col_src_out, int32_t* edge_dst_out, se3_stream_t stream);
 int se3_csr_transpose_i32(const int32_t* col_src, const int32_t* edge_dst, int64_t n_edges, int64_t n_src,
                           void* workspace, size_t workspace_bytes,
                           int32_t* t_row_ends, int32_t* t_edge, int32_t* t_dst, se3_stream_t stream);

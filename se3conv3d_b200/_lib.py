@@ -24,7 +24,9 @@ ABI_SYMBOLS = [
     "se3_conv_fwd_workspace_bytes", "se3_conv_bwd_workspace_bytes", "se3_conv_saved_bytes",
     "se3_conv_fwd", "se3_conv_bwd", "se3_gemm_bf16_tn", "se3_pack_records",
     "se3_ball_query_fill_csr", "se3_csr_transpose_i32", "se3_segment_first_i32", "se3_segment_pick",
-    "se3_hierarchy_build",
+    "se3_hierarchy_build", "se3_bbox", "se3_grid_extents", "se3_ball_query_src_workspace_bytes",
+    "se3_ball_query_dst_workspace_bytes", "se3_ball_query_prepare", "se3_ball_query_count_prepared",
+    "se3_ball_query_fill_csr_prepared",
 ]
 
 
@@ -98,7 +100,7 @@ def lib():
     L.se3_grid_setup.argtypes = [vp, vp, i64, i32, f32, f32, vp, vp, vp, vp]
     L.se3_grid_cells_workspace_bytes.argtypes = [i64]
     L.se3_grid_cells_workspace_bytes.restype = sz
-    L.se3_grid_cells.argtypes = [vp, vp, i64, vp, vp, f32, vp, sz, vp, vp, vp, vp, vp]
+    L.se3_grid_cells.argtypes = [vp, vp, i64, vp, vp, f32, vp, sz, vp, vp, vp, vp, i32, vp]
     L.se3_frames_select.argtypes = [vp, vp, i64, i32, i32, vp, vp]
     L.se3_ball_query_workspace_bytes.argtypes = [i64, i64]
     L.se3_ball_query_workspace_bytes.restype = sz
@@ -126,6 +128,15 @@ def lib():
     L.se3_csr_transpose_i32.argtypes = [vp, vp, i64, i64, vp, sz, vp, vp, vp, vp]
     L.se3_segment_first_i32.argtypes = [vp, vp, vp, i64, vp, vp]
     L.se3_segment_pick.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
+    L.se3_bbox.argtypes = [vp, vp, i64, i32, vp, vp, vp]
+    L.se3_grid_extents.argtypes = [vp, vp, i32, f32, f32, vp, vp, vp, vp]
+    L.se3_ball_query_src_workspace_bytes.argtypes = [i64, i64]
+    L.se3_ball_query_src_workspace_bytes.restype = sz
+    L.se3_ball_query_dst_workspace_bytes.argtypes = [i64]
+    L.se3_ball_query_dst_workspace_bytes.restype = sz
+    L.se3_ball_query_prepare.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, sz, i32, vp]
+    L.se3_ball_query_count_prepared.argtypes = [vp, vp, i64, i64, i64, vp, vp, vp, vp, sz, vp, sz, vp, vp, vp]
+    L.se3_ball_query_fill_csr_prepared.argtypes = [vp, i64, i64, i64, vp, vp, sz, vp, sz, vp, i64, vp, vp, vp]
     L.se3_hierarchy_build.argtypes = [C.POINTER(HierDesc), vp, vp, vp, vp, vp, sz, C.POINTER(HierResult), vp]
     L.se3_conv_bwd.argtypes = [dp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     for n in ABI_SYMBOLS:

@@ -154,6 +154,20 @@ __global__ void k_bbox_reduce(const float* __restrict__ pts, const int* __restri
   }
 }
 
+// raw per-batch bounding box (no padding): mn/mx [B,3]; batches without points keep (+inf, -inf)
+extern "C" int se3_bbox(const float* pts, const int32_t* batch_ids, int64_t n, int32_t n_batches, float* min_out,
+                        float* max_out, se3_stream_t stream) {
+  SE3_CHECK_ARG(n >= 0 && n_batches >= 1 && pts && batch_ids && min_out && max_out, "bad arguments");
+  cudaStream_t st = as_stream(stream);
+  k_bbox_init<<<(n_batches * 3 + 127) / 128, 128, 0, st>>>(min_out, max_out, n_batches * 3);
+  SE3_LAUNCH_CHECK();
+  if (n > 0) {
+    k_bbox_reduce<<<grid_for(n, 256), 256, 0, st>>>(pts, batch_ids, n, min_out, max_out);
+    SE3_LAUNCH_CHECK();
+  }
+  return SE3_OK;
+}
+
 __global__ void k_bbox_finalize(float* mn, float* mx, int nb, float cell, float max_pad, int* num_cells) {
   // one warp; batches without points keep (+inf, -inf) and do not contribute
   const int lane = threadIdx.x;
@@ -183,6 +197,28 @@ __global__ void k_bbox_finalize(float* mn, float* mx, int nb, float cell, float 
     for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
     if (lane == 0) num_cells[d] = v == INT_MIN ? 1 : v;
   }
+}
+
+__global__ void k_bbox_copy(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ ao,
+                            float* __restrict__ bo, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    ao[i] = a[i];
+    bo[i] = b[i];
+  }
+}
+
+// padded box + grid extents of a raw bounding box (se3_bbox) for one cell size: same arithmetic as se3_grid_setup
+extern "C" int se3_grid_extents(const float* raw_min, const float* raw_max, int32_t n_batches, float cell,
+                                float max_pad, float* min_pt_out, float* max_pt_out, int32_t* num_cells_out,
+                                se3_stream_t stream) {
+  SE3_CHECK_ARG(n_batches >= 1 && cell > 0.0f && raw_min && raw_max && min_pt_out && max_pt_out && num_cells_out,
+                "bad arguments");
+  cudaStream_t st = as_stream(stream);
+  k_bbox_copy<<<1, 128, 0, st>>>(raw_min, raw_max, min_pt_out, max_pt_out, n_batches * 3);
+  SE3_LAUNCH_CHECK();
+  k_bbox_finalize<<<1, 32, 0, st>>>(min_pt_out, max_pt_out, n_batches, cell, max_pad, num_cells_out);
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
 }
 
 extern "C" int se3_grid_setup(const float* pts, const int32_t* batch_ids, int64_t n, int32_t n_batches, float cell,
@@ -278,7 +314,7 @@ extern "C" size_t se3_grid_cells_workspace_bytes(int64_t n) {
 extern "C" int se3_grid_cells(const float* pts, const int32_t* batch_ids, int64_t n, const float* min_pt,
                               const int32_t* num_cells, float cell, void* workspace, size_t workspace_bytes,
                               int64_t* cell_ids, int64_t* sorted_ids, int32_t* cell_ends, int64_t* m_out,
-                              se3_stream_t stream) {
+                              int32_t key_bits, se3_stream_t stream) {
   SE3_CHECK_ARG(n >= 0 && n < (1ll << 31) && cell > 0.0f, "bad arguments");
   SE3_CHECK_ARG(m_out, "null m_out");
   cudaStream_t st = as_stream(stream);
@@ -296,8 +332,9 @@ extern "C" int se3_grid_cells(const float* pts, const int32_t* batch_ids, int64_
   k_cell_keys<<<grid_for(n, 256), 256, 0, st>>>(pts, batch_ids, n, min_pt, num_cells, cell, w.keys, w.iota);
   SE3_LAUNCH_CHECK();
   size_t cb = w.cub_bytes;
-  SE3_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, cb, w.keys, w.keys_sorted, w.iota, w.idx_sorted, (int)n, 0, 64, st));
-  count_launch(8);
+  const int end_bit = (key_bits > 0 && key_bits < 64) ? key_bits : 64;
+  SE3_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, cb, w.keys, w.keys_sorted, w.iota, w.idx_sorted, (int)n, 0, end_bit, st));
+  count_launch(1 + (end_bit + 7) / 8);
   k_cell_flags<<<grid_for(n, 256), 256, 0, st>>>(w.keys_sorted, n, w.flags);
   SE3_LAUNCH_CHECK();
   cb = w.cub_bytes;
@@ -366,36 +403,49 @@ static size_t bq_cub_bytes(int64_t n_src, int64_t n_dst) {
   return a > b ? a : b;
 }
 
+// source part: sorted keys / positions / coordinates (+ the CUB scratch); destination part: tube ranges, counts
+static size_t bq_src_bytes(int64_t n_src, int64_t n_dst) {
+  Arena ar(nullptr, 0);
+  ar.take<int64_t>(n_src); ar.take<int64_t>(n_src); ar.take<int>(n_src); ar.take<int>(n_src); ar.take<float4>(n_src);
+  ar.take<char>(bq_cub_bytes(n_src, n_dst));
+  return ar.off;
+}
+static size_t bq_dst_bytes(int64_t n_dst) {
+  Arena ar(nullptr, 0);
+  ar.take<int2>(n_dst * 9); ar.take<int>(n_dst);
+  return ar.off;
+}
+static bool bq_layout2(void* ws_src, size_t src_bytes, void* ws_dst, size_t dst_bytes, int64_t n_src, int64_t n_dst,
+                       int64_t n_dst_cub, BQWorkspace& w) {
+  Arena as(ws_src, src_bytes);
+  w.keys = as.take<int64_t>(n_src);
+  w.keys_sorted = as.take<int64_t>(n_src);
+  w.iota = as.take<int>(n_src);
+  w.idx_sorted = as.take<int>(n_src);
+  w.pts_sorted = as.take<float4>(n_src);
+  w.cub_bytes = bq_cub_bytes(n_src, n_dst_cub);
+  w.cub_tmp = as.take<char>(w.cub_bytes);
+  Arena ad(ws_dst, dst_bytes);
+  w.ranges = ad.take<int2>(n_dst * 9);
+  w.counts = ad.take<int>(n_dst);
+  return as.ok() && ad.ok();
+}
 static bool bq_layout(void* ws, size_t ws_bytes, int64_t n_src, int64_t n_dst, BQWorkspace& w) {
-  Arena ar(ws, ws_bytes);
-  w.keys = ar.take<int64_t>(n_src);
-  w.keys_sorted = ar.take<int64_t>(n_src);
-  w.iota = ar.take<int>(n_src);
-  w.idx_sorted = ar.take<int>(n_src);
-  w.pts_sorted = ar.take<float4>(n_src);
-  w.ranges = ar.take<int2>(n_dst * 9);
-  w.counts = ar.take<int>(n_dst);
-  w.cub_bytes = bq_cub_bytes(n_src, n_dst);
-  w.cub_tmp = ar.take<char>(w.cub_bytes);
-  return ar.ok();
+  const size_t sb = bq_src_bytes(n_src, n_dst);
+  if (ws_bytes < sb) return false;
+  return bq_layout2(ws, sb, reinterpret_cast<char*>(ws) + sb, ws_bytes - sb, n_src, n_dst, n_dst, w);
 }
 
 extern "C" size_t se3_ball_query_workspace_bytes(int64_t n_src, int64_t n_dst) {
   if (n_src < 1) n_src = 1;
   if (n_dst < 1) n_dst = 1;
-  BQWorkspace w;
-  Arena ar(nullptr, 0);
-  ar.take<int64_t>(n_src);
-  ar.take<int64_t>(n_src);
-  ar.take<int>(n_src);
-  ar.take<int>(n_src);
-  ar.take<float4>(n_src);
-  ar.take<int2>(n_dst * 9);
-  ar.take<int>(n_dst);
-  ar.take<char>(bq_cub_bytes(n_src, n_dst));
-  (void)w;
-  return ar.off + 256;
+  return bq_src_bytes(n_src, n_dst) + bq_dst_bytes(n_dst) + 256;
 }
+/* split workspace of the prepared variants: the source part is sized for queries of up to n_dst_max samples */
+extern "C" size_t se3_ball_query_src_workspace_bytes(int64_t n_src, int64_t n_dst_max) {
+  return bq_src_bytes(n_src < 1 ? 1 : n_src, n_dst_max < 1 ? 1 : n_dst_max) + 256;
+}
+extern "C" size_t se3_ball_query_dst_workspace_bytes(int64_t n_dst) { return bq_dst_bytes(n_dst < 1 ? 1 : n_dst) + 256; }
 
 __global__ void k_gather_sorted_pts(const float* __restrict__ pts, const int* __restrict__ idx_sorted, int64_t n,
                                     float4* __restrict__ out) {
@@ -494,6 +544,37 @@ __global__ void k_bq_total(const int* __restrict__ row_ends, int64_t n_dst, int6
   if (threadIdx.x == 0 && blockIdx.x == 0) *total = n_dst > 0 ? (int64_t)row_ends[n_dst - 1] : 0;
 }
 
+static int bq_prepare(const float* pts_src, const int32_t* batch_src, int64_t n_src, const float* min_pt,
+                      const int32_t* num_cells, const float* radius, BQWorkspace& w, int key_bits, cudaStream_t st) {
+  k_compute_keys<<<grid_for(n_src, 256), 256, 0, st>>>(pts_src, batch_src, n_src, min_pt, num_cells, radius, w.keys,
+                                                       w.iota);
+  SE3_LAUNCH_CHECK();
+  size_t cb = w.cub_bytes;
+  const int end_bit = (key_bits > 0 && key_bits < 64) ? key_bits : 64;
+  SE3_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, cb, w.keys, w.keys_sorted, w.iota, w.idx_sorted, (int)n_src, 0,
+                                           end_bit, st));
+  count_launch(1 + (end_bit + 7) / 8);
+  k_gather_sorted_pts<<<grid_for(n_src, 256), 256, 0, st>>>(pts_src, w.idx_sorted, n_src, w.pts_sorted);
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
+}
+
+static int bq_count(const float* pts_dst, const int32_t* batch_dst, int64_t n_src, int64_t n_dst, const float* min_pt,
+                    const int32_t* num_cells, const float* radius, BQWorkspace& w, int32_t* row_ends_out,
+                    int64_t* total_out, cudaStream_t st) {
+  const int blocks = grid_for(n_dst * 32, 256);
+  k_bq_scan<false><<<blocks, 256, 0, st>>>(pts_dst, batch_dst, n_dst, (int)n_src, min_pt, num_cells, radius,
+                                           w.keys_sorted, w.pts_sorted, w.idx_sorted, w.ranges, w.counts, nullptr,
+                                           nullptr, nullptr, nullptr);
+  SE3_LAUNCH_CHECK();
+  size_t cb = w.cub_bytes;
+  SE3_CUDA(cub::DeviceScan::InclusiveSum(w.cub_tmp, cb, w.counts, row_ends_out, (int)n_dst, st));
+  count_launch(1);
+  k_bq_total<<<1, 32, 0, st>>>(row_ends_out, n_dst, total_out);
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
+}
+
 extern "C" int se3_ball_query_count(const float* pts_src, const float* pts_dst, const int32_t* batch_src,
                                     const int32_t* batch_dst, int64_t n_src, int64_t n_dst, const float* min_pt,
                                     const int32_t* num_cells, const float* radius, void* workspace,
@@ -514,24 +595,63 @@ extern "C" int se3_ball_query_count(const float* pts_src, const float* pts_dst, 
     set_error("se3_ball_query_count: workspace too small");
     return SE3_EWORKSPACE;
   }
-  k_compute_keys<<<grid_for(n_src, 256), 256, 0, st>>>(pts_src, batch_src, n_src, min_pt, num_cells, radius, w.keys,
-                                                       w.iota);
-  SE3_LAUNCH_CHECK();
-  size_t cb = w.cub_bytes;
-  SE3_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, cb, w.keys, w.keys_sorted, w.iota, w.idx_sorted, (int)n_src, 0,
-                                           64, st));
-  count_launch(8);
-  k_gather_sorted_pts<<<grid_for(n_src, 256), 256, 0, st>>>(pts_src, w.idx_sorted, n_src, w.pts_sorted);
-  SE3_LAUNCH_CHECK();
+  if (int rc = bq_prepare(pts_src, batch_src, n_src, min_pt, num_cells, radius, w, 0, st)) return rc;
+  return bq_count(pts_dst, batch_dst, n_src, n_dst, min_pt, num_cells, radius, w, row_ends_out, total_out, st);
+}
+
+/* Prepared variants (fused hierarchy builder): one sorted source structure per (source cloud, radius) serves
+ * every query against it.  key_bits bounds the radix sort (0 = all 64 bits). */
+extern "C" int se3_ball_query_prepare(const float* pts_src, const int32_t* batch_src, int64_t n_src, int64_t n_dst_max,
+                                      const float* min_pt, const int32_t* num_cells, const float* radius,
+                                      void* ws_src, size_t ws_src_bytes, int32_t key_bits, se3_stream_t stream) {
+  SE3_CHECK_ARG(n_src >= 0 && n_src < (1ll << 31), "bad sizes");
+  if (n_src == 0) return SE3_OK;
+  SE3_CHECK_ARG(pts_src && batch_src && min_pt && num_cells && radius && ws_src, "null pointer");
+  BQWorkspace w;
+  char dummy[1];
+  if (!bq_layout2(ws_src, ws_src_bytes, dummy, (size_t)1 << 60, n_src, 0, n_dst_max < 1 ? 1 : n_dst_max, w)) {
+    set_error("se3_ball_query_prepare: workspace too small");
+    return SE3_EWORKSPACE;
+  }
+  return bq_prepare(pts_src, batch_src, n_src, min_pt, num_cells, radius, w, key_bits, as_stream(stream));
+}
+
+extern "C" int se3_ball_query_count_prepared(const float* pts_dst, const int32_t* batch_dst, int64_t n_src,
+                                             int64_t n_dst, int64_t n_dst_max, const float* min_pt,
+                                             const int32_t* num_cells, const float* radius, void* ws_src,
+                                             size_t ws_src_bytes, void* ws_dst, size_t ws_dst_bytes,
+                                             int32_t* row_ends_out, int64_t* total_out, se3_stream_t stream) {
+  SE3_CHECK_ARG(n_src >= 0 && n_dst >= 0 && n_src < (1ll << 31) && n_dst < (1ll << 31) && total_out, "bad arguments");
+  cudaStream_t st = as_stream(stream);
+  if (n_dst == 0 || n_src == 0) {
+    if (n_dst > 0) SE3_CUDA(cudaMemsetAsync(row_ends_out, 0, n_dst * sizeof(int32_t), st));
+    SE3_CUDA(cudaMemsetAsync(total_out, 0, sizeof(int64_t), st));
+    return SE3_OK;
+  }
+  SE3_CHECK_ARG(pts_dst && batch_dst && min_pt && num_cells && radius && ws_src && ws_dst && row_ends_out, "null pointer");
+  BQWorkspace w;
+  if (!bq_layout2(ws_src, ws_src_bytes, ws_dst, ws_dst_bytes, n_src, n_dst, n_dst_max < n_dst ? n_dst : n_dst_max, w)) {
+    set_error("se3_ball_query_count_prepared: workspace too small");
+    return SE3_EWORKSPACE;
+  }
+  return bq_count(pts_dst, batch_dst, n_src, n_dst, min_pt, num_cells, radius, w, row_ends_out, total_out, st);
+}
+
+extern "C" int se3_ball_query_fill_csr_prepared(const float* pts_dst, int64_t n_src, int64_t n_dst, int64_t n_dst_max,
+                                                const float* radius, void* ws_src, size_t ws_src_bytes, void* ws_dst,
+                                                size_t ws_dst_bytes, const int32_t* row_ends, int64_t n_edges,
+                                                int32_t* col_src_out, int32_t* edge_dst_out, se3_stream_t stream) {
+  if (n_edges == 0 || n_dst == 0 || n_src == 0) return SE3_OK;
+  SE3_CHECK_ARG(pts_dst && radius && ws_src && ws_dst && row_ends && col_src_out && edge_dst_out, "null pointer");
+  BQWorkspace w;
+  if (!bq_layout2(ws_src, ws_src_bytes, ws_dst, ws_dst_bytes, n_src, n_dst, n_dst_max < n_dst ? n_dst : n_dst_max, w)) {
+    set_error("se3_ball_query_fill_csr_prepared: workspace too small");
+    return SE3_EWORKSPACE;
+  }
   const int blocks = grid_for(n_dst * 32, 256);
-  k_bq_scan<false><<<blocks, 256, 0, st>>>(pts_dst, batch_dst, n_dst, (int)n_src, min_pt, num_cells, radius,
-                                           w.keys_sorted, w.pts_sorted, w.idx_sorted, w.ranges, w.counts, nullptr,
-                                           nullptr, nullptr, nullptr);
-  SE3_LAUNCH_CHECK();
-  cb = w.cub_bytes;
-  SE3_CUDA(cub::DeviceScan::InclusiveSum(w.cub_tmp, cb, w.counts, row_ends_out, (int)n_dst, st));
-  count_launch(1);
-  k_bq_total<<<1, 32, 0, st>>>(row_ends_out, n_dst, total_out);
+  k_bq_scan<true><<<blocks, 256, 0, as_stream(stream)>>>(pts_dst, nullptr, n_dst, (int)n_src, nullptr, nullptr,
+                                                         radius, w.keys_sorted, w.pts_sorted, w.idx_sorted, w.ranges,
+                                                         w.counts, row_ends, nullptr, col_src_out, edge_dst_out);
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }

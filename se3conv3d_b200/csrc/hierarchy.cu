@@ -82,34 +82,71 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
   const int n_clouds = d->n_pool + 1 + (d->out_cloud ? 1 : 0);
   out->n_clouds = n_clouds;
 
-  // small device scalars shared by every grid: min/max [B,3], num_cells [3], a count
-  const int64_t o_min = ar.take((size_t)d->n_batches * 3 * 4), o_max = ar.take((size_t)d->n_batches * 3 * 4);
+  // small device scalars: padded min/max [B,3] + num_cells [3] of the grid being built, counters, radii
+  const size_t bb = (size_t)d->n_batches * 3 * 4;
+  const int64_t o_min = ar.take(bb), o_max = ar.take(bb);
   const int64_t o_nc = ar.take(16), o_cnt = ar.take(8 * (SE3_HIER_MAX_NEIGH + 2)), o_rad = ar.take(16 * SE3_HIER_MAX_NEIGH);
+  int64_t o_rawmin[SE3_HIER_MAX_CLOUDS + 1], o_rawmax[SE3_HIER_MAX_CLOUDS + 1];  // raw boxes: [0] input cloud, [1+c] cloud c
+  for (int c = 0; c <= n_clouds; ++c) {
+    o_rawmin[c] = ar.take(bb);
+    o_rawmax[c] = ar.take(bb);
+  }
   HB_CHECK_ARENA("scalars");
   float* min_pt = ar.at<float>(o_min);
   float* max_pt = ar.at<float>(o_max);
   int32_t* num_cells = ar.at<int32_t>(o_nc);
   int64_t* d_cnt = ar.at<int64_t>(o_cnt);
 
-  // grid on (p, b, n) with voxel `cell`; fills g.cell_ids / sorted_ids / cell_ends / m (blocking read of m)
-  auto build_grid = [&](const float* p, const int32_t* b, int64_t n, float cell, se3_hier_cloud& g) -> int {
+  // ---- bounding box of the input cloud on the host (one early blocking read): every later cloud lies inside
+  // it, so the number of significant key bits of every grid is known up front and bounds the radix sorts.
+  HB_TRY(se3_bbox(pts, batch_ids, d->n, d->n_batches, ar.at<float>(o_rawmin[0]), ar.at<float>(o_rawmax[0]), stream));
+  float ext[3] = {0.f, 0.f, 0.f};
+  {
+    float* hf = reinterpret_cast<float*>(host);
+    // large batch counts: fall back to full-width sorts instead of a bigger host buffer
+    if ((size_t)d->n_batches * 6 * sizeof(float) <= 64 * sizeof(int64_t)) {
+      SE3_CUDA(cudaMemcpyAsync(hf, ar.at<float>(o_rawmin[0]), bb, cudaMemcpyDeviceToHost, st));
+      SE3_CUDA(cudaMemcpyAsync(hf + d->n_batches * 3, ar.at<float>(o_rawmax[0]), bb, cudaMemcpyDeviceToHost, st));
+      SE3_CUDA(cudaStreamSynchronize(st));
+      for (int b = 0; b < d->n_batches; ++b)
+        for (int k = 0; k < 3; ++k) {
+          const float lo = hf[3 * b + k], hi = hf[d->n_batches * 3 + 3 * b + k];
+          if (lo <= hi && hi - lo > ext[k]) ext[k] = hi - lo;
+        }
+    } else {
+      ext[0] = ext[1] = ext[2] = -1.0f;
+    }
+  }
+  auto key_bits_for = [&](float cell) -> int {
+    if (ext[0] < 0.0f) return 0;
+    double keys = (double)d->n_batches;
+    for (int k = 0; k < 3; ++k) keys *= (double)((int64_t)(ext[k] / cell) + 3);  // +1 exact, +2 padding / rounding slack
+    int bits = 1;
+    while (bits < 63 && (double)(1ull << bits) < keys) ++bits;
+    return bits;
+  };
+
+  // grid on (p, b, n) with voxel `cell` from the cloud's raw box; fills g.cell_ids / sorted_ids / cell_ends / m
+  // (blocking read of m)
+  auto build_grid = [&](const float* p, const int32_t* b, int64_t n, int raw_slot, float cell, se3_hier_cloud& g) -> int {
     g.cell_ids = ar.take((size_t)n * 8);
     g.sorted_ids = ar.take((size_t)n * 8);
     g.cell_ends = ar.take((size_t)n * 4);
     const size_t wsb = se3_grid_cells_workspace_bytes(n);
     const int64_t o_ws = ar.take(wsb);
     HB_CHECK_ARENA("grid");
-    HB_TRY(se3_grid_setup(p, b, n, d->n_batches, cell, 1e-6f, min_pt, max_pt, num_cells, stream));
+    HB_TRY(se3_grid_extents(ar.at<float>(o_rawmin[raw_slot]), ar.at<float>(o_rawmax[raw_slot]), d->n_batches, cell, 1e-6f,
+                            min_pt, max_pt, num_cells, stream));
     HB_TRY(se3_grid_cells(p, b, n, min_pt, num_cells, cell, ar.at<char>(o_ws), wsb, ar.at<int64_t>(g.cell_ids),
-                          ar.at<int64_t>(g.sorted_ids), ar.at<int32_t>(g.cell_ends), d_cnt, stream));
+                          ar.at<int64_t>(g.sorted_ids), ar.at<int32_t>(g.cell_ends), d_cnt, key_bits_for(cell), stream));
     SE3_CUDA(cudaMemcpyAsync(host, d_cnt, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     SE3_CUDA(cudaStreamSynchronize(st));
     g.m = host[0];
     return SE3_OK;
   };
-  // frames + records of cloud c (pts / batch already in place)
+  // frames + records + raw box of cloud c (pts / batch already in place)
   int64_t u_off = 0;
-  auto build_frames = [&](se3_hier_cloud& c) -> int {
+  auto build_frames = [&](se3_hier_cloud& c, int raw_slot) -> int {
     const int64_t n = c.n;
     c.frames = ar.take((size_t)n * F * 36);
     c.rec = ar.take((size_t)n * F * 48);
@@ -118,6 +155,8 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
     const size_t wsb = se3_knn_workspace_bytes(n);
     const int64_t o_ws = ar.take(wsb);
     HB_CHECK_ARENA("frames");
+    HB_TRY(se3_bbox(ar.at<float>(c.pts), ar.at<int32_t>(c.batch), n, d->n_batches, ar.at<float>(o_rawmin[raw_slot]),
+                    ar.at<float>(o_rawmax[raw_slot]), stream));
     if (n == 0) return SE3_OK;
     HB_TRY(se3_knn_query(ar.at<float>(c.pts), ar.at<int32_t>(c.batch), n, d->knn_k, ar.at<char>(o_ws), wsb,
                          ar.at<int32_t>(o_knn), stream));
@@ -143,16 +182,16 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
 
   // ---- level 0 and the output cloud share the raw cloud's init_cell grid
   out->raw.n = d->n;
-  HB_TRY(build_grid(pts, batch_ids, d->n, d->init_cell, out->raw));
+  HB_TRY(build_grid(pts, batch_ids, d->n, 0, d->init_cell, out->raw));
   HB_TRY(pool_cloud(pts, batch_ids, d->n, out->raw, out->clouds[0]));
-  HB_TRY(build_frames(out->clouds[0]));
+  HB_TRY(build_frames(out->clouds[0], 1));
   // ---- pooled levels
   for (int l = 0; l < d->n_pool; ++l) {
     se3_hier_cloud& src = out->clouds[l];
     SE3_CHECK_ARG(d->cells[l] > 0.0f, "cell sizes must be positive");
-    HB_TRY(build_grid(ar.at<float>(src.pts), ar.at<int32_t>(src.batch), src.n, d->cells[l], src));
+    HB_TRY(build_grid(ar.at<float>(src.pts), ar.at<int32_t>(src.batch), src.n, 1 + l, d->cells[l], src));
     HB_TRY(pool_cloud(ar.at<float>(src.pts), ar.at<int32_t>(src.batch), src.n, src, out->clouds[l + 1]));
-    HB_TRY(build_frames(out->clouds[l + 1]));
+    HB_TRY(build_frames(out->clouds[l + 1], 2 + l));
   }
   if (d->out_cloud) {
     se3_hier_cloud& oc = out->clouds[d->n_pool + 1];
@@ -164,12 +203,11 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
     HB_TRY(se3_segment_pick(pts, batch_ids, ar.at<int64_t>(out->raw.sorted_ids), ar.at<int32_t>(out->raw.cell_ends),
                             oc.n, u_cells, ar.at<float>(oc.pts), ar.at<int32_t>(oc.batch),
                             ar.at<int64_t>(out->out_picked), stream));
-    HB_TRY(build_frames(oc));
+    HB_TRY(build_frames(oc, d->n_pool + 2));
   }
 
-  // ---- neighbourhoods: all count passes, ONE blocking read of the edge totals, then fills + transposes
-  int64_t ws_off[SE3_HIER_MAX_NEIGH];
-  size_t ws_bytes[SE3_HIER_MAX_NEIGH];
+  // ---- neighbourhoods: one sorted source structure per (source cloud, radius), all count passes, ONE blocking
+  // read of the edge totals, then fills + transposes
   float h_rad[SE3_HIER_MAX_NEIGH * 4];
   for (int i = 0; i < d->n_neigh; ++i) {
     SE3_CHECK_ARG(d->neigh_src[i] >= 0 && d->neigh_src[i] < n_clouds && d->neigh_dst[i] >= 0 && d->neigh_dst[i] < n_clouds,
@@ -183,28 +221,68 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
     // pageable source: the copy is staged before the call returns, so the stack buffer is safe
     SE3_CUDA(cudaMemcpyAsync(d_rad, h_rad, sizeof(float) * 4 * d->n_neigh, cudaMemcpyHostToDevice, st));
   }
+  struct Source {
+    int cloud;
+    float radius;
+    int64_t n_dst_max, ws, mn, mx, nc;
+    size_t ws_bytes;
+  } sources[SE3_HIER_MAX_NEIGH];
+  int n_sources = 0, src_of[SE3_HIER_MAX_NEIGH];
   for (int i = 0; i < d->n_neigh; ++i) {
+    int f = -1;
+    for (int j = 0; j < n_sources; ++j)
+      if (sources[j].cloud == d->neigh_src[i] && sources[j].radius == d->neigh_radius[i]) f = j;
+    if (f < 0) {
+      f = n_sources++;
+      sources[f].cloud = d->neigh_src[i];
+      sources[f].radius = d->neigh_radius[i];
+      sources[f].n_dst_max = 0;
+    }
+    const int64_t nd = out->clouds[d->neigh_dst[i]].n;
+    if (nd > sources[f].n_dst_max) sources[f].n_dst_max = nd;
+    src_of[i] = f;
+  }
+  int rad_slot[SE3_HIER_MAX_NEIGH];
+  for (int j = 0; j < n_sources; ++j) {
+    Source& so = sources[j];
+    const se3_hier_cloud& s = out->clouds[so.cloud];
+    for (int i = 0; i < d->n_neigh; ++i)
+      if (src_of[i] == j) rad_slot[j] = i;
+    so.ws_bytes = se3_ball_query_src_workspace_bytes(s.n, so.n_dst_max);
+    so.ws = ar.take(so.ws_bytes);
+    so.mn = ar.take(bb);
+    so.mx = ar.take(bb);
+    so.nc = ar.take(16);
+    HB_CHECK_ARENA("ball-query source");
+    HB_TRY(se3_grid_extents(ar.at<float>(o_rawmin[1 + so.cloud]), ar.at<float>(o_rawmax[1 + so.cloud]), d->n_batches,
+                            so.radius, -1e-6f, ar.at<float>(so.mn), ar.at<float>(so.mx), ar.at<int32_t>(so.nc), stream));
+    HB_TRY(se3_ball_query_prepare(ar.at<float>(s.pts), ar.at<int32_t>(s.batch), s.n, so.n_dst_max, ar.at<float>(so.mn),
+                                  ar.at<int32_t>(so.nc), d_rad + 4 * rad_slot[j], ar.at<char>(so.ws), so.ws_bytes,
+                                  key_bits_for(so.radius), stream));
+  }
+  int64_t wd_off[SE3_HIER_MAX_NEIGH];
+  size_t wd_bytes[SE3_HIER_MAX_NEIGH];
+  for (int i = 0; i < d->n_neigh; ++i) {
+    const Source& so = sources[src_of[i]];
     const se3_hier_cloud& s = out->clouds[d->neigh_src[i]];
     const se3_hier_cloud& t = out->clouds[d->neigh_dst[i]];
     se3_hier_neigh& nb = out->neigh[i];
     nb.row_ends = ar.take((size_t)t.n * 4);
     nb.t_row_ends = ar.take((size_t)s.n * 4);
-    ws_bytes[i] = se3_ball_query_workspace_bytes(s.n, t.n);
-    ws_off[i] = ar.take(ws_bytes[i]);
-    // per-neighbourhood grid scalars (they must survive until the fill pass)
-    const int64_t o_mn = ar.take((size_t)d->n_batches * 3 * 4), o_mx = ar.take((size_t)d->n_batches * 3 * 4), o_n3 = ar.take(16);
+    wd_bytes[i] = se3_ball_query_dst_workspace_bytes(t.n);
+    wd_off[i] = ar.take(wd_bytes[i]);
     HB_CHECK_ARENA("ball-query workspace");
-    HB_TRY(se3_grid_setup(ar.at<float>(s.pts), ar.at<int32_t>(s.batch), s.n, d->n_batches, d->neigh_radius[i], -1e-6f,
-                          ar.at<float>(o_mn), ar.at<float>(o_mx), ar.at<int32_t>(o_n3), stream));
-    HB_TRY(se3_ball_query_count(ar.at<float>(s.pts), ar.at<float>(t.pts), ar.at<int32_t>(s.batch), ar.at<int32_t>(t.batch),
-                                s.n, t.n, ar.at<float>(o_mn), ar.at<int32_t>(o_n3), d_rad + 4 * i, ar.at<char>(ws_off[i]),
-                                ws_bytes[i], ar.at<int32_t>(nb.row_ends), d_cnt + 1 + i, stream));
+    HB_TRY(se3_ball_query_count_prepared(ar.at<float>(t.pts), ar.at<int32_t>(t.batch), s.n, t.n, so.n_dst_max,
+                                         ar.at<float>(so.mn), ar.at<int32_t>(so.nc), d_rad + 4 * i, ar.at<char>(so.ws),
+                                         so.ws_bytes, ar.at<char>(wd_off[i]), wd_bytes[i], ar.at<int32_t>(nb.row_ends),
+                                         d_cnt + 1 + i, stream));
   }
   if (d->n_neigh > 0) {
     SE3_CUDA(cudaMemcpyAsync(host, d_cnt + 1, sizeof(int64_t) * d->n_neigh, cudaMemcpyDeviceToHost, st));
     SE3_CUDA(cudaStreamSynchronize(st));
   }
   for (int i = 0; i < d->n_neigh; ++i) {
+    const Source& so = sources[src_of[i]];
     const se3_hier_cloud& s = out->clouds[d->neigh_src[i]];
     const se3_hier_cloud& t = out->clouds[d->neigh_dst[i]];
     se3_hier_neigh& nb = out->neigh[i];
@@ -216,9 +294,9 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
     const size_t twb = se3_csr_transpose_workspace_bytes(nb.e, s.n);
     const int64_t o_tw = ar.take(twb);
     HB_CHECK_ARENA("neighbourhood");
-    HB_TRY(se3_ball_query_fill_csr(ar.at<float>(t.pts), s.n, t.n, d_rad + 4 * i, ar.at<char>(ws_off[i]), ws_bytes[i],
-                                   ar.at<int32_t>(nb.row_ends), nb.e, ar.at<int32_t>(nb.col_src),
-                                   ar.at<int32_t>(nb.edge_dst), stream));
+    HB_TRY(se3_ball_query_fill_csr_prepared(ar.at<float>(t.pts), s.n, t.n, so.n_dst_max, d_rad + 4 * i, ar.at<char>(so.ws),
+                                            so.ws_bytes, ar.at<char>(wd_off[i]), wd_bytes[i], ar.at<int32_t>(nb.row_ends),
+                                            nb.e, ar.at<int32_t>(nb.col_src), ar.at<int32_t>(nb.edge_dst), stream));
     HB_TRY(se3_csr_transpose_i32(ar.at<int32_t>(nb.col_src), ar.at<int32_t>(nb.edge_dst), nb.e, s.n, ar.at<char>(o_tw), twb,
                                  ar.at<int32_t>(nb.t_row_ends), ar.at<int32_t>(nb.t_edge), ar.at<int32_t>(nb.t_dst), stream));
   }

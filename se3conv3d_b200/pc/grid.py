@@ -46,7 +46,7 @@ class Grid(object):
         m = torch.empty(1, dtype=torch.int64, device=dev)
         check(L.se3_grid_cells(ptr(pts), ptr(b), n, ptr(self.bounding_box_.min_), ptr(self.num_cells_),
                                float(self.cell_size_), ptr(ws), ws.numel(), ptr(self.cell_ids_), ptr(self.sorted_ids_),
-                               ptr(ends), ptr(m), stream()), "se3_grid_cells")
+                               ptr(ends), ptr(m), 0, stream()), "se3_grid_cells")
         self.num_used_cells_ = int(m.item())
         self.cell_ends_ = ends[:self.num_used_cells_]
 
