@@ -46,6 +46,14 @@ const char* se3_last_error(void);
 /* number of kernels launched by this library since load (all entry points); for gpu_launches */
 int64_t se3_launch_count(void);
 
+/* Optional device timing of the three dominant kernels (CUDA events on the launching stream around every
+ * launch; off by default): ids 0 = forward aggregation, 1 = transposed aggregation (data gradient),
+ * 2 = edge-gradient kernel.  se3_profile_read synchronises, returns the accumulated milliseconds and launch
+ * counts since the last read, and resets.  bench.py uses it for the per-kernel roofline. */
+#define SE3_PROF_KERNELS 3
+void se3_profile_enable(int32_t on);
+int se3_profile_read(double* ms_out, int64_t* count_out);
+
 /* ------------------------------------------------------------------------------------------
  * Grid keys.  Replaces compute_keys (custom_ops/ball_query/compute_keys.cu:76-125, cell/key
  * math custom_ops/ball_query/grid_utils.cuh:56-93; caller custom_ops/ComputeKeys.py:35-40).

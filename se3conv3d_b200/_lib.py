@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("SE3CONV3D_LIB") or os.path.join(_PKG, "lib", "libse3c
 
 # every symbol include/se3conv3d_b200.h declares (tests check the .so exports exactly these)
 ABI_SYMBOLS = [
-    "se3_abi_version", "se3_last_error", "se3_launch_count",
+    "se3_abi_version", "se3_last_error", "se3_launch_count", "se3_profile_enable", "se3_profile_read",
     "se3_compute_keys", "se3_grid_setup", "se3_grid_cells_workspace_bytes", "se3_grid_cells", "se3_frames_select",
     "se3_ball_query_workspace_bytes", "se3_ball_query_count", "se3_ball_query_fill",
     "se3_csr_transpose_workspace_bytes", "se3_csr_transpose",
@@ -96,6 +96,9 @@ def lib():
     L.se3_abi_version.restype = C.c_int
     L.se3_last_error.restype = C.c_char_p
     L.se3_launch_count.restype = i64
+    L.se3_profile_enable.argtypes = [i32]
+    L.se3_profile_enable.restype = None
+    L.se3_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.se3_compute_keys.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp]
     L.se3_grid_setup.argtypes = [vp, vp, i64, i32, f32, f32, vp, vp, vp, vp]
     L.se3_grid_cells_workspace_bytes.argtypes = [i64]
@@ -141,7 +144,7 @@ def lib():
     L.se3_conv_bwd.argtypes = [dp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     for n in ABI_SYMBOLS:
         f = getattr(L, n)
-        if n not in ("se3_last_error", "se3_launch_count") and not n.endswith("_bytes"):
+        if n not in ("se3_last_error", "se3_launch_count", "se3_profile_enable") and not n.endswith("_bytes"):
             f.restype = C.c_int
     _lib = L
     return L
@@ -216,6 +219,26 @@ def workspace(nbytes, device, tag=None):
         buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
         _ws_pool[key] = buf
     return buf
+
+
+PROF_KERNELS = ("k_agg_tc forward aggregation", "k_agg_tc transposed aggregation (data gradient)",
+                "k_edge_tc edge gradient")
+
+
+def profile_kernels(fn, reps=1):
+    """Runs fn() reps times with per-kernel device timing on; returns [(name, avg ms per launch, launches)]."""
+    L = lib()
+    ms = (C.c_double * 3)()
+    cnt = (C.c_int64 * 3)()
+    L.se3_profile_read(ms, cnt)  # drain
+    L.se3_profile_enable(1)
+    try:
+        for _ in range(reps):
+            fn()
+    finally:
+        L.se3_profile_enable(0)
+    check(L.se3_profile_read(ms, cnt), "se3_profile_read")
+    return [(PROF_KERNELS[i], (ms[i] / cnt[i]) if cnt[i] else 0.0, int(cnt[i])) for i in range(3)]
 
 
 def launch_count():

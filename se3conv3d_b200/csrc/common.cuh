@@ -10,6 +10,16 @@ namespace se3 {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
+// optional per-kernel timing (se3_profile_enable / se3_profile_read)
+void profile_begin(int id, cudaStream_t st, void** handle);
+void profile_end(void* handle, cudaStream_t st);
+struct ProfScope {
+  void* h;
+  cudaStream_t st;
+  ProfScope(int id, cudaStream_t s) : st(s) { profile_begin(id, s, &h); }
+  ~ProfScope() { profile_end(h, st); }
+};
+
 inline cudaStream_t as_stream(se3_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 #define SE3_CHECK_ARG(cond, msg)                     \

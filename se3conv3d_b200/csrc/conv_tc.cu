@@ -451,6 +451,7 @@ static int launch_agg_cfg(const TcAggArgs& a, int64_t n_g, cudaStream_t st) {
   const int64_t cap = (int64_t)num_sms() * SE3_AGG_MIN_BLOCKS * SE3_AGG_WAVES;  // persistent: the row pipeline
   if (blocks > cap) blocks = cap;                                               // needs many rows per warp
   if (blocks < 1) blocks = 1;
+  ProfScope prof(TR ? 1 : 0, st);
   if (a.act == 2) {
     auto kern = k_agg_tc<CB, FR, TR, 2>;
     SE3_SMEM_ONCE(kern, smem);
@@ -761,6 +762,222 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_EDGE_MIN_BLOCKS) k_edge_tc
   }
 }
 
+// ---- row-item variant for c <= CB (one channel block): one warp per OUTPUT POINT; its FR frames share the
+// gathered records / feature rows of every chunk (one gather instead of FR), the dT tiles of the row are
+// fetched once per row -- issued as soon as the previous row's last dH product has consumed the buffer.
+template <int CB, int FR>
+struct EdgeRowSmem {
+  static constexpr int XS = CB + 8, TS = 32 + 8, GB = 16 + 8;
+  static constexpr int X_BYTES = 32 * XS * 2;
+  static constexpr int RG_BYTES = 32 * 48;
+  static constexpr int T_BYTES = CB * TS * 2;  // one frame's dT tile
+  static constexpr int G_BYTES = 32 * GSTR * 4;
+  static constexpr int GB_BYTES = 32 * GB * 2;
+  static constexpr int RS_BYTES = ((FR * 48 + 63) / 64) * 64;
+  static constexpr int OFF_RG = 2 * X_BYTES;
+  static constexpr int OFF_T = OFF_RG + 2 * RG_BYTES;
+  static constexpr int OFF_G = OFF_T + FR * T_BYTES;
+  static constexpr int OFF_GB = OFF_G + G_BYTES;
+  static constexpr int OFF_RS = OFF_GB + GB_BYTES;
+  static constexpr int WARP_BYTES = OFF_RS + 2 * RS_BYTES;
+};
+
+template <int CB, int FR, int ACT>
+__global__ void __launch_bounds__(AGG_WARPS * 32, SE3_EDGE_MIN_BLOCKS) k_edge_row_tc(const TcEdgeArgs a) {
+  using SM = EdgeRowSmem<CB, FR>;
+  constexpr int TS = SM::TS, GB = SM::GB;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  unsigned char* wbase = smem_raw + wib * SM::WARP_BYTES;
+  const uint32_t wbase_s = smem_u32(wbase);
+  float* Gs = reinterpret_cast<float*>(wbase + SM::OFF_G);                    // [32][GSTR]
+  __nv_bfloat16* Gb = reinterpret_cast<__nv_bfloat16*>(wbase + SM::OFF_GB);   // [32][GB]
+  const int g = lane >> 2, t = lane & 3;
+  float accA[2][2][4];  // [k m-tile][d n-tile]
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int dd = 0; dd < 2; ++dd)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) accA[m][dd][i] = 0.0f;
+  const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+  const int total = (int)a.n_out;
+  int rp0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (rp0 < total) {
+    uint32_t aw[2][2][4];
+    load_w9_frags(a.w9, a.bias, g, t, act_pre_scale(a.act), aw);
+    auto issue_gather = [&](int rp, int lo, int nt, int idx, int base, int buf, int rb, bool with_row) {
+      const int gidx = chunk_gidx(a.col_src, lo, nt, idx, a.f_in, base, lane);
+      gather_chunk_async<CB>(a.rec_in, a.x, a.cs, 0, gidx, lane, wbase_s + SM::OFF_RG + buf * SM::RG_BYTES,
+                             wbase_s + buf * SM::X_BYTES);
+      if (with_row && lane < FR * 3)
+        cp_async16_ca(wbase_s + SM::OFF_RS + rb * SM::RS_BYTES + lane * 16,
+                      reinterpret_cast<const float4*>(a.rec_out) + (int64_t)rp * (FR * 3) + lane, true);
+    };
+    // [CB x 32] dT tile of (row, frame f): CB rows of 64 B = 4 x 16 B
+    auto issue_tile = [&](int rp, int f) {
+      const __nv_bfloat16* dTrow = a.dT + ((int64_t)rp * FR + f) * (int64_t)a.c * 32;
+#pragma unroll
+      for (int i0 = 0; i0 < CB * 4; i0 += 32) {
+        const int i = i0 + lane;
+        const int c = i >> 2, part = i & 3;
+        const bool ok = c < a.c;
+        cp_async16_ca(wbase_s + SM::OFF_T + f * SM::T_BYTES + (c * TS + part * 8) * 2, dTrow + (ok ? c * 32 + part * 8 : 0), ok);
+      }
+    };
+
+    int lo0 = rp0 > 0 ? __ldg(a.row_ends + rp0 - 1) : 0;
+    int ne0 = __ldg(a.row_ends + rp0) - lo0;
+    int idx0 = lane < ne0 ? __ldg(a.col_src + lo0 + lane) : 0;
+    int rp1 = rp0 + nwarps, lo1 = 0, ne1 = 0, idx1 = 0;
+    if (rp1 < total) {
+      lo1 = __ldg(a.row_ends + rp1 - 1);
+      ne1 = __ldg(a.row_ends + rp1) - lo1;
+      idx1 = lane < ne1 ? __ldg(a.col_src + lo1 + lane) : 0;
+    }
+    int rp2 = rp1 + nwarps, e2a = 0, e2b = 0;
+    if (rp2 < total) {
+      e2a = __ldg(a.row_ends + rp2 - 1);
+      e2b = __ldg(a.row_ends + rp2);
+    }
+    int buf = 0, rb = 0;
+    issue_gather(rp0, lo0, ne0 * a.f_in, idx0, 0, 0, 0, true);
+#pragma unroll
+    for (int f = 0; f < FR; ++f) issue_tile(rp0, f);
+    cp_async_commit();
+    cp_async_commit();  // keeps the two-groups-per-iteration cadence (see the wait below)
+
+    for (;;) {
+      const int nt0 = ne0 * a.f_in;
+      int base = 0;
+      do {
+        const bool last_chunk = base + 32 >= nt0;
+        // group A of this iteration: the next chunk's gather
+        if (!last_chunk) {
+          issue_gather(rp0, lo0, nt0, idx0, base + 32, buf ^ 1, rb, false);
+        } else if (rp1 < total) {
+          issue_gather(rp1, lo1, ne1 * a.f_in, idx1, 0, buf ^ 1, rb ^ 1, true);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();  // everything but group A: this chunk's gather and this row's dT tiles have landed
+        __syncwarp();
+        const bool valid = base + lane < nt0;
+        const int nq = (min(32, nt0 - base) + 7) >> 3;  // valid 8-neighbour groups (warp-uniform)
+        const float* Rs = reinterpret_cast<const float*>(wbase + SM::OFF_RS + rb * SM::RS_BYTES);
+        const float* rg = reinterpret_cast<const float*>(wbase + SM::OFF_RG + buf * SM::RG_BYTES) + lane * 12;
+        const __nv_bfloat16* Xs = reinterpret_cast<const __nv_bfloat16*>(wbase + buf * SM::X_BYTES);
+        float dx, dy, dz, Fq[9];
+        unpack_neighbour<false>(rg, Rs[0], Rs[1], Rs[2], a.norm, dx, dy, dz, Fq);
+#pragma unroll 1
+        for (int f = 0; f < FR; ++f) {
+          {
+            float Frow[9], gg[9];
+            load_row_frame(Rs, f, Frow);
+            geometry9<false>(Frow, Fq, dx, dy, dz, gg);
+            if (!valid) {
+#pragma unroll
+              for (int i = 0; i < 9; ++i) gg[i] = 0.0f;
+            }
+            store_geometry_row(Gs + lane * GSTR, gg, 1.0f);
+            uint4 p0, p1;
+            p0.x = pack_bf16(gg[0], gg[1]); p0.y = pack_bf16(gg[2], gg[3]);
+            p0.z = pack_bf16(gg[4], gg[5]); p0.w = pack_bf16(gg[6], gg[7]);
+            p1.x = pack_bf16(gg[8], valid ? 1.0f : 0.0f);  // column 9 = 1 -> bias gradient
+            p1.y = 0u; p1.z = 0u; p1.w = 0u;
+            uint4* gb = reinterpret_cast<uint4*>(Gb + lane * GB);
+            gb[0] = p0;
+            gb[1] = p1;
+          }
+          float dH[2][4][4];
+#pragma unroll
+          for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) dH[m][jj][i] = 0.0f;
+          __syncwarp();
+          const __nv_bfloat16* dTs = reinterpret_cast<const __nv_bfloat16*>(wbase + SM::OFF_T + f * SM::T_BYTES);
+          if (nq > 2)
+            edge_dh<CB, 2>(dH, dTs, Xs, lane);
+          else if (nq > 0)
+            edge_dh<CB, 1>(dH, dTs, Xs, lane);
+          if (last_chunk && rp1 < total) {
+            __syncwarp();            // every lane is done reading this frame's tile
+            issue_tile(rp1, f);      // group B: the next row's tile streams in behind the rest of this chunk
+          }
+          if (nq > 2)
+            edge_finish<2, ACT>(dH, accA, aw, Gs, Gb, lane, a.act);
+          else if (nq > 0)
+            edge_finish<1, ACT>(dH, accA, aw, Gs, Gb, lane, a.act);
+          __syncwarp();
+        }
+        cp_async_commit();  // group B (possibly empty)
+        buf ^= 1;
+        base += 32;
+      } while (base < nt0);
+      // ---- rotate the row pipeline
+      if (rp1 >= total) break;
+      rp0 = rp1; lo0 = lo1; ne0 = ne1; idx0 = idx1;
+      rb ^= 1;
+      rp1 = rp2;
+      if (rp1 < total) {
+        lo1 = e2a;
+        ne1 = e2b - e2a;
+        idx1 = lane < ne1 ? __ldg(a.col_src + lo1 + lane) : 0;
+      }
+      rp2 = rp1 + nwarps;
+      if (rp2 < total) {
+        e2a = __ldg(a.row_ends + rp2 - 1);
+        e2b = __ldg(a.row_ends + rp2);
+      }
+    }
+    cp_async_wait<0>();
+  }
+  // per-CTA partial [d (16)][k (32)]: warps -> shared memory (the staging area is free now), summed in
+  // warp order (deterministic)
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(smem_raw);  // [AGG_WARPS][512]
+  {
+    float* p = red + wib * 512;
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int dd = 0; dd < 2; ++dd) {
+        const int k = m * 16 + g, d = dd * 8 + 2 * t;
+        p[d * 32 + k] = accA[m][dd][0];
+        p[(d + 1) * 32 + k] = accA[m][dd][1];
+        p[d * 32 + k + 8] = accA[m][dd][2];
+        p[(d + 1) * 32 + k + 8] = accA[m][dd][3];
+      }
+  }
+  __syncthreads();
+  float* out = a.partials + (int64_t)blockIdx.x * 512;
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+    float s = red[i];
+#pragma unroll
+    for (int w = 1; w < AGG_WARPS; ++w) s += red[w * 512 + i];
+    out[i] = s;
+  }
+}
+
+template <int CB, int FR>
+static int launch_edge_row_cfg(const TcEdgeArgs& a, int n_warps, cudaStream_t st) {
+  static_assert(AGG_WARPS * EdgeRowSmem<CB, FR>::WARP_BYTES >= AGG_WARPS * 512 * 4, "partials must fit the staging area");
+  const size_t smem = AGG_WARPS * EdgeRowSmem<CB, FR>::WARP_BYTES;
+  ProfScope prof(2, st);
+  if (a.act == 2) {
+    auto kern = k_edge_row_tc<CB, FR, 2>;
+    SE3_SMEM_ONCE(kern, smem);
+    kern<<<n_warps / AGG_WARPS, AGG_WARPS * 32, smem, st>>>(a);
+  } else {
+    auto kern = k_edge_row_tc<CB, FR, -1>;
+    SE3_SMEM_ONCE(kern, smem);
+    kern<<<n_warps / AGG_WARPS, AGG_WARPS * 32, smem, st>>>(a);
+  }
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
+}
+
 // Ordered reduction of the per-CTA partials: block b owns outputs 32b..32b+31; warp w sums partials w, w+32, ...
 // (lane = output, 128-byte coalesced rows), then the 32 warp sums are added in warp order.
 __global__ void __launch_bounds__(1024) k_edge_tc_reduce(const float* __restrict__ partials, int n_partials,
@@ -796,6 +1013,7 @@ template <int CB>
 static int launch_edge_cfg(const TcEdgeArgs& a, int f_out, int n_warps, cudaStream_t st) {
   static_assert(AGG_WARPS * EdgeSmem<CB>::WARP_BYTES >= AGG_WARPS * 512 * 4, "partials must fit the staging area");
   const size_t smem = AGG_WARPS * EdgeSmem<CB>::WARP_BYTES;
+  ProfScope prof(2, st);
   if (a.act == 2) {
     auto kern = k_edge_tc<CB, 2>;
     SE3_SMEM_ONCE(kern, smem);
@@ -818,7 +1036,18 @@ static int launch_edge_tc(const TcEdgeArgs& a, int f_out, int64_t n_in, int n_wa
     set_error("launch_edge_tc: problem too large for 32-bit row offsets");
     return SE3_EINVAL;
   }
-  int rc = a.c <= 16 ? launch_edge_cfg<16>(a, f_out, n_warps, st) : launch_edge_cfg<32>(a, f_out, n_warps, st);
+  int rc;
+  if (a.c <= 64 && f_out <= 2) {
+    // one channel block: row items, the frames share the gather
+    if (a.c <= 16)
+      rc = f_out == 1 ? launch_edge_row_cfg<16, 1>(a, n_warps, st) : launch_edge_row_cfg<16, 2>(a, n_warps, st);
+    else if (a.c <= 32)
+      rc = f_out == 1 ? launch_edge_row_cfg<32, 1>(a, n_warps, st) : launch_edge_row_cfg<32, 2>(a, n_warps, st);
+    else
+      rc = f_out == 1 ? launch_edge_row_cfg<64, 1>(a, n_warps, st) : launch_edge_row_cfg<64, 2>(a, n_warps, st);
+  } else {
+    rc = a.c <= 16 ? launch_edge_cfg<16>(a, f_out, n_warps, st) : launch_edge_cfg<32>(a, f_out, n_warps, st);
+  }
   if (rc) return rc;
   k_edge_tc_reduce<<<10, 1024, 0, st>>>(a.partials, n_warps / AGG_WARPS, dA, dB);
   SE3_LAUNCH_CHECK();

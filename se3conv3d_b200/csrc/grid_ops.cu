@@ -18,6 +18,7 @@
 #include <stdarg.h>
 #include <atomic>
 #include <mutex>
+#include <vector>
 #include "common.cuh"
 
 namespace se3 {
@@ -30,7 +31,53 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+
+// ---- optional per-kernel device timing of the dominant kernels (bench.py's roofline): CUDA events on the
+// launching stream around each launch, summed on read.  Off by default: no events, no overhead.
+static bool g_prof_on = false;
+struct ProfRec { int id; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof;
+static std::mutex g_prof_mu;
+bool profile_enabled() { return g_prof_on; }
+void profile_begin(int id, cudaStream_t st, void** handle) {
+  *handle = nullptr;
+  if (!g_prof_on) return;
+  ProfRec* r = new ProfRec;
+  r->id = id;
+  if (cudaEventCreate(&r->a) != cudaSuccess || cudaEventCreate(&r->b) != cudaSuccess) { delete r; return; }
+  cudaEventRecord(r->a, st);
+  *handle = r;
+}
+void profile_end(void* handle, cudaStream_t st) {
+  if (!handle) return;
+  ProfRec* r = reinterpret_cast<ProfRec*>(handle);
+  cudaEventRecord(r->b, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(*r);
+  delete r;
+}
 }  // namespace se3
+
+extern "C" void se3_profile_enable(int32_t on) { se3::g_prof_on = on != 0; }
+// ms_out / count_out [SE3_PROF_KERNELS]: accumulated device time and launches per profiled kernel since the last
+// read (synchronises the device, then resets).
+extern "C" int se3_profile_read(double* ms_out, int64_t* count_out) {
+  using namespace se3;
+  for (int i = 0; i < SE3_PROF_KERNELS; ++i) { ms_out[i] = 0.0; count_out[i] = 0; }
+  if (cudaDeviceSynchronize() != cudaSuccess) { set_error("se3_profile_read: device synchronise failed"); return SE3_ECUDA; }
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess && r.id >= 0 && r.id < SE3_PROF_KERNELS) {
+      ms_out[r.id] += ms;
+      count_out[r.id] += 1;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  return SE3_OK;
+}
 
 using namespace se3;
 
