@@ -30,10 +30,12 @@ struct Bump {
   T* at(int64_t o) const { return reinterpret_cast<T*>(base + o); }
 };
 
+constexpr size_t kPinnedBytes = 16384;  // edge totals (<= 32 x 8 B) or the per-batch input boxes (B x 24 B)
+
 int64_t* pinned_scalars() {
   static int64_t* p = nullptr;
   if (!p) {
-    if (cudaHostAlloc(reinterpret_cast<void**>(&p), 64 * sizeof(int64_t), cudaHostAllocDefault) != cudaSuccess) p = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&p), kPinnedBytes, cudaHostAllocDefault) != cudaSuccess) p = nullptr;
   }
   return p;
 }
@@ -104,7 +106,7 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
   {
     float* hf = reinterpret_cast<float*>(host);
     // large batch counts: fall back to full-width sorts instead of a bigger host buffer
-    if ((size_t)d->n_batches * 6 * sizeof(float) <= 64 * sizeof(int64_t)) {
+    if ((size_t)d->n_batches * 6 * sizeof(float) <= kPinnedBytes) {
       SE3_CUDA(cudaMemcpyAsync(hf, ar.at<float>(o_rawmin[0]), bb, cudaMemcpyDeviceToHost, st));
       SE3_CUDA(cudaMemcpyAsync(hf + d->n_batches * 3, ar.at<float>(o_rawmax[0]), bb, cudaMemcpyDeviceToHost, st));
       SE3_CUDA(cudaStreamSynchronize(st));

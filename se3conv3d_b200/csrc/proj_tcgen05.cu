@@ -110,7 +110,7 @@ template <int BN, bool OUT_BF16>
 __global__ void __launch_bounds__(128) k_gemm_tcgen05(int M, int N, int K, float alpha, const __nv_bfloat16* __restrict__ A,
                                                       int64_t lda, const __nv_bfloat16* __restrict__ B, int64_t ldb,
                                                       void* __restrict__ Cout, int64_t ldc, int kb_per_split,
-                                                      int64_t split_stride) {
+                                                      int64_t split_stride, int nstages) {
   constexpr int B_STAGE_BYTES = BN * 128;
   constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   extern __shared__ unsigned char smem_dyn[];
@@ -120,7 +120,9 @@ __global__ void __launch_bounds__(128) k_gemm_tcgen05(int M, int N, int K, float
   // 1024-byte aligned operand ring
   const uint32_t raw = smem_u32(smem_dyn);
   const uint32_t ring = (raw + 1023u) & ~1023u;
-  const uint32_t a_ring = ring, b_ring = ring + STAGES * A_STAGE_BYTES;
+  // nstages (<= STAGES) ring slots are allocated: short-K products keep their footprint small enough for
+  // several CTAs per SM (their time is the epilogue, which needs the occupancy)
+  const uint32_t a_ring = ring, b_ring = ring + nstages * A_STAGE_BYTES;
   const int bm = blockIdx.y * BM, bn = blockIdx.x * BN;
   // split-K: blockIdx.z owns k-blocks [kb0, kb0 + nkb) and writes its partial tile to Cout + z * split_stride
   const int nkb_all = (K + BK - 1) / BK;
@@ -167,21 +169,27 @@ __global__ void __launch_bounds__(128) k_gemm_tcgen05(int M, int N, int K, float
     }
   };
 
-  for (int it = 0; it < nkb + STAGES - 1; ++it) {
+  for (int it = 0; it < nkb + nstages - 1; ++it) {
     if (it < nkb) {
-      const int s = it % STAGES;
-      if (it >= STAGES) mbar_wait(smem_u32(&bars[s]), (uint32_t)((it / STAGES - 1) & 1));  // slot consumed by the MMA
+      const int s = it % nstages;
+      if (it >= nstages) mbar_wait(smem_u32(&bars[s]), (uint32_t)((it / nstages - 1) & 1));  // slot consumed by the MMA
       load_stage(s, kb0 + it);
     }
     cp_async_commit();
-    const int c = it - (STAGES - 1);
+    const int c = it - (nstages - 1);
     if (c >= 0) {
-      cp_async_wait<STAGES - 1>();  // k-block c has landed (for this thread's copies)
+      // k-block c has landed (for this thread's copies): at most nstages - 1 younger groups may be pending
+      switch (nstages) {
+        case 1: cp_async_wait<0>(); break;
+        case 2: cp_async_wait<1>(); break;
+        case 3: cp_async_wait<2>(); break;
+        default: cp_async_wait<STAGES - 1>(); break;
+      }
       fence_proxy_async();          // make them visible to the tensor-core (async) proxy
       __syncthreads();
       if (tid == 0) {
         tc_fence_after();
-        const int s = c % STAGES;
+        const int s = c % nstages;
         const uint32_t as = a_ring + s * A_STAGE_BYTES;
         const uint32_t bs = b_ring + s * B_STAGE_BYTES;
 #pragma unroll
@@ -275,21 +283,24 @@ __global__ void __launch_bounds__(128) k_gemm_tcgen05(int M, int N, int K, float
 template <int BN, bool OB>
 int launch_cfg(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16* a, int64_t lda, const __nv_bfloat16* b,
                int64_t ldb, void* c, int64_t ldc, int splits, float* partials, cudaStream_t st) {
-  const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BN * 128) + 1024;
   auto kern = k_gemm_tcgen05<BN, OB>;
-  SE3_SMEM_ONCE(kern, smem);
   const int nkb = (int)((k + BK - 1) / BK);
   if (OB || partials == nullptr || splits < 1) splits = 1;
   int per = (nkb + splits - 1) / splits;
   splits = (nkb + per - 1) / per;
+  const int nstages = per < STAGES ? per : STAGES;
+  // the bf16 epilogue stages 4 KB per warp in the ring: keep at least 16 KB of it
+  size_t smem = (size_t)nstages * (A_STAGE_BYTES + BN * 128) + 1024;
+  if (smem < 16384 + 1024) smem = 16384 + 1024;
+  SE3_SMEM_ONCE(kern, (size_t)STAGES * (A_STAGE_BYTES + BN * 128) + 1024);
   dim3 grid((unsigned)((n + BN - 1) / BN), (unsigned)((m + BM - 1) / BM), (unsigned)splits);
   if (splits > 1) {
-    kern<<<grid, 128, smem, st>>>((int)m, (int)n, (int)k, 1.0f, a, lda, b, ldb, partials, n, per, m * n);
+    kern<<<grid, 128, smem, st>>>((int)m, (int)n, (int)k, 1.0f, a, lda, b, ldb, partials, n, per, m * n, nstages);
     SE3_LAUNCH_CHECK();
     splitk_reduce_launch(partials, splits, m * n, alpha, reinterpret_cast<float*>(c), st);
     SE3_LAUNCH_CHECK();
   } else {
-    kern<<<grid, 128, smem, st>>>((int)m, (int)n, (int)k, alpha, a, lda, b, ldb, c, ldc, nkb, (int64_t)0);
+    kern<<<grid, 128, smem, st>>>((int)m, (int)n, (int)k, alpha, a, lda, b, ldb, c, ldc, nkb, (int64_t)0, nstages);
     SE3_LAUNCH_CHECK();
   }
   return SE3_OK;

@@ -474,3 +474,29 @@ def wl_grid_of(pcs, lvl, step):
     from se3conv3d_b200 import workloads as wl
     from se3conv3d_b200.pc import Grid
     return Grid(pcs[lvl], wl.DFAUST_CFG["grid_subsamples"][lvl])
+
+
+@pytest.mark.parametrize("cin,cout,frames", [(64, 64, 2), (128, 32, 2), (1, 32, 2), (16, 48, 1), (48, 64, 1), (256, 128, 2)])
+def test_layer_bf16_matches_fp32_path_channel_sweep(cin, cout, frames):
+    """Every channel-block configuration of the tensor-core kernels (16 / 32 / 64-channel row items, multi-block
+    items, padded odd channel counts) against the fp32 exactness path on the same inputs: 3e-2 relative."""
+    from se3conv3d_b200.layers import PNEConvLayerRotEquiv
+    pc, neigh, x = _synthetic_layer_problem(1500, 0.2, frames, cin, cout, seed=5, batches=2)
+    torch.manual_seed(7)
+    layer = PNEConvLayerRotEquiv(9, cin, cout, 32, "mlp_gelu").to(DEV)
+    layer.norm_neigh_dist_.fill_(5.0)
+    layer.norm_num_neighs_.fill_(1500 / neigh.neighbors_.shape[0])
+    dy = torch.randn(1500 * frames, cout, generator=torch.Generator().manual_seed(9)).to(DEV)
+    res = []
+    for precision in (0, 1):
+        layer.precision = precision
+        layer.zero_grad()
+        xx = x.clone().requires_grad_(True)
+        y = layer(pc, pc, xx, neigh)
+        y.backward(dy)
+        res.append([t.detach().cpu().numpy() for t in (y, xx.grad, layer.conv_weights_.grad, layer.proj_axes_.grad,
+                                                       layer.proj_biases_.grad)])
+    for a, b, name in zip(res[1], res[0], ("y", "dx", "dW", "dA", "dB")):
+        err = rel_err(a, b)
+        print(cin, cout, frames, name, "bf16 vs fp32 rel err %.2e" % err)
+        assert err < 3e-2, name
