@@ -152,7 +152,7 @@ def main():
         return
     import torch
     import torch.distributed as dist
-    from se3conv3d_b200 import _lib, workloads as wl
+    from se3conv3d_b200 import _lib, shard, workloads as wl
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product has no CPU fallback)")
@@ -164,7 +164,7 @@ def main():
     L = _lib.lib()
 
     # ---- workload: 32 clouds x 6890 points per GPU (weak scaling: clouds are independent, no collective)
-    pts_h, batch_h = wl.synthetic_bodies(N_CLOUDS, N_POINTS, seed=rank)
+    pts_h, batch_h = wl.synthetic_bodies(N_CLOUDS, N_POINTS, seed=shard.shard_seed(rank))
     pts_h, batch_h = pts_h.pin_memory(), batch_h.pin_memory()
     step = wl.DfaustStep(dev, precision=args.precision, seed=0)
     pts_d, batch_d = pts_h.to(dev), batch_h.to(dev)
@@ -178,9 +178,7 @@ def main():
         return step.conv_fwd_bwd(pcs_, neighs_)
 
     def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        shard.barrier(dev)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -198,10 +196,7 @@ def main():
             tot += e0.elapsed_time(e1)
             step.zero_grad()
         barrier()
-        t = torch.tensor([tot], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return shard.max_over_ranks(tot, dev)
 
     clocks = ClockSampler(local_rank)
     clocks.start()

@@ -106,3 +106,18 @@ def frame_set_distance(a, b):
     """Max over points of the set distance between two frame sets [N,F,9] (order-free)."""
     d = (a[:, :, None, :] - b[:, None, :, :]).abs().amax(-1)   # [N,F,F]
     return torch.maximum(d.amin(2).amax(1), d.amin(1).amax(1))
+
+
+def standard_conv_forward(x, proj_axes, proj_biases, conv_weights, pts_in, pts_out, neighbors, norm_neigh_dist,
+                          norm_num_neighs, pne_type="mlp_gelu"):
+    """The non-equivariant PNEConvLayer with "add" aggregation: LinearPNE
+    (custom_ops/PNE.py:30-40: rel = (p_in[j] - p_out[i]) * norm; basis = rel @ A + b), activation, the scatter
+    formulation of FeatBasisProj, einsum with conv_weights_ and the norm_num_neighs_ scale
+    (layers/PNEConvLayer.py:161-229).  y [M, Cout]; differentiable wrt x and the three parameters."""
+    i, j = neighbors[:, 0].long(), neighbors[:, 1].long()
+    rel = (pts_in[j] - pts_out[i]) * norm_neigh_dist
+    h = act_fn(pne_type)(rel @ proj_axes + proj_biases[None, :])
+    cin, k, cout = conv_weights.shape
+    T = torch.zeros((pts_out.shape[0], cin, k), dtype=x.dtype)
+    T.index_add_(0, i, x[j][:, :, None] * h[:, None, :])
+    return torch.einsum("nik,iko->no", T, conv_weights) * norm_num_neighs

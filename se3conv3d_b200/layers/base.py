@@ -44,6 +44,17 @@ class IConvLayer(PreProcessModule, ABC):
     def __compute_convolution__(self, p_pc_in, p_pc_out, p_in_features, p_neighborhood):
         pass
 
+    def _host_scalars(self):
+        """Host copies of the two scalar buffers, refreshed only when a buffer was replaced or written
+        (pre-processing, load_state_dict, .fill_) -- so a steady-state forward never synchronises."""
+        key = (id(self.norm_neigh_dist_), self.norm_neigh_dist_._version, id(self.norm_num_neighs_),
+               self.norm_num_neighs_._version)
+        cache = getattr(self, "_scalar_cache", None)
+        if cache is None or cache[0] != key:
+            cache = (key, float(self.norm_neigh_dist_), float(self.norm_num_neighs_))
+            self._scalar_cache = cache
+        return cache[1], cache[2]
+
     def forward(self, p_pc_in, p_pc_out, p_in_features, p_neighborhood):
         if self.pre_process_:
             with torch.no_grad():

@@ -58,18 +58,6 @@ class PNEConvLayerRotEquiv(IConvLayer):
         return RotEquivConv.apply(p_in_features, self.proj_axes_, self.proj_biases_, self.conv_weights_, geom,
                                   ACT_CODES[self.pne_type_], int(self.precision), norm_dist, norm_num / geom.f_in)
 
-    def _host_scalars(self):
-        """Host copies of the two scalar buffers, refreshed only when a buffer was replaced or written
-        (pre-processing, load_state_dict, .fill_) -- so a steady-state forward never synchronises."""
-        key = (id(self.norm_neigh_dist_), self.norm_neigh_dist_._version, id(self.norm_num_neighs_),
-               self.norm_num_neighs_._version)
-        cache = getattr(self, "_scalar_cache", None)
-        if cache is None or cache[0] != key:
-            cache = (key, float(self.norm_neigh_dist_), float(self.norm_num_neighs_))
-            self._scalar_cache = cache
-        return cache[1], cache[2]
-
-
 class PNEConvLayerRotEquivFactory(IConvLayerFactory):
     """Factory with the reference's signature (layers/PNEConvLayerRotEquiv.py:236-281)."""
 

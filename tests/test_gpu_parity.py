@@ -500,3 +500,139 @@ def test_layer_bf16_matches_fp32_path_channel_sweep(cin, cout, frames):
         err = rel_err(a, b)
         print(cin, cout, frames, name, "bf16 vs fp32 rel err %.2e" % err)
         assert err < 3e-2, name
+
+
+@pytest.mark.parametrize("precision,tol", [(0, 1e-4), (1, 3e-2)])
+def test_standard_pne_conv_layer_matches_oracle(precision, tol):
+    """the non-equivariant PNEConvLayer (layers/PNEConvLayer.py:161-229) on the fused kernels
+    against the CPU oracle in float64, outputs and all gradients."""
+    from se3conv3d_b200.layers import PNEConvLayer
+    from se3conv3d_b200.pc import Pointcloud, BQNeighborhood
+    n, r = 3000, 0.15
+    pts = torch.rand(n, 3, generator=torch.Generator().manual_seed(11))
+    batch = torch.sort(torch.randint(0, 3, (n,), generator=torch.Generator().manual_seed(12)))[0].to(torch.int32)
+    pc = Pointcloud(pts.to(DEV), batch.to(DEV))
+    neigh = BQNeighborhood(pc, pc, r)
+    torch.manual_seed(13)
+    layer = PNEConvLayer(3, 24, 40, 32, "mlp_gelu").to(DEV)
+    layer.precision = precision
+    with torch.no_grad():
+        layer.proj_biases_.uniform_(-0.2, 0.2)
+    layer.norm_neigh_dist_.fill_(1.0 / r)
+    layer.norm_num_neighs_.fill_(n / neigh.neighbors_.shape[0])
+    x = torch.randn(n, 24, generator=torch.Generator().manual_seed(14)).to(DEV).requires_grad_(True)
+    dy = torch.randn(n, 40, generator=torch.Generator().manual_seed(15)).to(DEV)
+    y = layer(pc, pc, x, neigh)
+    y.backward(dy)
+    c = lambda t: t.detach().cpu().double()
+    xo = c(x).requires_grad_(True)
+    A, B, W = (c(p).requires_grad_(True) for p in (layer.proj_axes_, layer.proj_biases_, layer.conv_weights_))
+    yo = lo.standard_conv_forward(xo, A, B, W, c(pc.pts_), c(pc.pts_), neigh.neighbors_.cpu(),
+                                  float(layer.norm_neigh_dist_), float(layer.norm_num_neighs_))
+    yo.backward(c(dy))
+    assert layer.proj_axes_.grad.shape == (3, 32)
+    for got, want, name in ((y, yo, "y"), (x.grad, xo.grad, "dx"), (layer.conv_weights_.grad, W.grad, "dW"),
+                            (layer.proj_axes_.grad, A.grad, "dA"), (layer.proj_biases_.grad, B.grad, "dB")):
+        err = rel_err(got.detach().cpu().numpy(), want.detach().numpy())
+        print("standard layer precision", precision, name, "rel err %.2e" % err)
+        assert err < tol, name
+
+
+def test_config3_classification_shapes_mc_frames():
+    """BASELINE config 3 shapes at reduced batch: 1,024-point clouds on a sphere, F=4 Monte-Carlo frames (pca False),
+    4 -> 2 frame down-sampling conv: bf16 path vs fp32 path, determinism of the fp32 path."""
+    from se3conv3d_b200.layers import PNEConvLayerRotEquiv
+    from se3conv3d_b200.pc import PointcloudRotEquiv, BQNeighborhood, GridSubSample
+    g = torch.Generator().manual_seed(21)
+    b_items, n_pts = 8, 1024
+    p = torch.randn(b_items * n_pts, 3, generator=g)
+    p = p / p.norm(dim=1, keepdim=True) + 0.01 * torch.randn(b_items * n_pts, 3, generator=g)
+    batch = torch.arange(b_items).repeat_interleave(n_pts).to(torch.int32)
+    cfg4 = {"pca": False, "neigh_method": "knn", "neigh_kwargs": {"neigh_k": 16}, "fixed_axis": False, "n_frames": 4}
+    torch.manual_seed(22)
+    pc = PointcloudRotEquiv(p.to(DEV), batch.to(DEV), cfg4)
+    assert pc.local_frames_.shape == (b_items * n_pts, 4, 9)
+    samp = GridSubSample(pc, 0.1)
+    pc2 = PointcloudRotEquiv(samp.__subsample_tensor__(pc.pts_, "avg"), samp.__subsample_tensor__(pc.batch_ids_, "max"),
+                             dict(cfg4, n_frames=2))
+    for (pin, pout, fi, fo, cin, cout) in ((pc, pc, 4, 4, 16, 32), (pc, pc2, 4, 2, 32, 64)):
+        neigh = BQNeighborhood(pin, pout, 0.2)
+        torch.manual_seed(23)
+        layer = PNEConvLayerRotEquiv(9, cin, cout, 32, "mlp_gelu").to(DEV)
+        layer.norm_neigh_dist_.fill_(5.0)
+        layer.norm_num_neighs_.fill_(pout.pts_.shape[0] / neigh.neighbors_.shape[0])
+        x = torch.randn(pin.pts_.shape[0] * fi, cin, generator=torch.Generator().manual_seed(24)).to(DEV)
+        dy = torch.randn(pout.pts_.shape[0] * fo, cout, generator=torch.Generator().manual_seed(25)).to(DEV)
+        res = []
+        for precision in (0, 0, 1):
+            layer.precision = precision
+            layer.zero_grad()
+            xx = x.clone().requires_grad_(True)
+            y = layer(pin, pout, xx, neigh)
+            assert y.shape == (pout.pts_.shape[0] * fo, cout)
+            y.backward(dy)
+            res.append([t.detach().clone() for t in (y, xx.grad, layer.conv_weights_.grad, layer.proj_axes_.grad,
+                                                     layer.proj_biases_.grad)])
+        for a, b in zip(res[0], res[1]):
+            assert torch.equal(a, b), "the fp32 path must be deterministic"
+        for a, b, name in zip(res[2], res[0], ("y", "dx", "dW", "dA", "dB")):
+            err = rel_err(a.cpu().numpy(), b.cpu().numpy())
+            print("config3 F=%d->%d" % (fi, fo), name, "bf16 vs fp32 rel err %.2e" % err)
+            assert err < 3e-2, name
+
+
+def test_config4_scannet_shapes_fixed_axis():
+    """BASELINE config 4 shapes: one 150k-point room-like scene, F=1 PCA frames about a fixed up axis, 5-level
+    hierarchy through the fused builder; CSR properties at full size and a conv fwd+bwd (bf16 vs fp32)."""
+    from se3conv3d_b200.layers import PNEConvLayerRotEquiv
+    from se3conv3d_b200.pc import build_point_hierarchy
+    g = torch.Generator().manual_seed(31)
+    n = 150000
+    # points on the floor, two walls and a few boxes of an 8 x 6 x 3 m room
+    u = torch.rand(n, 3, generator=g)
+    which = torch.randint(0, 4, (n,), generator=g)
+    p = torch.stack((u[:, 0] * 8, u[:, 1] * 6, u[:, 2] * 3), 1)
+    p[which == 0, 2] = 0.0
+    p[which == 1, 0] = 0.0
+    p[which == 2, 1] = 0.0
+    p[which == 3] = p[which == 3] * torch.tensor([0.15, 0.2, 0.3]) + torch.tensor([3.0, 2.0, 0.0])
+    p = (p + 0.004 * torch.randn(n, 3, generator=g)).to(torch.float32)
+    batch = torch.zeros(n, dtype=torch.int32)
+    cfg = {"pca": True, "neigh_method": "knn", "neigh_kwargs": {"neigh_k": 16}, "fixed_axis": 2, "n_frames": 1}
+    grids = [0.2, 0.4, 0.8, 1.6]
+    wanted = [(0, 0, 0.2), (0, 1, 0.2), (1, 1, 0.4), (2, 1, 0.8), (4, 3, 3.2)]
+    h, _ = build_point_hierarchy(p.to(DEV), batch.to(DEV), cfg, 0.1, grids, neighborhoods=wanted, n_batches=1)
+    sizes = [pc.pts_.shape[0] for pc in h.pcs_]
+    assert len(sizes) == 5 and all(a > b for a, b in zip(sizes, sizes[1:])), sizes
+    for pc in h.pcs_:
+        assert pc.local_frames_.shape == (pc.pts_.shape[0], 1, 9)
+        R = pc.local_frames_.reshape(-1, 3, 3)
+        assert float((R @ R.transpose(1, 2) - torch.eye(3, device=DEV)).abs().max()) < 1e-4   # orthonormal frames
+    for nb, (s, t, r) in zip(h.fused_neighborhoods_, wanted):
+        ends = nb.start_ids_.to(torch.int64)
+        assert bool((ends[1:] >= ends[:-1]).all())
+        pairs = nb.neighbors_
+        assert int(ends[-1]) == pairs.shape[0]
+        d = (h.pcs_[s].pts_[pairs[:, 1]] - h.pcs_[t].pts_[pairs[:, 0]]).norm(dim=1)
+        assert float(d.max()) < r * (1 + 1e-5)
+        assert bool((pairs[1:, 0] >= pairs[:-1, 0]).all())          # grouped by sample
+    pc, nb = h.pcs_[0], h.fused_neighborhoods_[0]
+    torch.manual_seed(32)
+    layer = PNEConvLayerRotEquiv(9, 32, 32, 32, "mlp_gelu").to(DEV)
+    layer.norm_neigh_dist_.fill_(5.0)
+    layer.norm_num_neighs_.fill_(pc.pts_.shape[0] / nb.neighbors_.shape[0])
+    x = torch.randn(pc.pts_.shape[0], 32, generator=torch.Generator().manual_seed(33)).to(DEV)
+    dy = torch.randn(pc.pts_.shape[0], 32, generator=torch.Generator().manual_seed(34)).to(DEV)
+    res = []
+    for precision in (0, 1):
+        layer.precision = precision
+        layer.zero_grad()
+        xx = x.clone().requires_grad_(True)
+        y = layer(pc, pc, xx, nb)
+        y.backward(dy)
+        res.append([t.detach().cpu().numpy() for t in (y, xx.grad, layer.conv_weights_.grad, layer.proj_axes_.grad,
+                                                       layer.proj_biases_.grad)])
+    for a, b, name in zip(res[1], res[0], ("y", "dx", "dW", "dA", "dB")):
+        err = rel_err(a, b)
+        print("config4 F=1", name, "bf16 vs fp32 rel err %.2e" % err)
+        assert err < 3e-2, name
