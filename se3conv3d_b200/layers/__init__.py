@@ -2,3 +2,4 @@
 from .base import PreProcessModule, IConvLayer, IConvLayerFactory
 from .pne_conv_rot_equiv import PNEConvLayerRotEquiv, PNEConvLayerRotEquivFactory
 from .pne_conv import PNEConvLayer, PNEConvLayerFactory
+from .blocks import NormLayerPC, BatchNormPC, DropPathPC, SkipConnection, Block, ResNetFormer

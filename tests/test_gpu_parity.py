@@ -636,3 +636,24 @@ def test_config4_scannet_shapes_fixed_axis():
         err = rel_err(a, b)
         print("config4 F=1", name, "bf16 vs fp32 rel err %.2e" % err)
         assert err < 3e-2, name
+
+
+def test_resnetformer_block_forward_backward():
+    """Row f2: a ResNetFormer block around the fused conv trains: finite outputs / gradients for every parameter,
+    and with gamma = 1e-6 the block output is the skip path within 1e-4."""
+    from se3conv3d_b200.layers import ResNetFormer, BatchNormPC, PNEConvLayerRotEquivFactory
+    pc, neigh, x = _synthetic_layer_problem(2000, 0.18, 2, 32, 32, seed=41, batches=3)
+    torch.manual_seed(42)
+    fact = PNEConvLayerRotEquivFactory(9, 32, "mlp_gelu")
+    blk = ResNetFormer(32, 48, fact, BatchNormPC, 0.0).to(DEV)
+    blk.spatial_conv_.precision = 1
+    blk.spatial_conv_.norm_neigh_dist_.fill_(1 / 0.18)
+    blk.spatial_conv_.norm_num_neighs_.fill_(2000 / neigh.neighbors_.shape[0])
+    xx = x.clone().requires_grad_(True)
+    y = blk(pc, xx, neigh)
+    assert y.shape == (4000, 48) and bool(torch.isfinite(y).all())
+    assert rel_err(y.detach().cpu().numpy(), blk.skip_conv_(xx).detach().cpu().numpy()) < 1e-4
+    y.square().mean().backward()
+    for name, p in blk.named_parameters():
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all()), name
+    assert float(blk.spatial_conv_.conv_weights_.grad.abs().max()) > 0.0

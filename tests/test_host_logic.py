@@ -2,6 +2,7 @@
 factory behaviour, scatter helpers -- everything that does not need a kernel."""
 import types
 
+import pytest
 import torch
 
 from se3conv3d_b200.layers import PNEConvLayerRotEquiv, PNEConvLayerRotEquivFactory, PreProcessModule
@@ -71,3 +72,34 @@ def test_scatter_helpers():
     assert torch.equal(scatter.scatter_max(src, idx)[0], torch.tensor([[1.0, 2.0], [0.0, 0.0], [7.0, 7.0]]))
     assert torch.equal(scatter.scatter_min(src, idx)[0], torch.tensor([[-1.0, 0.0], [0.0, 0.0], [3.0, 5.0]]))
     assert all_index_combinations(2, 3).tolist() == [[0, 0], [0, 1], [0, 2], [1, 0], [1, 1], [1, 2]]
+
+
+def test_block_modules_state_dict_and_drop_path():
+    """Row f2: ResNetFormer / BatchNormPC / SkipConnection / DropPathPC keep the reference's parameter names
+    (layers/ResNetFormer.py:37-52, SkipConnection.py:27-29, BatchNormPC.py:21) and drop-path semantics."""
+    import types
+    from se3conv3d_b200.layers import (ResNetFormer, BatchNormPC, SkipConnection, DropPathPC,
+                                       PNEConvLayerRotEquivFactory)
+    fact = PNEConvLayerRotEquivFactory(9, 32, "mlp_gelu")
+    blk = ResNetFormer(16, 24, fact, BatchNormPC, 0.1)
+    keys = set(blk.state_dict().keys())
+    for k in ("spatial_conv_.proj_axes_", "spatial_conv_.conv_weights_", "norm_1_.layer_.weight",
+              "norm_2_.layer_.running_mean", "linear_1_.weight", "linear_2_.bias", "skip_path_1_.gamma_",
+              "skip_path_2_.gamma_", "skip_conv_.weight"):
+        assert k in keys, k
+    assert blk.linear_1_.weight.shape == (32, 16) and blk.linear_2_.weight.shape == (24, 32)
+    assert float(blk.skip_path_1_.gamma_[0, 0]) == pytest.approx(1e-6)
+    assert blk.norm_1_.layer_.momentum == 0.2 and len(fact.conv_list_) == 1
+    # drop path: identity in eval mode; in training whole batch items are zeroed and the rest rescaled
+    pc = types.SimpleNamespace(batch_size_=torch.tensor(4), batch_ids_=torch.tensor([0, 0, 1, 2, 3, 3], dtype=torch.int32))
+    dp = DropPathPC(0.5)
+    x = torch.ones(6, 3)
+    dp.eval()
+    assert torch.equal(dp(x, pc), x)
+    dp.train()
+    torch.manual_seed(0)
+    y = dp(x, pc)
+    assert set(y.unique().tolist()) <= {0.0, 2.0}
+    assert torch.equal(y[0], y[1]) and torch.equal(y[4], y[5])
+    sk = SkipConnection(0.0, 3)
+    assert torch.allclose(sk(x, 2 * x, pc), 2 * x + 1e-6)

@@ -1,9 +1,5 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/bench_v16.log 2>&1; python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/bench_v16.log').read().strip().splitlines()[-1])
-print(d['value'], d['ms_per_step'], d['breakdown_ms'])
-r=d['roofline']; print(r['kernel'], r['frac'], r['kernel_ms'])
-for k in r['gather_kernels_per_step']: print(k)
-for k in r['largest_launch_all_kernels']: print(k)
-PY
+for v in 1 0; do
+export SE3_AGG_PAIR=$v; echo "SE3_AGG_PAIR=$v"
+python tools/layer_kernel_table.py 2>&1 | grep -E "seg_head|patch_dec0|dec2|enc0_block0|fpn0|enc1_block0|total"
+done
