@@ -657,3 +657,57 @@ def test_resnetformer_block_forward_backward():
     for name, p in blk.named_parameters():
         assert p.grad is not None and bool(torch.isfinite(p.grad).all()), name
     assert float(blk.spatial_conv_.conv_weights_.grad.abs().max()) > 0.0
+
+
+@pytest.mark.parametrize("precision,tol", [(0, 1e-4), (1, 3e-2)])
+def test_layer_ragged_rows_and_empty_neighbourhoods(precision, tol):
+    """Ragged CSR: output points without any neighbour (empty rows -> exact zeros), rows longer than one 32-entry
+    chunk and longer than the 32-edge id prefetch, two batch items of very different size; plus a neighbourhood
+    with no edge at all (zero output, zero gradients)."""
+    from se3conv3d_b200.layers import PNEConvLayerRotEquiv
+    from se3conv3d_b200.pc import PointcloudRotEquiv, BQNeighborhood
+    g = torch.Generator().manual_seed(51)
+    cfg = {"pca": True, "neigh_method": "knn", "neigh_kwargs": {"neigh_k": 16}, "fixed_axis": False, "n_frames": 2}
+    dense = torch.rand(900, 3, generator=g) * 0.3                       # item 0: dense blob (rows of ~100+ edges)
+    sparse = torch.rand(60, 3, generator=g) * 4.0 + 10.0                # item 1: isolated points
+    src_pts = torch.cat((dense, sparse))
+    src_b = torch.cat((torch.zeros(900), torch.ones(60))).to(torch.int32)
+    dst_pts = torch.cat((torch.rand(200, 3, generator=g) * 0.3, torch.rand(40, 3, generator=g) * 4.0 + 30.0))
+    dst_b = torch.cat((torch.zeros(200), torch.ones(40))).to(torch.int32)
+    torch.manual_seed(52)
+    pc_in = PointcloudRotEquiv(src_pts.to(DEV), src_b.to(DEV), cfg)
+    pc_out = PointcloudRotEquiv(dst_pts.to(DEV), dst_b.to(DEV), cfg)
+    neigh = BQNeighborhood(pc_in, pc_out, 0.12)
+    ends = neigh.start_ids_.cpu().numpy()
+    counts = np.diff(ends, prepend=0)
+    assert counts[200:].max() == 0 and counts[:200].max() > 40          # empty rows and rows > 32 edges
+    torch.manual_seed(53)
+    layer = PNEConvLayerRotEquiv(9, 32, 32, 32, "mlp_gelu").to(DEV)
+    layer.precision = precision
+    layer.norm_neigh_dist_.fill_(1 / 0.12)
+    layer.norm_num_neighs_.fill_(240 / max(neigh.neighbors_.shape[0], 1))
+    x = torch.randn(960 * 2, 32, generator=torch.Generator().manual_seed(54)).to(DEV).requires_grad_(True)
+    dy = torch.randn(240 * 2, 32, generator=torch.Generator().manual_seed(55)).to(DEV)
+    y = layer(pc_in, pc_out, x, neigh)
+    y.backward(dy)
+    assert float(y[400:].abs().max()) == 0.0                             # rows without neighbours
+    assert float(x.grad[1800:].abs().max()) == 0.0                       # sources nobody gathers
+    c = lambda t: t.detach().cpu().double()
+    xo = c(x).requires_grad_(True)
+    A, B, W = (c(p).requires_grad_(True) for p in (layer.proj_axes_, layer.proj_biases_, layer.conv_weights_))
+    yo = lo.conv_forward(xo, A, B, W, c(pc_in.pts_), c(pc_out.pts_), c(pc_in.local_frames_), c(pc_out.local_frames_),
+                         neigh.neighbors_.cpu(), float(layer.norm_neigh_dist_), float(layer.norm_num_neighs_))
+    yo.backward(c(dy))
+    for got, want, name in ((y, yo, "y"), (x.grad, xo.grad, "dx"), (layer.conv_weights_.grad, W.grad, "dW"),
+                            (layer.proj_axes_.grad, A.grad, "dA"), (layer.proj_biases_.grad, B.grad, "dB")):
+        assert rel_err(got.detach().cpu().numpy(), want.detach().numpy()) < tol, name
+    # no edge at all
+    far = PointcloudRotEquiv((dst_pts + 100.0).to(DEV), dst_b.to(DEV), cfg)
+    none = BQNeighborhood(pc_in, far, 0.05)
+    assert none.neighbors_.shape[0] == 0
+    layer.zero_grad()
+    x2 = x.detach().clone().requires_grad_(True)
+    y0 = layer(pc_in, far, x2, none)
+    y0.backward(dy)
+    assert float(y0.abs().max()) == 0.0 and float(x2.grad.abs().max()) == 0.0
+    assert float(layer.conv_weights_.grad.abs().max()) == 0.0 and float(layer.proj_axes_.grad.abs().max()) == 0.0
