@@ -20,6 +20,34 @@ struct ProfScope {
   ~ProfScope() { profile_end(h, st); }
 };
 
+// key sort shared by the grid / ball-query / kNN builders (grid_ops.cu): per-batch-item CTA sort when
+// 0 < max_seg <= 7168 points per item, device-wide radix sort otherwise
+constexpr int kSegSortMax = 7168;
+size_t sort_pairs_tmp_bytes(int64_t n);
+int batch_counts(const int32_t* batch_ids, int64_t n, int32_t n_batches, int32_t* counts_out, cudaStream_t st);
+int sort_keys_u64(const uint64_t* keys_in, const int* iota, const int* batch, int64_t n, int n_batches, int max_seg,
+                  uint64_t* keys_out, int* idx_out, int end_bit, void* cub_tmp, size_t cub_bytes, cudaStream_t st);
+// entry points with the batch-size hint of the fused hierarchy builder (the extern "C" versions pass 0 = unknown)
+int grid_cells_impl(const float* pts, const int32_t* batch_ids, int64_t n, const float* min_pt, const int32_t* num_cells,
+                    float cell, void* workspace, size_t workspace_bytes, int64_t* cell_ids, int64_t* sorted_ids,
+                    int32_t* cell_ends, int64_t* m_out, int32_t key_bits, int32_t n_batches, int32_t max_seg,
+                    int32_t* batch_cells, se3_stream_t stream);
+int ball_query_prepare_impl(const float* pts_src, const int32_t* batch_src, int64_t n_src, int64_t n_dst_max,
+                            const float* min_pt, const int32_t* num_cells, const float* radius, void* ws_src,
+                            size_t ws_src_bytes, int32_t key_bits, int32_t n_batches, int32_t max_seg, se3_stream_t stream);
+int bq_count_transposed(const float* pts_dst, const int32_t* batch_dst, int64_t n_src, int64_t n_dst, int64_t n_dst_max,
+                        const float* min_pt, const int32_t* num_cells, const float* radius, void* ws_src,
+                        size_t ws_src_bytes, void* ws_dst, size_t ws_dst_bytes, int32_t* row_ends_out, int32_t* t_row_out,
+                        int64_t* total_out, se3_stream_t stream);
+int bq_fill_transposed(const float* pts_dst, int64_t n_src, int64_t n_dst, int64_t n_dst_max, const float* radius,
+                       void* ws_src, size_t ws_src_bytes, void* ws_dst, size_t ws_dst_bytes, const int32_t* row_ends,
+                       int64_t n_edges, int32_t* col_src_out, int32_t* edge_dst_out, int32_t* t_row, int32_t* t_edge,
+                       int32_t* t_dst, se3_stream_t stream);
+int frames_select_pack(const float* cand, const float* u, int64_t n, int32_t n_cand, int32_t n_keep, float* out,
+                       const float* pts, float* rec, se3_stream_t stream);
+int knn_query_impl(const float* pts, const int32_t* batch_ids, int64_t n, int32_t k, void* workspace,
+                   size_t workspace_bytes, int32_t* out, int32_t n_batches, int32_t max_seg, se3_stream_t stream);
+
 inline cudaStream_t as_stream(se3_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 #define SE3_CHECK_ARG(cond, msg)                     \

@@ -201,11 +201,57 @@ __global__ void k_bbox_reduce(const float* __restrict__ pts, const int* __restri
   }
 }
 
+// one CTA per batch item (batch ids are non-decreasing): no initialisation pass, no atomics
+__global__ void __launch_bounds__(256) k_bbox_seg(const float* __restrict__ pts, const int* __restrict__ batch, int n,
+                                                  float* __restrict__ mn, float* __restrict__ mx) {
+  __shared__ int s_lo, s_hi;
+  __shared__ float s_red[8][6];
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (batch[mid] < b) lo = mid + 1; else hi = mid; }
+    s_lo = lo;
+    hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (batch[mid] < b + 1) lo = mid + 1; else hi = mid; }
+    s_hi = lo;
+  }
+  __syncthreads();
+  float v[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  for (int i = s_lo + threadIdx.x; i < s_hi; i += blockDim.x) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float x = pts[3 * (int64_t)i + d];
+      v[d] = fminf(v[d], x);
+      v[3 + d] = fmaxf(v[3 + d], x);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 6; ++d)
+    for (int o = 16; o > 0; o >>= 1) {
+      const float y = __shfl_xor_sync(0xffffffffu, v[d], o);
+      v[d] = d < 3 ? fminf(v[d], y) : fmaxf(v[d], y);
+    }
+  if ((threadIdx.x & 31) == 0)
+    for (int d = 0; d < 6; ++d) s_red[threadIdx.x >> 5][d] = v[d];
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    const int d = threadIdx.x;
+    float r = s_red[0][d];
+    for (int w = 1; w < 8; ++w) r = d < 3 ? fminf(r, s_red[w][d]) : fmaxf(r, s_red[w][d]);
+    if (d < 3) mn[3 * b + d] = r; else mx[3 * b + d - 3] = r;
+  }
+}
+
 // raw per-batch bounding box (no padding): mn/mx [B,3]; batches without points keep (+inf, -inf)
 extern "C" int se3_bbox(const float* pts, const int32_t* batch_ids, int64_t n, int32_t n_batches, float* min_out,
                         float* max_out, se3_stream_t stream) {
   SE3_CHECK_ARG(n >= 0 && n_batches >= 1 && pts && batch_ids && min_out && max_out, "bad arguments");
   cudaStream_t st = as_stream(stream);
+  if (n < (1ll << 31) && n_batches <= 65535 && n / n_batches <= 16384) {
+    k_bbox_seg<<<n_batches, 256, 0, st>>>(pts, batch_ids, (int)n, min_out, max_out);
+    SE3_LAUNCH_CHECK();
+    return SE3_OK;
+  }
   k_bbox_init<<<(n_batches * 3 + 127) / 128, 128, 0, st>>>(min_out, max_out, n_batches * 3);
   SE3_LAUNCH_CHECK();
   if (n > 0) {
@@ -215,8 +261,10 @@ extern "C" int se3_bbox(const float* pts, const int32_t* batch_ids, int64_t n, i
   return SE3_OK;
 }
 
-__global__ void k_bbox_finalize(float* mn, float* mx, int nb, float cell, float max_pad, int* num_cells) {
-  // one warp; batches without points keep (+inf, -inf) and do not contribute
+__global__ void k_bbox_finalize(const float* raw_mn, const float* raw_mx, float* mn, float* mx,
+                                int nb, float cell, float max_pad, int* num_cells) {
+  // one warp; raw box in (may alias the padded box out); batches without points keep (+inf, -inf) in the raw box,
+  // get a zero box and do not contribute
   const int lane = threadIdx.x;
   const float inv = __fdiv_rn(1.0f, cell);
   int best[3] = {1, 1, 1};
@@ -224,7 +272,7 @@ __global__ void k_bbox_finalize(float* mn, float* mx, int nb, float cell, float 
   for (int b = lane; b < nb; b += 32) {
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      const float lo = mn[3 * b + d], hi = mx[3 * b + d];
+      const float lo = raw_mn[3 * b + d], hi = raw_mx[3 * b + d];
       if (lo <= hi) {
         const float plo = __fsub_rn(lo, 1e-6f), phi = __fadd_rn(hi, max_pad);
         mn[3 * b + d] = plo;
@@ -236,21 +284,13 @@ __global__ void k_bbox_finalize(float* mn, float* mx, int nb, float cell, float 
         mx[3 * b + d] = 0.0f;
       }
     }
-    if (mn[3 * b] <= mx[3 * b]) any = true;
+    any = true;
   }
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     int v = any ? best[d] : INT_MIN;
     for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
     if (lane == 0) num_cells[d] = v == INT_MIN ? 1 : v;
-  }
-}
-
-__global__ void k_bbox_copy(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ ao,
-                            float* __restrict__ bo, int n) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    ao[i] = a[i];
-    bo[i] = b[i];
   }
 }
 
@@ -261,9 +301,7 @@ extern "C" int se3_grid_extents(const float* raw_min, const float* raw_max, int3
   SE3_CHECK_ARG(n_batches >= 1 && cell > 0.0f && raw_min && raw_max && min_pt_out && max_pt_out && num_cells_out,
                 "bad arguments");
   cudaStream_t st = as_stream(stream);
-  k_bbox_copy<<<1, 128, 0, st>>>(raw_min, raw_max, min_pt_out, max_pt_out, n_batches * 3);
-  SE3_LAUNCH_CHECK();
-  k_bbox_finalize<<<1, 32, 0, st>>>(min_pt_out, max_pt_out, n_batches, cell, max_pad, num_cells_out);
+  k_bbox_finalize<<<1, 32, 0, st>>>(raw_min, raw_max, min_pt_out, max_pt_out, n_batches, cell, max_pad, num_cells_out);
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }
@@ -280,14 +318,16 @@ extern "C" int se3_grid_setup(const float* pts, const int32_t* batch_ids, int64_
     k_bbox_reduce<<<grid_for(n, 256), 256, 0, st>>>(pts, batch_ids, n, min_pt_out, max_pt_out);
     SE3_LAUNCH_CHECK();
   }
-  k_bbox_finalize<<<1, 32, 0, st>>>(min_pt_out, max_pt_out, n_batches, cell, max_pad, num_cells_out);
+  k_bbox_finalize<<<1, 32, 0, st>>>(min_pt_out, max_pt_out, min_pt_out, max_pt_out, n_batches, cell, max_pad,
+                                    num_cells_out);
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }
 
 __global__ void k_cell_keys(const float* __restrict__ pts, const int* __restrict__ batch, int64_t n,
                             const float* __restrict__ aabb_min, const int* __restrict__ num_cells, float cell,
-                            int64_t* __restrict__ keys, int* __restrict__ iota) {
+                            int64_t* __restrict__ keys, int* __restrict__ iota, int* __restrict__ zero, int n_zero) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_zero; i += gridDim.x * blockDim.x) zero[i] = 0;
   GridParams g;
   g.nx = num_cells[0]; g.ny = num_cells[1]; g.nz = num_cells[2];
   g.ix = g.iy = g.iz = __fdiv_rn(1.0f, cell);
@@ -306,9 +346,12 @@ __global__ void k_cell_flags(const int64_t* __restrict__ keys_sorted, int64_t n,
     flags[i] = (i == 0 || keys_sorted[i] != keys_sorted[i - 1]) ? 1 : 0;
 }
 
+// batch / batch_cells (optional): batch_cells[b] = number of cells of batch item b, i.e. the size of item b in the
+// pooled cloud (the caller zeroes it; the host uses the largest one to pick the per-item sort of the next level)
 __global__ void k_cell_ranks(const int* __restrict__ rank1, const int* __restrict__ idx_sorted, int64_t n,
                              int64_t* __restrict__ cell_ids, int64_t* __restrict__ sorted_ids,
-                             int* __restrict__ cell_ends, int64_t* __restrict__ m_out) {
+                             int* __restrict__ cell_ends, int64_t* __restrict__ m_out,
+                             const int* __restrict__ batch, int* __restrict__ batch_cells) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int r = rank1[i] - 1;
     const int src = idx_sorted[i];
@@ -316,8 +359,113 @@ __global__ void k_cell_ranks(const int* __restrict__ rank1, const int* __restric
     sorted_ids[i] = src;
     if (i == n - 1 || rank1[i + 1] - 1 != r) cell_ends[r] = (int)(i + 1);
     if (i == n - 1) *m_out = r + 1;
+    if (batch_cells) {
+      // first / last sorted position of a batch item: +-(rank) contributions give its cell count without ordering
+      const int b = batch[src];
+      if (i == n - 1 || batch[idx_sorted[i + 1]] != b) atomicAdd(batch_cells + b, r + 1);
+      if (i == 0 || batch[idx_sorted[i - 1]] != b) atomicAdd(batch_cells + b, -r);
+    }
   }
 }
+
+// ---------------------------------------------------------------------------------------------
+// key sort: one CTA per batch item when every item fits a CTA, CUB device radix sort otherwise
+// ---------------------------------------------------------------------------------------------
+// Batch ids are non-decreasing and every key carries its batch id in the leading position, so sorting each batch
+// item's slice on its own and leaving the slices in place IS the global stable sort.  A cloud of a few thousand
+// points per item (DFAUST: 6890, pooled levels: hundreds) then needs ONE launch instead of the histogram +
+// scan + one pass per 8 key bits of the device-wide sort, whose launches -- not its bandwidth -- dominate at
+// this size.  Values are the global positions (the sort produces the permutation).
+__device__ __forceinline__ int lower_bound_i32(const int* __restrict__ a, int n, int v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+constexpr int kSegThreads = 1024;
+template <int ITEMS>
+__global__ void __launch_bounds__(kSegThreads) k_seg_sort_u64(const uint64_t* __restrict__ keys_in,
+                                                              const int* __restrict__ batch, int n,
+                                                              uint64_t* __restrict__ keys_out, int* __restrict__ idx_out,
+                                                              int end_bit) {
+  using Sort = cub::BlockRadixSort<uint64_t, kSegThreads, ITEMS, int>;
+  extern __shared__ __align__(16) unsigned char seg_smem[];
+  typename Sort::TempStorage& tmp = *reinterpret_cast<typename Sort::TempStorage*>(seg_smem);
+  __shared__ int s_lo, s_hi;
+  if (threadIdx.x == 0) {
+    s_lo = lower_bound_i32(batch, n, (int)blockIdx.x);
+    s_hi = lower_bound_i32(batch, n, (int)blockIdx.x + 1);
+  }
+  __syncthreads();
+  const int lo = s_lo, cnt = s_hi - lo;
+  if (cnt <= 0) return;
+  uint64_t k[ITEMS];
+  int v[ITEMS];
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const int p = threadIdx.x * ITEMS + i;
+    k[i] = p < cnt ? keys_in[lo + p] : ~0ull;  // padding sorts last (stable: it also comes last in the input)
+    v[i] = lo + p;
+  }
+  Sort(tmp).Sort(k, v, 0, end_bit);
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const int p = threadIdx.x * ITEMS + i;
+    if (p < cnt) {
+      keys_out[lo + p] = k[i];
+      idx_out[lo + p] = v[i];
+    }
+  }
+}
+
+template <int ITEMS>
+static int launch_seg_sort(const uint64_t* keys_in, const int* batch, int n, int n_batches, uint64_t* keys_out,
+                           int* idx_out, int end_bit, cudaStream_t st) {
+  using Sort = cub::BlockRadixSort<uint64_t, kSegThreads, ITEMS, int>;
+  auto kern = k_seg_sort_u64<ITEMS>;
+  const size_t smem = sizeof(typename Sort::TempStorage);
+  SE3_SMEM_ONCE(kern, smem);
+  kern<<<n_batches, kSegThreads, smem, st>>>(keys_in, batch, n, keys_out, idx_out, end_bit);
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
+}
+
+__global__ void k_batch_counts(const int* __restrict__ batch, int n, int n_batches, int* __restrict__ counts) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n_batches; b += gridDim.x * blockDim.x)
+    counts[b] = lower_bound_i32(batch, n, b + 1) - lower_bound_i32(batch, n, b);
+}
+
+namespace se3 {
+int batch_counts(const int32_t* batch_ids, int64_t n, int32_t n_batches, int32_t* counts_out, cudaStream_t st) {
+  k_batch_counts<<<(n_batches + 127) / 128, 128, 0, st>>>(batch_ids, (int)n, n_batches, counts_out);
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
+}
+size_t sort_pairs_tmp_bytes(int64_t n) {
+  size_t a = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, a, (uint64_t*)nullptr, (uint64_t*)nullptr, (int*)nullptr, (int*)nullptr, (int)n);
+  return a;
+}
+// keys_in [n] (64-bit, non-negative), iota [n] = 0..n-1 -> keys_out ascending (stable), idx_out the permutation.
+// max_seg = the largest number of points in one batch item (0 = unknown -> device-wide sort).
+int sort_keys_u64(const uint64_t* keys_in, const int* iota, const int* batch, int64_t n, int n_batches, int max_seg,
+                  uint64_t* keys_out, int* idx_out, int end_bit, void* cub_tmp, size_t cub_bytes, cudaStream_t st) {
+  if (end_bit <= 0 || end_bit > 64) end_bit = 64;
+  if (max_seg > 0 && n_batches >= 1 && n_batches <= 65535 && batch != nullptr) {
+    if (max_seg <= kSegThreads * 1) return launch_seg_sort<1>(keys_in, batch, (int)n, n_batches, keys_out, idx_out, end_bit, st);
+    if (max_seg <= kSegThreads * 2) return launch_seg_sort<2>(keys_in, batch, (int)n, n_batches, keys_out, idx_out, end_bit, st);
+    if (max_seg <= kSegThreads * 4) return launch_seg_sort<4>(keys_in, batch, (int)n, n_batches, keys_out, idx_out, end_bit, st);
+    if (max_seg <= kSegSortMax) return launch_seg_sort<7>(keys_in, batch, (int)n, n_batches, keys_out, idx_out, end_bit, st);
+  }
+  size_t cb = cub_bytes;
+  SE3_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cb, keys_in, keys_out, iota, idx_out, (int)n, 0, end_bit, st));
+  count_launch(1 + (end_bit + 7) / 8);
+  return SE3_OK;
+}
+}  // namespace se3
 
 struct CellsWorkspace {
   int64_t* keys;
@@ -362,6 +510,14 @@ extern "C" int se3_grid_cells(const float* pts, const int32_t* batch_ids, int64_
                               const int32_t* num_cells, float cell, void* workspace, size_t workspace_bytes,
                               int64_t* cell_ids, int64_t* sorted_ids, int32_t* cell_ends, int64_t* m_out,
                               int32_t key_bits, se3_stream_t stream) {
+  return se3::grid_cells_impl(pts, batch_ids, n, min_pt, num_cells, cell, workspace, workspace_bytes, cell_ids,
+                              sorted_ids, cell_ends, m_out, key_bits, 0, 0, nullptr, stream);
+}
+
+int se3::grid_cells_impl(const float* pts, const int32_t* batch_ids, int64_t n, const float* min_pt,
+                         const int32_t* num_cells, float cell, void* workspace, size_t workspace_bytes,
+                         int64_t* cell_ids, int64_t* sorted_ids, int32_t* cell_ends, int64_t* m_out, int32_t key_bits,
+                         int32_t n_batches, int32_t max_seg, int32_t* batch_cells, se3_stream_t stream) {
   SE3_CHECK_ARG(n >= 0 && n < (1ll << 31) && cell > 0.0f, "bad arguments");
   SE3_CHECK_ARG(m_out, "null m_out");
   cudaStream_t st = as_stream(stream);
@@ -376,24 +532,29 @@ extern "C" int se3_grid_cells(const float* pts, const int32_t* batch_ids, int64_
     set_error("se3_grid_cells: workspace too small");
     return SE3_EWORKSPACE;
   }
-  k_cell_keys<<<grid_for(n, 256), 256, 0, st>>>(pts, batch_ids, n, min_pt, num_cells, cell, w.keys, w.iota);
+  k_cell_keys<<<grid_for(n, 256), 256, 0, st>>>(pts, batch_ids, n, min_pt, num_cells, cell, w.keys, w.iota, batch_cells,
+                                                batch_cells ? n_batches : 0);
   SE3_LAUNCH_CHECK();
   size_t cb = w.cub_bytes;
   const int end_bit = (key_bits > 0 && key_bits < 64) ? key_bits : 64;
-  SE3_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, cb, w.keys, w.keys_sorted, w.iota, w.idx_sorted, (int)n, 0, end_bit, st));
-  count_launch(1 + (end_bit + 7) / 8);
+  if (int rc = sort_keys_u64(reinterpret_cast<const uint64_t*>(w.keys), w.iota, batch_ids, n, n_batches, max_seg,
+                             reinterpret_cast<uint64_t*>(w.keys_sorted), w.idx_sorted, end_bit, w.cub_tmp, w.cub_bytes, st))
+    return rc;
   k_cell_flags<<<grid_for(n, 256), 256, 0, st>>>(w.keys_sorted, n, w.flags);
   SE3_LAUNCH_CHECK();
   cb = w.cub_bytes;
   SE3_CUDA(cub::DeviceScan::InclusiveSum(w.cub_tmp, cb, w.flags, w.rank1, (int)n, st));
   count_launch(1);
-  k_cell_ranks<<<grid_for(n, 256), 256, 0, st>>>(w.rank1, w.idx_sorted, n, cell_ids, sorted_ids, cell_ends, m_out);
+  k_cell_ranks<<<grid_for(n, 256), 256, 0, st>>>(w.rank1, w.idx_sorted, n, cell_ids, sorted_ids, cell_ends, m_out,
+                                                 batch_ids, batch_cells);
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }
 
+// pts / rec (optional): also packs the gather records (p, R) of the kept frames (se3_pack_records layout)
 __global__ void k_frames_select(const float* __restrict__ cand, const float* __restrict__ u, int64_t n, int n_cand,
-                                int n_keep, float* __restrict__ out) {
+                                int n_keep, float* __restrict__ out, const float* __restrict__ pts,
+                                float4* __restrict__ rec) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int perm[4] = {0, 1, 2, 3};
     if (u) {
@@ -411,8 +572,15 @@ __global__ void k_frames_select(const float* __restrict__ cand, const float* __r
     for (int f = 0; f < n_keep; ++f) {
       const float* src = cand + (i * n_cand + perm[f]) * 9;
       float* dst = out + (i * n_keep + f) * 9;
+      float fr[9];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) dst[k] = src[k];
+      for (int k = 0; k < 9; ++k) { fr[k] = src[k]; dst[k] = fr[k]; }
+      if (rec) {
+        float4* r = rec + 3 * (i * n_keep + f);
+        r[0] = make_float4(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], fr[0]);
+        r[1] = make_float4(fr[1], fr[2], fr[3], fr[4]);
+        r[2] = make_float4(fr[5], fr[6], fr[7], fr[8]);
+      }
     }
   }
 }
@@ -422,7 +590,18 @@ extern "C" int se3_frames_select(const float* cand, const float* u, int64_t n, i
   SE3_CHECK_ARG(n >= 0 && n_cand >= 1 && n_cand <= 4 && n_keep >= 1 && n_keep <= n_cand, "bad arguments");
   if (n == 0) return SE3_OK;
   SE3_CHECK_ARG(cand && out, "null pointer");
-  k_frames_select<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(cand, u, n, n_cand, n_keep, out);
+  k_frames_select<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(cand, u, n, n_cand, n_keep, out, nullptr, nullptr);
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
+}
+
+int se3::frames_select_pack(const float* cand, const float* u, int64_t n, int32_t n_cand, int32_t n_keep, float* out,
+                            const float* pts, float* rec, se3_stream_t stream) {
+  SE3_CHECK_ARG(n >= 0 && n_cand >= 1 && n_cand <= 4 && n_keep >= 1 && n_keep <= n_cand, "bad arguments");
+  if (n == 0) return SE3_OK;
+  SE3_CHECK_ARG(cand && out && pts && rec && (reinterpret_cast<uintptr_t>(rec) & 15) == 0, "bad pointer");
+  k_frames_select<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(cand, u, n, n_cand, n_keep, out, pts,
+                                                                   reinterpret_cast<float4*>(rec));
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }
@@ -438,9 +617,17 @@ struct BQWorkspace {
   float4* pts_sorted;    // [N]  xyz of the source points in key order
   int2* ranges;          // [M*9]
   int* counts;           // [M]
-  void* cub_tmp;
+  void* cub_tmp;         // source part: radix-sort scratch
   size_t cub_bytes;
+  void* scan_tmp;        // destination part: scan scratch (queries sharing a source may run on different streams)
+  size_t scan_bytes;
 };
+
+static size_t bq_scan_bytes(int64_t n_dst) {
+  size_t b = 0;
+  cub::DeviceScan::InclusiveSum(nullptr, b, (int*)nullptr, (int*)nullptr, (int)n_dst);
+  return b;
+}
 
 static size_t bq_cub_bytes(int64_t n_src, int64_t n_dst) {
   size_t a = 0, b = 0;
@@ -460,6 +647,7 @@ static size_t bq_src_bytes(int64_t n_src, int64_t n_dst) {
 static size_t bq_dst_bytes(int64_t n_dst) {
   Arena ar(nullptr, 0);
   ar.take<int2>(n_dst * 9); ar.take<int>(n_dst);
+  ar.take<char>(bq_scan_bytes(n_dst));
   return ar.off;
 }
 static bool bq_layout2(void* ws_src, size_t src_bytes, void* ws_dst, size_t dst_bytes, int64_t n_src, int64_t n_dst,
@@ -475,6 +663,8 @@ static bool bq_layout2(void* ws_src, size_t src_bytes, void* ws_dst, size_t dst_
   Arena ad(ws_dst, dst_bytes);
   w.ranges = ad.take<int2>(n_dst * 9);
   w.counts = ad.take<int>(n_dst);
+  w.scan_bytes = bq_scan_bytes(n_dst);
+  w.scan_tmp = ad.take<char>(w.scan_bytes);
   return as.ok() && ad.ok();
 }
 static bool bq_layout(void* ws, size_t ws_bytes, int64_t n_src, int64_t n_dst, BQWorkspace& w) {
@@ -532,7 +722,12 @@ __global__ void __launch_bounds__(256) k_bq_scan(const float* __restrict__ pts_d
                                                  const int* __restrict__ idx_sorted, int2* __restrict__ ranges,
                                                  int* __restrict__ counts, const int* __restrict__ row_ends,
                                                  int64_t* __restrict__ neighbors, int* __restrict__ col_src,
-                                                 int* __restrict__ edge_dst) {
+                                                 int* __restrict__ edge_dst, int* __restrict__ t_cursor,
+                                                 int* __restrict__ t_edge) {
+  // t_cursor (optional, fused hierarchy builder): the transposed CSR is built alongside.  Count pass: histogram of
+  // the hit sources (t_cursor zeroed by the caller).  Fill pass: t_cursor holds the exclusive row starts and is
+  // advanced per hit, so it ends as the inclusive row ends; t_edge receives the edge ids in arrival order
+  // (k_t_rows_finish orders every row afterwards, so the result does not depend on the arrival order).
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -576,10 +771,13 @@ __global__ void __launch_bounds__(256) k_bq_scan(const float* __restrict__ pts_d
             neighbors[2 * slot] = s;
             neighbors[2 * slot + 1] = (int64_t)idx_sorted[p];
           } else {
-            col_src[slot] = idx_sorted[p];
+            const int src = idx_sorted[p];
+            col_src[slot] = src;
             edge_dst[slot] = (int)s;
+            if (t_cursor) t_edge[atomicAdd(t_cursor + src, 1)] = (int)slot;
           }
         }
+        if (!FILL && hit && t_cursor) atomicAdd(t_cursor + idx_sorted[p], 1);
         total += __popc(m);
       }
     }
@@ -592,15 +790,15 @@ __global__ void k_bq_total(const int* __restrict__ row_ends, int64_t n_dst, int6
 }
 
 static int bq_prepare(const float* pts_src, const int32_t* batch_src, int64_t n_src, const float* min_pt,
-                      const int32_t* num_cells, const float* radius, BQWorkspace& w, int key_bits, cudaStream_t st) {
+                      const int32_t* num_cells, const float* radius, BQWorkspace& w, int key_bits, cudaStream_t st,
+                      int n_batches = 0, int max_seg = 0) {
   k_compute_keys<<<grid_for(n_src, 256), 256, 0, st>>>(pts_src, batch_src, n_src, min_pt, num_cells, radius, w.keys,
                                                        w.iota);
   SE3_LAUNCH_CHECK();
-  size_t cb = w.cub_bytes;
   const int end_bit = (key_bits > 0 && key_bits < 64) ? key_bits : 64;
-  SE3_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, cb, w.keys, w.keys_sorted, w.iota, w.idx_sorted, (int)n_src, 0,
-                                           end_bit, st));
-  count_launch(1 + (end_bit + 7) / 8);
+  if (int rc = sort_keys_u64(reinterpret_cast<const uint64_t*>(w.keys), w.iota, batch_src, n_src, n_batches, max_seg,
+                             reinterpret_cast<uint64_t*>(w.keys_sorted), w.idx_sorted, end_bit, w.cub_tmp, w.cub_bytes, st))
+    return rc;
   k_gather_sorted_pts<<<grid_for(n_src, 256), 256, 0, st>>>(pts_src, w.idx_sorted, n_src, w.pts_sorted);
   SE3_LAUNCH_CHECK();
   return SE3_OK;
@@ -612,10 +810,10 @@ static int bq_count(const float* pts_dst, const int32_t* batch_dst, int64_t n_sr
   const int blocks = grid_for(n_dst * 32, 256);
   k_bq_scan<false><<<blocks, 256, 0, st>>>(pts_dst, batch_dst, n_dst, (int)n_src, min_pt, num_cells, radius,
                                            w.keys_sorted, w.pts_sorted, w.idx_sorted, w.ranges, w.counts, nullptr,
-                                           nullptr, nullptr, nullptr);
+                                           nullptr, nullptr, nullptr, nullptr, nullptr);
   SE3_LAUNCH_CHECK();
-  size_t cb = w.cub_bytes;
-  SE3_CUDA(cub::DeviceScan::InclusiveSum(w.cub_tmp, cb, w.counts, row_ends_out, (int)n_dst, st));
+  size_t cb = w.scan_bytes;
+  SE3_CUDA(cub::DeviceScan::InclusiveSum(w.scan_tmp, cb, w.counts, row_ends_out, (int)n_dst, st));
   count_launch(1);
   k_bq_total<<<1, 32, 0, st>>>(row_ends_out, n_dst, total_out);
   SE3_LAUNCH_CHECK();
@@ -651,6 +849,14 @@ extern "C" int se3_ball_query_count(const float* pts_src, const float* pts_dst, 
 extern "C" int se3_ball_query_prepare(const float* pts_src, const int32_t* batch_src, int64_t n_src, int64_t n_dst_max,
                                       const float* min_pt, const int32_t* num_cells, const float* radius,
                                       void* ws_src, size_t ws_src_bytes, int32_t key_bits, se3_stream_t stream) {
+  return se3::ball_query_prepare_impl(pts_src, batch_src, n_src, n_dst_max, min_pt, num_cells, radius, ws_src,
+                                      ws_src_bytes, key_bits, 0, 0, stream);
+}
+
+int se3::ball_query_prepare_impl(const float* pts_src, const int32_t* batch_src, int64_t n_src, int64_t n_dst_max,
+                                 const float* min_pt, const int32_t* num_cells, const float* radius, void* ws_src,
+                                 size_t ws_src_bytes, int32_t key_bits, int32_t n_batches, int32_t max_seg,
+                                 se3_stream_t stream) {
   SE3_CHECK_ARG(n_src >= 0 && n_src < (1ll << 31), "bad sizes");
   if (n_src == 0) return SE3_OK;
   SE3_CHECK_ARG(pts_src && batch_src && min_pt && num_cells && radius && ws_src, "null pointer");
@@ -660,7 +866,7 @@ extern "C" int se3_ball_query_prepare(const float* pts_src, const int32_t* batch
     set_error("se3_ball_query_prepare: workspace too small");
     return SE3_EWORKSPACE;
   }
-  return bq_prepare(pts_src, batch_src, n_src, min_pt, num_cells, radius, w, key_bits, as_stream(stream));
+  return bq_prepare(pts_src, batch_src, n_src, min_pt, num_cells, radius, w, key_bits, as_stream(stream), n_batches, max_seg);
 }
 
 extern "C" int se3_ball_query_count_prepared(const float* pts_dst, const int32_t* batch_dst, int64_t n_src,
@@ -698,7 +904,8 @@ extern "C" int se3_ball_query_fill_csr_prepared(const float* pts_dst, int64_t n_
   const int blocks = grid_for(n_dst * 32, 256);
   k_bq_scan<true><<<blocks, 256, 0, as_stream(stream)>>>(pts_dst, nullptr, n_dst, (int)n_src, nullptr, nullptr,
                                                          radius, w.keys_sorted, w.pts_sorted, w.idx_sorted, w.ranges,
-                                                         w.counts, row_ends, nullptr, col_src_out, edge_dst_out);
+                                                         w.counts, row_ends, nullptr, col_src_out, edge_dst_out, nullptr,
+                                                         nullptr);
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }
@@ -716,7 +923,8 @@ extern "C" int se3_ball_query_fill(const float* pts_dst, int64_t n_src, int64_t 
   const int blocks = grid_for(n_dst * 32, 256);
   k_bq_scan<true><<<blocks, 256, 0, as_stream(stream)>>>(pts_dst, nullptr, n_dst, (int)n_src, nullptr, nullptr,
                                                          radius, w.keys_sorted, w.pts_sorted, w.idx_sorted, w.ranges,
-                                                         w.counts, row_ends, neighbors_out, nullptr, nullptr);
+                                                         w.counts, row_ends, neighbors_out, nullptr, nullptr, nullptr,
+                                                         nullptr);
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }
@@ -735,10 +943,188 @@ extern "C" int se3_ball_query_fill_csr(const float* pts_dst, int64_t n_src, int6
   const int blocks = grid_for(n_dst * 32, 256);
   k_bq_scan<true><<<blocks, 256, 0, as_stream(stream)>>>(pts_dst, nullptr, n_dst, (int)n_src, nullptr, nullptr,
                                                          radius, w.keys_sorted, w.pts_sorted, w.idx_sorted, w.ranges,
-                                                         w.counts, row_ends, nullptr, col_src_out, edge_dst_out);
+                                                         w.counts, row_ends, nullptr, col_src_out, edge_dst_out, nullptr,
+                                                         nullptr);
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// ball query + transposed CSR in one go (fused hierarchy builder)
+// ---------------------------------------------------------------------------------------------
+// Single-CTA scans (two independent jobs per launch): the arrays here are one cloud level long (<= a few 10^5
+// entries), where the device-wide scan's second launch and its tile-state initialisation cost more than the scan.
+struct ScanJob {
+  const int* in;
+  int* out;
+  int n;
+  int exclusive;
+  int64_t* total;
+};
+__global__ void __launch_bounds__(1024) k_scan_small(const ScanJob j0, const ScanJob j1) {
+  const ScanJob j = blockIdx.x == 0 ? j0 : j1;
+  using BS = cub::BlockScan<int, 1024>;
+  __shared__ typename BS::TempStorage tmp;
+  constexpr int IT = 8;
+  int carry = 0;
+  for (int base = 0; base < j.n; base += 1024 * IT) {
+    int v[IT];
+    int sum = 0;
+    const int p0 = base + threadIdx.x * IT;
+#pragma unroll
+    for (int i = 0; i < IT; ++i) {
+      v[i] = (p0 + i < j.n) ? j.in[p0 + i] : 0;
+      sum += v[i];
+    }
+    int excl, agg;
+    BS(tmp).ExclusiveSum(sum, excl, agg);
+    int run = carry + excl;
+#pragma unroll
+    for (int i = 0; i < IT; ++i) {
+      if (p0 + i < j.n) {
+        if (j.exclusive) {
+          j.out[p0 + i] = run;
+          run += v[i];
+        } else {
+          run += v[i];
+          j.out[p0 + i] = run;
+        }
+      }
+    }
+    carry += agg;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && j.total) *j.total = carry;
+}
+
+// Every transposed row in ascending edge order (= the order a stable sort by source would give), then the sample
+// of every transposed entry.  One warp per row, any row length: chunks of up to T_CHUNK entries are sorted in shared
+// memory (bitonic network), longer rows are finished by rank-merging the sorted runs, ping-ponging between the row's
+// t_edge slice and its (not yet written) t_dst slice.  Edge ids are distinct, so ranks are unambiguous.
+constexpr int T_CHUNK = 2048;
+constexpr int T_WARPS = 4;
+__device__ __forceinline__ int lower_bound_run(const int* __restrict__ a, int n, int v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__global__ void __launch_bounds__(T_WARPS * 32) k_t_rows_finish(const int* __restrict__ t_row_ends, int64_t n_src,
+                                                                int* __restrict__ t_edge, const int* __restrict__ edge_dst,
+                                                                int* __restrict__ t_dst) {
+  __shared__ int s_buf[T_WARPS][T_CHUNK];
+  const int lane = threadIdx.x & 31;
+  int* sb = s_buf[threadIdx.x >> 5];
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t j = warp; j < n_src; j += nwarps) {
+    const int lo = j > 0 ? t_row_ends[j - 1] : 0, hi = t_row_ends[j];
+    const int len = hi - lo;
+    if (len <= 0) continue;
+    int* row = t_edge + lo;
+    int* alt = t_dst + lo;
+    for (int c0 = 0; c0 < len; c0 += T_CHUNK) {
+      const int cn = min(T_CHUNK, len - c0);
+      int P = 32;
+      while (P < cn) P <<= 1;
+      for (int t = lane; t < P; t += 32) sb[t] = t < cn ? row[c0 + t] : INT_MAX;
+      __syncwarp();
+      for (int k = 2; k <= P; k <<= 1)
+        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+          for (int t = lane; t < (P >> 1); t += 32) {
+            const int i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
+            const int a = sb[i], b = sb[i | jj];
+            if ((a > b) == ((i & k) == 0)) { sb[i] = b; sb[i | jj] = a; }
+          }
+          __syncwarp();
+        }
+      for (int t = lane; t < cn; t += 32) row[c0 + t] = sb[t];
+      __syncwarp();
+    }
+    // rank-merge the sorted runs (only rows longer than one chunk)
+    int* src = row;
+    int* dst = alt;
+    for (int width = T_CHUNK; width < len; width <<= 1) {
+      for (int r0 = 0; r0 < len; r0 += 2 * width) {
+        const int na = min(width, len - r0), nb = max(0, min(width, len - r0 - width));
+        const int* A = src + r0;
+        const int* B = src + r0 + na;
+        for (int t = lane; t < na; t += 32) dst[r0 + t + lower_bound_run(B, nb, A[t])] = A[t];
+        for (int t = lane; t < nb; t += 32) dst[r0 + t + lower_bound_run(A, na, B[t])] = B[t];
+      }
+      __syncwarp();
+      int* tmp = src; src = dst; dst = tmp;
+    }
+    if (src != row) {
+      for (int t = lane; t < len; t += 32) row[t] = src[t];
+      __syncwarp();
+    }
+    for (int t = lane; t < len; t += 32) alt[t] = edge_dst[row[t]];
+  }
+}
+
+namespace se3 {
+// count pass of a prepared query; also the histogram of the hit sources.  Outputs: row_ends [n_dst] inclusive,
+// t_row [n_src] EXCLUSIVE starts of the transposed rows (bq_fill_transposed turns them into inclusive ends),
+// *total_out = E.
+int bq_count_transposed(const float* pts_dst, const int32_t* batch_dst, int64_t n_src, int64_t n_dst, int64_t n_dst_max,
+                        const float* min_pt, const int32_t* num_cells, const float* radius, void* ws_src,
+                        size_t ws_src_bytes, void* ws_dst, size_t ws_dst_bytes, int32_t* row_ends_out, int32_t* t_row_out,
+                        int64_t* total_out, se3_stream_t stream) {
+  SE3_CHECK_ARG(n_src >= 0 && n_dst >= 0 && n_src < (1ll << 31) && n_dst < (1ll << 31) && total_out, "bad arguments");
+  cudaStream_t st = as_stream(stream);
+  if (n_src > 0) SE3_CUDA(cudaMemsetAsync(t_row_out, 0, n_src * sizeof(int32_t), st));
+  if (n_dst == 0 || n_src == 0) {
+    if (n_dst > 0) SE3_CUDA(cudaMemsetAsync(row_ends_out, 0, n_dst * sizeof(int32_t), st));
+    SE3_CUDA(cudaMemsetAsync(total_out, 0, sizeof(int64_t), st));
+    return SE3_OK;
+  }
+  SE3_CHECK_ARG(pts_dst && batch_dst && min_pt && num_cells && radius && ws_src && ws_dst && row_ends_out && t_row_out,
+                "null pointer");
+  BQWorkspace w;
+  if (!bq_layout2(ws_src, ws_src_bytes, ws_dst, ws_dst_bytes, n_src, n_dst, n_dst_max < n_dst ? n_dst : n_dst_max, w)) {
+    set_error("bq_count_transposed: workspace too small");
+    return SE3_EWORKSPACE;
+  }
+  const int blocks = grid_for(n_dst * 32, 256);
+  k_bq_scan<false><<<blocks, 256, 0, st>>>(pts_dst, batch_dst, n_dst, (int)n_src, min_pt, num_cells, radius,
+                                           w.keys_sorted, w.pts_sorted, w.idx_sorted, w.ranges, w.counts, nullptr,
+                                           nullptr, nullptr, nullptr, t_row_out, nullptr);
+  SE3_LAUNCH_CHECK();
+  ScanJob j0{w.counts, row_ends_out, (int)n_dst, 0, total_out};
+  ScanJob j1{t_row_out, t_row_out, (int)n_src, 1, nullptr};
+  k_scan_small<<<2, 1024, 0, st>>>(j0, j1);
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
+}
+
+// fill pass: col_src / edge_dst [E] (the CSR columns and the sample of every edge) and the transposed CSR
+// (t_row: exclusive starts in, inclusive ends out; t_edge / t_dst [E], rows in ascending edge order)
+int bq_fill_transposed(const float* pts_dst, int64_t n_src, int64_t n_dst, int64_t n_dst_max, const float* radius,
+                       void* ws_src, size_t ws_src_bytes, void* ws_dst, size_t ws_dst_bytes, const int32_t* row_ends,
+                       int64_t n_edges, int32_t* col_src_out, int32_t* edge_dst_out, int32_t* t_row, int32_t* t_edge,
+                       int32_t* t_dst, se3_stream_t stream) {
+  if (n_edges == 0 || n_dst == 0 || n_src == 0) return SE3_OK;  // t_row is all zero already
+  SE3_CHECK_ARG(pts_dst && radius && ws_src && ws_dst && row_ends && col_src_out && edge_dst_out && t_row && t_edge && t_dst,
+                "null pointer");
+  BQWorkspace w;
+  if (!bq_layout2(ws_src, ws_src_bytes, ws_dst, ws_dst_bytes, n_src, n_dst, n_dst_max < n_dst ? n_dst : n_dst_max, w)) {
+    set_error("bq_fill_transposed: workspace too small");
+    return SE3_EWORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  const int blocks = grid_for(n_dst * 32, 256);
+  k_bq_scan<true><<<blocks, 256, 0, st>>>(pts_dst, nullptr, n_dst, (int)n_src, nullptr, nullptr, radius, w.keys_sorted,
+                                          w.pts_sorted, w.idx_sorted, w.ranges, w.counts, row_ends, nullptr, col_src_out,
+                                          edge_dst_out, t_row, t_edge);
+  SE3_LAUNCH_CHECK();
+  k_t_rows_finish<<<grid_for(n_src * 32, T_WARPS * 32), T_WARPS * 32, 0, st>>>(t_row, n_src, t_edge, edge_dst_out, t_dst);
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
+}
+}  // namespace se3
 
 // ---------------------------------------------------------------------------------------------
 // CSR transpose

@@ -30,7 +30,7 @@ struct Bump {
   T* at(int64_t o) const { return reinterpret_cast<T*>(base + o); }
 };
 
-constexpr size_t kPinnedBytes = 16384;  // edge totals (<= 32 x 8 B) or the per-batch input boxes (B x 24 B)
+constexpr size_t kPinnedBytes = 65536;  // edge totals (<= 32 x 8 B) or the per-batch input boxes (B x 24 B)
 
 int64_t* pinned_scalars() {
   static int64_t* p = nullptr;
@@ -38,6 +38,33 @@ int64_t* pinned_scalars() {
     if (cudaHostAlloc(reinterpret_cast<void**>(&p), kPinnedBytes, cudaHostAllocDefault) != cudaSuccess) p = nullptr;
   }
   return p;
+}
+
+// Side streams of the builder: the pooling chain (grid -> pooled cloud -> next grid) is the critical path and stays
+// on the caller's stream; frames (kNN + PCA), ball-query sources, counts, fills and transposes of different clouds /
+// neighbourhoods are independent and fan out over kSide streams, ordered by events and joined back into the
+// caller's stream before every host read and before the call returns.
+constexpr int kSide = 4;
+struct Lanes {
+  bool ready = false;
+  cudaStream_t s[kSide];
+  cudaEvent_t fork, join[kSide], cloud[SE3_HIER_MAX_CLOUDS + 1], frames[SE3_HIER_MAX_CLOUDS + 1], src[SE3_HIER_MAX_NEIGH];
+};
+Lanes* lanes_for_device() {
+  static Lanes all[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  Lanes& l = all[dev];
+  if (!l.ready) {
+    auto ev = [](cudaEvent_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
+    bool ok = ev(&l.fork);
+    for (int i = 0; i < kSide; ++i) ok = ok && cudaStreamCreateWithFlags(&l.s[i], cudaStreamNonBlocking) == cudaSuccess && ev(&l.join[i]);
+    for (int i = 0; i <= SE3_HIER_MAX_CLOUDS; ++i) ok = ok && ev(&l.cloud[i]) && ev(&l.frames[i]);
+    for (int i = 0; i < SE3_HIER_MAX_NEIGH; ++i) ok = ok && ev(&l.src[i]);
+    if (!ok) return nullptr;
+    l.ready = true;
+  }
+  return &l;
 }
 
 }  // namespace
@@ -88,6 +115,9 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
   const size_t bb = (size_t)d->n_batches * 3 * 4;
   const int64_t o_min = ar.take(bb), o_max = ar.take(bb);
   const int64_t o_nc = ar.take(16), o_cnt = ar.take(8 * (SE3_HIER_MAX_NEIGH + 2)), o_rad = ar.take(16 * SE3_HIER_MAX_NEIGH);
+  // [int64 m][int32 per-batch-item sizes of the pooled cloud]: one read per grid
+  const size_t lvl_bytes = 8 + (size_t)d->n_batches * 4;
+  const int64_t o_lvl = ar.take(lvl_bytes);
   int64_t o_rawmin[SE3_HIER_MAX_CLOUDS + 1], o_rawmax[SE3_HIER_MAX_CLOUDS + 1];  // raw boxes: [0] input cloud, [1+c] cloud c
   for (int c = 0; c <= n_clouds; ++c) {
     o_rawmin[c] = ar.take(bb);
@@ -98,18 +128,33 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
   float* max_pt = ar.at<float>(o_max);
   int32_t* num_cells = ar.at<int32_t>(o_nc);
   int64_t* d_cnt = ar.at<int64_t>(o_cnt);
+  int64_t* d_m = ar.at<int64_t>(o_lvl);
+  int32_t* d_items = reinterpret_cast<int32_t*>(ar.at<char>(o_lvl) + 8);
+  const bool track_items = lvl_bytes <= kPinnedBytes && (size_t)d->n_batches * 28 <= kPinnedBytes;
 
   // ---- bounding box of the input cloud on the host (one early blocking read): every later cloud lies inside
   // it, so the number of significant key bits of every grid is known up front and bounds the radix sorts.
   HB_TRY(se3_bbox(pts, batch_ids, d->n, d->n_batches, ar.at<float>(o_rawmin[0]), ar.at<float>(o_rawmax[0]), stream));
+  if (track_items) HB_TRY(batch_counts(batch_ids, d->n, d->n_batches, d_items, st));
   float ext[3] = {0.f, 0.f, 0.f};
+  // largest batch item of the cloud about to be sorted (0 = unknown -> device-wide sorts); pooled clouds are
+  // re-measured at every grid read, so small levels get the small per-item sort
+  auto max_item = [&](const int32_t* h, int nb) -> int {
+    int mx = 0;
+    for (int b = 0; b < nb; ++b) mx = h[b] > mx ? h[b] : mx;
+    return mx;
+  };
+  int seg_raw = 0;
   {
     float* hf = reinterpret_cast<float*>(host);
     // large batch counts: fall back to full-width sorts instead of a bigger host buffer
     if ((size_t)d->n_batches * 6 * sizeof(float) <= kPinnedBytes) {
       SE3_CUDA(cudaMemcpyAsync(hf, ar.at<float>(o_rawmin[0]), bb, cudaMemcpyDeviceToHost, st));
       SE3_CUDA(cudaMemcpyAsync(hf + d->n_batches * 3, ar.at<float>(o_rawmax[0]), bb, cudaMemcpyDeviceToHost, st));
+      if (track_items)
+        SE3_CUDA(cudaMemcpyAsync(hf + d->n_batches * 6, d_items, (size_t)d->n_batches * 4, cudaMemcpyDeviceToHost, st));
       SE3_CUDA(cudaStreamSynchronize(st));
+      if (track_items) seg_raw = max_item(reinterpret_cast<const int32_t*>(hf + d->n_batches * 6), d->n_batches);
       for (int b = 0; b < d->n_batches; ++b)
         for (int k = 0; k < 3; ++k) {
           const float lo = hf[3 * b + k], hi = hf[d->n_batches * 3 + 3 * b + k];
@@ -130,7 +175,9 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
 
   // grid on (p, b, n) with voxel `cell` from the cloud's raw box; fills g.cell_ids / sorted_ids / cell_ends / m
   // (blocking read of m)
-  auto build_grid = [&](const float* p, const int32_t* b, int64_t n, int raw_slot, float cell, se3_hier_cloud& g) -> int {
+  int seg_next = 0;  // largest batch item of the cloud the last grid pooled
+  auto build_grid = [&](const float* p, const int32_t* b, int64_t n, int raw_slot, float cell, se3_hier_cloud& g,
+                        int max_seg) -> int {
     g.cell_ids = ar.take((size_t)n * 8);
     g.sorted_ids = ar.take((size_t)n * 8);
     g.cell_ends = ar.take((size_t)n * 4);
@@ -139,16 +186,24 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
     HB_CHECK_ARENA("grid");
     HB_TRY(se3_grid_extents(ar.at<float>(o_rawmin[raw_slot]), ar.at<float>(o_rawmax[raw_slot]), d->n_batches, cell, 1e-6f,
                             min_pt, max_pt, num_cells, stream));
-    HB_TRY(se3_grid_cells(p, b, n, min_pt, num_cells, cell, ar.at<char>(o_ws), wsb, ar.at<int64_t>(g.cell_ids),
-                          ar.at<int64_t>(g.sorted_ids), ar.at<int32_t>(g.cell_ends), d_cnt, key_bits_for(cell), stream));
-    SE3_CUDA(cudaMemcpyAsync(host, d_cnt, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    HB_TRY(grid_cells_impl(p, b, n, min_pt, num_cells, cell, ar.at<char>(o_ws), wsb, ar.at<int64_t>(g.cell_ids),
+                           ar.at<int64_t>(g.sorted_ids), ar.at<int32_t>(g.cell_ends), d_m, key_bits_for(cell),
+                           d->n_batches, max_seg, track_items ? d_items : nullptr, stream));
+    SE3_CUDA(cudaMemcpyAsync(host, d_m, track_items ? lvl_bytes : sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     SE3_CUDA(cudaStreamSynchronize(st));
     g.m = host[0];
+    seg_next = track_items && n > 0 ? max_item(reinterpret_cast<const int32_t*>(host + 1), d->n_batches) : 0;
     return SE3_OK;
   };
-  // frames + records + raw box of cloud c (pts / batch already in place)
+  // raw box of cloud c (on the caller's stream: the next grid of the pooling chain needs it)
+  auto cloud_bbox = [&](se3_hier_cloud& c, int raw_slot, se3_stream_t s) -> int {
+    return se3_bbox(ar.at<float>(c.pts), ar.at<int32_t>(c.batch), c.n, d->n_batches, ar.at<float>(o_rawmin[raw_slot]),
+                    ar.at<float>(o_rawmax[raw_slot]), s);
+  };
+  // frames + records of cloud c (pts / batch already in place) on stream s
   int64_t u_off = 0;
-  auto build_frames = [&](se3_hier_cloud& c, int raw_slot) -> int {
+  int cloud_seg[SE3_HIER_MAX_CLOUDS + 1] = {0};  // largest batch item per cloud (0 = unknown)
+  auto build_frames = [&](se3_hier_cloud& c, int max_seg, se3_stream_t s) -> int {
     const int64_t n = c.n;
     c.frames = ar.take((size_t)n * F * 36);
     c.rec = ar.take((size_t)n * F * 48);
@@ -157,16 +212,13 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
     const size_t wsb = se3_knn_workspace_bytes(n);
     const int64_t o_ws = ar.take(wsb);
     HB_CHECK_ARENA("frames");
-    HB_TRY(se3_bbox(ar.at<float>(c.pts), ar.at<int32_t>(c.batch), n, d->n_batches, ar.at<float>(o_rawmin[raw_slot]),
-                    ar.at<float>(o_rawmax[raw_slot]), stream));
     if (n == 0) return SE3_OK;
-    HB_TRY(se3_knn_query(ar.at<float>(c.pts), ar.at<int32_t>(c.batch), n, d->knn_k, ar.at<char>(o_ws), wsb,
-                         ar.at<int32_t>(o_knn), stream));
-    HB_TRY(se3_pca_frames(ar.at<float>(c.pts), ar.at<int32_t>(o_knn), n, d->knn_k, d->fixed_axis, ar.at<float>(o_cand),
-                          stream));
-    HB_TRY(se3_frames_select(ar.at<float>(o_cand), u_frames + u_off, n, n_cand, F, ar.at<float>(c.frames), stream));
+    HB_TRY(knn_query_impl(ar.at<float>(c.pts), ar.at<int32_t>(c.batch), n, d->knn_k, ar.at<char>(o_ws), wsb,
+                          ar.at<int32_t>(o_knn), d->n_batches, max_seg, s));
+    HB_TRY(se3_pca_frames(ar.at<float>(c.pts), ar.at<int32_t>(o_knn), n, d->knn_k, d->fixed_axis, ar.at<float>(o_cand), s));
+    HB_TRY(frames_select_pack(ar.at<float>(o_cand), u_frames + u_off, n, n_cand, F, ar.at<float>(c.frames),
+                              ar.at<float>(c.pts), ar.at<float>(c.rec), s));
     u_off += n;
-    HB_TRY(se3_pack_records(ar.at<float>(c.pts), ar.at<float>(c.frames), n, F, ar.at<float>(c.rec), stream));
     return SE3_OK;
   };
   // cloud `dst` = grid-average pooling of (p, b) over grid g
@@ -182,34 +234,12 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
     return SE3_OK;
   };
 
-  // ---- level 0 and the output cloud share the raw cloud's init_cell grid
-  out->raw.n = d->n;
-  HB_TRY(build_grid(pts, batch_ids, d->n, 0, d->init_cell, out->raw));
-  HB_TRY(pool_cloud(pts, batch_ids, d->n, out->raw, out->clouds[0]));
-  HB_TRY(build_frames(out->clouds[0], 1));
-  // ---- pooled levels
-  for (int l = 0; l < d->n_pool; ++l) {
-    se3_hier_cloud& src = out->clouds[l];
-    SE3_CHECK_ARG(d->cells[l] > 0.0f, "cell sizes must be positive");
-    HB_TRY(build_grid(ar.at<float>(src.pts), ar.at<int32_t>(src.batch), src.n, 1 + l, d->cells[l], src));
-    HB_TRY(pool_cloud(ar.at<float>(src.pts), ar.at<int32_t>(src.batch), src.n, src, out->clouds[l + 1]));
-    HB_TRY(build_frames(out->clouds[l + 1], 2 + l));
+  // ---- side streams (see Lanes): fork from the caller's stream
+  Lanes* ln = lanes_for_device();
+  if (!ln) {
+    set_error("se3_hierarchy_build: cannot create the side streams");
+    return SE3_ECUDA;
   }
-  if (d->out_cloud) {
-    se3_hier_cloud& oc = out->clouds[d->n_pool + 1];
-    oc.n = out->raw.m;
-    oc.pts = ar.take((size_t)oc.n * 12);
-    oc.batch = ar.take((size_t)oc.n * 4);
-    out->out_picked = ar.take((size_t)oc.n * 8);
-    HB_CHECK_ARENA("output cloud");
-    HB_TRY(se3_segment_pick(pts, batch_ids, ar.at<int64_t>(out->raw.sorted_ids), ar.at<int32_t>(out->raw.cell_ends),
-                            oc.n, u_cells, ar.at<float>(oc.pts), ar.at<int32_t>(oc.batch),
-                            ar.at<int64_t>(out->out_picked), stream));
-    HB_TRY(build_frames(oc, d->n_pool + 2));
-  }
-
-  // ---- neighbourhoods: one sorted source structure per (source cloud, radius), all count passes, ONE blocking
-  // read of the edge totals, then fills + transposes
   float h_rad[SE3_HIER_MAX_NEIGH * 4];
   for (int i = 0; i < d->n_neigh; ++i) {
     SE3_CHECK_ARG(d->neigh_src[i] >= 0 && d->neigh_src[i] < n_clouds && d->neigh_dst[i] >= 0 && d->neigh_dst[i] < n_clouds,
@@ -223,6 +253,67 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
     // pageable source: the copy is staged before the call returns, so the stack buffer is safe
     SE3_CUDA(cudaMemcpyAsync(d_rad, h_rad, sizeof(float) * 4 * d->n_neigh, cudaMemcpyHostToDevice, st));
   }
+  // everything after the fork runs inside `body`, so that EVERY exit path (errors, arena retries) joins the side
+  // streams before the caller can free or reuse the arena
+  auto body = [&]() -> int {
+  SE3_CUDA(cudaEventRecord(ln->fork, st));
+  for (int k = 0; k < kSide; ++k) SE3_CUDA(cudaStreamWaitEvent(ln->s[k], ln->fork, 0));
+  int side_rr = 0;
+  // joins every side stream back into the caller's stream (before host reads and before returning)
+  auto join_all = [&]() -> int {
+    for (int k = 0; k < kSide; ++k) {
+      SE3_CUDA(cudaEventRecord(ln->join[k], ln->s[k]));
+      SE3_CUDA(cudaStreamWaitEvent(st, ln->join[k], 0));
+    }
+    return SE3_OK;
+  };
+  // cloud c is complete on the caller's stream (points, batch ids, raw box): its frames go to a side stream
+  auto cloud_ready = [&](int c, int raw_slot) -> int {
+    HB_TRY(cloud_bbox(out->clouds[c], raw_slot, stream));
+    SE3_CUDA(cudaEventRecord(ln->cloud[c], st));
+    cudaStream_t s = ln->s[side_rr++ % kSide];
+    SE3_CUDA(cudaStreamWaitEvent(s, ln->cloud[c], 0));
+    HB_TRY(build_frames(out->clouds[c], cloud_seg[c], reinterpret_cast<se3_stream_t>(s)));
+    SE3_CUDA(cudaEventRecord(ln->frames[c], s));
+    return SE3_OK;
+  };
+
+  // ---- level 0 and the output cloud share the raw cloud's init_cell grid
+  out->raw.n = d->n;
+  HB_TRY(build_grid(pts, batch_ids, d->n, 0, d->init_cell, out->raw, seg_raw));
+  cloud_seg[0] = seg_next;
+  if (d->out_cloud) cloud_seg[d->n_pool + 1] = seg_next;  // one point per raw cell, like level 0
+  HB_TRY(pool_cloud(pts, batch_ids, d->n, out->raw, out->clouds[0]));
+  HB_TRY(cloud_ready(0, 1));
+  if (d->out_cloud) {
+    // only needs the raw grid: picked now, so its kNN / PCA (the largest frame job) overlaps the pooling chain.
+    // Its frame variates are the last n of u_frames (the levels consume at most (n_pool + 1) * n).
+    se3_hier_cloud& oc = out->clouds[d->n_pool + 1];
+    oc.n = out->raw.m;
+    oc.pts = ar.take((size_t)oc.n * 12);
+    oc.batch = ar.take((size_t)oc.n * 4);
+    out->out_picked = ar.take((size_t)oc.n * 8);
+    HB_CHECK_ARENA("output cloud");
+    HB_TRY(se3_segment_pick(pts, batch_ids, ar.at<int64_t>(out->raw.sorted_ids), ar.at<int32_t>(out->raw.cell_ends),
+                            oc.n, u_cells, ar.at<float>(oc.pts), ar.at<int32_t>(oc.batch),
+                            ar.at<int64_t>(out->out_picked), stream));
+    const int64_t u_keep = u_off;
+    u_off = (int64_t)(d->n_pool + 1) * d->n;
+    HB_TRY(cloud_ready(d->n_pool + 1, d->n_pool + 2));
+    u_off = u_keep;
+  }
+  // ---- pooled levels
+  for (int l = 0; l < d->n_pool; ++l) {
+    se3_hier_cloud& src = out->clouds[l];
+    SE3_CHECK_ARG(d->cells[l] > 0.0f, "cell sizes must be positive");
+    HB_TRY(build_grid(ar.at<float>(src.pts), ar.at<int32_t>(src.batch), src.n, 1 + l, d->cells[l], src, cloud_seg[l]));
+    cloud_seg[l + 1] = seg_next;
+    HB_TRY(pool_cloud(ar.at<float>(src.pts), ar.at<int32_t>(src.batch), src.n, src, out->clouds[l + 1]));
+    HB_TRY(cloud_ready(l + 1, 2 + l));
+  }
+
+  // ---- neighbourhoods: one sorted source structure per (source cloud, radius), all count passes, ONE blocking
+  // read of the edge totals, then fills + transposes -- each on the side stream of its neighbourhood
   struct Source {
     int cloud;
     float radius;
@@ -256,11 +347,15 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
     so.mx = ar.take(bb);
     so.nc = ar.take(16);
     HB_CHECK_ARENA("ball-query source");
+    cudaStream_t sj = ln->s[j % kSide];
+    se3_stream_t sjs = reinterpret_cast<se3_stream_t>(sj);
+    SE3_CUDA(cudaStreamWaitEvent(sj, ln->cloud[so.cloud], 0));
     HB_TRY(se3_grid_extents(ar.at<float>(o_rawmin[1 + so.cloud]), ar.at<float>(o_rawmax[1 + so.cloud]), d->n_batches,
-                            so.radius, -1e-6f, ar.at<float>(so.mn), ar.at<float>(so.mx), ar.at<int32_t>(so.nc), stream));
-    HB_TRY(se3_ball_query_prepare(ar.at<float>(s.pts), ar.at<int32_t>(s.batch), s.n, so.n_dst_max, ar.at<float>(so.mn),
-                                  ar.at<int32_t>(so.nc), d_rad + 4 * rad_slot[j], ar.at<char>(so.ws), so.ws_bytes,
-                                  key_bits_for(so.radius), stream));
+                            so.radius, -1e-6f, ar.at<float>(so.mn), ar.at<float>(so.mx), ar.at<int32_t>(so.nc), sjs));
+    HB_TRY(ball_query_prepare_impl(ar.at<float>(s.pts), ar.at<int32_t>(s.batch), s.n, so.n_dst_max, ar.at<float>(so.mn),
+                                   ar.at<int32_t>(so.nc), d_rad + 4 * rad_slot[j], ar.at<char>(so.ws), so.ws_bytes,
+                                   key_bits_for(so.radius), d->n_batches, cloud_seg[so.cloud], sjs));
+    SE3_CUDA(cudaEventRecord(ln->src[j], sj));
   }
   int64_t wd_off[SE3_HIER_MAX_NEIGH];
   size_t wd_bytes[SE3_HIER_MAX_NEIGH];
@@ -274,11 +369,15 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
     wd_bytes[i] = se3_ball_query_dst_workspace_bytes(t.n);
     wd_off[i] = ar.take(wd_bytes[i]);
     HB_CHECK_ARENA("ball-query workspace");
-    HB_TRY(se3_ball_query_count_prepared(ar.at<float>(t.pts), ar.at<int32_t>(t.batch), s.n, t.n, so.n_dst_max,
-                                         ar.at<float>(so.mn), ar.at<int32_t>(so.nc), d_rad + 4 * i, ar.at<char>(so.ws),
-                                         so.ws_bytes, ar.at<char>(wd_off[i]), wd_bytes[i], ar.at<int32_t>(nb.row_ends),
-                                         d_cnt + 1 + i, stream));
+    cudaStream_t si = ln->s[i % kSide];
+    SE3_CUDA(cudaStreamWaitEvent(si, ln->src[src_of[i]], 0));
+    SE3_CUDA(cudaStreamWaitEvent(si, ln->cloud[d->neigh_dst[i]], 0));
+    HB_TRY(bq_count_transposed(ar.at<float>(t.pts), ar.at<int32_t>(t.batch), s.n, t.n, so.n_dst_max, ar.at<float>(so.mn),
+                               ar.at<int32_t>(so.nc), d_rad + 4 * i, ar.at<char>(so.ws), so.ws_bytes,
+                               ar.at<char>(wd_off[i]), wd_bytes[i], ar.at<int32_t>(nb.row_ends),
+                               ar.at<int32_t>(nb.t_row_ends), d_cnt + 1 + i, reinterpret_cast<se3_stream_t>(si)));
   }
+  HB_TRY(join_all());
   if (d->n_neigh > 0) {
     SE3_CUDA(cudaMemcpyAsync(host, d_cnt + 1, sizeof(int64_t) * d->n_neigh, cudaMemcpyDeviceToHost, st));
     SE3_CUDA(cudaStreamSynchronize(st));
@@ -293,15 +392,26 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
     nb.edge_dst = ar.take((size_t)nb.e * 4);
     nb.t_edge = ar.take((size_t)nb.e * 4);
     nb.t_dst = ar.take((size_t)nb.e * 4);
-    const size_t twb = se3_csr_transpose_workspace_bytes(nb.e, s.n);
-    const int64_t o_tw = ar.take(twb);
     HB_CHECK_ARENA("neighbourhood");
-    HB_TRY(se3_ball_query_fill_csr_prepared(ar.at<float>(t.pts), s.n, t.n, so.n_dst_max, d_rad + 4 * i, ar.at<char>(so.ws),
-                                            so.ws_bytes, ar.at<char>(wd_off[i]), wd_bytes[i], ar.at<int32_t>(nb.row_ends),
-                                            nb.e, ar.at<int32_t>(nb.col_src), ar.at<int32_t>(nb.edge_dst), stream));
-    HB_TRY(se3_csr_transpose_i32(ar.at<int32_t>(nb.col_src), ar.at<int32_t>(nb.edge_dst), nb.e, s.n, ar.at<char>(o_tw), twb,
-                                 ar.at<int32_t>(nb.t_row_ends), ar.at<int32_t>(nb.t_edge), ar.at<int32_t>(nb.t_dst), stream));
+    // everything issued so far has completed (the blocking read above), so the side streams need no further waits
+    se3_stream_t sis = reinterpret_cast<se3_stream_t>(ln->s[i % kSide]);
+    HB_TRY(bq_fill_transposed(ar.at<float>(t.pts), s.n, t.n, so.n_dst_max, d_rad + 4 * i, ar.at<char>(so.ws), so.ws_bytes,
+                              ar.at<char>(wd_off[i]), wd_bytes[i], ar.at<int32_t>(nb.row_ends), nb.e,
+                              ar.at<int32_t>(nb.col_src), ar.at<int32_t>(nb.edge_dst), ar.at<int32_t>(nb.t_row_ends),
+                              ar.at<int32_t>(nb.t_edge), ar.at<int32_t>(nb.t_dst), sis));
   }
+    return SE3_OK;
+  };
+  const int rc = body();
+  bool joined = true;
+  for (int k = 0; k < kSide; ++k) {
+    joined = joined && cudaEventRecord(ln->join[k], ln->s[k]) == cudaSuccess;
+    joined = joined && cudaStreamWaitEvent(st, ln->join[k], 0) == cudaSuccess;
+  }
+  if (!joined) {
+    for (int k = 0; k < kSide; ++k) cudaStreamSynchronize(ln->s[k]);
+  }
+  if (rc != SE3_OK) return rc;
   out->arena_used = (int64_t)ar.off;
   return SE3_OK;
 }

@@ -320,6 +320,11 @@ extern "C" size_t se3_knn_workspace_bytes(int64_t n) {
 
 extern "C" int se3_knn_query(const float* pts, const int32_t* batch_ids, int64_t n, int32_t k, void* workspace,
                              size_t workspace_bytes, int32_t* out, se3_stream_t stream) {
+  return se3::knn_query_impl(pts, batch_ids, n, k, workspace, workspace_bytes, out, 0, 0, stream);
+}
+
+int se3::knn_query_impl(const float* pts, const int32_t* batch_ids, int64_t n, int32_t k, void* workspace,
+                        size_t workspace_bytes, int32_t* out, int32_t n_batches, int32_t max_seg, se3_stream_t stream) {
   SE3_CHECK_ARG(n >= 0 && n < (1ll << 31), "bad n");
   SE3_CHECK_ARG(k >= 1 && k <= 32, "k must be in 1..32");
   if (n == 0) return SE3_OK;
@@ -336,10 +341,10 @@ extern "C" int se3_knn_query(const float* pts, const int32_t* batch_ids, int64_t
   SE3_LAUNCH_CHECK();
   k_knn_keys<<<grid_for(n, 256), 256, 0, st>>>(pts, batch_ids, n, w.minmax, w.keys, w.iota);
   SE3_LAUNCH_CHECK();
-  size_t cb = w.cub_bytes;
-  SE3_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, cb, w.keys, w.keys_sorted, w.iota, w.idx_sorted, (int)n, 0, 64,
-                                           st));
-  count_launch(8);
+  // per batch item the keys differ in the low 32 bits only (the float bits of the sweep coordinate)
+  if (int rc = sort_keys_u64(w.keys, w.iota, batch_ids, n, n_batches, max_seg, w.keys_sorted, w.idx_sorted,
+                             (max_seg > 0 && max_seg <= kSegSortMax) ? 32 : 64, w.cub_tmp, w.cub_bytes, st))
+    return rc;
   k_knn_gather<<<grid_for(n, 256), 256, 0, st>>>(pts, batch_ids, w.idx_sorted, n, w.pts_sorted);
   SE3_LAUNCH_CHECK();
   k_knn_sweep<<<grid_for(n * 32, 256), 256, 0, st>>>(w.pts_sorted, w.idx_sorted, (int)n, k, w.minmax, out);

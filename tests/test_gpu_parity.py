@@ -469,6 +469,33 @@ def test_fused_hierarchy_matches_per_object_path():
         assert torch.equal(g_ref.rec_in, g.rec_in) and torch.equal(g_ref.rec_out, g.rec_out)
 
 
+def test_fused_hierarchy_long_transposed_rows():
+    """Coarse sources against a fine cloud: transposed CSR rows tens of thousands of entries long (the row-ordering
+    kernel's chunk sort + rank-merge path) and empty rows; bit-exact against the per-object transpose."""
+    from se3conv3d_b200.pc import build_point_hierarchy, BQNeighborhood
+    g = torch.Generator().manual_seed(41)
+    n = 40000
+    pts = torch.rand(n, 3, generator=g)
+    batch = torch.sort(torch.randint(0, 2, (n,), generator=g))[0].to(torch.int32)
+    cfg = {"pca": True, "neigh_method": "knn", "neigh_kwargs": {"neigh_k": 16}, "fixed_axis": False, "n_frames": 2}
+    wanted = [(1, 0, 1.0), (0, 1, 0.3), (1, 1, 0.6), (0, 0, 0.03)]
+    h, _ = build_point_hierarchy(pts.to(DEV), batch.to(DEV), cfg, 0.02, [0.5], neighborhoods=wanted, n_batches=2)
+    assert h.pcs_[1].pts_.shape[0] <= 16 and h.pcs_[0].pts_.shape[0] > 20000
+    longest = 0
+    for nb in h.fused_neighborhoods_:
+        ref = BQNeighborhood(nb.pc_src_, nb.samples_, nb.radius_)
+        g_ref = ref.conv_geometry(nb.pc_src_, nb.samples_)
+        gg = list(nb.conv_geometry_cache_.values())[0]
+        e = gg.n_edges
+        assert e == g_ref.n_edges and torch.equal(ref.start_ids_, nb.start_ids_)
+        for k in ("col_src", "t_edge", "t_dst"):
+            assert torch.equal(getattr(g_ref, k)[:e], getattr(gg, k)[:e]), k
+        assert torch.equal(g_ref.t_row_ends[:gg.n_in], gg.t_row_ends[:gg.n_in])
+        te = torch.cat((torch.zeros(1, dtype=torch.int32, device=DEV), gg.t_row_ends[:gg.n_in]))
+        longest = max(longest, int((te[1:] - te[:-1]).max()))
+    assert longest > 4096, longest
+
+
 def wl_grid_of(pcs, lvl, step):
     """Grid of level `lvl` -> `lvl + 1` rebuilt with the per-object API (for comparison)."""
     from se3conv3d_b200 import workloads as wl
