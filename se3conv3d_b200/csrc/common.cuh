@@ -23,6 +23,7 @@ struct ProfScope {
 // key sort shared by the grid / ball-query / kNN builders (grid_ops.cu): per-batch-item CTA sort when
 // 0 < max_seg <= 7168 points per item, device-wide radix sort otherwise
 constexpr int kSegSortMax = 7168;
+size_t cub_tmp_bytes(int kind, int64_t n);
 size_t sort_pairs_tmp_bytes(int64_t n);
 int batch_counts(const int32_t* batch_ids, int64_t n, int32_t n_batches, int32_t* counts_out, cudaStream_t st);
 int sort_keys_u64(const uint64_t* keys_in, const int* iota, const int* batch, int64_t n, int n_batches, int max_seg,

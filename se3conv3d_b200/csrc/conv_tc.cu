@@ -179,8 +179,7 @@ __device__ __forceinline__ void basis_pre(const uint32_t (&aw)[2][2][4], const f
   if (t < 3) gv = *reinterpret_cast<const float4*>(grow + 4 * t);
 #pragma unroll
   for (int m = 0; m < 2; ++m) {
-    d[m][0] = d[m][1] = d[m][2] = d[m][3] = 0.0f;
-    mma_tf32(d[m], aw[m][0], __float_as_uint(gv.x), __float_as_uint(gv.y));
+    mma_tf32_zero(d[m], aw[m][0], __float_as_uint(gv.x), __float_as_uint(gv.y));
     mma_tf32(d[m], aw[m][1], __float_as_uint(gv.z), __float_as_uint(gv.w));
   }
 }

@@ -81,6 +81,28 @@ extern "C" int se3_profile_read(double* ms_out, int64_t* count_out) {
 
 using namespace se3;
 
+// CUB temporary-storage sizes, memoised per (kind, next power of two >= n): the size queries walk the device
+// attributes / kernel occupancy and cost microseconds each -- the builders ask dozens of times per call.
+//   kind 0: SortPairs(64-bit key, int value)   1: InclusiveSum(int)   2: SortPairs(int key, int value)
+size_t se3::cub_tmp_bytes(int kind, int64_t n) {
+  static size_t memo[3][40] = {};
+  int lg = 10;
+  while ((1ll << lg) < n && lg < 31) ++lg;
+  size_t& m = memo[kind][lg];
+  if (m == 0) {
+    const int nn = (int)((1ll << lg) > 2147483647ll ? 2147483647ll : (1ll << lg));
+    size_t b = 0;
+    if (kind == 0)
+      cub::DeviceRadixSort::SortPairs(nullptr, b, (uint64_t*)nullptr, (uint64_t*)nullptr, (int*)nullptr, (int*)nullptr, nn);
+    else if (kind == 1)
+      cub::DeviceScan::InclusiveSum(nullptr, b, (int*)nullptr, (int*)nullptr, nn);
+    else
+      cub::DeviceRadixSort::SortPairs(nullptr, b, (int*)nullptr, (int*)nullptr, (int*)nullptr, (int*)nullptr, nn);
+    m = b ? b : 1;
+  }
+  return m;
+}
+
 extern "C" int se3_abi_version(void) { return 1; }
 extern "C" const char* se3_last_error(void) { return se3::g_err; }
 extern "C" int64_t se3_launch_count(void) { return se3::g_launches.load(); }
@@ -385,13 +407,12 @@ __device__ __forceinline__ int lower_bound_i32(const int* __restrict__ a, int n,
   return lo;
 }
 
-constexpr int kSegThreads = 1024;
-template <int ITEMS>
-__global__ void __launch_bounds__(kSegThreads) k_seg_sort_u64(const uint64_t* __restrict__ keys_in,
-                                                              const int* __restrict__ batch, int n,
-                                                              uint64_t* __restrict__ keys_out, int* __restrict__ idx_out,
-                                                              int end_bit) {
-  using Sort = cub::BlockRadixSort<uint64_t, kSegThreads, ITEMS, int>;
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS) k_seg_sort_u64(const uint64_t* __restrict__ keys_in,
+                                                          const int* __restrict__ batch, int n,
+                                                          uint64_t* __restrict__ keys_out, int* __restrict__ idx_out,
+                                                          int end_bit) {
+  using Sort = cub::BlockRadixSort<uint64_t, THREADS, ITEMS, int>;
   extern __shared__ __align__(16) unsigned char seg_smem[];
   typename Sort::TempStorage& tmp = *reinterpret_cast<typename Sort::TempStorage*>(seg_smem);
   __shared__ int s_lo, s_hi;
@@ -421,14 +442,14 @@ __global__ void __launch_bounds__(kSegThreads) k_seg_sort_u64(const uint64_t* __
   }
 }
 
-template <int ITEMS>
+template <int THREADS, int ITEMS>
 static int launch_seg_sort(const uint64_t* keys_in, const int* batch, int n, int n_batches, uint64_t* keys_out,
                            int* idx_out, int end_bit, cudaStream_t st) {
-  using Sort = cub::BlockRadixSort<uint64_t, kSegThreads, ITEMS, int>;
-  auto kern = k_seg_sort_u64<ITEMS>;
+  using Sort = cub::BlockRadixSort<uint64_t, THREADS, ITEMS, int>;
+  auto kern = k_seg_sort_u64<THREADS, ITEMS>;
   const size_t smem = sizeof(typename Sort::TempStorage);
   SE3_SMEM_ONCE(kern, smem);
-  kern<<<n_batches, kSegThreads, smem, st>>>(keys_in, batch, n, keys_out, idx_out, end_bit);
+  kern<<<n_batches, THREADS, smem, st>>>(keys_in, batch, n, keys_out, idx_out, end_bit);
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }
@@ -444,21 +465,22 @@ int batch_counts(const int32_t* batch_ids, int64_t n, int32_t n_batches, int32_t
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }
-size_t sort_pairs_tmp_bytes(int64_t n) {
-  size_t a = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, a, (uint64_t*)nullptr, (uint64_t*)nullptr, (int*)nullptr, (int*)nullptr, (int)n);
-  return a;
-}
+size_t sort_pairs_tmp_bytes(int64_t n) { return cub_tmp_bytes(0, n); }
 // keys_in [n] (64-bit, non-negative), iota [n] = 0..n-1 -> keys_out ascending (stable), idx_out the permutation.
 // max_seg = the largest number of points in one batch item (0 = unknown -> device-wide sort).
 int sort_keys_u64(const uint64_t* keys_in, const int* iota, const int* batch, int64_t n, int n_batches, int max_seg,
                   uint64_t* keys_out, int* idx_out, int end_bit, void* cub_tmp, size_t cub_bytes, cudaStream_t st) {
   if (end_bit <= 0 || end_bit > 64) end_bit = 64;
   if (max_seg > 0 && n_batches >= 1 && n_batches <= 65535 && batch != nullptr) {
-    if (max_seg <= kSegThreads * 1) return launch_seg_sort<1>(keys_in, batch, (int)n, n_batches, keys_out, idx_out, end_bit, st);
-    if (max_seg <= kSegThreads * 2) return launch_seg_sort<2>(keys_in, batch, (int)n, n_batches, keys_out, idx_out, end_bit, st);
-    if (max_seg <= kSegThreads * 4) return launch_seg_sort<4>(keys_in, batch, (int)n, n_batches, keys_out, idx_out, end_bit, st);
-    if (max_seg <= kSegSortMax) return launch_seg_sort<7>(keys_in, batch, (int)n, n_batches, keys_out, idx_out, end_bit, st);
+#define SE3_SEG_CASE(T, I)                                                                                     \
+  if (max_seg <= (T) * (I)) return launch_seg_sort<T, I>(keys_in, batch, (int)n, n_batches, keys_out, idx_out, end_bit, st)
+    SE3_SEG_CASE(64, 4);
+    SE3_SEG_CASE(128, 8);
+    SE3_SEG_CASE(256, 8);
+    SE3_SEG_CASE(512, 8);
+    SE3_SEG_CASE(1024, 7);
+#undef SE3_SEG_CASE
+    static_assert(kSegSortMax == 1024 * 7, "largest per-item sort");
   }
   size_t cb = cub_bytes;
   SE3_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cb, keys_in, keys_out, iota, idx_out, (int)n, 0, end_bit, st));
@@ -479,9 +501,7 @@ struct CellsWorkspace {
 };
 
 static size_t cells_cub_bytes(int64_t n) {
-  size_t a = 0, b = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, a, (int64_t*)nullptr, (int64_t*)nullptr, (int*)nullptr, (int*)nullptr, (int)n);
-  cub::DeviceScan::InclusiveSum(nullptr, b, (int*)nullptr, (int*)nullptr, (int)n);
+  const size_t a = cub_tmp_bytes(0, n), b = cub_tmp_bytes(1, n);
   return a > b ? a : b;
 }
 
@@ -623,17 +643,10 @@ struct BQWorkspace {
   size_t scan_bytes;
 };
 
-static size_t bq_scan_bytes(int64_t n_dst) {
-  size_t b = 0;
-  cub::DeviceScan::InclusiveSum(nullptr, b, (int*)nullptr, (int*)nullptr, (int)n_dst);
-  return b;
-}
+static size_t bq_scan_bytes(int64_t n_dst) { return cub_tmp_bytes(1, n_dst); }
 
 static size_t bq_cub_bytes(int64_t n_src, int64_t n_dst) {
-  size_t a = 0, b = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, a, (int64_t*)nullptr, (int64_t*)nullptr, (int*)nullptr, (int*)nullptr,
-                                  (int)n_src);
-  cub::DeviceScan::InclusiveSum(nullptr, b, (int*)nullptr, (int*)nullptr, (int)n_dst);
+  const size_t a = cub_tmp_bytes(0, n_src), b = cub_tmp_bytes(1, n_dst);
   return a > b ? a : b;
 }
 
@@ -965,31 +978,42 @@ __global__ void __launch_bounds__(1024) k_scan_small(const ScanJob j0, const Sca
   const ScanJob j = blockIdx.x == 0 ? j0 : j1;
   using BS = cub::BlockScan<int, 1024>;
   __shared__ typename BS::TempStorage tmp;
-  constexpr int IT = 8;
+  constexpr int IT = 16;  // 16 K entries per tile: four 128-bit loads in flight per thread (arrays are 16-byte aligned)
   int carry = 0;
   for (int base = 0; base < j.n; base += 1024 * IT) {
     int v[IT];
-    int sum = 0;
     const int p0 = base + threadIdx.x * IT;
+    if (p0 + IT <= j.n) {
+      const int4* src = reinterpret_cast<const int4*>(j.in + p0);
 #pragma unroll
-    for (int i = 0; i < IT; ++i) {
-      v[i] = (p0 + i < j.n) ? j.in[p0 + i] : 0;
-      sum += v[i];
+      for (int q = 0; q < IT / 4; ++q) {
+        const int4 t = src[q];
+        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < IT; ++i) v[i] = (p0 + i < j.n) ? j.in[p0 + i] : 0;
     }
+    int sum = 0;
+#pragma unroll
+    for (int i = 0; i < IT; ++i) sum += v[i];
     int excl, agg;
     BS(tmp).ExclusiveSum(sum, excl, agg);
     int run = carry + excl;
 #pragma unroll
     for (int i = 0; i < IT; ++i) {
-      if (p0 + i < j.n) {
-        if (j.exclusive) {
-          j.out[p0 + i] = run;
-          run += v[i];
-        } else {
-          run += v[i];
-          j.out[p0 + i] = run;
-        }
-      }
+      const int before = run;
+      run += v[i];
+      v[i] = j.exclusive ? before : run;
+    }
+    if (p0 + IT <= j.n) {
+      int4* dst = reinterpret_cast<int4*>(j.out + p0);
+#pragma unroll
+      for (int q = 0; q < IT / 4; ++q) dst[q] = make_int4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < IT; ++i)
+        if (p0 + i < j.n) j.out[p0 + i] = v[i];
     }
     carry += agg;
     __syncthreads();
@@ -1155,11 +1179,7 @@ __global__ void k_transposed_rows(const int* __restrict__ src_sorted, const int*
   }
 }
 
-static size_t tr_cub_bytes(int64_t e) {
-  size_t a = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, a, (int*)nullptr, (int*)nullptr, (int*)nullptr, (int*)nullptr, (int)e);
-  return a;
-}
+static size_t tr_cub_bytes(int64_t e) { return cub_tmp_bytes(2, e); }
 
 extern "C" size_t se3_csr_transpose_workspace_bytes(int64_t n_edges, int64_t n_src) {
   (void)n_src;

@@ -4,6 +4,8 @@
 // object, several tensor allocations and one blocking size read per grid / neighbourhood become
 // (n_pool + 2) size reads in total and a bump allocator over a caller-provided arena.
 #include <string.h>
+#include <stdlib.h>
+#include <chrono>
 #include "common.cuh"
 
 namespace se3 {
@@ -98,6 +100,14 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
   SE3_CHECK_ARG(pts && batch_ids && u_frames, "null input");
   SE3_CHECK_ARG(!d->out_cloud || u_cells, "the output cloud needs u_cells");
   cudaStream_t st = as_stream(stream);
+  // SE3_HIER_TRACE=1: host time stamps of the build phases on stderr (debugging aid)
+  static const bool trace = getenv("SE3_HIER_TRACE") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto stamp = [&](const char* what) {
+    if (trace)
+      fprintf(stderr, "[se3_hierarchy_build] %-28s %8.1f us\n", what,
+              std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count());
+  };
   int64_t* host = pinned_scalars();
   if (!host) {
     set_error("se3_hierarchy_build: cannot allocate pinned host scalars");
@@ -154,6 +164,7 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
       if (track_items)
         SE3_CUDA(cudaMemcpyAsync(hf + d->n_batches * 6, d_items, (size_t)d->n_batches * 4, cudaMemcpyDeviceToHost, st));
       SE3_CUDA(cudaStreamSynchronize(st));
+      stamp("input box read");
       if (track_items) seg_raw = max_item(reinterpret_cast<const int32_t*>(hf + d->n_batches * 6), d->n_batches);
       for (int b = 0; b < d->n_batches; ++b)
         for (int k = 0; k < 3; ++k) {
@@ -192,6 +203,7 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
     SE3_CUDA(cudaMemcpyAsync(host, d_m, track_items ? lvl_bytes : sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     SE3_CUDA(cudaStreamSynchronize(st));
     g.m = host[0];
+    stamp("grid size read");
     seg_next = track_items && n > 0 ? max_item(reinterpret_cast<const int32_t*>(host + 1), d->n_batches) : 0;
     return SE3_OK;
   };
@@ -267,6 +279,78 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
     }
     return SE3_OK;
   };
+  // ---- neighbourhoods: one sorted source structure per (source cloud, radius) and one count pass per
+  // neighbourhood, issued on the side streams as soon as the clouds they touch exist (the large neighbourhoods
+  // of the fine levels then run underneath the rest of the pooling chain); ONE blocking read of the edge totals
+  // at the end, then fills + transposed rows
+  struct Source {
+    int cloud;
+    float radius;
+    int64_t ws, mn, mx, nc;
+    size_t ws_bytes;
+    bool issued;
+  } sources[SE3_HIER_MAX_NEIGH];
+  int n_sources = 0, src_of[SE3_HIER_MAX_NEIGH], rad_slot[SE3_HIER_MAX_NEIGH];
+  for (int i = 0; i < d->n_neigh; ++i) {
+    int f = -1;
+    for (int j = 0; j < n_sources; ++j)
+      if (sources[j].cloud == d->neigh_src[i] && sources[j].radius == d->neigh_radius[i]) f = j;
+    if (f < 0) {
+      f = n_sources++;
+      sources[f].cloud = d->neigh_src[i];
+      sources[f].radius = d->neigh_radius[i];
+      sources[f].issued = false;
+      rad_slot[f] = i;
+    }
+    src_of[i] = f;
+  }
+  bool cloud_done[SE3_HIER_MAX_CLOUDS + 1] = {false}, nb_issued[SE3_HIER_MAX_NEIGH] = {false};
+  int64_t wd_off[SE3_HIER_MAX_NEIGH];
+  size_t wd_bytes[SE3_HIER_MAX_NEIGH];
+  auto issue_ready = [&]() -> int {
+    for (int j = 0; j < n_sources; ++j) {
+      Source& so = sources[j];
+      if (so.issued || !cloud_done[so.cloud]) continue;
+      const se3_hier_cloud& s = out->clouds[so.cloud];
+      so.ws_bytes = se3_ball_query_src_workspace_bytes(s.n, 1);
+      so.ws = ar.take(so.ws_bytes);
+      so.mn = ar.take(bb);
+      so.mx = ar.take(bb);
+      so.nc = ar.take(16);
+      HB_CHECK_ARENA("ball-query source");
+      cudaStream_t sj = ln->s[j % kSide];
+      se3_stream_t sjs = reinterpret_cast<se3_stream_t>(sj);
+      SE3_CUDA(cudaStreamWaitEvent(sj, ln->cloud[so.cloud], 0));
+      HB_TRY(se3_grid_extents(ar.at<float>(o_rawmin[1 + so.cloud]), ar.at<float>(o_rawmax[1 + so.cloud]), d->n_batches,
+                              so.radius, -1e-6f, ar.at<float>(so.mn), ar.at<float>(so.mx), ar.at<int32_t>(so.nc), sjs));
+      HB_TRY(ball_query_prepare_impl(ar.at<float>(s.pts), ar.at<int32_t>(s.batch), s.n, 1, ar.at<float>(so.mn),
+                                     ar.at<int32_t>(so.nc), d_rad + 4 * rad_slot[j], ar.at<char>(so.ws), so.ws_bytes,
+                                     key_bits_for(so.radius), d->n_batches, cloud_seg[so.cloud], sjs));
+      SE3_CUDA(cudaEventRecord(ln->src[j], sj));
+      so.issued = true;
+    }
+    for (int i = 0; i < d->n_neigh; ++i) {
+      const Source& so = sources[src_of[i]];
+      if (nb_issued[i] || !so.issued || !cloud_done[d->neigh_dst[i]]) continue;
+      const se3_hier_cloud& s = out->clouds[d->neigh_src[i]];
+      const se3_hier_cloud& t = out->clouds[d->neigh_dst[i]];
+      se3_hier_neigh& nb = out->neigh[i];
+      nb.row_ends = ar.take((size_t)t.n * 4);
+      nb.t_row_ends = ar.take((size_t)s.n * 4);
+      wd_bytes[i] = se3_ball_query_dst_workspace_bytes(t.n);
+      wd_off[i] = ar.take(wd_bytes[i]);
+      HB_CHECK_ARENA("ball-query workspace");
+      cudaStream_t si = ln->s[i % kSide];
+      SE3_CUDA(cudaStreamWaitEvent(si, ln->src[src_of[i]], 0));
+      SE3_CUDA(cudaStreamWaitEvent(si, ln->cloud[d->neigh_dst[i]], 0));
+      HB_TRY(bq_count_transposed(ar.at<float>(t.pts), ar.at<int32_t>(t.batch), s.n, t.n, 1, ar.at<float>(so.mn),
+                                 ar.at<int32_t>(so.nc), d_rad + 4 * i, ar.at<char>(so.ws), so.ws_bytes,
+                                 ar.at<char>(wd_off[i]), wd_bytes[i], ar.at<int32_t>(nb.row_ends),
+                                 ar.at<int32_t>(nb.t_row_ends), d_cnt + 1 + i, reinterpret_cast<se3_stream_t>(si)));
+      nb_issued[i] = true;
+    }
+    return SE3_OK;
+  };
   // cloud c is complete on the caller's stream (points, batch ids, raw box): its frames go to a side stream
   auto cloud_ready = [&](int c, int raw_slot) -> int {
     HB_TRY(cloud_bbox(out->clouds[c], raw_slot, stream));
@@ -275,7 +359,8 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
     SE3_CUDA(cudaStreamWaitEvent(s, ln->cloud[c], 0));
     HB_TRY(build_frames(out->clouds[c], cloud_seg[c], reinterpret_cast<se3_stream_t>(s)));
     SE3_CUDA(cudaEventRecord(ln->frames[c], s));
-    return SE3_OK;
+    cloud_done[c] = true;
+    return issue_ready();
   };
 
   // ---- level 0 and the output cloud share the raw cloud's init_cell grid
@@ -312,76 +397,15 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
     HB_TRY(cloud_ready(l + 1, 2 + l));
   }
 
-  // ---- neighbourhoods: one sorted source structure per (source cloud, radius), all count passes, ONE blocking
-  // read of the edge totals, then fills + transposes -- each on the side stream of its neighbourhood
-  struct Source {
-    int cloud;
-    float radius;
-    int64_t n_dst_max, ws, mn, mx, nc;
-    size_t ws_bytes;
-  } sources[SE3_HIER_MAX_NEIGH];
-  int n_sources = 0, src_of[SE3_HIER_MAX_NEIGH];
-  for (int i = 0; i < d->n_neigh; ++i) {
-    int f = -1;
-    for (int j = 0; j < n_sources; ++j)
-      if (sources[j].cloud == d->neigh_src[i] && sources[j].radius == d->neigh_radius[i]) f = j;
-    if (f < 0) {
-      f = n_sources++;
-      sources[f].cloud = d->neigh_src[i];
-      sources[f].radius = d->neigh_radius[i];
-      sources[f].n_dst_max = 0;
-    }
-    const int64_t nd = out->clouds[d->neigh_dst[i]].n;
-    if (nd > sources[f].n_dst_max) sources[f].n_dst_max = nd;
-    src_of[i] = f;
-  }
-  int rad_slot[SE3_HIER_MAX_NEIGH];
-  for (int j = 0; j < n_sources; ++j) {
-    Source& so = sources[j];
-    const se3_hier_cloud& s = out->clouds[so.cloud];
-    for (int i = 0; i < d->n_neigh; ++i)
-      if (src_of[i] == j) rad_slot[j] = i;
-    so.ws_bytes = se3_ball_query_src_workspace_bytes(s.n, so.n_dst_max);
-    so.ws = ar.take(so.ws_bytes);
-    so.mn = ar.take(bb);
-    so.mx = ar.take(bb);
-    so.nc = ar.take(16);
-    HB_CHECK_ARENA("ball-query source");
-    cudaStream_t sj = ln->s[j % kSide];
-    se3_stream_t sjs = reinterpret_cast<se3_stream_t>(sj);
-    SE3_CUDA(cudaStreamWaitEvent(sj, ln->cloud[so.cloud], 0));
-    HB_TRY(se3_grid_extents(ar.at<float>(o_rawmin[1 + so.cloud]), ar.at<float>(o_rawmax[1 + so.cloud]), d->n_batches,
-                            so.radius, -1e-6f, ar.at<float>(so.mn), ar.at<float>(so.mx), ar.at<int32_t>(so.nc), sjs));
-    HB_TRY(ball_query_prepare_impl(ar.at<float>(s.pts), ar.at<int32_t>(s.batch), s.n, so.n_dst_max, ar.at<float>(so.mn),
-                                   ar.at<int32_t>(so.nc), d_rad + 4 * rad_slot[j], ar.at<char>(so.ws), so.ws_bytes,
-                                   key_bits_for(so.radius), d->n_batches, cloud_seg[so.cloud], sjs));
-    SE3_CUDA(cudaEventRecord(ln->src[j], sj));
-  }
-  int64_t wd_off[SE3_HIER_MAX_NEIGH];
-  size_t wd_bytes[SE3_HIER_MAX_NEIGH];
-  for (int i = 0; i < d->n_neigh; ++i) {
-    const Source& so = sources[src_of[i]];
-    const se3_hier_cloud& s = out->clouds[d->neigh_src[i]];
-    const se3_hier_cloud& t = out->clouds[d->neigh_dst[i]];
-    se3_hier_neigh& nb = out->neigh[i];
-    nb.row_ends = ar.take((size_t)t.n * 4);
-    nb.t_row_ends = ar.take((size_t)s.n * 4);
-    wd_bytes[i] = se3_ball_query_dst_workspace_bytes(t.n);
-    wd_off[i] = ar.take(wd_bytes[i]);
-    HB_CHECK_ARENA("ball-query workspace");
-    cudaStream_t si = ln->s[i % kSide];
-    SE3_CUDA(cudaStreamWaitEvent(si, ln->src[src_of[i]], 0));
-    SE3_CUDA(cudaStreamWaitEvent(si, ln->cloud[d->neigh_dst[i]], 0));
-    HB_TRY(bq_count_transposed(ar.at<float>(t.pts), ar.at<int32_t>(t.batch), s.n, t.n, so.n_dst_max, ar.at<float>(so.mn),
-                               ar.at<int32_t>(so.nc), d_rad + 4 * i, ar.at<char>(so.ws), so.ws_bytes,
-                               ar.at<char>(wd_off[i]), wd_bytes[i], ar.at<int32_t>(nb.row_ends),
-                               ar.at<int32_t>(nb.t_row_ends), d_cnt + 1 + i, reinterpret_cast<se3_stream_t>(si)));
-  }
+  stamp("pooling chain done");
+  HB_TRY(issue_ready());
+  stamp("counts issued");
   HB_TRY(join_all());
   if (d->n_neigh > 0) {
     SE3_CUDA(cudaMemcpyAsync(host, d_cnt + 1, sizeof(int64_t) * d->n_neigh, cudaMemcpyDeviceToHost, st));
     SE3_CUDA(cudaStreamSynchronize(st));
   }
+  stamp("edge totals read");
   for (int i = 0; i < d->n_neigh; ++i) {
     const Source& so = sources[src_of[i]];
     const se3_hier_cloud& s = out->clouds[d->neigh_src[i]];
@@ -395,7 +419,7 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
     HB_CHECK_ARENA("neighbourhood");
     // everything issued so far has completed (the blocking read above), so the side streams need no further waits
     se3_stream_t sis = reinterpret_cast<se3_stream_t>(ln->s[i % kSide]);
-    HB_TRY(bq_fill_transposed(ar.at<float>(t.pts), s.n, t.n, so.n_dst_max, d_rad + 4 * i, ar.at<char>(so.ws), so.ws_bytes,
+    HB_TRY(bq_fill_transposed(ar.at<float>(t.pts), s.n, t.n, 1, d_rad + 4 * i, ar.at<char>(so.ws), so.ws_bytes,
                               ar.at<char>(wd_off[i]), wd_bytes[i], ar.at<int32_t>(nb.row_ends), nb.e,
                               ar.at<int32_t>(nb.col_src), ar.at<int32_t>(nb.edge_dst), ar.at<int32_t>(nb.t_row_ends),
                               ar.at<int32_t>(nb.t_edge), ar.at<int32_t>(nb.t_dst), sis));
@@ -411,6 +435,7 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
   if (!joined) {
     for (int k = 0; k < kSide; ++k) cudaStreamSynchronize(ln->s[k]);
   }
+  stamp("fills issued, joined");
   if (rc != SE3_OK) return rc;
   out->arena_used = (int64_t)ar.off;
   return SE3_OK;

@@ -27,12 +27,7 @@ struct KnnWorkspace {
   size_t cub_bytes;
 };
 
-size_t knn_cub_bytes(int64_t n) {
-  size_t a = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, a, (uint64_t*)nullptr, (uint64_t*)nullptr, (int*)nullptr, (int*)nullptr,
-                                  (int)n);
-  return a;
-}
+size_t knn_cub_bytes(int64_t n) { return se3::cub_tmp_bytes(0, n); }
 
 bool knn_layout(void* ws, size_t bytes, int64_t n, KnnWorkspace& w) {
   Arena ar(ws, bytes);
