@@ -78,6 +78,21 @@ class HierResult(C.Structure):
 _lib = None
 
 
+class LazyAttrs(object):
+    """Attributes that are windows into the fused hierarchy arena are created on first access: an object built by
+    pc.build_point_hierarchy carries `_lazy = {name: thunk}`; everything else behaves like a plain attribute.
+    (A training step touches a handful of the ~150 tensors one hierarchy exposes; creating all of them eagerly
+    cost more host time than the native build call.)"""
+
+    def __getattr__(self, name):
+        lazy = self.__dict__.get("_lazy")
+        if lazy is not None and name in lazy:
+            val = lazy.pop(name)()
+            self.__dict__[name] = val
+            return val
+        raise AttributeError("%s has no attribute %r" % (type(self).__name__, name))
+
+
 class Se3Error(RuntimeError):
     pass
 

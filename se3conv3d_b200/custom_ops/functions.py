@@ -87,11 +87,16 @@ def make_conv_desc(geom, c_in, c_out, k, act, precision, norm_neigh_dist, out_sc
         d.n_in, d.n_out, d.n_edges = geom.n_in, geom.n_out, geom.n_edges
         d.f_in, d.f_out, d.c_in, d.c_out, d.k = geom.f_in, geom.f_out, key[0], key[1], key[2]
         d.act, d.precision, d.reserved = key[3], key[4], 0
-        d.pts_in, d.pts_out = ptr(geom.pts_in), ptr(geom.pts_out)
-        d.frames_in, d.frames_out = ptr(geom.frames_in), ptr(geom.frames_out)
-        d.row_ends, d.col_src = ptr(geom.row_ends), ptr(geom.col_src)
-        d.t_row_ends, d.t_edge, d.t_dst = ptr(geom.t_row_ends), ptr(geom.t_edge), ptr(geom.t_dst)
-        d.rec_in, d.rec_out = ptr(geom.rec_in), ptr(geom.rec_out)
+        addr = geom.__dict__.get("_addr")
+        if addr is not None:      # geometry from the fused hierarchy builder: device addresses, no tensor objects
+            for name, a in addr.items():
+                setattr(d, name, a)
+        else:
+            d.pts_in, d.pts_out = ptr(geom.pts_in), ptr(geom.pts_out)
+            d.frames_in, d.frames_out = ptr(geom.frames_in), ptr(geom.frames_out)
+            d.row_ends, d.col_src = ptr(geom.row_ends), ptr(geom.col_src)
+            d.t_row_ends, d.t_edge, d.t_dst = ptr(geom.t_row_ends), ptr(geom.t_edge), ptr(geom.t_dst)
+            d.rec_in, d.rec_out = ptr(geom.rec_in), ptr(geom.rec_out)
         L = lib()
         ref = C.byref(d)
         entry = (d, ref, int(L.se3_conv_saved_bytes(ref)), int(L.se3_conv_fwd_workspace_bytes(ref)),

@@ -9,6 +9,7 @@ same classes with the same attributes, their tensors are views into one device a
     h.create_neighborhood(1, 1, "ball_query", bq_radius=0.1)   # served from the pre-filled cache
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -20,15 +21,18 @@ from .pointcloud_rot_equiv import PointcloudRotEquiv
 from .subsample import GridSubSample
 
 _arena_hint = {}
+_EAGER = bool(os.environ.get("SE3_EAGER_VIEWS"))
 
 
 class _Views(object):
     """Typed windows into the arena (byte offsets from the native result -> tensors, one op each)."""
 
     def __init__(self, arena):
+        self.arena = arena
         self.f32 = arena.view(torch.float32)
         self.i32 = arena.view(torch.int32)
         self.i64 = arena.view(torch.int64)
+        self.base_addr = arena.data_ptr()
 
     def f(self, off, *shape):
         return self._v(self.f32, off, 4, shape)
@@ -63,8 +67,13 @@ def _make_cloud(v, c, cfg, n_frames, n_batches):
     pc.n_frames_ = n_frames
     pc.local_frames_ = v.f(c.frames, c.n, n_frames, 9)
     pc._batch_ids_frames = None
-    rec = v.f(c.rec, max(c.n * n_frames, 1), 12)
-    pc._se3_records = ((id(pc.pts_), id(pc.local_frames_), pc.pts_._version, pc.local_frames_._version), rec)
+    n, rec_off = c.n, c.rec
+
+    def records():
+        rec = v.f(rec_off, max(n * n_frames, 1), 12)
+        return ((id(pc.pts_), id(pc.local_frames_), pc.pts_._version, pc.local_frames_._version), rec)
+    pc._lazy = {"_se3_records": records}
+    pc._rec_addr = v.base_addr + rec_off
     return pc
 
 
@@ -79,11 +88,11 @@ def _make_sampler(v, pc_src, c, cell, rnd=False):
     g.cell_size_ = cell
     g.bounding_box_ = None   # the fused builder does not keep per-grid bounding boxes
     g.num_cells_ = None
-    g.cell_ids_ = v.l(c.cell_ids, c.n)
-    g.sorted_ids_ = v.l(c.sorted_ids, c.n)
     g._sorted_cell_ids = None
     g.num_used_cells_ = int(c.m)
-    g.cell_ends_ = v.i(c.cell_ends, int(c.m))
+    n, m, o_ids, o_sorted, o_ends = c.n, int(c.m), c.cell_ids, c.sorted_ids, c.cell_ends
+    g._lazy = {"cell_ids_": lambda: v.l(o_ids, n), "sorted_ids_": lambda: v.l(o_sorted, n),
+               "cell_ends_": lambda: v.i(o_ends, m)}
     samp.grid_ = g
     return samp
 
@@ -140,38 +149,59 @@ def build_point_hierarchy(p_pts, p_batch_ids, p_ref_frames_config, p_init_subsam
     h.neigh_cache_ = {}
     h.fused_arena_ = arena
     # the raw cloud's init_cell grid (pooling raw features to level 0 / labels of the output cloud)
-    h.init_cell_ids_ = v.l(res.raw.cell_ids, n)
-    h.init_sorted_ids_ = v.l(res.raw.sorted_ids, n)
-    h.init_cell_ends_ = v.i(res.raw.cell_ends, int(res.raw.m))
+    raw_m, o_ci, o_si, o_ce = int(res.raw.m), res.raw.cell_ids, res.raw.sorted_ids, res.raw.cell_ends
+    h._lazy = {"init_cell_ids_": lambda: v.l(o_ci, n), "init_sorted_ids_": lambda: v.l(o_si, n),
+               "init_cell_ends_": lambda: v.i(o_ce, raw_m)}
     out_pc = clouds[n_pool + 1] if output_cloud else None
     if out_pc is not None:
-        out_pc.picked_ids_ = v.l(res.out_picked, int(res.clouds[n_pool + 1].n))
+        o_pick, n_out_pc = res.out_picked, int(res.clouds[n_pool + 1].n)
+        out_pc._lazy["picked_ids_"] = lambda: v.l(o_pick, n_out_pc)
     neighs = []
+    base = v.base_addr
     for i, (s, t, r) in enumerate(neighborhoods):
-        nr = res.neigh[i]
-        src, dst = clouds[s], clouds[t]
-        e = int(nr.e)
-        nb = BQNeighborhood.__new__(BQNeighborhood)
-        nb.radius_ = r
-        nb.max_neighbors_ = 0
-        nb.pc_src_, nb.samples_ = src, dst
-        nb._neighbors = None
-        nb.start_ids_ = v.i(nr.row_ends, int(dst.pts_.shape[0]))
-        col_src, edge_dst = v.i(nr.col_src, max(e, 1)), v.i(nr.edge_dst, max(e, 1))
-        nb._csr_columns = (edge_dst[:e], col_src[:e])
-        geom = ConvGeometry.__new__(ConvGeometry)
-        geom.n_in, geom.n_out, geom.n_edges = int(src.pts_.shape[0]), int(dst.pts_.shape[0]), e
-        geom.f_in = geom.f_out = n_frames
-        geom.pts_in, geom.pts_out = src.pts_, dst.pts_
-        geom.frames_in, geom.frames_out = src.local_frames_, dst.local_frames_
-        geom.rec_in, geom.rec_out = src._se3_records[1], dst._se3_records[1]
-        geom.row_ends, geom.col_src = nb.start_ids_, col_src
-        geom.t_row_ends = v.i(nr.t_row_ends, max(geom.n_in, 1))
-        geom.t_edge, geom.t_dst = v.i(nr.t_edge, max(e, 1)), v.i(nr.t_dst, max(e, 1))
-        nb.conv_geometry_cache_ = {(id(src), id(dst), id(src.local_frames_), id(dst.local_frames_),
-                                    nb._neighbors_token()): geom}
-        neighs.append(nb)
+        neighs.append(_make_neighborhood(v, base, res.neigh[i], clouds[s], clouds[t], r, n_frames))
         if s <= n_pool and t <= n_pool:
-            h.neigh_cache_[str(s) + "_" + str(t) + "_ball_query" + str(r)] = nb
+            h.neigh_cache_[str(s) + "_" + str(t) + "_ball_query" + str(r)] = neighs[-1]
     h.fused_neighborhoods_ = neighs
+    if _EAGER:   # A/B aid: materialise every window right away
+        objs = clouds + [sm.grid_ for sm in h.sub_sampled_objs_] + neighs + [h]
+        objs += [g for nb in neighs for g in nb.conv_geometry_cache_.values()]
+        for o in objs:
+            for name in list(o.__dict__.get("_lazy", {})):
+                getattr(o, name)
     return h, out_pc
+
+
+def _make_neighborhood(v, base, nr, src, dst, r, n_frames):
+    """BQNeighborhood + its ConvGeometry over arena windows.  The conv calls only need device addresses
+    (`geom._addr`, read by custom_ops.make_conv_desc); the tensors of the reference contract (`start_ids_`,
+    `neighbors_`, the CSR columns, ...) are created when somebody asks for them."""
+    e = int(nr.e)
+    n_in, n_out = int(src.pts_.shape[0]), int(dst.pts_.shape[0])
+    o_re, o_cs, o_ed, o_tre, o_te, o_td = nr.row_ends, nr.col_src, nr.edge_dst, nr.t_row_ends, nr.t_edge, nr.t_dst
+    nb = BQNeighborhood.__new__(BQNeighborhood)
+    nb.radius_ = r
+    nb.max_neighbors_ = 0
+    nb.pc_src_, nb.samples_ = src, dst
+    nb._neighbors = None
+    nb._fused_token = base + o_cs
+    nb.n_edges_ = e
+    nb._lazy = {"start_ids_": lambda: v.i(o_re, n_out),
+                "_csr_columns": lambda: (v.i(o_ed, max(e, 1))[:e], v.i(o_cs, max(e, 1))[:e])}
+    geom = ConvGeometry.__new__(ConvGeometry)
+    geom.n_in, geom.n_out, geom.n_edges = n_in, n_out, e
+    geom.f_in = geom.f_out = n_frames
+    geom._addr = {"pts_in": src.pts_.data_ptr(), "pts_out": dst.pts_.data_ptr(),
+                  "frames_in": src.local_frames_.data_ptr(), "frames_out": dst.local_frames_.data_ptr(),
+                  "rec_in": src._rec_addr, "rec_out": dst._rec_addr, "row_ends": base + o_re, "col_src": base + o_cs,
+                  "t_row_ends": base + o_tre, "t_edge": base + o_te, "t_dst": base + o_td}
+    geom._keep = (src, dst, v)   # the arena outlives the geometry
+    geom._lazy = {"pts_in": lambda: src.pts_, "pts_out": lambda: dst.pts_,
+                  "frames_in": lambda: src.local_frames_, "frames_out": lambda: dst.local_frames_,
+                  "rec_in": lambda: src._se3_records[1], "rec_out": lambda: dst._se3_records[1],
+                  "row_ends": lambda: nb.start_ids_, "col_src": lambda: v.i(o_cs, max(e, 1)),
+                  "t_row_ends": lambda: v.i(o_tre, max(n_in, 1)), "t_edge": lambda: v.i(o_te, max(e, 1)),
+                  "t_dst": lambda: v.i(o_td, max(e, 1))}
+    nb.conv_geometry_cache_ = {(id(src), id(dst), id(src.local_frames_), id(dst.local_frames_),
+                                nb._neighbors_token()): geom}
+    return nb

@@ -1,6 +1,6 @@
 import torch
 
-from .._lib import lib, check, ptr, stream, workspace, grid_setup, num_batches
+from .._lib import lib, check, ptr, stream, workspace, grid_setup, num_batches, LazyAttrs
 
 
 class BoundingBox(object):
@@ -14,7 +14,7 @@ class BoundingBox(object):
         return "### Min:\n{}\n### Max:\n{}".format(self.min_, self.max_)
 
 
-class Grid(object):
+class Grid(LazyAttrs):
     """Regular voxel grid over a point cloud (pc/Grid.py:9-58).
 
     `cell_ids_` [N] are dense cell ranks in sorted-key order, `sorted_ids_` = argsort(cell_ids_),

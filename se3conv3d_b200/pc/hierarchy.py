@@ -2,10 +2,10 @@ from .pointcloud import Pointcloud
 from .pointcloud_rot_equiv import PointcloudRotEquiv
 from .subsample import GridSubSample
 from .neighborhood import KnnNeighborhood, BQNeighborhood
-from .._lib import Se3Error, num_batches
+from .._lib import Se3Error, num_batches, LazyAttrs
 
 
-class PointHierarchy(object):
+class PointHierarchy(LazyAttrs):
     """Hierarchy of progressively sub-sampled clouds: `pcs_`, `sub_sampled_objs_`, `neigh_cache_`
     (pc/PointHierarchy.py:10-92; kwargs `grid_radii`, and the misspelt `neihg_k`, are API)."""
 

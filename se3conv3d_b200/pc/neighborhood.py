@@ -2,7 +2,7 @@ from abc import ABC, abstractmethod
 
 import torch
 
-from .._lib import lib, check, ptr, stream, workspace, Se3Error, num_batches
+from .._lib import lib, check, ptr, stream, workspace, Se3Error, num_batches, LazyAttrs
 from ..custom_ops import BallQuery, KNNQuery
 
 
@@ -26,7 +26,7 @@ def gather_records(p_pc):
     return rec
 
 
-class ConvGeometry(object):
+class ConvGeometry(LazyAttrs):
     """Device-resident record a conv call needs: forward CSR (int32), transposed CSR, coordinates
     and frames.  Built once per (neighbourhood, pc_in, pc_out) and cached on the neighbourhood; it
     replaces the reference's per-call sha256-keyed rot-tensor cache
@@ -65,7 +65,7 @@ class ConvGeometry(object):
                                   stream()), "se3_csr_transpose")
 
 
-class Neighborhood(ABC):
+class Neighborhood(LazyAttrs, ABC):
     """Neighbourhood interface: `neighbors_` [E,2] (sample, source), `start_ids_` [M] inclusive
     row ends (pc/Neighborhood.py:7-37)."""
 
@@ -127,6 +127,8 @@ class BQNeighborhood(Neighborhood):
         self._neighbors = v
 
     def _neighbors_token(self):
+        if self._neighbors is None and self.__dict__.get("_fused_token") is not None:
+            return self._fused_token        # fused builder: the CSR columns are still unmaterialised arena windows
         cols = getattr(self, "_csr_columns", None)
         return id(cols[1]) if (self._neighbors is None and cols is not None) else id(self._neighbors)
 

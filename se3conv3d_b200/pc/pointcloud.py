@@ -1,5 +1,7 @@
 import torch
 
+from .._lib import LazyAttrs
+
 from ..scatter import scatter_add, scatter_max, scatter_mean, scatter_min
 
 
@@ -16,7 +18,7 @@ def pool_by_index(p_in_tensor, p_index, p_pooling_method):
     raise ValueError("unknown pooling method " + str(p_pooling_method))
 
 
-class Pointcloud(object):
+class Pointcloud(LazyAttrs):
     """A batch of point clouds: `pts_` [N,D], `batch_ids_` [N], `batch_size_`
     (same constructor and attributes as pc/Pointcloud.py:6-30)."""
 

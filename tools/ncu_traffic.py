@@ -18,10 +18,10 @@ def to_bytes(v, unit):
     return float(v.replace(",", "")) * mult
 
 
-res = {"source": os.path.basename(rep), "command": "python tools/dfaust_layer_run.py seg_head 4 1"}
+res = {"source": os.path.basename(rep), "command": "python tools/dfaust_layer_run.py seg_head 3 1"}
 for r in data:
     name = r[col["Kernel Name"]]
-    if "k_edge_tc<" in name:
+    if "k_edge_tc<" in name or "k_edge_row_tc<" in name:
         key = "k_edge_tc"
     elif "k_agg_tc<" in name:
         key = "k_agg_tc_tr" if ", 1, " in name.split("<")[1] else "k_agg_tc_fwd"
