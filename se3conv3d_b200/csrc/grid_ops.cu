@@ -454,6 +454,177 @@ static int launch_seg_sort(const uint64_t* keys_in, const int* batch, int n, int
   return SE3_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// one launch per sorted structure (fused hierarchy builder, clouds whose batch items fit a CTA)
+// ---------------------------------------------------------------------------------------------
+// CTA b builds batch item b's slice of a sorted structure from the raw per-item boxes: grid extents (KIND 0) or
+// the sweep axis (KIND 1), the keys, the per-item sort and the key-ordered coordinates -- the work of se3_grid_extents
+// / k_minmax, k_cell_keys / k_compute_keys / k_knn_keys, the radix sort and the gather kernels in ONE launch.  The
+// arithmetic is the same as in those kernels (same rounding, same order), so the results are bit-identical.
+//   KIND 0: voxel keys of a grid with cell size `cell` (pooling grids and ball-query sources)
+//   KIND 1: kNN sweep order (batch, coordinate along the widest axis of the whole cloud)
+struct SegBuildArgs {
+  const float* pts;
+  const int* batch;
+  int n, n_batches;
+  const float* raw_min;  // [B,3] raw boxes (se3_bbox)
+  const float* raw_max;
+  float cell, max_pad;   // KIND 0
+  uint64_t* keys_sorted;  // KIND 0: [n] full keys, ascending
+  int* idx_sorted;        // [n] sorted position -> point
+  float4* pts_sorted;     // [n] xyz (+ batch id bits, KIND 1) in sorted order; optional for KIND 0
+  float* mn_out;          // KIND 0: padded boxes [B,3] and grid extents [3] (written by CTA 0)
+  float* mx_out;
+  int* nc_out;
+  float* mm_out;          // KIND 1: min / max of the whole cloud [6] (written by CTA 0)
+  int* zero;              // optional: n_zero ints cleared by CTA 0
+  int n_zero;
+};
+
+template <int THREADS, int ITEMS, int KIND>
+__global__ void __launch_bounds__(THREADS) k_seg_build(const SegBuildArgs a) {
+  using Sort = cub::BlockRadixSort<uint64_t, THREADS, ITEMS, int>;
+  extern __shared__ __align__(16) unsigned char seg_smem[];
+  typename Sort::TempStorage& tmp = *reinterpret_cast<typename Sort::TempStorage*>(seg_smem);
+  __shared__ int s_lo, s_hi, s_nc[3];
+  __shared__ float s_mm[6];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) {
+    s_lo = lower_bound_i32(a.batch, a.n, b);
+    s_hi = lower_bound_i32(a.batch, a.n, b + 1);
+    s_nc[0] = s_nc[1] = s_nc[2] = 1;
+    s_mm[0] = s_mm[1] = s_mm[2] = INFINITY;
+    s_mm[3] = s_mm[4] = s_mm[5] = -INFINITY;
+  }
+  if (b == 0)
+    for (int i = tid; i < a.n_zero; i += THREADS) a.zero[i] = 0;
+  __syncthreads();
+  const float inv = __fdiv_rn(1.0f, a.cell);
+  // ---- extents over all batch items (every CTA needs them; CTA 0 also publishes them)
+  for (int bb = tid; bb < a.n_batches; bb += THREADS) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float lo = a.raw_min[3 * bb + d], hi = a.raw_max[3 * bb + d];
+      if (KIND == 0) {
+        float plo = 0.0f, phi = 0.0f;
+        if (lo <= hi) {
+          plo = __fsub_rn(lo, 1e-6f);
+          phi = __fadd_rn(hi, a.max_pad);
+          atomicMax(&s_nc[d], (int)__fmul_rn(__fsub_rn(phi, plo), inv) + 1);
+        }
+        if (b == 0) {
+          a.mn_out[3 * bb + d] = plo;
+          a.mx_out[3 * bb + d] = phi;
+        }
+      } else if (lo <= hi) {
+        atomic_min_f32(&s_mm[d], lo);
+        atomic_max_f32(&s_mm[3 + d], hi);
+      }
+    }
+  }
+  __syncthreads();
+  if (b == 0 && tid < 3 && KIND == 0) a.nc_out[tid] = s_nc[tid];
+  if (b == 0 && tid < 6 && KIND == 1) a.mm_out[tid] = s_mm[tid];
+  const int lo = s_lo, cnt = s_hi - lo;
+  if (cnt <= 0) return;
+  uint64_t k[ITEMS];
+  int v[ITEMS];
+  int end_bit = 32;
+  uint64_t key_base = 0;
+  if (KIND == 0) {
+    GridParams g;
+    g.nx = s_nc[0]; g.ny = s_nc[1]; g.nz = s_nc[2];
+    g.ix = g.iy = g.iz = inv;
+    float mn[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float rl = a.raw_min[3 * b + d], rh = a.raw_max[3 * b + d];
+      mn[d] = rl <= rh ? __fsub_rn(rl, 1e-6f) : 0.0f;
+    }
+    const uint64_t cells = (uint64_t)g.nx * (uint64_t)g.ny * (uint64_t)g.nz;
+    key_base = (uint64_t)b * cells;
+    end_bit = cells > 1 ? 64 - __clzll((long long)(cells - 1)) : 1;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int p = tid * ITEMS + i;
+      k[i] = ~0ull;
+      v[i] = lo + p;
+      if (p < cnt) {
+        const int64_t q = lo + p;
+        int cx, cy, cz;
+        point_cell(g, a.pts[3 * q], a.pts[3 * q + 1], a.pts[3 * q + 2], mn[0], mn[1], mn[2], cx, cy, cz);
+        k[i] = (uint64_t)(((int64_t)cx * g.ny + cy) * g.nz + cz);
+      }
+    }
+    // the padding keys must stay above every real key inside the sorted bit range
+    if (end_bit < 64) {
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i)
+        if (tid * ITEMS + i >= cnt) k[i] = (1ull << end_bit) - 1;
+    }
+  } else {
+    // torch::argmax(max - min): first maximal index (knn_query.cu:143-149), as sort_dim_of in knn_frames.cu
+    const float e0 = s_mm[3] - s_mm[0], e1 = s_mm[4] - s_mm[1], e2 = s_mm[5] - s_mm[2];
+    int sd = 0;
+    float best = e0;
+    if (e1 > best) { best = e1; sd = 1; }
+    if (e2 > best) sd = 2;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int p = tid * ITEMS + i;
+      k[i] = 0xffffffffull;
+      v[i] = lo + p;
+      if (p < cnt) {
+        unsigned u = __float_as_uint(a.pts[3 * (int64_t)(lo + p) + sd]);
+        u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // order-preserving float -> uint
+        k[i] = u;
+      }
+    }
+  }
+  Sort(tmp).Sort(k, v, 0, end_bit);
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const int p = tid * ITEMS + i;
+    if (p < cnt) {
+      const int src = v[i];
+      if (KIND == 0) a.keys_sorted[lo + p] = key_base + k[i];
+      a.idx_sorted[lo + p] = src;
+      if (a.pts_sorted)
+        a.pts_sorted[lo + p] = make_float4(a.pts[3 * (int64_t)src], a.pts[3 * (int64_t)src + 1], a.pts[3 * (int64_t)src + 2],
+                                           KIND == 1 ? __int_as_float(b) : 0.0f);
+    }
+  }
+}
+
+template <int THREADS, int ITEMS, int KIND>
+static int launch_seg_build_cfg(const SegBuildArgs& a, cudaStream_t st) {
+  using Sort = cub::BlockRadixSort<uint64_t, THREADS, ITEMS, int>;
+  auto kern = k_seg_build<THREADS, ITEMS, KIND>;
+  const size_t smem = sizeof(typename Sort::TempStorage);
+  SE3_SMEM_ONCE(kern, smem);
+  kern<<<a.n_batches, THREADS, smem, st>>>(a);
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
+}
+
+bool se3::seg_build_possible(int n_batches, int max_seg) {
+  return max_seg > 0 && max_seg <= kSegSortMax && n_batches >= 1 && n_batches <= 65535;
+}
+// kind 0 / 1 as above; the caller has checked seg_build_possible
+static int launch_seg_build(int kind, const SegBuildArgs& a, int max_seg, cudaStream_t st) {
+#define SE3_SB_CASE(T, I)                                                                      \
+  if (max_seg <= (T) * (I))                                                                    \
+    return kind == 0 ? launch_seg_build_cfg<T, I, 0>(a, st) : launch_seg_build_cfg<T, I, 1>(a, st)
+  SE3_SB_CASE(64, 4);
+  SE3_SB_CASE(128, 8);
+  SE3_SB_CASE(256, 8);
+  SE3_SB_CASE(512, 8);
+  SE3_SB_CASE(1024, 7);
+#undef SE3_SB_CASE
+  set_error("launch_seg_build: batch item too large");
+  return SE3_EINVAL;
+}
+
 __global__ void k_batch_counts(const int* __restrict__ batch, int n, int n_batches, int* __restrict__ counts) {
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n_batches; b += gridDim.x * blockDim.x)
     counts[b] = lower_bound_i32(batch, n, b + 1) - lower_bound_i32(batch, n, b);
@@ -563,6 +734,37 @@ int se3::grid_cells_impl(const float* pts, const int32_t* batch_ids, int64_t n, 
   k_cell_flags<<<grid_for(n, 256), 256, 0, st>>>(w.keys_sorted, n, w.flags);
   SE3_LAUNCH_CHECK();
   cb = w.cub_bytes;
+  SE3_CUDA(cub::DeviceScan::InclusiveSum(w.cub_tmp, cb, w.flags, w.rank1, (int)n, st));
+  count_launch(1);
+  k_cell_ranks<<<grid_for(n, 256), 256, 0, st>>>(w.rank1, w.idx_sorted, n, cell_ids, sorted_ids, cell_ends, m_out,
+                                                 batch_ids, batch_cells);
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
+}
+
+// grid of a cloud whose batch items fit a CTA, straight from the raw boxes: extents + keys + sort in one launch
+// (k_seg_build), then the unique / rank pass.  Also writes the padded box and the grid extents.
+int se3::grid_cells_fused(const float* pts, const int32_t* batch_ids, int64_t n, const float* raw_min, const float* raw_max,
+                          float cell, float* min_pt_out, float* max_pt_out, int32_t* num_cells_out, void* workspace,
+                          size_t workspace_bytes, int64_t* cell_ids, int64_t* sorted_ids, int32_t* cell_ends,
+                          int64_t* m_out, int32_t n_batches, int32_t max_seg, int32_t* batch_cells, se3_stream_t stream) {
+  SE3_CHECK_ARG(n >= 1 && n < (1ll << 31) && cell > 0.0f && seg_build_possible(n_batches, max_seg), "bad arguments");
+  cudaStream_t st = as_stream(stream);
+  CellsWorkspace w;
+  if (!cells_layout(workspace, workspace_bytes, n, w)) {
+    set_error("grid_cells_fused: workspace too small");
+    return SE3_EWORKSPACE;
+  }
+  SegBuildArgs a;
+  a.pts = pts; a.batch = batch_ids; a.n = (int)n; a.n_batches = n_batches;
+  a.raw_min = raw_min; a.raw_max = raw_max; a.cell = cell; a.max_pad = 1e-6f;
+  a.keys_sorted = reinterpret_cast<uint64_t*>(w.keys_sorted); a.idx_sorted = w.idx_sorted; a.pts_sorted = nullptr;
+  a.mn_out = min_pt_out; a.mx_out = max_pt_out; a.nc_out = num_cells_out; a.mm_out = nullptr;
+  a.zero = batch_cells; a.n_zero = batch_cells ? n_batches : 0;
+  if (int rc = launch_seg_build(0, a, max_seg, st)) return rc;
+  k_cell_flags<<<grid_for(n, 256), 256, 0, st>>>(w.keys_sorted, n, w.flags);
+  SE3_LAUNCH_CHECK();
+  size_t cb = w.cub_bytes;
   SE3_CUDA(cub::DeviceScan::InclusiveSum(w.cub_tmp, cb, w.flags, w.rank1, (int)n, st));
   count_launch(1);
   k_cell_ranks<<<grid_for(n, 256), 256, 0, st>>>(w.rank1, w.idx_sorted, n, cell_ids, sorted_ids, cell_ends, m_out,
@@ -880,6 +1082,41 @@ int se3::ball_query_prepare_impl(const float* pts_src, const int32_t* batch_src,
     return SE3_EWORKSPACE;
   }
   return bq_prepare(pts_src, batch_src, n_src, min_pt, num_cells, radius, w, key_bits, as_stream(stream), n_batches, max_seg);
+}
+
+int se3::knn_sorted_fused(const float* pts, const int32_t* batch_ids, int64_t n, const float* raw_min, const float* raw_max,
+                          int* idx_sorted, void* pts_sorted_f4, float* minmax, int32_t n_batches, int32_t max_seg,
+                          se3_stream_t stream) {
+  SE3_CHECK_ARG(n >= 1 && n < (1ll << 31) && seg_build_possible(n_batches, max_seg), "bad arguments");
+  SegBuildArgs a;
+  a.pts = pts; a.batch = batch_ids; a.n = (int)n; a.n_batches = n_batches;
+  a.raw_min = raw_min; a.raw_max = raw_max; a.cell = 1.0f; a.max_pad = 0.0f;
+  a.keys_sorted = nullptr; a.idx_sorted = idx_sorted; a.pts_sorted = reinterpret_cast<float4*>(pts_sorted_f4);
+  a.mn_out = nullptr; a.mx_out = nullptr; a.nc_out = nullptr; a.mm_out = minmax;
+  a.zero = nullptr; a.n_zero = 0;
+  return launch_seg_build(1, a, max_seg, as_stream(stream));
+}
+
+// sorted source structure of a ball query straight from the raw boxes (one launch); also writes the padded box
+// and the grid extents the count pass reads
+int se3::ball_query_prepare_fused(const float* pts_src, const int32_t* batch_src, int64_t n_src, const float* raw_min,
+                                  const float* raw_max, float radius, float* min_pt_out, float* max_pt_out,
+                                  int32_t* num_cells_out, void* ws_src, size_t ws_src_bytes, int32_t n_batches,
+                                  int32_t max_seg, se3_stream_t stream) {
+  SE3_CHECK_ARG(n_src >= 1 && n_src < (1ll << 31) && radius > 0.0f && seg_build_possible(n_batches, max_seg), "bad arguments");
+  BQWorkspace w;
+  char dummy[1];
+  if (!bq_layout2(ws_src, ws_src_bytes, dummy, (size_t)1 << 60, n_src, 0, 1, w)) {
+    set_error("ball_query_prepare_fused: workspace too small");
+    return SE3_EWORKSPACE;
+  }
+  SegBuildArgs a;
+  a.pts = pts_src; a.batch = batch_src; a.n = (int)n_src; a.n_batches = n_batches;
+  a.raw_min = raw_min; a.raw_max = raw_max; a.cell = radius; a.max_pad = -1e-6f;
+  a.keys_sorted = reinterpret_cast<uint64_t*>(w.keys_sorted); a.idx_sorted = w.idx_sorted; a.pts_sorted = w.pts_sorted;
+  a.mn_out = min_pt_out; a.mx_out = max_pt_out; a.nc_out = num_cells_out; a.mm_out = nullptr;
+  a.zero = nullptr; a.n_zero = 0;
+  return launch_seg_build(0, a, max_seg, as_stream(stream));
 }
 
 extern "C" int se3_ball_query_count_prepared(const float* pts_dst, const int32_t* batch_dst, int64_t n_src,

@@ -187,20 +187,34 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
   // grid on (p, b, n) with voxel `cell` from the cloud's raw box; fills g.cell_ids / sorted_ids / cell_ends / m
   // (blocking read of m)
   int seg_next = 0;  // largest batch item of the cloud the last grid pooled
-  auto build_grid = [&](const float* p, const int32_t* b, int64_t n, int raw_slot, float cell, se3_hier_cloud& g,
-                        int max_seg) -> int {
+  // grid on (p, b, n) with voxel `cell` from the cloud's raw box; fills g.cell_ids / sorted_ids / cell_ends.
+  // grid_launch issues the kernels and the read of (m, per-item sizes); grid_finish blocks on it.  Whatever the
+  // host issues in between (the side-stream work of the previous cloud) overlaps the grid chain on the GPU.
+  auto grid_launch = [&](const float* p, const int32_t* b, int64_t n, int raw_slot, float cell, se3_hier_cloud& g,
+                         int max_seg) -> int {
     g.cell_ids = ar.take((size_t)n * 8);
     g.sorted_ids = ar.take((size_t)n * 8);
     g.cell_ends = ar.take((size_t)n * 4);
     const size_t wsb = se3_grid_cells_workspace_bytes(n);
     const int64_t o_ws = ar.take(wsb);
     HB_CHECK_ARENA("grid");
-    HB_TRY(se3_grid_extents(ar.at<float>(o_rawmin[raw_slot]), ar.at<float>(o_rawmax[raw_slot]), d->n_batches, cell, 1e-6f,
-                            min_pt, max_pt, num_cells, stream));
-    HB_TRY(grid_cells_impl(p, b, n, min_pt, num_cells, cell, ar.at<char>(o_ws), wsb, ar.at<int64_t>(g.cell_ids),
-                           ar.at<int64_t>(g.sorted_ids), ar.at<int32_t>(g.cell_ends), d_m, key_bits_for(cell),
-                           d->n_batches, max_seg, track_items ? d_items : nullptr, stream));
+    if (n > 0 && seg_build_possible(d->n_batches, max_seg)) {
+      // every batch item fits a CTA: extents + keys + sort in one launch, straight from the raw boxes
+      HB_TRY(grid_cells_fused(p, b, n, ar.at<float>(o_rawmin[raw_slot]), ar.at<float>(o_rawmax[raw_slot]), cell, min_pt,
+                              max_pt, num_cells, ar.at<char>(o_ws), wsb, ar.at<int64_t>(g.cell_ids),
+                              ar.at<int64_t>(g.sorted_ids), ar.at<int32_t>(g.cell_ends), d_m, d->n_batches, max_seg,
+                              track_items ? d_items : nullptr, stream));
+    } else {
+      HB_TRY(se3_grid_extents(ar.at<float>(o_rawmin[raw_slot]), ar.at<float>(o_rawmax[raw_slot]), d->n_batches, cell,
+                              1e-6f, min_pt, max_pt, num_cells, stream));
+      HB_TRY(grid_cells_impl(p, b, n, min_pt, num_cells, cell, ar.at<char>(o_ws), wsb, ar.at<int64_t>(g.cell_ids),
+                             ar.at<int64_t>(g.sorted_ids), ar.at<int32_t>(g.cell_ends), d_m, key_bits_for(cell),
+                             d->n_batches, max_seg, track_items ? d_items : nullptr, stream));
+    }
     SE3_CUDA(cudaMemcpyAsync(host, d_m, track_items ? lvl_bytes : sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    return SE3_OK;
+  };
+  auto grid_finish = [&](int64_t n, se3_hier_cloud& g) -> int {
     SE3_CUDA(cudaStreamSynchronize(st));
     g.m = host[0];
     stamp("grid size read");
@@ -215,7 +229,7 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
   // frames + records of cloud c (pts / batch already in place) on stream s
   int64_t u_off = 0;
   int cloud_seg[SE3_HIER_MAX_CLOUDS + 1] = {0};  // largest batch item per cloud (0 = unknown)
-  auto build_frames = [&](se3_hier_cloud& c, int max_seg, se3_stream_t s) -> int {
+  auto build_frames = [&](se3_hier_cloud& c, int max_seg, int raw_slot, se3_stream_t s) -> int {
     const int64_t n = c.n;
     c.frames = ar.take((size_t)n * F * 36);
     c.rec = ar.take((size_t)n * F * 48);
@@ -226,7 +240,8 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
     HB_CHECK_ARENA("frames");
     if (n == 0) return SE3_OK;
     HB_TRY(knn_query_impl(ar.at<float>(c.pts), ar.at<int32_t>(c.batch), n, d->knn_k, ar.at<char>(o_ws), wsb,
-                          ar.at<int32_t>(o_knn), d->n_batches, max_seg, s));
+                          ar.at<int32_t>(o_knn), d->n_batches, max_seg, s, ar.at<float>(o_rawmin[raw_slot]),
+                          ar.at<float>(o_rawmax[raw_slot])));
     HB_TRY(se3_pca_frames(ar.at<float>(c.pts), ar.at<int32_t>(o_knn), n, d->knn_k, d->fixed_axis, ar.at<float>(o_cand), s));
     HB_TRY(frames_select_pack(ar.at<float>(o_cand), u_frames + u_off, n, n_cand, F, ar.at<float>(c.frames),
                               ar.at<float>(c.pts), ar.at<float>(c.rec), s));
@@ -321,11 +336,18 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
       cudaStream_t sj = ln->s[j % kSide];
       se3_stream_t sjs = reinterpret_cast<se3_stream_t>(sj);
       SE3_CUDA(cudaStreamWaitEvent(sj, ln->cloud[so.cloud], 0));
-      HB_TRY(se3_grid_extents(ar.at<float>(o_rawmin[1 + so.cloud]), ar.at<float>(o_rawmax[1 + so.cloud]), d->n_batches,
-                              so.radius, -1e-6f, ar.at<float>(so.mn), ar.at<float>(so.mx), ar.at<int32_t>(so.nc), sjs));
-      HB_TRY(ball_query_prepare_impl(ar.at<float>(s.pts), ar.at<int32_t>(s.batch), s.n, 1, ar.at<float>(so.mn),
-                                     ar.at<int32_t>(so.nc), d_rad + 4 * rad_slot[j], ar.at<char>(so.ws), so.ws_bytes,
-                                     key_bits_for(so.radius), d->n_batches, cloud_seg[so.cloud], sjs));
+      if (s.n > 0 && seg_build_possible(d->n_batches, cloud_seg[so.cloud])) {
+        HB_TRY(ball_query_prepare_fused(ar.at<float>(s.pts), ar.at<int32_t>(s.batch), s.n,
+                                        ar.at<float>(o_rawmin[1 + so.cloud]), ar.at<float>(o_rawmax[1 + so.cloud]),
+                                        so.radius, ar.at<float>(so.mn), ar.at<float>(so.mx), ar.at<int32_t>(so.nc),
+                                        ar.at<char>(so.ws), so.ws_bytes, d->n_batches, cloud_seg[so.cloud], sjs));
+      } else {
+        HB_TRY(se3_grid_extents(ar.at<float>(o_rawmin[1 + so.cloud]), ar.at<float>(o_rawmax[1 + so.cloud]), d->n_batches,
+                                so.radius, -1e-6f, ar.at<float>(so.mn), ar.at<float>(so.mx), ar.at<int32_t>(so.nc), sjs));
+        HB_TRY(ball_query_prepare_impl(ar.at<float>(s.pts), ar.at<int32_t>(s.batch), s.n, 1, ar.at<float>(so.mn),
+                                       ar.at<int32_t>(so.nc), d_rad + 4 * rad_slot[j], ar.at<char>(so.ws), so.ws_bytes,
+                                       key_bits_for(so.radius), d->n_batches, cloud_seg[so.cloud], sjs));
+      }
       SE3_CUDA(cudaEventRecord(ln->src[j], sj));
       so.issued = true;
     }
@@ -351,13 +373,17 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
     }
     return SE3_OK;
   };
-  // cloud c is complete on the caller's stream (points, batch ids, raw box): its frames go to a side stream
-  auto cloud_ready = [&](int c, int raw_slot) -> int {
+  // cloud c is complete on the caller's stream (points, batch ids): raw box + the event the side streams wait on
+  auto cloud_mark = [&](int c, int raw_slot) -> int {
     HB_TRY(cloud_bbox(out->clouds[c], raw_slot, stream));
     SE3_CUDA(cudaEventRecord(ln->cloud[c], st));
+    return SE3_OK;
+  };
+  // ... its frames go to a side stream, and every source / count that has become possible is issued
+  auto cloud_side = [&](int c) -> int {
     cudaStream_t s = ln->s[side_rr++ % kSide];
     SE3_CUDA(cudaStreamWaitEvent(s, ln->cloud[c], 0));
-    HB_TRY(build_frames(out->clouds[c], cloud_seg[c], reinterpret_cast<se3_stream_t>(s)));
+    HB_TRY(build_frames(out->clouds[c], cloud_seg[c], 1 + c, reinterpret_cast<se3_stream_t>(s)));
     SE3_CUDA(cudaEventRecord(ln->frames[c], s));
     cloud_done[c] = true;
     return issue_ready();
@@ -365,36 +391,45 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
 
   // ---- level 0 and the output cloud share the raw cloud's init_cell grid
   out->raw.n = d->n;
-  HB_TRY(build_grid(pts, batch_ids, d->n, 0, d->init_cell, out->raw, seg_raw));
+  HB_TRY(grid_launch(pts, batch_ids, d->n, 0, d->init_cell, out->raw, seg_raw));
+  HB_TRY(grid_finish(d->n, out->raw));
   cloud_seg[0] = seg_next;
   if (d->out_cloud) cloud_seg[d->n_pool + 1] = seg_next;  // one point per raw cell, like level 0
   HB_TRY(pool_cloud(pts, batch_ids, d->n, out->raw, out->clouds[0]));
-  HB_TRY(cloud_ready(0, 1));
-  if (d->out_cloud) {
-    // only needs the raw grid: picked now, so its kNN / PCA (the largest frame job) overlaps the pooling chain.
-    // Its frame variates are the last n of u_frames (the levels consume at most (n_pool + 1) * n).
-    se3_hier_cloud& oc = out->clouds[d->n_pool + 1];
-    oc.n = out->raw.m;
-    oc.pts = ar.take((size_t)oc.n * 12);
-    oc.batch = ar.take((size_t)oc.n * 4);
-    out->out_picked = ar.take((size_t)oc.n * 8);
-    HB_CHECK_ARENA("output cloud");
-    HB_TRY(se3_segment_pick(pts, batch_ids, ar.at<int64_t>(out->raw.sorted_ids), ar.at<int32_t>(out->raw.cell_ends),
-                            oc.n, u_cells, ar.at<float>(oc.pts), ar.at<int32_t>(oc.batch),
-                            ar.at<int64_t>(out->out_picked), stream));
-    const int64_t u_keep = u_off;
-    u_off = (int64_t)(d->n_pool + 1) * d->n;
-    HB_TRY(cloud_ready(d->n_pool + 1, d->n_pool + 2));
-    u_off = u_keep;
-  }
-  // ---- pooled levels
-  for (int l = 0; l < d->n_pool; ++l) {
+  HB_TRY(cloud_mark(0, 1));
+  // ---- pooled levels.  Order per level: launch the grid of cloud l, THEN issue cloud l's side work (the host is the
+  // bottleneck of this build: its launches now overlap the grid chain on the GPU), then block on the grid size.
+  for (int l = 0; l <= d->n_pool; ++l) {
     se3_hier_cloud& src = out->clouds[l];
-    SE3_CHECK_ARG(d->cells[l] > 0.0f, "cell sizes must be positive");
-    HB_TRY(build_grid(ar.at<float>(src.pts), ar.at<int32_t>(src.batch), src.n, 1 + l, d->cells[l], src, cloud_seg[l]));
-    cloud_seg[l + 1] = seg_next;
-    HB_TRY(pool_cloud(ar.at<float>(src.pts), ar.at<int32_t>(src.batch), src.n, src, out->clouds[l + 1]));
-    HB_TRY(cloud_ready(l + 1, 2 + l));
+    if (l < d->n_pool) {
+      SE3_CHECK_ARG(d->cells[l] > 0.0f, "cell sizes must be positive");
+      HB_TRY(grid_launch(ar.at<float>(src.pts), ar.at<int32_t>(src.batch), src.n, 1 + l, d->cells[l], src, cloud_seg[l]));
+    }
+    HB_TRY(cloud_side(l));
+    if (l == 0 && d->out_cloud) {
+      // only needs the raw grid: picked early, so its kNN / PCA (the largest frame job) overlaps the pooling chain.
+      // Its frame variates are the last n of u_frames (the levels consume at most (n_pool + 1) * n).
+      se3_hier_cloud& oc = out->clouds[d->n_pool + 1];
+      oc.n = out->raw.m;
+      oc.pts = ar.take((size_t)oc.n * 12);
+      oc.batch = ar.take((size_t)oc.n * 4);
+      out->out_picked = ar.take((size_t)oc.n * 8);
+      HB_CHECK_ARENA("output cloud");
+      HB_TRY(se3_segment_pick(pts, batch_ids, ar.at<int64_t>(out->raw.sorted_ids), ar.at<int32_t>(out->raw.cell_ends),
+                              oc.n, u_cells, ar.at<float>(oc.pts), ar.at<int32_t>(oc.batch),
+                              ar.at<int64_t>(out->out_picked), stream));
+      const int64_t u_keep = u_off;
+      u_off = (int64_t)(d->n_pool + 1) * d->n;
+      HB_TRY(cloud_mark(d->n_pool + 1, d->n_pool + 2));
+      HB_TRY(cloud_side(d->n_pool + 1));
+      u_off = u_keep;
+    }
+    if (l < d->n_pool) {
+      HB_TRY(grid_finish(src.n, src));
+      cloud_seg[l + 1] = seg_next;
+      HB_TRY(pool_cloud(ar.at<float>(src.pts), ar.at<int32_t>(src.batch), src.n, src, out->clouds[l + 1]));
+      HB_TRY(cloud_mark(l + 1, 2 + l));
+    }
   }
 
   stamp("pooling chain done");

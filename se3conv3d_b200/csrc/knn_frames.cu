@@ -319,7 +319,8 @@ extern "C" int se3_knn_query(const float* pts, const int32_t* batch_ids, int64_t
 }
 
 int se3::knn_query_impl(const float* pts, const int32_t* batch_ids, int64_t n, int32_t k, void* workspace,
-                        size_t workspace_bytes, int32_t* out, int32_t n_batches, int32_t max_seg, se3_stream_t stream) {
+                        size_t workspace_bytes, int32_t* out, int32_t n_batches, int32_t max_seg, se3_stream_t stream,
+                        const float* raw_min, const float* raw_max) {
   SE3_CHECK_ARG(n >= 0 && n < (1ll << 31), "bad n");
   SE3_CHECK_ARG(k >= 1 && k <= 32, "k must be in 1..32");
   if (n == 0) return SE3_OK;
@@ -329,6 +330,15 @@ int se3::knn_query_impl(const float* pts, const int32_t* batch_ids, int64_t n, i
   if (!knn_layout(workspace, workspace_bytes, n, w)) {
     set_error("se3_knn_query: workspace too small");
     return SE3_EWORKSPACE;
+  }
+  if (raw_min && raw_max && seg_build_possible(n_batches, max_seg)) {
+    // per-item boxes are known and every batch item fits a CTA: sweep axis, keys, sort and gather in one launch
+    if (int rc = knn_sorted_fused(pts, batch_ids, n, raw_min, raw_max, w.idx_sorted, w.pts_sorted, w.minmax, n_batches,
+                                  max_seg, stream))
+      return rc;
+    k_knn_sweep<<<grid_for(n * 32, 256), 256, 0, st>>>(w.pts_sorted, w.idx_sorted, (int)n, k, w.minmax, out);
+    SE3_LAUNCH_CHECK();
+    return SE3_OK;
   }
   k_minmax_init<<<1, 32, 0, st>>>(w.minmax);
   SE3_LAUNCH_CHECK();

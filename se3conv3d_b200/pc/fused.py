@@ -69,9 +69,12 @@ def _make_cloud(v, c, cfg, n_frames, n_batches):
     pc._batch_ids_frames = None
     n, rec_off = c.n, c.rec
 
+    pts_t, frames_t = pc.pts_, pc.local_frames_   # (the thunks must not refer to their owner: no reference cycles,
+                                                  # so dropping a hierarchy returns its arena to the allocator at once)
+
     def records():
         rec = v.f(rec_off, max(n * n_frames, 1), 12)
-        return ((id(pc.pts_), id(pc.local_frames_), pc.pts_._version, pc.local_frames_._version), rec)
+        return ((id(pts_t), id(frames_t), pts_t._version, frames_t._version), rec)
     pc._lazy = {"_se3_records": records}
     pc._rec_addr = v.base_addr + rec_off
     return pc
@@ -138,7 +141,10 @@ def build_point_hierarchy(p_pts, p_batch_ids, p_ref_frames_config, p_init_subsam
             break
         nbytes = max(2 * nbytes, int(res.arena_used * 1.5))
     check(rc, "se3_hierarchy_build")
-    _arena_hint[key] = int(res.arena_used * 1.25) + (4 << 20)
+    # monotone and quantised (32 MB): consecutive builds of similar clouds then ask the caching allocator for the SAME
+    # size, so the previous steps' arenas are reused instead of new device allocations (which synchronise)
+    want = ((int(res.arena_used * 1.25) + (4 << 20) + (32 << 20) - 1) >> 25) << 25
+    _arena_hint[key] = max(want, _arena_hint.get(key, 0)) if rc == 0 and nbytes <= 4 * want else want
 
     v = _Views(arena)
     n_frames = d.n_frames
@@ -199,7 +205,7 @@ def _make_neighborhood(v, base, nr, src, dst, r, n_frames):
     geom._lazy = {"pts_in": lambda: src.pts_, "pts_out": lambda: dst.pts_,
                   "frames_in": lambda: src.local_frames_, "frames_out": lambda: dst.local_frames_,
                   "rec_in": lambda: src._se3_records[1], "rec_out": lambda: dst._se3_records[1],
-                  "row_ends": lambda: nb.start_ids_, "col_src": lambda: v.i(o_cs, max(e, 1)),
+                  "row_ends": lambda: v.i(o_re, n_out), "col_src": lambda: v.i(o_cs, max(e, 1)),
                   "t_row_ends": lambda: v.i(o_tre, max(n_in, 1)), "t_edge": lambda: v.i(o_te, max(e, 1)),
                   "t_dst": lambda: v.i(o_td, max(e, 1))}
     nb.conv_geometry_cache_ = {(id(src), id(dst), id(src.local_frames_), id(dst.local_frames_),

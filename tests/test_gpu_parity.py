@@ -496,6 +496,28 @@ def test_fused_hierarchy_long_transposed_rows():
     assert longest > 4096, longest
 
 
+def test_fused_hierarchy_objects_release_their_arena_without_gc():
+    """The objects of a fused build hold no reference cycles: dropping them frees the arena by reference counting,
+    so the next step reuses the block (a cycle would park ~300 MB per step until the cyclic collector runs)."""
+    import gc
+    import weakref
+    from se3conv3d_b200 import workloads as wl
+    pts, b = wl.synthetic_bodies(2, 2000, seed=5)
+    step = wl.DfaustStep(DEV, precision=1)
+    gc.collect()
+    gc.disable()
+    try:
+        pcs, neighs = step.build_hierarchy(pts.to(DEV), b.to(DEV), fused=True, n_batches=2)
+        _ = neighs[0].start_ids_, neighs[0].neighbors_, pcs[0]._se3_records        # touch a few lazy windows
+        _ = list(neighs[3].conv_geometry_cache_.values())[0].t_dst, step.hierarchy.init_cell_ids_
+        ref = weakref.ref(step.hierarchy.fused_arena_)
+        del pcs, neighs, _
+        step.hierarchy = None
+        assert ref() is None, "the arena is still referenced after the hierarchy objects were dropped"
+    finally:
+        gc.enable()
+
+
 def wl_grid_of(pcs, lvl, step):
     """Grid of level `lvl` -> `lvl + 1` rebuilt with the per-object API (for comparison)."""
     from se3conv3d_b200 import workloads as wl
