@@ -16,6 +16,7 @@
 // The tcgen05/TMEM projection kernel lives in proj_tcgen05.cu and replaces k_gemm_bf16 for the
 // K-major x K-major products when it is enabled.
 #include <stdlib.h>
+#include <algorithm>
 #include "conv_simt.cuh"
 #include "tc_common.cuh"
 
@@ -1306,6 +1307,57 @@ __global__ void k_prep_weights(const float* __restrict__ w, int c_in, int k, int
   }
 }
 
+// Forward preparation in ONE launch: blocks [0, w_blocks) write the three bf16 operand layouts of conv_weights_
+// (one (input channel, 256-column chunk) slab per block, staged in shared memory so that all three stores are
+// coalesced), the remaining blocks convert the feature rows x -> bf16 [rows][cs] (zero padded to cs).
+__global__ void __launch_bounds__(256) k_fwd_prep(const float* __restrict__ w, int c_in, int k, int c_out, int o_chunks,
+                                                  __nv_bfloat16* __restrict__ wt, __nv_bfloat16* __restrict__ wb,
+                                                  __nv_bfloat16* __restrict__ wp, int w_blocks,
+                                                  const float* __restrict__ x, int64_t rows, int c, int cs,
+                                                  __nv_bfloat16* __restrict__ xb) {
+  extern __shared__ float slab[];  // [k][oc + 1]
+  const int tid = threadIdx.x;
+  if ((int)blockIdx.x < w_blocks) {
+    const int ci = blockIdx.x / o_chunks, o0 = (blockIdx.x - ci * o_chunks) * 256;
+    const int oc = min(256, c_out - o0), ld = oc + 1;
+    const int64_t ck = (int64_t)c_in * k;
+    const float* src = w + (int64_t)ci * k * c_out;
+    for (int i = tid; i < k * oc; i += 256) {
+      const int kk = i / oc, o = i - kk * oc;
+      const float v = src[(int64_t)kk * c_out + o0 + o];
+      slab[kk * ld + o] = v;
+      wb[((int64_t)ci * k + kk) * c_out + o0 + o] = __float2bfloat16(v);
+    }
+    __syncthreads();
+    for (int i = tid; i < k * oc; i += 256) {
+      const int o = i / k, kk = i - o * k;
+      const __nv_bfloat16 v = __float2bfloat16(slab[kk * ld + o]);
+      wt[(int64_t)(o0 + o) * ck + (int64_t)ci * k + kk] = v;
+      wp[((int64_t)ci * c_out + o0 + o) * k + kk] = v;
+    }
+    return;
+  }
+  const int64_t xblocks = (int64_t)gridDim.x - w_blocks;
+  const int64_t stride = xblocks * 256;
+  const int64_t t0 = ((int64_t)blockIdx.x - w_blocks) * 256 + tid;
+  if (cs == c && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(xb) & 15) == 0) {
+    const int64_t n8 = (rows * cs) >> 3;  // cs % 8 == 0
+    for (int64_t i = t0; i < n8; i += stride) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(x) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(x) + 2 * i + 1);
+      uint4 p;
+      p.x = pack_bf16(a.x, a.y); p.y = pack_bf16(a.z, a.w); p.z = pack_bf16(b.x, b.y); p.w = pack_bf16(b.z, b.w);
+      reinterpret_cast<uint4*>(xb)[i] = p;
+    }
+  } else {
+    const int64_t total = rows * cs;
+    for (int64_t i = t0; i < total; i += stride) {
+      const int64_t r = i / cs;
+      const int ch = (int)(i - r * cs);
+      xb[i] = __float2bfloat16(ch < c ? x[r * c + ch] : 0.0f);
+    }
+  }
+}
+
 static inline int blocks_for(int64_t n) {
   int64_t b = (n + 255) / 256;
   const int64_t cap = (int64_t)num_sms() * 16;
@@ -1392,13 +1444,14 @@ int conv_tc_fwd(const se3_conv_desc* d, const float* x, float* y, void* saved, v
   const TcSaved sv = tc_saved_layout(d, saved);
   const int cs = pad8(d->c_in);
   const int64_t Nf = d->n_in * d->f_in;
-  k_prep_weights<<<blocks_for(ck * d->c_out), 256, 0, st>>>(d->conv_weights, d->c_in, d->k, d->c_out, sv.Wt, sv.Wb, sv.Wp);
-  SE3_LAUNCH_CHECK();
-  if (Nf > 0) {
-    if (cs == d->c_in)
-      k_f32_to_bf16<<<blocks_for(Nf * cs / 8), 256, 0, st>>>(x, Nf * cs, sv.xb);
-    else
-      k_rows_to_bf16<<<blocks_for(Nf * cs), 256, 0, st>>>(x, Nf, d->c_in, cs, sv.xb);
+  {
+    const int o_chunks = (d->c_out + 255) / 256;
+    const int w_blocks = d->c_in * o_chunks;
+    const int64_t work = cs == d->c_in ? Nf * cs / 8 : Nf * cs;
+    const int x_blocks = Nf > 0 ? blocks_for(work) : 0;
+    const size_t smem = (size_t)d->k * (std::min(256, d->c_out) + 1) * sizeof(float);
+    k_fwd_prep<<<w_blocks + x_blocks, 256, smem, st>>>(d->conv_weights, d->c_in, d->k, d->c_out, o_chunks, sv.Wt, sv.Wb,
+                                                       sv.Wp, w_blocks, x, Nf, d->c_in, cs, sv.xb);
     SE3_LAUNCH_CHECK();
   }
   TcAggArgs a;

@@ -124,7 +124,11 @@ __global__ void __launch_bounds__(128) k_gemm_tcgen05(int M, int N, int K, float
   // nstages (<= STAGES) ring slots are allocated: short-K products keep their footprint small enough for
   // several CTAs per SM (their time is the epilogue, which needs the occupancy)
   const uint32_t a_ring = ring, b_ring = ring + nstages * A_STAGE_BYTES;
-  const int bm = blockIdx.y * BM, bn = blockIdx.x * BN;
+  // Row tiles are walked from the LAST to the first.  The A operand of the forward projection / dx product was just
+  // written, front to back, by the aggregation kernel, and the tail of a tensor larger than L2 is what is still
+  // resident: reading it back to front turns that tail into L2 hits instead of evicting it first.  The dT product
+  // writes back to front for the same reason (the edge-gradient kernel reads dT front to back right after).
+  const int bm = (int)(gridDim.y - 1 - blockIdx.y) * BM, bn = blockIdx.x * BN;
   // split-K: blockIdx.z owns k-blocks [kb0, kb0 + nkb) and writes its partial tile to Cout + z * split_stride
   const int nkb_all = (K + BK - 1) / BK;
   const int kb0 = blockIdx.z * kb_per_split;

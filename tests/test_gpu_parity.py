@@ -421,17 +421,20 @@ def test_projection_gemm_matches_fp64(impl, m, n, k):
         assert rel_err(c.double().cpu(), ref.cpu()) < tol
 
 
-def test_fused_hierarchy_matches_per_object_path():
+@pytest.mark.parametrize("n_clouds,n_points,n_batches", [(4, 3000, 4), (2, 6890, 2), (3, 900, 5), (2, 8000, 2)])
+def test_fused_hierarchy_matches_per_object_path(n_clouds, n_points, n_batches):
     """se3_hierarchy_build (one native call) against the per-object chain with the reference's API on the
     same synthetic bodies: level clouds, grids and every CSR bit-exact; frames drawn from the same PCA
-    candidates; the output cloud picks one raw point of every init voxel."""
+    candidates; the output cloud picks one raw point of every init voxel.  The cases cover the per-item CTA sorts
+    of every size class (6890 points: the 1024 x 7 configuration), trailing empty batch items (n_batches larger than
+    the ids present) and clouds too large for a CTA (8000 points: the device-wide sorts for the raw grid)."""
     from se3conv3d_b200 import workloads as wl
     from se3conv3d_b200.pc import BQNeighborhood
-    pts, b = wl.synthetic_bodies(4, 3000, seed=3)
+    pts, b = wl.synthetic_bodies(n_clouds, n_points, seed=3)
     pts, b = pts.to(DEV), b.to(DEV)
     step = wl.DfaustStep(DEV, precision=1)
     pcs_u, neighs_u = step.build_hierarchy(pts, b, fused=False)
-    pcs_f, neighs_f = step.build_hierarchy(pts, b, fused=True, n_batches=4)
+    pcs_f, neighs_f = step.build_hierarchy(pts, b, fused=True, n_batches=n_batches)
     h = step.hierarchy
     assert len(pcs_u) == len(pcs_f) == 6
     for lvl in range(5):
