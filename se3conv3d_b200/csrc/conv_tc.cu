@@ -45,6 +45,7 @@ struct TcAggArgs {
   int act;
   __nv_bfloat16* out;
   int64_t n_rows;
+  int f_row;  // frames per row point (the kernel's FR frames per item may be a divisor of it: frame groups)
 };
 
 // geometry of one (row frame, gathered frame) pair for this lane's neighbour
@@ -291,28 +292,34 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_AGG_MIN_BLOCKS) k_agg_tc(c
   float* Gs = reinterpret_cast<float*>(wbase + SM::OFF_G);  // [FR][32][GSTR]
   const int g = lane >> 2, t = lane & 3;
   const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
-  const int total = (int)a.n_rows * ncb;
+  // an item = (row point, frame group, channel block); nfg = f_row / FR frame groups of FR row frames each.  The
+  // basis is evaluated once per (row frame, gathered frame) pair whatever the split: frame groups only repeat the
+  // gather, channel blocks repeat the basis too -- so many frames are split into groups first.
+  const int nfg = a.f_row / FR, per_row = ncb * nfg;
+  const int total = (int)a.n_rows * per_row;
   const int mid = lane >> 3, mr = lane & 7;  // ldmatrix: matrix id, row inside the matrix
   int item0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (item0 >= total) return;
   uint32_t aw[2][2][4];
   load_w9_frags(a.w9, a.bias, g, t, act_pre_scale(a.act), aw);
 
+  // c0 carries the channel offset in its low 16 bits and the first row frame of the item above them
   auto row_of = [&](int item, int& rp, int& c0) {
     rp = item;
     c0 = 0;
-    if (ncb > 1) {
-      rp = item / ncb;
-      c0 = (item - rp * ncb) * CB;
+    if (per_row > 1) {
+      rp = item / per_row;
+      const int sub = item - rp * per_row, fgi = sub / ncb;
+      c0 = ((sub - fgi * ncb) * CB) | ((fgi * FR) << 16);
     }
   };
   auto issue = [&](int rp, int c0, int lo, int nt, int idx, int base, int buf, int rb, bool with_row) {
     const int gidx = chunk_gidx(a.nbr, lo, nt, idx, a.f_g, base, lane);
-    gather_chunk_async<CB>(a.rec_g, a.feat, a.cs, c0, gidx, lane, wbase_s + SM::OFF_RG + buf * SM::RG_BYTES,
+    gather_chunk_async<CB>(a.rec_g, a.feat, a.cs, c0 & 0xffff, gidx, lane, wbase_s + SM::OFF_RG + buf * SM::RG_BYTES,
                            wbase_s + buf * SM::X_BYTES);
     if (with_row && lane < FR * 3)
       cp_async16_ca(wbase_s + SM::OFF_RS + rb * SM::RS_BYTES + lane * 16,
-                    reinterpret_cast<const float4*>(a.rec_row) + (int64_t)rp * (FR * 3) + lane, true);
+                    reinterpret_cast<const float4*>(a.rec_row) + ((int64_t)rp * a.f_row + (c0 >> 16)) * 3 + lane, true);
   };
 
   // ---- prologue: row 0 bounds + ids (synchronous, once), row 1 bounds (synchronous) + ids (in flight),
@@ -408,11 +415,12 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_AGG_MIN_BLOCKS) k_agg_tc(c
 #pragma unroll
     for (int f = 0; f < FR; ++f) {
       const uint4* ts = reinterpret_cast<const uint4*>(Gs + f * 32 * GSTR);
-      __nv_bfloat16* o = a.out + ((int64_t)rp0 * FR + f) * (int64_t)a.c * 32 + (int64_t)c00 * 32;
+      const int ch0 = c00 & 0xffff;
+      __nv_bfloat16* o = a.out + ((int64_t)rp0 * a.f_row + (c00 >> 16) + f) * (int64_t)a.c * 32 + (int64_t)ch0 * 32;
 #pragma unroll
       for (int it = 0; it < CB / 8; ++it) {
         const int row = it * 8 + (lane >> 2), part = lane & 3;
-        if (c00 + row < a.c) reinterpret_cast<uint4*>(o + row * 32)[part] = ts[row * 4 + (part ^ ((row >> 1) & 3))];
+        if (ch0 + row < a.c) reinterpret_cast<uint4*>(o + row * 32)[part] = ts[row * 4 + (part ^ ((row >> 1) & 3))];
       }
     }
     __syncwarp();
@@ -442,7 +450,7 @@ template <int CB, int FR, bool TR>
 static int launch_agg_cfg(const TcAggArgs& a, int64_t n_g, cudaStream_t st) {
   const size_t smem = AGG_WARPS * AggSmem<CB, FR>::WARP_BYTES;
   const int ncb = (a.c + CB - 1) / CB;
-  const int64_t warps = a.n_rows * ncb;
+  const int64_t warps = a.n_rows * ncb * (a.f_row / FR);
   if (warps >= (int64_t)1 << 30 || n_g * a.f_g * a.cs >= (int64_t)1 << 31 || (a.cs & 7) || a.cs < a.c) {
     set_error("launch_agg_tc: problem too large for 32-bit row offsets");
     return SE3_EINVAL;
@@ -466,13 +474,17 @@ static int launch_agg_cfg(const TcAggArgs& a, int64_t n_g, cudaStream_t st) {
 }
 
 template <bool TR>
-static int launch_agg_tc(const TcAggArgs& a, int f_row, int64_t n_g, cudaStream_t st) {
-  if (a.n_rows == 0) return SE3_OK;
+static int launch_agg_tc(const TcAggArgs& a0, int f_row, int64_t n_g, cudaStream_t st) {
+  if (a0.n_rows == 0) return SE3_OK;
+  TcAggArgs a = a0;
+  a.f_row = f_row;
+  // more than 16 channels with 3 / 4 row frames: items of one / two frames over 32-channel blocks (frame groups
+  // repeat only the gather; 16-channel blocks would evaluate the basis once per block)
   switch (f_row) {
     case 1: return a.c > 16 ? launch_agg_cfg<32, 1, TR>(a, n_g, st) : launch_agg_cfg<16, 1, TR>(a, n_g, st);
     case 2: return a.c > 16 ? launch_agg_cfg<32, 2, TR>(a, n_g, st) : launch_agg_cfg<16, 2, TR>(a, n_g, st);
-    case 3: return launch_agg_cfg<16, 3, TR>(a, n_g, st);
-    case 4: return launch_agg_cfg<16, 4, TR>(a, n_g, st);
+    case 3: return a.c > 16 ? launch_agg_cfg<32, 1, TR>(a, n_g, st) : launch_agg_cfg<16, 3, TR>(a, n_g, st);
+    case 4: return a.c > 16 ? launch_agg_cfg<32, 2, TR>(a, n_g, st) : launch_agg_cfg<16, 4, TR>(a, n_g, st);
   }
   set_error("launch_agg_tc: unsupported frame count");
   return SE3_EINVAL;

@@ -58,8 +58,14 @@ def main():
         x.grad = None
         layer.zero_grad()
     tf, tb = tf / a.iters, tb / a.iters
-    print(json.dumps({"n": a.n, "edges": e, "kbar": e / a.n, "frames": a.frames, "cin": a.cin, "cout": a.cout,
-                      "precision": a.precision, "fwd_ms": tf, "bwd_ms": tb, "points_per_s": a.n / ((tf + tb) * 1e-3)}))
+    # SURVEY 8(d) gather model, fp32 features: algorithmic bytes of one forward + backward
+    kbar, f, w = e / a.n, a.frames, (a.cin * 32 * a.cout + 9 * 32 + 32) * 4
+    fwd_b = a.n * (kbar * (16 + 36 * f + f * a.cin * 4) + (16 + 36 * f) + f * a.cout * 4) + w
+    bwd_b = a.n * (kbar * (2 * (16 + 36 * f) + f * a.cin * 4 + f * a.cout * 4) + f * a.cout * 4 + f * a.cin * 4) + 2 * w
+    print(json.dumps({"n": a.n, "edges": e, "kbar": round(e / a.n, 2), "frames": a.frames, "cin": a.cin, "cout": a.cout,
+                      "precision": a.precision, "fwd_ms": round(tf, 4), "bwd_ms": round(tb, 4),
+                      "points_per_s": round(a.n / ((tf + tb) * 1e-3)),
+                      "alg_gbs_fwd": round(fwd_b / (tf * 1e-3) / 1e9, 1), "alg_gbs_fwd_bwd": round((fwd_b + bwd_b) / ((tf + tb) * 1e-3) / 1e9, 1)}))
 
 
 if __name__ == "__main__":
