@@ -257,7 +257,9 @@ struct AggSmem {
   static constexpr int XS = CB + 8;
   static constexpr int X_BYTES = 32 * XS * 2;         // one feature buffer (bf16)
   static constexpr int RG_BYTES = 32 * 48;            // one record buffer
-  static constexpr int G_BYTES = FR * 32 * GSTR * 4;  // geometry rows; reused as the T staging tiles (2 KB per frame)
+  // geometry rows [FR][32][GSTR]; reused as the T staging tiles ([CB][64 B] per frame), whichever is larger
+  static constexpr int G_FRAME_BYTES = (32 * GSTR * 4 > CB * 64) ? 32 * GSTR * 4 : CB * 64;
+  static constexpr int G_BYTES = FR * G_FRAME_BYTES;
   static constexpr int RS_BYTES = ((FR * 48 + 63) / 64) * 64;  // one row-record buffer
   static constexpr int OFF_RG = 2 * X_BYTES;
   static constexpr int OFF_G = OFF_RG + 2 * RG_BYTES;
@@ -282,6 +284,7 @@ struct AggSmem {
 // sits on the critical path after the first chunk.
 template <int CB, int FR, bool TR, int ACT>
 __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_AGG_MIN_BLOCKS) k_agg_tc(const TcAggArgs a, const int ncb) {
+  static_assert(FR == 1 || CB * 64 <= 32 * GSTR * 4, "the T staging tiles of consecutive frames would overlap");
   using SM = AggSmem<CB, FR>;
   constexpr int XS = SM::XS;
   constexpr int MT = CB / 16;
@@ -480,6 +483,11 @@ static int launch_agg_tc(const TcAggArgs& a0, int f_row, int64_t n_g, cudaStream
   a.f_row = f_row;
   // more than 16 channels with 3 / 4 row frames: items of one / two frames over 32-channel blocks (frame groups
   // repeat only the gather; 16-channel blocks would evaluate the basis once per block)
+  // more than 32 channels: one row frame per item over 64-channel blocks -- the same 64 accumulators per lane as two
+  // frames x 32 channels, but half the basis evaluations (the dominant cost), since every channel block of an item
+  // re-evaluates the basis of the item's frames
+  static const bool no_cb64 = getenv("SE3_AGG_NO_CB64") != nullptr;  // tuning aid
+  if (a.c > 32 && f_row >= 1 && f_row <= 4 && !no_cb64) return launch_agg_cfg<64, 1, TR>(a, n_g, st);
   switch (f_row) {
     case 1: return a.c > 16 ? launch_agg_cfg<32, 1, TR>(a, n_g, st) : launch_agg_cfg<16, 1, TR>(a, n_g, st);
     case 2: return a.c > 16 ? launch_agg_cfg<32, 2, TR>(a, n_g, st) : launch_agg_cfg<16, 2, TR>(a, n_g, st);
