@@ -103,3 +103,25 @@ def test_block_modules_state_dict_and_drop_path():
     assert torch.equal(y[0], y[1]) and torch.equal(y[4], y[5])
     sk = SkipConnection(0.0, 3)
     assert torch.allclose(sk(x, 2 * x, pc), 2 * x + 1e-6)
+
+
+def test_lazy_attrs_materialise_once_and_keep_plain_attribute_semantics():
+    """LazyAttrs (the windows of a fused hierarchy arena): a thunk runs on first access only, the value then is a
+    plain attribute; names without a thunk raise AttributeError (so hasattr / getattr-with-default keep working)."""
+    from se3conv3d_b200._lib import LazyAttrs
+
+    class Obj(LazyAttrs):
+        pass
+
+    calls = []
+    o = Obj()
+    o.plain = 1
+    o._lazy = {"window": lambda: calls.append(1) or "tensor"}
+    assert o.plain == 1 and not hasattr(o, "missing") and getattr(o, "missing", None) is None
+    assert o.window == "tensor" and o.window == "tensor" and calls == [1]
+    assert "window" in o.__dict__ and "window" not in o._lazy
+    o.window = "replaced"
+    assert o.window == "replaced"
+    bare = Obj()                      # objects built by the per-object path carry no thunks at all
+    with pytest.raises(AttributeError):
+        bare.window
