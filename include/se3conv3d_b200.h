@@ -212,7 +212,8 @@ typedef struct se3_hier_desc {
   int32_t n_pool;        /* grid-average levels below level 0 */
   float init_cell;       /* level 0 = grid average of the raw cloud with this voxel size (> 0) */
   float cells[SE3_HIER_MAX_CLOUDS]; /* voxel size of pooling step l -> l+1 */
-  int32_t knn_k;         /* PCA frames: k nearest neighbours (<= 32) */
+  int32_t knn_k;         /* PCA frames: k nearest neighbours (<= 32); 0 = sampled frames: u_frames holds Gaussian
+                            quaternion components [(n_pool + 2) * n * n_frames, 4] instead of uniform variates */
   int32_t n_frames;      /* frames kept per point (1..4) */
   int32_t fixed_axis;    /* -1 none */
   int32_t out_cloud;     /* 1: also build the output cloud (index n_pool + 1) */

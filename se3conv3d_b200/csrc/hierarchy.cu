@@ -95,7 +95,10 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
   SE3_CHECK_ARG(d->n >= 1 && d->n < (1ll << 31) && d->n_batches >= 1, "bad sizes");
   SE3_CHECK_ARG(d->n_pool >= 0 && d->n_pool + 2 <= SE3_HIER_MAX_CLOUDS, "too many levels");
   SE3_CHECK_ARG(d->init_cell > 0.0f, "init_cell must be positive");
-  SE3_CHECK_ARG(d->knn_k >= 1 && d->knn_k <= 32 && d->n_frames >= 1 && d->n_frames <= 4, "bad frame configuration");
+  SE3_CHECK_ARG(d->knn_k >= 0 && d->knn_k <= 32 && d->n_frames >= 1 && d->n_frames <= 4, "bad frame configuration");
+  // knn_k == 0: sampled (Monte-Carlo) frames -- u_frames then holds Gaussian quaternion components, 4 per (point, frame)
+  const bool mc_frames = d->knn_k == 0;
+  SE3_CHECK_ARG(!mc_frames || d->fixed_axis <= 0, "sampled frames about a fixed axis are not fused");
   SE3_CHECK_ARG(d->n_neigh >= 0 && d->n_neigh <= SE3_HIER_MAX_NEIGH, "too many neighbourhoods");
   SE3_CHECK_ARG(pts && batch_ids && u_frames, "null input");
   SE3_CHECK_ARG(!d->out_cloud || u_cells, "the output cloud needs u_cells");
@@ -117,7 +120,7 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
   Bump ar(arena, arena_bytes);
   const int n_cand = d->fixed_axis > 0 ? 2 : 4;
   const int F = d->n_frames;
-  SE3_CHECK_ARG(F <= n_cand, "n_frames exceeds the PCA candidates");
+  SE3_CHECK_ARG(mc_frames || F <= n_cand, "n_frames exceeds the PCA candidates");
   const int n_clouds = d->n_pool + 1 + (d->out_cloud ? 1 : 0);
   out->n_clouds = n_clouds;
 
@@ -233,6 +236,14 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
     const int64_t n = c.n;
     c.frames = ar.take((size_t)n * F * 36);
     c.rec = ar.take((size_t)n * F * 48);
+    if (mc_frames) {
+      // pc/RotationFunctions.py:428-508 (free SO(3) branch): one normalised Gaussian quaternion per (point, frame)
+      HB_CHECK_ARENA("frames");
+      if (n == 0) return SE3_OK;
+      HB_TRY(se3_quat_frames(u_frames + 4 * (int64_t)F * u_off, n * F, ar.at<float>(c.frames), s));
+      u_off += n;
+      return se3_pack_records(ar.at<float>(c.pts), ar.at<float>(c.frames), n, F, ar.at<float>(c.rec), s);
+    }
     const int64_t o_knn = ar.take((size_t)n * d->knn_k * 4);
     const int64_t o_cand = ar.take((size_t)n * n_cand * 36);
     const size_t wsb = se3_knn_workspace_bytes(n);

@@ -105,8 +105,11 @@ def build_point_hierarchy(p_pts, p_batch_ids, p_ref_frames_config, p_init_subsam
     """Returns (PointHierarchyRotEquiv, output PointcloudRotEquiv or None).  `neighborhoods` lists
     (src_level, dst_level, radius) ball queries; level len(p_grid_subsamples) + 1 is the output cloud."""
     cfg = p_ref_frames_config
-    if not cfg["pca"] or cfg["neigh_method"] != "knn":
-        raise Se3Error("build_point_hierarchy: only k-NN PCA reference frames are fused (use the per-object path)")
+    sampled = not cfg["pca"]
+    if sampled and cfg.get("fixed_axis"):
+        raise Se3Error("build_point_hierarchy: sampled frames about a fixed axis are not fused (use the per-object path)")
+    if not sampled and cfg["neigh_method"] != "knn":
+        raise Se3Error("build_point_hierarchy: PCA frames are fused for k-NN neighbourhoods only (use the per-object path)")
     pts = p_pts.detach().to(torch.float32).contiguous()
     b = p_batch_ids.to(torch.int32).contiguous()
     dev = pts.device
@@ -121,21 +124,25 @@ def build_point_hierarchy(p_pts, p_batch_ids, p_ref_frames_config, p_init_subsam
     d.n, d.n_batches, d.n_pool, d.init_cell = n, int(n_batches), n_pool, float(p_init_subsample)
     for i, c in enumerate(p_grid_subsamples):
         d.cells[i] = float(c)
-    d.knn_k = int(cfg["neigh_kwargs"]["neigh_k"])
+    d.knn_k = 0 if sampled else int(cfg["neigh_kwargs"]["neigh_k"])
     d.n_frames = int(cfg["n_frames"])
     d.fixed_axis = -1 if (fixed is None or fixed is False or not fixed) else int(fixed)
     d.out_cloud = 1 if output_cloud else 0
     d.n_neigh = len(neighborhoods)
     for i, (s, t, r) in enumerate(neighborhoods):
         d.neigh_src[i], d.neigh_dst[i], d.neigh_radius[i] = int(s), int(t), float(r)
-    u = torch.rand((n_pool + 3) * n, device=dev, dtype=torch.float32)
+    if sampled:   # Gaussian quaternion components for every (point, frame) of every cloud, then the cell variates
+        nq = (n_pool + 2) * n * int(cfg["n_frames"]) * 4
+        u = torch.cat((torch.randn(nq, device=dev, dtype=torch.float32), torch.rand(n, device=dev, dtype=torch.float32)))
+    else:
+        u = torch.rand((n_pool + 3) * n, device=dev, dtype=torch.float32)
     key = (n, n_pool, len(neighborhoods), bool(output_cloud), str(dev))
     nbytes = _arena_hint.get(key, (64 << 20) + n * 4096)
     res = HierResult()
     L = lib()
     for _ in range(6):
         arena = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        rc = L.se3_hierarchy_build(C.byref(d), ptr(pts), ptr(b), ptr(u), ptr(u[(n_pool + 2) * n:]), ptr(arena),
+        rc = L.se3_hierarchy_build(C.byref(d), ptr(pts), ptr(b), ptr(u), ptr(u[u.numel() - n:]), ptr(arena),
                                    arena.numel(), C.byref(res), stream())
         if rc != -3:  # SE3_EWORKSPACE
             break

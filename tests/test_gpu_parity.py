@@ -633,6 +633,59 @@ def test_config3_classification_shapes_mc_frames():
             assert err < 3e-2, name
 
 
+def test_fused_hierarchy_sampled_frames_config3():
+    """Sampled (Monte-Carlo) frames through the fused builder (BASELINE config 3 shapes at reduced batch): the frames
+    are the quaternion -> matrix images of the builder's Gaussian draws (re-created from the seed), the level clouds
+    equal the per-object grid pooling, and an F = 4 convolution runs on the fused neighbourhood."""
+    from se3conv3d_b200.layers import PNEConvLayerRotEquiv
+    from se3conv3d_b200.pc import build_point_hierarchy, quaternion_to_matrix, Pointcloud, GridSubSample
+    g = torch.Generator().manual_seed(51)
+    b_items, n_pts, F = 8, 1024, 4
+    p = torch.randn(b_items * n_pts, 3, generator=g)
+    p = (p / p.norm(dim=1, keepdim=True) + 0.01 * torch.randn(b_items * n_pts, 3, generator=g)).to(DEV)
+    batch = torch.arange(b_items).repeat_interleave(n_pts).to(torch.int32).to(DEV)
+    cfg = {"pca": False, "neigh_method": "knn", "neigh_kwargs": {"neigh_k": 16}, "fixed_axis": False, "n_frames": F}
+    grids = [0.1, 0.2, 0.4]
+    wanted = [(0, 0, 0.1), (0, 1, 0.2), (1, 1, 0.2), (2, 2, 0.4)]
+    n = p.shape[0]
+    torch.manual_seed(52)
+    h, _ = build_point_hierarchy(p, batch, cfg, 0.05, grids, neighborhoods=wanted, n_batches=b_items)
+    torch.manual_seed(52)
+    q = torch.randn((len(grids) + 2) * n * F * 4, device=DEV)      # the builder's first draw
+    off = 0
+    pc_ref = Pointcloud(p, batch)
+    samp = GridSubSample(pc_ref, 0.05)
+    ref_pts = samp.__subsample_tensor__(pc_ref.pts_, "avg")
+    for lvl, pc in enumerate(h.pcs_):
+        m = pc.pts_.shape[0]
+        if lvl == 0:
+            assert torch.equal(pc.pts_, ref_pts)
+        want = quaternion_to_matrix(q[off * F * 4:(off + m) * F * 4].reshape(-1, 4)).reshape(m, F, 9)
+        assert torch.equal(pc.local_frames_, want), lvl
+        R = pc.local_frames_.reshape(-1, 3, 3)
+        assert float((R @ R.transpose(1, 2) - torch.eye(3, device=DEV)).abs().max()) < 1e-5
+        assert float((torch.linalg.det(R) - 1).abs().max()) < 1e-5
+        off += m
+    sizes = [pc.pts_.shape[0] for pc in h.pcs_]
+    assert all(a > b for a, b in zip(sizes, sizes[1:])), sizes
+    nb, pc0, pc1 = h.fused_neighborhoods_[1], h.pcs_[0], h.pcs_[1]
+    layer = PNEConvLayerRotEquiv(9, 32, 64, 32, "mlp_gelu").to(DEV)
+    layer.norm_neigh_dist_.fill_(5.0)
+    layer.norm_num_neighs_.fill_(pc1.pts_.shape[0] / nb.neighbors_.shape[0])
+    x = torch.randn(pc0.pts_.shape[0] * F, 32, generator=torch.Generator().manual_seed(53)).to(DEV)
+    dy = torch.randn(pc1.pts_.shape[0] * F, 64, generator=torch.Generator().manual_seed(54)).to(DEV)
+    res = []
+    for precision in (0, 1):
+        layer.precision = precision
+        layer.zero_grad()
+        xx = x.clone().requires_grad_(True)
+        y = layer(pc0, pc1, xx, nb)
+        y.backward(dy)
+        res.append([t.detach().cpu().numpy() for t in (y, xx.grad, layer.conv_weights_.grad, layer.proj_axes_.grad)])
+    for a, b, name in zip(res[1], res[0], ("y", "dx", "dW", "dA")):
+        assert rel_err(a, b) < 3e-2, name
+
+
 def test_config4_scannet_shapes_fixed_axis():
     """BASELINE config 4 shapes: one 150k-point room-like scene, F=1 PCA frames about a fixed up axis, 5-level
     hierarchy through the fused builder; CSR properties at full size and a conv fwd+bwd (bf16 vs fp32)."""
