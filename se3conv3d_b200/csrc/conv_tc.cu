@@ -29,6 +29,10 @@ int tcgen05_gemm_splits(int64_t m, int64_t n, int64_t k);
 int launch_gemm_tcgen05(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16* a, int64_t lda,
                         const __nv_bfloat16* b, int64_t ldb, void* c, int64_t ldc, bool out_bf16, int splits,
                         float* partials, cudaStream_t st);
+bool tcgen05_gemm_mn_supported(int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb);
+int launch_gemm_tcgen05_mn(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16* a, int64_t lda,
+                           const __nv_bfloat16* b, int64_t ldb, float* c, int64_t ldc, int splits, float* partials,
+                           cudaStream_t st);
 
 struct TcAggArgs {
   const int* row_ends;
@@ -1508,9 +1512,15 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
   SE3_LAUNCH_CHECK();
   if (dW) {
     // dW[(c,k), o] = s * sum_r T[r,(c,k)] dy[r,o]
-    if (int rc = launch_gemm_cfg<false, false, false>(ck, d->c_out, R, d->out_scale, T, ck, dyb, d->c_out, dW, d->c_out,
-                                                      splits, dWp, st))
+    // tcgen05 (MN-major operands) when c_out is a whole number of 64-column atoms, mma.sync otherwise
+    static const bool dw_mma = getenv("SE3_DW_IMPL") && getenv("SE3_DW_IMPL")[0] == 'm';  // A/B aid
+    if (!dw_mma && gemm_impl_env() != 1 && tcgen05_gemm_mn_supported(ck, d->c_out, R, ck, d->c_out)) {
+      if (int rc = launch_gemm_tcgen05_mn(ck, d->c_out, R, d->out_scale, T, ck, dyb, d->c_out, dW, d->c_out, splits, dWp, st))
+        return rc;
+    } else if (int rc = launch_gemm_cfg<false, false, false>(ck, d->c_out, R, d->out_scale, T, ck, dyb, d->c_out, dW,
+                                                             d->c_out, splits, dWp, st)) {
       return rc;
+    }
   }
   if (dA || dB) {
     // dT[r,(c,k)] = s * sum_o dy[r,o] W[(c,k),o]

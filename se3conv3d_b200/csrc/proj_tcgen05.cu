@@ -326,6 +326,179 @@ int launch_cfg(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16
   return SE3_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// MN-major variant: C[M,N] = alpha * A^T * B with A stored [K][M] (M contiguous) and B stored [K][N] (N contiguous)
+// -- the weight gradient dW[(c,k), o] = sum_r T[r,(c,k)] dy[r,o], whose contraction index r is the ROW index of both
+// operands.  Same ring / mbarrier / TMEM structure as k_gemm_tcgen05; the operand tiles are the canonical UMMA
+// "MN-major SWIZZLE_128B" layout (cute::UMMA::make_umma_desc<Major::MN>): 128-byte lines of 64 consecutive M (or N)
+// elements, one line per k, 8 lines = one 1024-byte swizzle atom (16-byte chunk index XOR line % 8), k-groups
+// SBO = 1024 bytes apart, 64-element MN atoms LBO = 8 KB apart (all 8 k-groups of a stage).  A 16-byte cp.async
+// moves 8 consecutive elements of one operand row -- exactly the global layout, no transposition anywhere.
+// fp32 output only; split-K over the rows (blockIdx.z) with the ordered reduction of the K-major kernel.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int MN_BK = 64;                       // operand rows (k) per stage
+constexpr uint32_t MN_LBO = (MN_BK / 8) * 1024; // bytes between 64-element MN atoms
+
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(MN_LBO >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor with both operands MN-major (a_major = bit 15, b_major = bit 16)
+__host__ __device__ constexpr uint32_t make_idesc_mn(int m, int n) { return make_idesc(m, n) | (1u << 15) | (1u << 16); }
+
+template <int BN>
+__global__ void __launch_bounds__(128) k_gemm_tcgen05_mn(int M, int N, int K, float alpha, const __nv_bfloat16* __restrict__ A,
+                                                         int64_t lda, const __nv_bfloat16* __restrict__ B, int64_t ldb,
+                                                         float* __restrict__ Cout, int64_t ldc, int kb_per_split,
+                                                         int64_t split_stride, int nstages) {
+  static_assert(BN % 64 == 0 && BN <= 256, "whole 64-element N atoms");
+  constexpr int A_BYTES = BM * MN_BK * 2;  // 16 KB: two M atoms
+  constexpr int B_BYTES = BN * MN_BK * 2;
+  constexpr int TMEM_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ __align__(8) uint64_t bars[STAGES + 1];
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t raw = smem_u32(smem_dyn);
+  const uint32_t ring = (raw + 1023u) & ~1023u;
+  const uint32_t a_ring = ring, b_ring = ring + nstages * A_BYTES;
+  const int bm = blockIdx.y * BM, bn = blockIdx.x * BN;
+  const int nkb_all = (K + MN_BK - 1) / MN_BK;
+  const int kb0 = blockIdx.z * kb_per_split;
+  const int nkb = min(kb_per_split, nkb_all - kb0);
+  if (split_stride) Cout += (int64_t)blockIdx.z * split_stride;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i <= STAGES; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_slot;
+  constexpr uint32_t IDESC = make_idesc_mn(BM, BN);
+
+  // element (k-row r, column col) of a tile -> atom col / 64, k-group r / 8, line r % 8, chunk (col % 64) / 8
+  auto load_stage = [&](int stage, int kb) {
+    const int k0 = kb * MN_BK;
+    const uint32_t as = a_ring + stage * A_BYTES;
+    const uint32_t bs = b_ring + stage * B_BYTES;
+#pragma unroll
+    for (int i = 0; i < MN_BK * (BM / 8) / 128; ++i) {
+      const int id = tid + i * 128;
+      const int r = id / (BM / 8), cc = id % (BM / 8), atom = cc >> 3, c = cc & 7;
+      const bool p = (k0 + r < K) && (bm + cc * 8 < M);
+      const __nv_bfloat16* src = p ? A + (int64_t)(k0 + r) * lda + bm + cc * 8 : A;
+      cp_async16(as + atom * MN_LBO + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4), src, p);
+    }
+#pragma unroll
+    for (int i = 0; i < MN_BK * (BN / 8) / 128; ++i) {
+      const int id = tid + i * 128;
+      const int r = id / (BN / 8), cc = id % (BN / 8), atom = cc >> 3, c = cc & 7;
+      const bool p = (k0 + r < K) && (bn + cc * 8 < N);
+      const __nv_bfloat16* src = p ? B + (int64_t)(k0 + r) * ldb + bn + cc * 8 : B;
+      cp_async16(bs + atom * MN_LBO + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4), src, p);
+    }
+  };
+
+  for (int it = 0; it < nkb + nstages - 1; ++it) {
+    if (it < nkb) {
+      const int s = it % nstages;
+      if (it >= nstages) mbar_wait(smem_u32(&bars[s]), (uint32_t)((it / nstages - 1) & 1));
+      load_stage(s, kb0 + it);
+    }
+    cp_async_commit();
+    const int c = it - (nstages - 1);
+    if (c >= 0) {
+      switch (nstages) {
+        case 1: cp_async_wait<0>(); break;
+        case 2: cp_async_wait<1>(); break;
+        case 3: cp_async_wait<2>(); break;
+        default: cp_async_wait<STAGES - 1>(); break;
+      }
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const int s = c % nstages;
+        const uint32_t as = a_ring + s * A_BYTES;
+        const uint32_t bs = b_ring + s * B_BYTES;
+#pragma unroll
+        for (int k4 = 0; k4 < MN_BK / 16; ++k4) {
+          // advancing K by 16 = two 8-line k-groups = 2048 bytes
+          umma_f16(tmem_d, make_desc_mn_sw128(as + k4 * 2048), make_desc_mn_sw128(bs + k4 * 2048), IDESC,
+                   (c > 0 || k4 > 0) ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&bars[s]));
+        if (c == nkb - 1) umma_commit(smem_u32(&bars[STAGES]));
+      }
+    }
+  }
+  mbar_wait(smem_u32(&bars[STAGES]), 0u);
+  tc_fence_after();
+  const int row = bm + warp * 32 + lane;
+#pragma unroll
+  for (int c0 = 0; c0 < BN; c0 += 8) {
+    float v[8];
+    tmem_ld8(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+    const int col = bn + c0;
+    if (row < M && col < N) {
+      float* C = Cout + (int64_t)row * ldc + col;
+      if (col + 8 <= N && ((reinterpret_cast<uintptr_t>(C) & 15) == 0)) {
+        *reinterpret_cast<float4*>(C) = make_float4(alpha * v[0], alpha * v[1], alpha * v[2], alpha * v[3]);
+        *reinterpret_cast<float4*>(C + 4) = make_float4(alpha * v[4], alpha * v[5], alpha * v[6], alpha * v[7]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (col + i < N) C[i] = alpha * v[i];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+template <int BN>
+int launch_mn_cfg(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16* a, int64_t lda, const __nv_bfloat16* b,
+                  int64_t ldb, float* c, int64_t ldc, int splits, float* partials, cudaStream_t st) {
+  auto kern = k_gemm_tcgen05_mn<BN>;
+  const int nkb = (int)((k + MN_BK - 1) / MN_BK);
+  if (partials == nullptr || splits < 1 || ldc != n) splits = 1;
+  int per = (nkb + splits - 1) / splits;
+  splits = (nkb + per - 1) / per;
+  const int max_stages = BN <= 64 ? 4 : (BN <= 128 ? 4 : 3);
+  const int nstages = per < max_stages ? per : max_stages;
+  const size_t stage = (size_t)BM * MN_BK * 2 + (size_t)BN * MN_BK * 2;
+  const size_t smem = nstages * stage + 1024;
+  SE3_SMEM_ONCE(kern, (size_t)STAGES * stage + 1024);
+  dim3 grid((unsigned)((n + BN - 1) / BN), (unsigned)((m + BM - 1) / BM), (unsigned)splits);
+  if (splits > 1) {
+    kern<<<grid, 128, smem, st>>>((int)m, (int)n, (int)k, 1.0f, a, lda, b, ldb, partials, n, per, m * n, nstages);
+    SE3_LAUNCH_CHECK();
+    splitk_reduce_launch(partials, splits, m * n, alpha, c, st);
+    SE3_LAUNCH_CHECK();
+  } else {
+    kern<<<grid, 128, smem, st>>>((int)m, (int)n, (int)k, alpha, a, lda, b, ldb, c, ldc, nkb, (int64_t)0, nstages);
+    SE3_LAUNCH_CHECK();
+  }
+  return SE3_OK;
+}
+
 }  // namespace
 
 bool tcgen05_gemm_supported(int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb) {
@@ -370,6 +543,25 @@ int launch_gemm_tcgen05(int64_t m, int64_t n, int64_t k, float alpha, const __nv
   }
 #undef SE3_TC_CASE
   return SE3_EINVAL;
+}
+
+// C[M,N] = alpha * A^T B, A stored [K][M], B stored [K][N] (bf16, fp32 output): the weight gradient on tcgen05.
+bool tcgen05_gemm_mn_supported(int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb) {
+  return m >= 1 && k >= 1 && n >= 64 && (n % 64) == 0 && (m % 8) == 0 && (lda % 8) == 0 && (ldb % 8) == 0;
+}
+int launch_gemm_tcgen05_mn(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16* a, int64_t lda,
+                           const __nv_bfloat16* b, int64_t ldb, float* c, int64_t ldc, int splits, float* partials,
+                           cudaStream_t st) {
+  if (!tcgen05_gemm_mn_supported(m, n, k, lda, ldb)) {
+    set_error("launch_gemm_tcgen05_mn: unsupported shape m=%lld n=%lld k=%lld", (long long)m, (long long)n, (long long)k);
+    return SE3_EINVAL;
+  }
+  const int bn = n <= 64 ? 64 : (n <= 128 ? 128 : 256);
+  switch (bn) {
+    case 64: return launch_mn_cfg<64>(m, n, k, alpha, a, lda, b, ldb, c, ldc, splits, partials, st);
+    case 128: return launch_mn_cfg<128>(m, n, k, alpha, a, lda, b, ldb, c, ldc, splits, partials, st);
+    default: return launch_mn_cfg<256>(m, n, k, alpha, a, lda, b, ldb, c, ldc, splits, partials, st);
+  }
 }
 
 }  // namespace se3
