@@ -101,6 +101,34 @@ inline cudaStream_t as_stream(se3_stream_t s) { return reinterpret_cast<cudaStre
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
+// Programmatic dependent launch (the kernels of one convolution call form chains of short launches): the grid may be
+// scheduled while the previous kernel of the stream drains, which hides the launch latency behind that kernel's tail.
+// A kernel launched this way MUST call pdl_wait() before it reads or writes anything in global memory (the wait
+// returns once the previous grid has completed and its writes are visible); only on-chip set-up may precede it.
+// SE3_PDL=0 launches the same kernels without the attribute.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Lets the next kernel of the stream start being scheduled (it still waits for this grid to finish in its own
+// pdl_wait).  Used by the persistent kernels, whose CTAs are all resident from the start: the dependent grid then
+// fills the SMs as these CTAs retire instead of after the last one.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 // Bump allocator over a caller-provided workspace.
 struct Arena {
   char* base;

@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(256) k_sgemm(int M, int N, int K, float alpha,
 
 __global__ void k_splitk_reduce(const float* __restrict__ partials, int splits, int64_t mn, float alpha,
                                 float* __restrict__ c) {
+  pdl_wait();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < mn; i += (int64_t)gridDim.x * blockDim.x) {
     float s = 0.0f;
     for (int z = 0; z < splits; ++z) s += partials[(int64_t)z * mn + i];
@@ -190,7 +191,7 @@ __global__ void k_splitk_reduce(const float* __restrict__ partials, int splits, 
 void splitk_reduce_launch(const float* partials, int splits, int64_t mn, float alpha, float* c, cudaStream_t st) {
   int64_t blocks = (mn + 255) / 256;
   if (blocks > (int64_t)num_sms() * 8) blocks = (int64_t)num_sms() * 8;
-  k_splitk_reduce<<<(int)blocks, 256, 0, st>>>(partials, splits, mn, alpha, c);
+  launch_pdl(k_splitk_reduce, dim3((unsigned)blocks), dim3(256), 0, st, partials, splits, mn, alpha, c);
 }
 
 int launch_sgemm(bool at, bool bt, int64_t m, int64_t n, int64_t k, float alpha, const float* a, int64_t lda,

@@ -306,6 +306,8 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_AGG_MIN_BLOCKS) k_agg_tc(c
   const int total = (int)a.n_rows * per_row;
   const int mid = lane >> 3, mr = lane & 7;  // ldmatrix: matrix id, row inside the matrix
   int item0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  pdl_wait();
+  pdl_trigger();
   if (item0 >= total) return;
   uint32_t aw[2][2][4];
   load_w9_frags(a.w9, a.bias, g, t, act_pre_scale(a.act), aw);
@@ -470,11 +472,11 @@ static int launch_agg_cfg(const TcAggArgs& a, int64_t n_g, cudaStream_t st) {
   if (a.act == 2) {
     auto kern = k_agg_tc<CB, FR, TR, 2>;
     SE3_SMEM_ONCE(kern, smem);
-    kern<<<(int)blocks, AGG_WARPS * 32, smem, st>>>(a, ncb);
+    SE3_CUDA(launch_pdl(kern, dim3((unsigned)blocks), dim3(AGG_WARPS * 32), smem, st, a, ncb));
   } else {
     auto kern = k_agg_tc<CB, FR, TR, -1>;
     SE3_SMEM_ONCE(kern, smem);
-    kern<<<(int)blocks, AGG_WARPS * 32, smem, st>>>(a, ncb);
+    SE3_CUDA(launch_pdl(kern, dim3((unsigned)blocks), dim3(AGG_WARPS * 32), smem, st, a, ncb));
   }
   SE3_LAUNCH_CHECK();
   return SE3_OK;
@@ -632,6 +634,8 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_EDGE_MIN_BLOCKS) k_edge_tc
   const int ncb = (a.c + CB - 1) / CB;
   const int total = (int)a.n_out * f_out;
   int item0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  pdl_wait();
+  pdl_trigger();
   if (item0 < total) {
     uint32_t aw[2][2][4];
     load_w9_frags(a.w9, a.bias, g, t, act_pre_scale(a.act), aw);
@@ -827,6 +831,8 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_EDGE_MIN_BLOCKS) k_edge_ro
   const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
   const int total = (int)a.n_out;
   int rp0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  pdl_wait();
+  pdl_trigger();
   if (rp0 < total) {
     uint32_t aw[2][2][4];
     load_w9_frags(a.w9, a.bias, g, t, act_pre_scale(a.act), aw);
@@ -992,11 +998,11 @@ static int launch_edge_row_cfg(const TcEdgeArgs& a, int n_warps, cudaStream_t st
   if (a.act == 2) {
     auto kern = k_edge_row_tc<CB, FR, 2>;
     SE3_SMEM_ONCE(kern, smem);
-    kern<<<n_warps / AGG_WARPS, AGG_WARPS * 32, smem, st>>>(a);
+    SE3_CUDA(launch_pdl(kern, dim3((unsigned)(n_warps / AGG_WARPS)), dim3(AGG_WARPS * 32), smem, st, a));
   } else {
     auto kern = k_edge_row_tc<CB, FR, -1>;
     SE3_SMEM_ONCE(kern, smem);
-    kern<<<n_warps / AGG_WARPS, AGG_WARPS * 32, smem, st>>>(a);
+    SE3_CUDA(launch_pdl(kern, dim3((unsigned)(n_warps / AGG_WARPS)), dim3(AGG_WARPS * 32), smem, st, a));
   }
   SE3_LAUNCH_CHECK();
   return SE3_OK;
@@ -1009,6 +1015,7 @@ __global__ void __launch_bounds__(1024) k_edge_tc_reduce(const float* __restrict
   __shared__ float sm[32][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int out = blockIdx.x * 32 + lane;
+  pdl_wait();
   float s = 0.0f;
   for (int p = w; p < n_partials; p += 32) s += partials[(int64_t)p * 512 + out];
   sm[w][lane] = s;
@@ -1041,11 +1048,11 @@ static int launch_edge_cfg(const TcEdgeArgs& a, int f_out, int n_warps, cudaStre
   if (a.act == 2) {
     auto kern = k_edge_tc<CB, 2>;
     SE3_SMEM_ONCE(kern, smem);
-    kern<<<n_warps / AGG_WARPS, AGG_WARPS * 32, smem, st>>>(a, f_out);
+    SE3_CUDA(launch_pdl(kern, dim3((unsigned)(n_warps / AGG_WARPS)), dim3(AGG_WARPS * 32), smem, st, a, f_out));
   } else {
     auto kern = k_edge_tc<CB, -1>;
     SE3_SMEM_ONCE(kern, smem);
-    kern<<<n_warps / AGG_WARPS, AGG_WARPS * 32, smem, st>>>(a, f_out);
+    SE3_CUDA(launch_pdl(kern, dim3((unsigned)(n_warps / AGG_WARPS)), dim3(AGG_WARPS * 32), smem, st, a, f_out));
   }
   SE3_LAUNCH_CHECK();
   return SE3_OK;
@@ -1073,7 +1080,7 @@ static int launch_edge_tc(const TcEdgeArgs& a, int f_out, int64_t n_in, int n_wa
     rc = a.c <= 16 ? launch_edge_cfg<16>(a, f_out, n_warps, st) : launch_edge_cfg<32>(a, f_out, n_warps, st);
   }
   if (rc) return rc;
-  k_edge_tc_reduce<<<10, 1024, 0, st>>>(a.partials, n_warps / AGG_WARPS, dA, dB);
+  SE3_CUDA(launch_pdl(k_edge_tc_reduce, dim3(10), dim3(1024), 0, st, (const float*)a.partials, n_warps / AGG_WARPS, dA, dB));
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }
@@ -1100,6 +1107,7 @@ __global__ void __launch_bounds__(256) k_gemm_bf16(int M, int N, int K, float al
   const int k_end = min(K, k_begin + kchunk);
   const int ktiles = (k_end - k_begin + BK - 1) / BK;
   const int mid = lane >> 3, mr = lane & 7, g = lane >> 2, t = lane & 3;
+  pdl_wait();
 
   auto load_stage = [&](int stage, int kt) {
     const int k0 = k_begin + kt * BK;
@@ -1221,12 +1229,12 @@ static int launch_gemm_cfg(int64_t m, int64_t n, int64_t k, float alpha, const _
   auto kern = k_gemm_bf16<AK, BK_, OB>;
   SE3_SMEM_ONCE(kern, smem);
   if (splits > 1) {
-    kern<<<grid, 256, smem, st>>>((int)m, (int)n, (int)k, alpha, a, lda, b, ldb, partials, n, kchunk, m * n);
+    SE3_CUDA(launch_pdl(kern, grid, dim3(256), smem, st, (int)m, (int)n, (int)k, alpha, a, lda, b, ldb, (void*)partials, n, kchunk, m * n));
     SE3_LAUNCH_CHECK();
     splitk_reduce_launch(partials, splits, m * n, alpha, reinterpret_cast<float*>(c), st);
     SE3_LAUNCH_CHECK();
   } else {
-    kern<<<grid, 256, smem, st>>>((int)m, (int)n, (int)k, alpha, a, lda, b, ldb, c, ldc, kchunk, 0);
+    SE3_CUDA(launch_pdl(kern, grid, dim3(256), smem, st, (int)m, (int)n, (int)k, alpha, a, lda, b, ldb, c, ldc, kchunk, (int64_t)0));
     SE3_LAUNCH_CHECK();
   }
   return SE3_OK;
@@ -1278,6 +1286,7 @@ __global__ void k_transpose_w_bf16(const float* __restrict__ w, int64_t ck, int 
 }
 
 __global__ void k_f32_to_bf16(const float* __restrict__ in, int64_t n, __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
   const int64_t n8 = n >> 3;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   if ((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
@@ -1341,6 +1350,7 @@ __global__ void __launch_bounds__(256) k_fwd_prep(const float* __restrict__ w, i
                                                   __nv_bfloat16* __restrict__ xb) {
   extern __shared__ float slab[];  // [k][oc + 1]
   const int tid = threadIdx.x;
+  pdl_wait();
   if ((int)blockIdx.x < w_blocks) {
     const int ci = blockIdx.x / o_chunks, o0 = (blockIdx.x - ci * o_chunks) * 256;
     const int oc = min(256, c_out - o0), ld = oc + 1;
@@ -1474,8 +1484,8 @@ int conv_tc_fwd(const se3_conv_desc* d, const float* x, float* y, void* saved, v
     const int64_t work = cs == d->c_in ? Nf * cs / 8 : Nf * cs;
     const int x_blocks = Nf > 0 ? blocks_for(work) : 0;
     const size_t smem = (size_t)d->k * (std::min(256, d->c_out) + 1) * sizeof(float);
-    k_fwd_prep<<<w_blocks + x_blocks, 256, smem, st>>>(d->conv_weights, d->c_in, d->k, d->c_out, o_chunks, sv.Wt, sv.Wb,
-                                                       sv.Wp, w_blocks, x, Nf, d->c_in, cs, sv.xb);
+    SE3_CUDA(launch_pdl(k_fwd_prep, dim3(w_blocks + x_blocks), dim3(256), smem, st, d->conv_weights, d->c_in, d->k, d->c_out,
+                        o_chunks, sv.Wt, sv.Wb, sv.Wp, w_blocks, x, Nf, d->c_in, cs, sv.xb));
     SE3_LAUNCH_CHECK();
   }
   TcAggArgs a;
@@ -1508,7 +1518,7 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
   if (!ar.ok()) { set_error("conv_tc_bwd: workspace too small"); return SE3_EWORKSPACE; }
   const TcSaved sv = tc_saved_layout(d, const_cast<void*>(saved));
   const __nv_bfloat16 *T = sv.T, *xb = sv.xb, *Wb = sv.Wb, *Wpb = sv.Wp;
-  k_f32_to_bf16<<<blocks_for(R * d->c_out / 8), 256, 0, st>>>(dy, R * d->c_out, dyb);
+  SE3_CUDA(launch_pdl(k_f32_to_bf16, dim3(blocks_for(R * d->c_out / 8)), dim3(256), 0, st, dy, R * d->c_out, dyb));
   SE3_LAUNCH_CHECK();
   if (dW) {
     // dW[(c,k), o] = s * sum_r T[r,(c,k)] dy[r,o]

@@ -16,6 +16,7 @@
 //           with d = (sample - point) * (1/radius)
 #include <cub/cub.cuh>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -31,6 +32,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+bool pdl_enabled() {
+  static const bool on = !(getenv("SE3_PDL") && getenv("SE3_PDL")[0] == '0');
+  return on;
+}
 
 // ---- optional per-kernel device timing of the dominant kernels (bench.py's roofline): CUDA events on the
 // launching stream around each launch, summed on read.  Off by default: no events, no overhead.

@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(128) k_gemm_tcgen05(int M, int N, int K, float
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // barriers and tensor memory are set up; everything below touches global memory
   const uint32_t tmem_d = tmem_base_slot;
   constexpr uint32_t IDESC = make_idesc(BM, BN);
 
@@ -315,12 +316,12 @@ int launch_cfg(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16
   }
   dim3 grid((unsigned)((n + BN - 1) / BN), (unsigned)((m + BM - 1) / BM), (unsigned)splits);
   if (splits > 1) {
-    kern<<<grid, 128, smem, st>>>((int)m, (int)n, (int)k, 1.0f, a, lda, b, ldb, partials, n, per, m * n, nstages);
+    SE3_CUDA(launch_pdl(kern, grid, dim3(128), smem, st, (int)m, (int)n, (int)k, 1.0f, a, lda, b, ldb, partials, n, per, m * n, nstages));
     SE3_LAUNCH_CHECK();
     splitk_reduce_launch(partials, splits, m * n, alpha, reinterpret_cast<float*>(c), st);
     SE3_LAUNCH_CHECK();
   } else {
-    kern<<<grid, 128, smem, st>>>((int)m, (int)n, (int)k, alpha, a, lda, b, ldb, c, ldc, nkb, (int64_t)0, nstages);
+    SE3_CUDA(launch_pdl(kern, grid, dim3(128), smem, st, (int)m, (int)n, (int)k, alpha, a, lda, b, ldb, c, ldc, nkb, (int64_t)0, nstages));
     SE3_LAUNCH_CHECK();
   }
   return SE3_OK;
@@ -387,6 +388,7 @@ __global__ void __launch_bounds__(128) k_gemm_tcgen05_mn(int M, int N, int K, fl
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // barriers and tensor memory are set up; everything below touches global memory
   const uint32_t tmem_d = tmem_base_slot;
   constexpr uint32_t IDESC = make_idesc_mn(BM, BN);
 
@@ -488,12 +490,12 @@ int launch_mn_cfg(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloa
   SE3_SMEM_ONCE(kern, (size_t)STAGES * stage + 1024);
   dim3 grid((unsigned)((n + BN - 1) / BN), (unsigned)((m + BM - 1) / BM), (unsigned)splits);
   if (splits > 1) {
-    kern<<<grid, 128, smem, st>>>((int)m, (int)n, (int)k, 1.0f, a, lda, b, ldb, partials, n, per, m * n, nstages);
+    SE3_CUDA(launch_pdl(kern, grid, dim3(128), smem, st, (int)m, (int)n, (int)k, 1.0f, a, lda, b, ldb, partials, n, per, m * n, nstages));
     SE3_LAUNCH_CHECK();
     splitk_reduce_launch(partials, splits, m * n, alpha, c, st);
     SE3_LAUNCH_CHECK();
   } else {
-    kern<<<grid, 128, smem, st>>>((int)m, (int)n, (int)k, alpha, a, lda, b, ldb, c, ldc, nkb, (int64_t)0, nstages);
+    SE3_CUDA(launch_pdl(kern, grid, dim3(128), smem, st, (int)m, (int)n, (int)k, alpha, a, lda, b, ldb, c, ldc, nkb, (int64_t)0, nstages));
     SE3_LAUNCH_CHECK();
   }
   return SE3_OK;
