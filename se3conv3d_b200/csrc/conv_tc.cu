@@ -290,7 +290,6 @@ template <int CB, int FR, bool TR, int ACT>
 __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_AGG_MIN_BLOCKS) k_agg_tc(const TcAggArgs a, const int ncb) {
   static_assert(FR == 1 || CB * 64 <= 32 * GSTR * 4, "the T staging tiles of consecutive frames would overlap");
   using SM = AggSmem<CB, FR>;
-  constexpr int XS = SM::XS;
   constexpr int MT = CB / 16;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -304,7 +303,6 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_AGG_MIN_BLOCKS) k_agg_tc(c
   // gather, channel blocks repeat the basis too -- so many frames are split into groups first.
   const int nfg = a.f_row / FR, per_row = ncb * nfg;
   const int total = (int)a.n_rows * per_row;
-  const int mid = lane >> 3, mr = lane & 7;  // ldmatrix: matrix id, row inside the matrix
   int item0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   pdl_wait();
   pdl_trigger();
@@ -614,7 +612,7 @@ struct EdgeSmem {
 template <int CB, int ACT>
 __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_EDGE_MIN_BLOCKS) k_edge_tc(const TcEdgeArgs a, const int f_out) {
   using SM = EdgeSmem<CB>;
-  constexpr int XS = SM::XS, TS = SM::TS, GB = SM::GB;
+  constexpr int TS = SM::TS, GB = SM::GB;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   unsigned char* wbase = smem_raw + wib * SM::WARP_BYTES;
@@ -622,7 +620,6 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_EDGE_MIN_BLOCKS) k_edge_tc
   float* Gs = reinterpret_cast<float*>(wbase + SM::OFF_G);                    // [32][GSTR]
   __nv_bfloat16* Gb = reinterpret_cast<__nv_bfloat16*>(wbase + SM::OFF_GB);   // [32][GB]
   const int g = lane >> 2, t = lane & 3;
-  const int mid = lane >> 3, mr = lane & 7;
   float accA[2][2][4];  // [k m-tile][d n-tile]
 #pragma unroll
   for (int m = 0; m < 2; ++m)
@@ -1276,15 +1273,6 @@ int gemm_tn(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16* a
 // --------------------------------------------------------------------------------------------
 // conversions
 // --------------------------------------------------------------------------------------------
-// wt[o][ck] = w[ck][o]  (bf16): K-major B operand of the forward projection
-__global__ void k_transpose_w_bf16(const float* __restrict__ w, int64_t ck, int c_out, __nv_bfloat16* __restrict__ wt) {
-  const int64_t total = ck * c_out;
-  for (int64_t tix = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; tix < total; tix += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t o = tix / ck, r = tix - o * ck;
-    wt[tix] = __float2bfloat16(w[r * c_out + o]);
-  }
-}
-
 __global__ void k_f32_to_bf16(const float* __restrict__ in, int64_t n, __nv_bfloat16* __restrict__ out) {
   pdl_wait();
   const int64_t n8 = n >> 3;
@@ -1302,44 +1290,6 @@ __global__ void k_f32_to_bf16(const float* __restrict__ in, int64_t n, __nv_bflo
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) out[i] = __float2bfloat16(in[i]);
   }
 }
-// out[r][0..cs) = bf16(in[r][0..c)), zero padded: the gathered feature rows of the tensor-core kernels
-// (cs = c when c % 8 == 0, handled by the vectorised plain conversion)
-__global__ void k_rows_to_bf16(const float* __restrict__ in, int64_t rows, int c, int cs, __nv_bfloat16* __restrict__ out) {
-  const int64_t total = rows * cs;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / cs;
-    const int ch = (int)(i - r * cs);
-    out[i] = __float2bfloat16(ch < c ? in[r * c + ch] : 0.0f);
-  }
-}
-// wp[c][o][k] = w[c][k][o]  (bf16)
-__global__ void k_permute_w_bf16(const float* __restrict__ w, int c_in, int k, int c_out, __nv_bfloat16* __restrict__ wp) {
-  const int64_t total = (int64_t)c_in * k * c_out;
-  for (int64_t tix = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; tix < total; tix += (int64_t)gridDim.x * blockDim.x) {
-    const int kk = (int)(tix % k);
-    const int64_t co = tix / k;
-    const int o = (int)(co % c_out);
-    const int64_t c = co / c_out;
-    wp[tix] = __float2bfloat16(w[(c * k + kk) * c_out + o]);
-  }
-}
-
-// the three bf16 operand layouts of conv_weights_ [c_in][k][c_out] in one pass:
-//   wt[o][(c,k)] (forward projection), wb[(c,k)][o] (dT = dy . W^T), wp[c][(o,k)] (dx = U . Wp^T)
-__global__ void k_prep_weights(const float* __restrict__ w, int c_in, int k, int c_out, __nv_bfloat16* __restrict__ wt,
-                               __nv_bfloat16* __restrict__ wb, __nv_bfloat16* __restrict__ wp) {
-  const int64_t ck = (int64_t)c_in * k, total = ck * c_out;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / c_out;            // (c,k)
-    const int o = (int)(i - r * c_out);
-    const int c = (int)(r / k), kk = (int)(r - (int64_t)c * k);
-    const __nv_bfloat16 v = __float2bfloat16(w[i]);
-    wb[i] = v;
-    wt[(int64_t)o * ck + r] = v;
-    wp[((int64_t)c * c_out + o) * k + kk] = v;
-  }
-}
-
 // Forward preparation in ONE launch: blocks [0, w_blocks) write the three bf16 operand layouts of conv_weights_
 // (one (input channel, 256-column chunk) slab per block, staged in shared memory so that all three stores are
 // coalesced), the remaining blocks convert the feature rows x -> bf16 [rows][cs] (zero padded to cs).

@@ -396,13 +396,13 @@ __global__ void k_cell_ranks(const int* __restrict__ rank1, const int* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// key sort: one CTA per batch item when every item fits a CTA, CUB device radix sort otherwise
+// per-batch-item sorted structures
 // ---------------------------------------------------------------------------------------------
 // Batch ids are non-decreasing and every key carries its batch id in the leading position, so sorting each batch
 // item's slice on its own and leaving the slices in place IS the global stable sort.  A cloud of a few thousand
-// points per item (DFAUST: 6890, pooled levels: hundreds) then needs ONE launch instead of the histogram +
-// scan + one pass per 8 key bits of the device-wide sort, whose launches -- not its bandwidth -- dominate at
-// this size.  Values are the global positions (the sort produces the permutation).
+// points per item (DFAUST: 6890, pooled levels: hundreds) then needs ONE launch (k_seg_build below) instead of the
+// histogram + scan + one pass per 8 key bits of the device-wide sort, whose launches -- not its bandwidth --
+// dominate at this size.  Values are the global positions (the sort produces the permutation).
 __device__ __forceinline__ int lower_bound_i32(const int* __restrict__ a, int n, int v) {
   int lo = 0, hi = n;
   while (lo < hi) {
@@ -410,53 +410,6 @@ __device__ __forceinline__ int lower_bound_i32(const int* __restrict__ a, int n,
     if (a[mid] < v) lo = mid + 1; else hi = mid;
   }
   return lo;
-}
-
-template <int THREADS, int ITEMS>
-__global__ void __launch_bounds__(THREADS) k_seg_sort_u64(const uint64_t* __restrict__ keys_in,
-                                                          const int* __restrict__ batch, int n,
-                                                          uint64_t* __restrict__ keys_out, int* __restrict__ idx_out,
-                                                          int end_bit) {
-  using Sort = cub::BlockRadixSort<uint64_t, THREADS, ITEMS, int>;
-  extern __shared__ __align__(16) unsigned char seg_smem[];
-  typename Sort::TempStorage& tmp = *reinterpret_cast<typename Sort::TempStorage*>(seg_smem);
-  __shared__ int s_lo, s_hi;
-  if (threadIdx.x == 0) {
-    s_lo = lower_bound_i32(batch, n, (int)blockIdx.x);
-    s_hi = lower_bound_i32(batch, n, (int)blockIdx.x + 1);
-  }
-  __syncthreads();
-  const int lo = s_lo, cnt = s_hi - lo;
-  if (cnt <= 0) return;
-  uint64_t k[ITEMS];
-  int v[ITEMS];
-#pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    const int p = threadIdx.x * ITEMS + i;
-    k[i] = p < cnt ? keys_in[lo + p] : ~0ull;  // padding sorts last (stable: it also comes last in the input)
-    v[i] = lo + p;
-  }
-  Sort(tmp).Sort(k, v, 0, end_bit);
-#pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    const int p = threadIdx.x * ITEMS + i;
-    if (p < cnt) {
-      keys_out[lo + p] = k[i];
-      idx_out[lo + p] = v[i];
-    }
-  }
-}
-
-template <int THREADS, int ITEMS>
-static int launch_seg_sort(const uint64_t* keys_in, const int* batch, int n, int n_batches, uint64_t* keys_out,
-                           int* idx_out, int end_bit, cudaStream_t st) {
-  using Sort = cub::BlockRadixSort<uint64_t, THREADS, ITEMS, int>;
-  auto kern = k_seg_sort_u64<THREADS, ITEMS>;
-  const size_t smem = sizeof(typename Sort::TempStorage);
-  SE3_SMEM_ONCE(kern, smem);
-  kern<<<n_batches, THREADS, smem, st>>>(keys_in, batch, n, keys_out, idx_out, end_bit);
-  SE3_LAUNCH_CHECK();
-  return SE3_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -647,17 +600,7 @@ size_t sort_pairs_tmp_bytes(int64_t n) { return cub_tmp_bytes(0, n); }
 int sort_keys_u64(const uint64_t* keys_in, const int* iota, const int* batch, int64_t n, int n_batches, int max_seg,
                   uint64_t* keys_out, int* idx_out, int end_bit, void* cub_tmp, size_t cub_bytes, cudaStream_t st) {
   if (end_bit <= 0 || end_bit > 64) end_bit = 64;
-  if (max_seg > 0 && n_batches >= 1 && n_batches <= 65535 && batch != nullptr) {
-#define SE3_SEG_CASE(T, I)                                                                                     \
-  if (max_seg <= (T) * (I)) return launch_seg_sort<T, I>(keys_in, batch, (int)n, n_batches, keys_out, idx_out, end_bit, st)
-    SE3_SEG_CASE(64, 4);
-    SE3_SEG_CASE(128, 8);
-    SE3_SEG_CASE(256, 8);
-    SE3_SEG_CASE(512, 8);
-    SE3_SEG_CASE(1024, 7);
-#undef SE3_SEG_CASE
-    static_assert(kSegSortMax == 1024 * 7, "largest per-item sort");
-  }
+  (void)batch; (void)n_batches; (void)max_seg;  // per-item sorts live in k_seg_build (the fused builders)
   size_t cb = cub_bytes;
   SE3_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cb, keys_in, keys_out, iota, idx_out, (int)n, 0, end_bit, st));
   count_launch(1 + (end_bit + 7) / 8);
