@@ -808,7 +808,7 @@ struct EdgeRowSmem {
 };
 
 template <int CB, int FR, int ACT>
-__global__ void __launch_bounds__(AGG_WARPS * 32, SE3_EDGE_MIN_BLOCKS) k_edge_row_tc(const TcEdgeArgs a) {
+__global__ void __launch_bounds__(AGG_WARPS * 32, CB >= 64 ? 2 : SE3_EDGE_MIN_BLOCKS) k_edge_row_tc(const TcEdgeArgs a) {
   using SM = EdgeRowSmem<CB, FR>;
   constexpr int TS = SM::TS, GB = SM::GB;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1029,9 +1029,12 @@ __global__ void __launch_bounds__(1024) k_edge_tc_reduce(const float* __restrict
   }
 }
 
-static int edge_tc_warps(int64_t n_items) {
+// CTAs per SM of the edge-gradient kernel that launch_edge_tc picks: the 64-channel row kernel runs two (at three
+// its 168-register budget spills and it measured 133 vs 105 us on the dfaust level-2 -> 1 layer)
+static int edge_blocks_per_sm(int c, int f_out) { return (c > 32 && c <= 64 && f_out <= 2) ? 2 : SE3_EDGE_MIN_BLOCKS; }
+static int edge_tc_warps(int64_t n_items, int c, int f_out) {
   int64_t blocks = (n_items + AGG_WARPS - 1) / AGG_WARPS;
-  const int64_t cap = (int64_t)num_sms() * SE3_EDGE_MIN_BLOCKS;
+  const int64_t cap = (int64_t)num_sms() * edge_blocks_per_sm(c, f_out);
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks * AGG_WARPS;
@@ -1409,7 +1412,7 @@ size_t conv_tc_bwd_workspace_bytes(const se3_conv_desc* d) {
   b += align_up((size_t)R * ck * 2);                                              // dT bf16
   b += align_up((size_t)Nf * d->c_out * d->k * 2);                                // U bf16
   b += align_up((size_t)splits_for_tc(ck, d->c_out, R) * ck * d->c_out * 4);      // dW partials
-  b += align_up((size_t)edge_tc_warps(d->n_out * d->f_out) * 512 * 4);                       // basis-gradient partials
+  b += align_up((size_t)edge_tc_warps(d->n_out * d->f_out, d->c_in, d->f_out) * 512 * 4);                       // basis-gradient partials
   b += gemm_tn_partial_bytes(Nf, d->c_in, (int64_t)d->c_out * d->k);                         // dx split-K partials
   return b + 256;
 }
@@ -1461,7 +1464,7 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
   __nv_bfloat16* U = ar.take<__nv_bfloat16>(Nf * ok);
   const int splits = splits_for_tc(ck, d->c_out, R);
   float* dWp = ar.take<float>((size_t)splits * ck * d->c_out);
-  const int n_warps = edge_tc_warps(d->n_out * d->f_out);
+  const int n_warps = edge_tc_warps(d->n_out * d->f_out, d->c_in, d->f_out);
   float* eg = ar.take<float>((size_t)n_warps * 512);
   const size_t dx_pbytes = gemm_tn_partial_bytes(Nf, d->c_in, ok);
   float* dx_partials = dx_pbytes ? ar.take<float>(dx_pbytes / 4) : nullptr;
