@@ -56,6 +56,28 @@ int ball_query_prepare_fused(const float* pts_src, const int32_t* batch_src, int
                              int32_t* num_cells_out, void* ws_src, size_t ws_src_bytes, int32_t n_batches,
                              int32_t max_seg, se3_stream_t stream);
 // kNN sweep structure in one launch (grid_ops.cu): idx_sorted / pts_sorted (xyz + batch bits) / minmax [6]
+constexpr int kBqBatch = 16;  // prepared ball queries per batched launch (bounded by the kernel parameter space)
+// one prepared ball query of a batched count / fill launch (fused hierarchy builder)
+struct BqBatchItem {
+  const float* pts_dst;
+  const int32_t* batch_dst;
+  int64_t n_src, n_dst;
+  const float* min_pt;
+  const int32_t* num_cells;
+  const float* radius;
+  void* ws_src;
+  size_t ws_src_bytes;
+  void* ws_dst;
+  size_t ws_dst_bytes;
+  int32_t* row_ends;   // [n_dst] inclusive
+  int32_t* t_row;      // [n_src] transposed rows: exclusive starts after the count, inclusive ends after the fill
+  int64_t* total_out;  // device: E
+  int64_t n_edges;     // fill: E (host)
+  int32_t *col_src, *edge_dst, *t_edge, *t_dst;  // fill outputs [E]
+};
+int bq_count_transposed_batch(const BqBatchItem* items, int n, void* t_row_block, size_t t_row_block_bytes,
+                              se3_stream_t stream);
+int bq_fill_transposed_batch(const BqBatchItem* items, int n, se3_stream_t stream);
 int knn_sorted_fused(const float* pts, const int32_t* batch_ids, int64_t n, const float* raw_min, const float* raw_max,
                      int* idx_sorted, void* pts_sorted_f4, float* minmax, int32_t n_batches, int32_t max_seg,
                      se3_stream_t stream);

@@ -876,17 +876,51 @@ __device__ __forceinline__ bool bq_hit(float sx, float sy, float sz, const float
 
 // One warp per sample.  FILL=false: find the 9 tube ranges, cache them, count hits.
 // FILL=true: rescan the cached ranges and write (sample, source) pairs.
+struct BqScanArgs {
+  const float* pts_dst;
+  const int* batch_dst;
+  int64_t n_dst;
+  int n_src;
+  const float* min_pt;
+  const int* num_cells;
+  const float* radius;
+  const int64_t* keys_sorted;
+  const float4* pts_sorted;
+  const int* idx_sorted;
+  int2* ranges;
+  int* counts;
+  const int* row_ends;
+  int64_t* neighbors;
+  int* col_src;
+  int* edge_dst;
+  int* t_cursor;
+  int* t_edge;
+};
+constexpr int BQ_BATCH = kBqBatch;  // queries per batched launch (kernel parameter space)
+struct BqScanBatch {
+  BqScanArgs q[BQ_BATCH];
+};
+
 template <bool FILL>
-__global__ void __launch_bounds__(256) k_bq_scan(const float* __restrict__ pts_dst, const int* __restrict__ batch_dst,
-                                                 int64_t n_dst, int n_src, const float* __restrict__ min_pt,
-                                                 const int* __restrict__ num_cells, const float* __restrict__ radius,
-                                                 const int64_t* __restrict__ keys_sorted,
-                                                 const float4* __restrict__ pts_sorted,
-                                                 const int* __restrict__ idx_sorted, int2* __restrict__ ranges,
-                                                 int* __restrict__ counts, const int* __restrict__ row_ends,
-                                                 int64_t* __restrict__ neighbors, int* __restrict__ col_src,
-                                                 int* __restrict__ edge_dst, int* __restrict__ t_cursor,
-                                                 int* __restrict__ t_edge) {
+__device__ __forceinline__ void bq_scan_body(const BqScanArgs& a) {
+  const float* __restrict__ pts_dst = a.pts_dst;
+  const int* __restrict__ batch_dst = a.batch_dst;
+  const int64_t n_dst = a.n_dst;
+  const int n_src = a.n_src;
+  const float* __restrict__ min_pt = a.min_pt;
+  const int* __restrict__ num_cells = a.num_cells;
+  const float* __restrict__ radius = a.radius;
+  const int64_t* __restrict__ keys_sorted = a.keys_sorted;
+  const float4* __restrict__ pts_sorted = a.pts_sorted;
+  const int* __restrict__ idx_sorted = a.idx_sorted;
+  int2* __restrict__ ranges = a.ranges;
+  int* __restrict__ counts = a.counts;
+  const int* __restrict__ row_ends = a.row_ends;
+  int64_t* __restrict__ neighbors = a.neighbors;
+  int* __restrict__ col_src = a.col_src;
+  int* __restrict__ edge_dst = a.edge_dst;
+  int* __restrict__ t_cursor = a.t_cursor;
+  int* __restrict__ t_edge = a.t_edge;
   // t_cursor (optional, fused hierarchy builder): the transposed CSR is built alongside.  Count pass: histogram of
   // the hit sources (t_cursor zeroed by the caller).  Fill pass: t_cursor holds the exclusive row starts and is
   // advanced per hit, so it ends as the inclusive row ends; t_edge receives the edge ids in arrival order
@@ -948,6 +982,17 @@ __global__ void __launch_bounds__(256) k_bq_scan(const float* __restrict__ pts_d
   }
 }
 
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_bq_scan(const BqScanArgs a) {
+  bq_scan_body<FILL>(a);
+}
+// several queries in one launch: blockIdx.y selects the query (the fused builder batches the neighbourhoods that
+// become possible together; a launch costs the host more than most of these queries cost the GPU)
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_bq_scan_multi(const BqScanBatch b) {
+  bq_scan_body<FILL>(b.q[blockIdx.y]);
+}
+
 __global__ void k_bq_total(const int* __restrict__ row_ends, int64_t n_dst, int64_t* __restrict__ total) {
   if (threadIdx.x == 0 && blockIdx.x == 0) *total = n_dst > 0 ? (int64_t)row_ends[n_dst - 1] : 0;
 }
@@ -971,9 +1016,10 @@ static int bq_count(const float* pts_dst, const int32_t* batch_dst, int64_t n_sr
                     const int32_t* num_cells, const float* radius, BQWorkspace& w, int32_t* row_ends_out,
                     int64_t* total_out, cudaStream_t st) {
   const int blocks = grid_for(n_dst * 32, 256);
-  k_bq_scan<false><<<blocks, 256, 0, st>>>(pts_dst, batch_dst, n_dst, (int)n_src, min_pt, num_cells, radius,
-                                           w.keys_sorted, w.pts_sorted, w.idx_sorted, w.ranges, w.counts, nullptr,
-                                           nullptr, nullptr, nullptr, nullptr, nullptr);
+  {
+    const BqScanArgs qa{pts_dst, batch_dst, n_dst, (int)n_src, min_pt, num_cells, radius, w.keys_sorted, w.pts_sorted, w.idx_sorted, w.ranges, w.counts, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    k_bq_scan<false><<<blocks, 256, 0, st>>>(qa);
+  }
   SE3_LAUNCH_CHECK();
   size_t cb = w.scan_bytes;
   SE3_CUDA(cub::DeviceScan::InclusiveSum(w.scan_tmp, cb, w.counts, row_ends_out, (int)n_dst, st));
@@ -1100,10 +1146,10 @@ extern "C" int se3_ball_query_fill_csr_prepared(const float* pts_dst, int64_t n_
     return SE3_EWORKSPACE;
   }
   const int blocks = grid_for(n_dst * 32, 256);
-  k_bq_scan<true><<<blocks, 256, 0, as_stream(stream)>>>(pts_dst, nullptr, n_dst, (int)n_src, nullptr, nullptr,
-                                                         radius, w.keys_sorted, w.pts_sorted, w.idx_sorted, w.ranges,
-                                                         w.counts, row_ends, nullptr, col_src_out, edge_dst_out, nullptr,
-                                                         nullptr);
+  {
+    const BqScanArgs qa{pts_dst, nullptr, n_dst, (int)n_src, nullptr, nullptr, radius, w.keys_sorted, w.pts_sorted, w.idx_sorted, w.ranges, w.counts, row_ends, nullptr, col_src_out, edge_dst_out, nullptr, nullptr};
+    k_bq_scan<true><<<blocks, 256, 0, as_stream(stream)>>>(qa);
+  }
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }
@@ -1119,10 +1165,10 @@ extern "C" int se3_ball_query_fill(const float* pts_dst, int64_t n_src, int64_t 
     return SE3_EWORKSPACE;
   }
   const int blocks = grid_for(n_dst * 32, 256);
-  k_bq_scan<true><<<blocks, 256, 0, as_stream(stream)>>>(pts_dst, nullptr, n_dst, (int)n_src, nullptr, nullptr,
-                                                         radius, w.keys_sorted, w.pts_sorted, w.idx_sorted, w.ranges,
-                                                         w.counts, row_ends, neighbors_out, nullptr, nullptr, nullptr,
-                                                         nullptr);
+  {
+    const BqScanArgs qa{pts_dst, nullptr, n_dst, (int)n_src, nullptr, nullptr, radius, w.keys_sorted, w.pts_sorted, w.idx_sorted, w.ranges, w.counts, row_ends, neighbors_out, nullptr, nullptr, nullptr, nullptr};
+    k_bq_scan<true><<<blocks, 256, 0, as_stream(stream)>>>(qa);
+  }
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }
@@ -1139,10 +1185,10 @@ extern "C" int se3_ball_query_fill_csr(const float* pts_dst, int64_t n_src, int6
     return SE3_EWORKSPACE;
   }
   const int blocks = grid_for(n_dst * 32, 256);
-  k_bq_scan<true><<<blocks, 256, 0, as_stream(stream)>>>(pts_dst, nullptr, n_dst, (int)n_src, nullptr, nullptr,
-                                                         radius, w.keys_sorted, w.pts_sorted, w.idx_sorted, w.ranges,
-                                                         w.counts, row_ends, nullptr, col_src_out, edge_dst_out, nullptr,
-                                                         nullptr);
+  {
+    const BqScanArgs qa{pts_dst, nullptr, n_dst, (int)n_src, nullptr, nullptr, radius, w.keys_sorted, w.pts_sorted, w.idx_sorted, w.ranges, w.counts, row_ends, nullptr, col_src_out, edge_dst_out, nullptr, nullptr};
+    k_bq_scan<true><<<blocks, 256, 0, as_stream(stream)>>>(qa);
+  }
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }
@@ -1159,8 +1205,7 @@ struct ScanJob {
   int exclusive;
   int64_t* total;
 };
-__global__ void __launch_bounds__(1024) k_scan_small(const ScanJob j0, const ScanJob j1) {
-  const ScanJob j = blockIdx.x == 0 ? j0 : j1;
+__device__ __forceinline__ void scan_small_body(const ScanJob& j) {
   using BS = cub::BlockScan<int, 1024>;
   __shared__ typename BS::TempStorage tmp;
   constexpr int IT = 16;  // 16 K entries per tile: four 128-bit loads in flight per thread (arrays are 16-byte aligned)
@@ -1205,6 +1250,14 @@ __global__ void __launch_bounds__(1024) k_scan_small(const ScanJob j0, const Sca
   }
   if (threadIdx.x == 0 && j.total) *j.total = carry;
 }
+__global__ void __launch_bounds__(1024) k_scan_small(const ScanJob j0, const ScanJob j1) {
+  scan_small_body(blockIdx.x == 0 ? j0 : j1);
+}
+
+struct ScanBatch {
+  ScanJob j[2 * BQ_BATCH];
+};
+__global__ void __launch_bounds__(1024) k_scan_multi(const ScanBatch b) { scan_small_body(b.j[blockIdx.x]); }
 
 // Every transposed row in ascending edge order (= the order a stable sort by source would give), then the sample
 // of every transposed entry.  One warp per row, any row length: chunks of up to T_CHUNK entries are sorted in shared
@@ -1220,9 +1273,19 @@ __device__ __forceinline__ int lower_bound_run(const int* __restrict__ a, int n,
   }
   return lo;
 }
-__global__ void __launch_bounds__(T_WARPS * 32) k_t_rows_finish(const int* __restrict__ t_row_ends, int64_t n_src,
-                                                                int* __restrict__ t_edge, const int* __restrict__ edge_dst,
-                                                                int* __restrict__ t_dst) {
+struct FinishJob {
+  const int* t_row_ends;
+  int64_t n_src;
+  int* t_edge;
+  const int* edge_dst;
+  int* t_dst;
+};
+struct FinishBatch {
+  FinishJob j[BQ_BATCH];
+};
+__device__ __forceinline__ void t_rows_finish_body(const int* __restrict__ t_row_ends, int64_t n_src,
+                                                   int* __restrict__ t_edge, const int* __restrict__ edge_dst,
+                                                   int* __restrict__ t_dst) {
   __shared__ int s_buf[T_WARPS][T_CHUNK];
   const int lane = threadIdx.x & 31;
   int* sb = s_buf[threadIdx.x >> 5];
@@ -1273,6 +1336,15 @@ __global__ void __launch_bounds__(T_WARPS * 32) k_t_rows_finish(const int* __res
     for (int t = lane; t < len; t += 32) alt[t] = edge_dst[row[t]];
   }
 }
+__global__ void __launch_bounds__(T_WARPS * 32) k_t_rows_finish(const int* __restrict__ t_row_ends, int64_t n_src,
+                                                                int* __restrict__ t_edge, const int* __restrict__ edge_dst,
+                                                                int* __restrict__ t_dst) {
+  t_rows_finish_body(t_row_ends, n_src, t_edge, edge_dst, t_dst);
+}
+__global__ void __launch_bounds__(T_WARPS * 32) k_t_rows_finish_multi(const FinishBatch b) {
+  const FinishJob& j = b.j[blockIdx.y];
+  t_rows_finish_body(j.t_row_ends, j.n_src, j.t_edge, j.edge_dst, j.t_dst);
+}
 
 namespace se3 {
 // count pass of a prepared query; also the histogram of the hit sources.  Outputs: row_ends [n_dst] inclusive,
@@ -1298,9 +1370,10 @@ int bq_count_transposed(const float* pts_dst, const int32_t* batch_dst, int64_t 
     return SE3_EWORKSPACE;
   }
   const int blocks = grid_for(n_dst * 32, 256);
-  k_bq_scan<false><<<blocks, 256, 0, st>>>(pts_dst, batch_dst, n_dst, (int)n_src, min_pt, num_cells, radius,
-                                           w.keys_sorted, w.pts_sorted, w.idx_sorted, w.ranges, w.counts, nullptr,
-                                           nullptr, nullptr, nullptr, t_row_out, nullptr);
+  {
+    const BqScanArgs qa{pts_dst, batch_dst, n_dst, (int)n_src, min_pt, num_cells, radius, w.keys_sorted, w.pts_sorted, w.idx_sorted, w.ranges, w.counts, nullptr, nullptr, nullptr, nullptr, t_row_out, nullptr};
+    k_bq_scan<false><<<blocks, 256, 0, st>>>(qa);
+  }
   SE3_LAUNCH_CHECK();
   ScanJob j0{w.counts, row_ends_out, (int)n_dst, 0, total_out};
   ScanJob j1{t_row_out, t_row_out, (int)n_src, 1, nullptr};
@@ -1325,11 +1398,83 @@ int bq_fill_transposed(const float* pts_dst, int64_t n_src, int64_t n_dst, int64
   }
   cudaStream_t st = as_stream(stream);
   const int blocks = grid_for(n_dst * 32, 256);
-  k_bq_scan<true><<<blocks, 256, 0, st>>>(pts_dst, nullptr, n_dst, (int)n_src, nullptr, nullptr, radius, w.keys_sorted,
-                                          w.pts_sorted, w.idx_sorted, w.ranges, w.counts, row_ends, nullptr, col_src_out,
-                                          edge_dst_out, t_row, t_edge);
+  {
+    const BqScanArgs qa{pts_dst, nullptr, n_dst, (int)n_src, nullptr, nullptr, radius, w.keys_sorted, w.pts_sorted, w.idx_sorted, w.ranges, w.counts, row_ends, nullptr, col_src_out, edge_dst_out, t_row, t_edge};
+    k_bq_scan<true><<<blocks, 256, 0, st>>>(qa);
+  }
   SE3_LAUNCH_CHECK();
   k_t_rows_finish<<<grid_for(n_src * 32, T_WARPS * 32), T_WARPS * 32, 0, st>>>(t_row, n_src, t_edge, edge_dst_out, t_dst);
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
+}
+}  // namespace se3
+
+namespace se3 {
+// Batched forms of bq_count_transposed / bq_fill_transposed: up to BQ_BATCH prepared queries per launch.  The t_row
+// arrays of a batch must lie in one contiguous block [t_row_block, t_row_block + t_row_block_bytes) (one memset).
+int bq_count_transposed_batch(const BqBatchItem* it, int n, void* t_row_block, size_t t_row_block_bytes,
+                              se3_stream_t stream) {
+  SE3_CHECK_ARG(n >= 1 && n <= BQ_BATCH && it, "bad batch");
+  cudaStream_t st = as_stream(stream);
+  if (t_row_block_bytes) SE3_CUDA(cudaMemsetAsync(t_row_block, 0, t_row_block_bytes, st));
+  BqScanBatch qb;
+  ScanBatch sb;
+  int nq = 0, blocks = 1;
+  for (int i = 0; i < n; ++i) {
+    const BqBatchItem& q = it[i];
+    SE3_CHECK_ARG(q.n_src >= 0 && q.n_dst >= 0 && q.n_src < (1ll << 31) && q.n_dst < (1ll << 31) && q.total_out, "bad sizes");
+    if (q.n_dst == 0 || q.n_src == 0) {
+      if (q.n_dst > 0) SE3_CUDA(cudaMemsetAsync(q.row_ends, 0, q.n_dst * sizeof(int32_t), st));
+      SE3_CUDA(cudaMemsetAsync(q.total_out, 0, sizeof(int64_t), st));
+      continue;
+    }
+    BQWorkspace w;
+    if (!bq_layout2(q.ws_src, q.ws_src_bytes, q.ws_dst, q.ws_dst_bytes, q.n_src, q.n_dst, 1, w)) {
+      set_error("bq_count_transposed_batch: workspace too small");
+      return SE3_EWORKSPACE;
+    }
+    qb.q[nq] = BqScanArgs{q.pts_dst, q.batch_dst, q.n_dst, (int)q.n_src, q.min_pt, q.num_cells, q.radius, w.keys_sorted,
+                          w.pts_sorted, w.idx_sorted, w.ranges, w.counts, nullptr, nullptr, nullptr, nullptr, q.t_row, nullptr};
+    sb.j[2 * nq] = ScanJob{w.counts, q.row_ends, (int)q.n_dst, 0, q.total_out};
+    sb.j[2 * nq + 1] = ScanJob{q.t_row, q.t_row, (int)q.n_src, 1, nullptr};
+    const int bx = grid_for(q.n_dst * 32, 256);
+    if (bx > blocks) blocks = bx;
+    ++nq;
+  }
+  if (nq == 0) return SE3_OK;
+  k_bq_scan_multi<false><<<dim3(blocks, nq), 256, 0, st>>>(qb);
+  SE3_LAUNCH_CHECK();
+  k_scan_multi<<<2 * nq, 1024, 0, st>>>(sb);
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
+}
+
+int bq_fill_transposed_batch(const BqBatchItem* it, int n, se3_stream_t stream) {
+  SE3_CHECK_ARG(n >= 1 && n <= BQ_BATCH && it, "bad batch");
+  cudaStream_t st = as_stream(stream);
+  BqScanBatch qb;
+  FinishBatch fb;
+  int nq = 0, blocks = 1, fblocks = 1;
+  for (int i = 0; i < n; ++i) {
+    const BqBatchItem& q = it[i];
+    if (q.n_edges == 0 || q.n_dst == 0 || q.n_src == 0) continue;  // t_row is all zero already
+    BQWorkspace w;
+    if (!bq_layout2(q.ws_src, q.ws_src_bytes, q.ws_dst, q.ws_dst_bytes, q.n_src, q.n_dst, 1, w)) {
+      set_error("bq_fill_transposed_batch: workspace too small");
+      return SE3_EWORKSPACE;
+    }
+    qb.q[nq] = BqScanArgs{q.pts_dst, nullptr, q.n_dst, (int)q.n_src, nullptr, nullptr, q.radius, w.keys_sorted, w.pts_sorted,
+                          w.idx_sorted, w.ranges, w.counts, q.row_ends, nullptr, q.col_src, q.edge_dst, q.t_row, q.t_edge};
+    fb.j[nq] = FinishJob{q.t_row, q.n_src, q.t_edge, q.edge_dst, q.t_dst};
+    const int bx = grid_for(q.n_dst * 32, 256), fx = grid_for(q.n_src * 32, T_WARPS * 32);
+    if (bx > blocks) blocks = bx;
+    if (fx > fblocks) fblocks = fx;
+    ++nq;
+  }
+  if (nq == 0) return SE3_OK;
+  k_bq_scan_multi<true><<<dim3(blocks, nq), 256, 0, st>>>(qb);
+  SE3_LAUNCH_CHECK();
+  k_t_rows_finish_multi<<<dim3(fblocks, nq), T_WARPS * 32, 0, st>>>(fb);
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }

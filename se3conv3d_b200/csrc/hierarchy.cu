@@ -331,6 +331,7 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
     src_of[i] = f;
   }
   bool cloud_done[SE3_HIER_MAX_CLOUDS + 1] = {false}, nb_issued[SE3_HIER_MAX_NEIGH] = {false};
+  int batch_rr = 0;
   int64_t wd_off[SE3_HIER_MAX_NEIGH];
   size_t wd_bytes[SE3_HIER_MAX_NEIGH];
   auto issue_ready = [&]() -> int {
@@ -362,25 +363,43 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
       SE3_CUDA(cudaEventRecord(ln->src[j], sj));
       so.issued = true;
     }
-    for (int i = 0; i < d->n_neigh; ++i) {
-      const Source& so = sources[src_of[i]];
-      if (nb_issued[i] || !so.issued || !cloud_done[d->neigh_dst[i]]) continue;
-      const se3_hier_cloud& s = out->clouds[d->neigh_src[i]];
-      const se3_hier_cloud& t = out->clouds[d->neigh_dst[i]];
-      se3_hier_neigh& nb = out->neigh[i];
-      nb.row_ends = ar.take((size_t)t.n * 4);
-      nb.t_row_ends = ar.take((size_t)s.n * 4);
-      wd_bytes[i] = se3_ball_query_dst_workspace_bytes(t.n);
-      wd_off[i] = ar.take(wd_bytes[i]);
+    // every neighbourhood that has become possible goes into ONE batched count launch (+ one batched scan launch)
+    int ready[SE3_HIER_MAX_NEIGH], n_ready = 0;
+    for (int i = 0; i < d->n_neigh; ++i)
+      if (!nb_issued[i] && sources[src_of[i]].issued && cloud_done[d->neigh_dst[i]]) ready[n_ready++] = i;
+    for (int r0 = 0; r0 < n_ready; r0 += kBqBatch) {
+      const int nb_n = n_ready - r0 < kBqBatch ? n_ready - r0 : kBqBatch;
+      BqBatchItem items[kBqBatch];
+      // the transposed row arrays of a batch are taken back to back: one memset clears them all
+      const int64_t t_block = (int64_t)ar.off;
+      for (int k = 0; k < nb_n; ++k) out->neigh[ready[r0 + k]].t_row_ends = ar.take((size_t)out->clouds[d->neigh_src[ready[r0 + k]]].n * 4);
+      const size_t t_block_bytes = ar.off - (size_t)t_block;
+      cudaStream_t sb = ln->s[batch_rr++ % kSide];
+      for (int k = 0; k < nb_n; ++k) {
+        const int i = ready[r0 + k];
+        const Source& so = sources[src_of[i]];
+        const se3_hier_cloud& s = out->clouds[d->neigh_src[i]];
+        const se3_hier_cloud& t = out->clouds[d->neigh_dst[i]];
+        se3_hier_neigh& nb = out->neigh[i];
+        nb.row_ends = ar.take((size_t)t.n * 4);
+        wd_bytes[i] = se3_ball_query_dst_workspace_bytes(t.n);
+        wd_off[i] = ar.take(wd_bytes[i]);
+        HB_CHECK_ARENA("ball-query workspace");
+        SE3_CUDA(cudaStreamWaitEvent(sb, ln->src[src_of[i]], 0));
+        SE3_CUDA(cudaStreamWaitEvent(sb, ln->cloud[d->neigh_dst[i]], 0));
+        BqBatchItem& q = items[k];
+        memset(&q, 0, sizeof(q));
+        q.pts_dst = ar.at<float>(t.pts); q.batch_dst = ar.at<int32_t>(t.batch);
+        q.n_src = s.n; q.n_dst = t.n;
+        q.min_pt = ar.at<float>(so.mn); q.num_cells = ar.at<int32_t>(so.nc); q.radius = d_rad + 4 * i;
+        q.ws_src = ar.at<char>(so.ws); q.ws_src_bytes = so.ws_bytes;
+        q.ws_dst = ar.at<char>(wd_off[i]); q.ws_dst_bytes = wd_bytes[i];
+        q.row_ends = ar.at<int32_t>(nb.row_ends); q.t_row = ar.at<int32_t>(nb.t_row_ends);
+        q.total_out = d_cnt + 1 + i;
+        nb_issued[i] = true;
+      }
       HB_CHECK_ARENA("ball-query workspace");
-      cudaStream_t si = ln->s[i % kSide];
-      SE3_CUDA(cudaStreamWaitEvent(si, ln->src[src_of[i]], 0));
-      SE3_CUDA(cudaStreamWaitEvent(si, ln->cloud[d->neigh_dst[i]], 0));
-      HB_TRY(bq_count_transposed(ar.at<float>(t.pts), ar.at<int32_t>(t.batch), s.n, t.n, 1, ar.at<float>(so.mn),
-                                 ar.at<int32_t>(so.nc), d_rad + 4 * i, ar.at<char>(so.ws), so.ws_bytes,
-                                 ar.at<char>(wd_off[i]), wd_bytes[i], ar.at<int32_t>(nb.row_ends),
-                                 ar.at<int32_t>(nb.t_row_ends), d_cnt + 1 + i, reinterpret_cast<se3_stream_t>(si)));
-      nb_issued[i] = true;
+      HB_TRY(bq_count_transposed_batch(items, nb_n, ar.at<char>(t_block), t_block_bytes, reinterpret_cast<se3_stream_t>(sb)));
     }
     return SE3_OK;
   };
@@ -452,23 +471,35 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
     SE3_CUDA(cudaStreamSynchronize(st));
   }
   stamp("edge totals read");
-  for (int i = 0; i < d->n_neigh; ++i) {
-    const Source& so = sources[src_of[i]];
-    const se3_hier_cloud& s = out->clouds[d->neigh_src[i]];
-    const se3_hier_cloud& t = out->clouds[d->neigh_dst[i]];
-    se3_hier_neigh& nb = out->neigh[i];
-    nb.e = host[i];
-    nb.col_src = ar.take((size_t)nb.e * 4);
-    nb.edge_dst = ar.take((size_t)nb.e * 4);
-    nb.t_edge = ar.take((size_t)nb.e * 4);
-    nb.t_dst = ar.take((size_t)nb.e * 4);
-    HB_CHECK_ARENA("neighbourhood");
-    // everything issued so far has completed (the blocking read above), so the side streams need no further waits
-    se3_stream_t sis = reinterpret_cast<se3_stream_t>(ln->s[i % kSide]);
-    HB_TRY(bq_fill_transposed(ar.at<float>(t.pts), s.n, t.n, 1, d_rad + 4 * i, ar.at<char>(so.ws), so.ws_bytes,
-                              ar.at<char>(wd_off[i]), wd_bytes[i], ar.at<int32_t>(nb.row_ends), nb.e,
-                              ar.at<int32_t>(nb.col_src), ar.at<int32_t>(nb.edge_dst), ar.at<int32_t>(nb.t_row_ends),
-                              ar.at<int32_t>(nb.t_edge), ar.at<int32_t>(nb.t_dst), sis));
+  for (int i0 = 0; i0 < d->n_neigh; i0 += kBqBatch) {
+    const int nb_n = d->n_neigh - i0 < kBqBatch ? d->n_neigh - i0 : kBqBatch;
+    BqBatchItem items[kBqBatch];
+    for (int k = 0; k < nb_n; ++k) {
+      const int i = i0 + k;
+      const Source& so = sources[src_of[i]];
+      const se3_hier_cloud& s = out->clouds[d->neigh_src[i]];
+      const se3_hier_cloud& t = out->clouds[d->neigh_dst[i]];
+      se3_hier_neigh& nb = out->neigh[i];
+      nb.e = host[i];
+      nb.col_src = ar.take((size_t)nb.e * 4);
+      nb.edge_dst = ar.take((size_t)nb.e * 4);
+      nb.t_edge = ar.take((size_t)nb.e * 4);
+      nb.t_dst = ar.take((size_t)nb.e * 4);
+      HB_CHECK_ARENA("neighbourhood");
+      BqBatchItem& q = items[k];
+      memset(&q, 0, sizeof(q));
+      q.pts_dst = ar.at<float>(t.pts);
+      q.n_src = s.n; q.n_dst = t.n; q.radius = d_rad + 4 * i;
+      q.ws_src = ar.at<char>(so.ws); q.ws_src_bytes = so.ws_bytes;
+      q.ws_dst = ar.at<char>(wd_off[i]); q.ws_dst_bytes = wd_bytes[i];
+      q.row_ends = ar.at<int32_t>(nb.row_ends); q.t_row = ar.at<int32_t>(nb.t_row_ends);
+      q.n_edges = nb.e;
+      q.col_src = ar.at<int32_t>(nb.col_src); q.edge_dst = ar.at<int32_t>(nb.edge_dst);
+      q.t_edge = ar.at<int32_t>(nb.t_edge); q.t_dst = ar.at<int32_t>(nb.t_dst);
+    }
+    // everything issued so far has completed (the blocking read above): all fills in one launch on the caller's
+    // stream (blockIdx.y = neighbourhood), all row orderings in a second one
+    HB_TRY(bq_fill_transposed_batch(items, nb_n, stream));
   }
     return SE3_OK;
   };
