@@ -47,10 +47,11 @@ int bq_fill_transposed(const float* pts_dst, int64_t n_src, int64_t n_dst, int64
 int frames_select_pack(const float* cand, const float* u, int64_t n, int32_t n_cand, int32_t n_keep, float* out,
                        const float* pts, float* rec, se3_stream_t stream);
 bool seg_build_possible(int n_batches, int max_seg);
-int grid_cells_fused(const float* pts, const int32_t* batch_ids, int64_t n, const float* raw_min, const float* raw_max,
-                     float cell, float* min_pt_out, float* max_pt_out, int32_t* num_cells_out, void* workspace,
-                     size_t workspace_bytes, int64_t* cell_ids, int64_t* sorted_ids, int32_t* cell_ends, int64_t* m_out,
-                     int32_t n_batches, int32_t max_seg, int32_t* batch_cells, se3_stream_t stream);
+int grid_level_fused(const float* pts, const int32_t* batch_ids, int64_t n, const float* raw_min, const float* raw_max,
+                     float cell, float* min_pt_out, float* max_pt_out, int32_t* num_cells_out, int64_t* cell_ids,
+                     int64_t* sorted_ids, int32_t* cell_ends, int64_t* m_out, int32_t n_batches, int32_t max_seg,
+                     int32_t* batch_cells, int32_t* state, float* pool_pts, int32_t* pool_batch, float* pool_min,
+                     float* pool_max, se3_stream_t stream);
 int ball_query_prepare_fused(const float* pts_src, const int32_t* batch_src, int64_t n_src, const float* raw_min,
                              const float* raw_max, float radius, float* min_pt_out, float* max_pt_out,
                              int32_t* num_cells_out, void* ws_src, size_t ws_src_bytes, int32_t n_batches,

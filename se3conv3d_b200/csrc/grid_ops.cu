@@ -554,6 +554,206 @@ __global__ void __launch_bounds__(THREADS) k_seg_build(const SegBuildArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// one launch per pooling level (fused hierarchy builder, batch items that fit a CTA)
+// ---------------------------------------------------------------------------------------------
+// CTA b does for batch item b everything se3_grid_extents + se3_grid_cells + se3_segment_pool_f32 +
+// se3_segment_first_i32 + se3_bbox do for a level: grid extents from the raw boxes, voxel keys, the per-item sort,
+// the dense cell ranks (a block scan; the rank offset of item b is the number of cells of the items before it, read
+// from a small look-back array the CTAs publish into -- CTAs are dispatched in index order, so the ones a CTA waits
+// for are running or done), the pooled cloud (cell means, summed in sorted order like k_segment_pool) and the raw
+// boxes of the pooled cloud for the next level.  Same arithmetic and order as those kernels: bit-identical results.
+struct GridLevelArgs {
+  const float* pts;
+  const int* batch;
+  int n, n_batches;
+  const float* raw_min;  // [B,3] raw boxes of the cloud being pooled
+  const float* raw_max;
+  float cell;
+  float* mn_out;  // padded boxes [B,3] + grid extents [3] (CTA 0)
+  float* mx_out;
+  int* nc_out;
+  int64_t* cell_ids;    // [n]
+  int64_t* sorted_ids;  // [n]
+  int* cell_ends;       // [<= n]
+  int64_t* m_out;       // number of cells = points of the pooled cloud
+  int* batch_cells;     // [B] cells per batch item (optional)
+  int* state;           // [B] look-back: (cells of item b) << 1 | 1, zeroed by the caller
+  float* pool_pts;      // [<= n, 3]
+  int* pool_batch;      // [<= n]
+  float* pool_min;      // [B,3] raw boxes of the pooled cloud
+  float* pool_max;
+};
+
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS) k_grid_level(const GridLevelArgs a) {
+  using Sort = cub::BlockRadixSort<uint64_t, THREADS, ITEMS, int>;
+  using Disc = cub::BlockDiscontinuity<uint64_t, THREADS>;
+  using Scan = cub::BlockScan<int, THREADS>;
+  constexpr int CAP = THREADS * ITEMS;
+  extern __shared__ __align__(16) unsigned char seg_smem[];
+  typename Sort::TempStorage& tmp = *reinterpret_cast<typename Sort::TempStorage*>(seg_smem);
+  int* s_idx = reinterpret_cast<int*>(seg_smem);  // after the sort the same bytes hold three int arrays [CAP]
+  int* s_rank = s_idx + CAP;
+  int* s_cend = s_rank + CAP;
+  __shared__ typename Disc::TempStorage disc_tmp;
+  __shared__ typename Scan::TempStorage scan_tmp;
+  __shared__ int s_lo, s_hi, s_nc[3], s_off;
+  __shared__ float s_red[THREADS / 32][6];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) {
+    s_lo = lower_bound_i32(a.batch, a.n, b);
+    s_hi = lower_bound_i32(a.batch, a.n, b + 1);
+    s_nc[0] = s_nc[1] = s_nc[2] = 1;
+  }
+  __syncthreads();
+  const float inv = __fdiv_rn(1.0f, a.cell);
+  for (int bb = tid; bb < a.n_batches; bb += THREADS) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float lo = a.raw_min[3 * bb + d], hi = a.raw_max[3 * bb + d];
+      float plo = 0.0f, phi = 0.0f;
+      if (lo <= hi) {
+        plo = __fsub_rn(lo, 1e-6f);
+        phi = __fadd_rn(hi, 1e-6f);
+        atomicMax(&s_nc[d], (int)__fmul_rn(__fsub_rn(phi, plo), inv) + 1);
+      }
+      if (b == 0) {
+        a.mn_out[3 * bb + d] = plo;
+        a.mx_out[3 * bb + d] = phi;
+      }
+    }
+  }
+  __syncthreads();
+  if (b == 0 && tid < 3) a.nc_out[tid] = s_nc[tid];
+  const int lo = s_lo, cnt = s_hi - lo;
+  int v[ITEMS], r1[ITEMS];
+  int m_b = 0;
+  if (cnt > 0) {
+    uint64_t k[ITEMS];
+    GridParams g;
+    g.nx = s_nc[0]; g.ny = s_nc[1]; g.nz = s_nc[2];
+    g.ix = g.iy = g.iz = inv;
+    float mn[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float rl = a.raw_min[3 * b + d], rh = a.raw_max[3 * b + d];
+      mn[d] = rl <= rh ? __fsub_rn(rl, 1e-6f) : 0.0f;
+    }
+    const uint64_t cells = (uint64_t)g.nx * (uint64_t)g.ny * (uint64_t)g.nz;
+    const int end_bit = cells > 1 ? 64 - __clzll((long long)(cells - 1)) : 1;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int p = tid * ITEMS + i;
+      k[i] = ~0ull;  // padding: last in the sorted bit range (stable) and different from every real key as a whole
+      v[i] = lo + p;
+      if (p < cnt) {
+        const int64_t q = lo + p;
+        int cx, cy, cz;
+        point_cell(g, a.pts[3 * q], a.pts[3 * q + 1], a.pts[3 * q + 2], mn[0], mn[1], mn[2], cx, cy, cz);
+        k[i] = (uint64_t)(((int64_t)cx * g.ny + cy) * g.nz + cz);
+      }
+    }
+    Sort(tmp).Sort(k, v, 0, end_bit);
+    int head[ITEMS];
+    Disc(disc_tmp).FlagHeads(head, k, cub::Inequality());
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i)
+      if (tid * ITEMS + i >= cnt) head[i] = 0;
+    Scan(scan_tmp).InclusiveSum(head, r1, m_b);
+    __syncthreads();  // the sort's shared memory is free: sorted indices and ranks for the cell ends and the pooling
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int p = tid * ITEMS + i;
+      if (p < cnt) {
+        s_idx[p] = v[i];
+        s_rank[p] = r1[i];
+      }
+    }
+  }
+  __syncthreads();
+  // ---- rank offset of this item: cells of the items before it
+  if (tid < 32) {
+    if (tid == 0) *reinterpret_cast<volatile int*>(a.state + b) = (m_b << 1) | 1;
+    int sum = 0;
+    for (int base = 0; base < b; base += 32) {
+      const int bb = base + lane;
+      if (bb < b) {
+        int val;
+        do {
+          val = *reinterpret_cast<volatile const int*>(a.state + bb);
+        } while (!(val & 1));
+        sum += val >> 1;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (tid == 0) s_off = sum;
+  }
+  __syncthreads();
+  const int off = s_off;
+  if (tid == 0) {
+    if (a.batch_cells) a.batch_cells[b] = m_b;
+    if (b == a.n_batches - 1) *a.m_out = (int64_t)off + m_b;
+  }
+  float bx[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  if (cnt > 0) {
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int p = tid * ITEMS + i;
+      if (p < cnt) {
+        const int r = r1[i] - 1;
+        a.cell_ids[v[i]] = off + r;
+        a.sorted_ids[lo + p] = v[i];
+        if (p == cnt - 1 || s_rank[p + 1] != r1[i]) {
+          a.cell_ends[off + r] = lo + p + 1;
+          s_cend[r] = p + 1;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- pooled cloud: mean of every cell in sorted order (k_segment_pool), batch id, raw box
+    for (int c = tid; c < m_b; c += THREADS) {
+      const int p0 = c > 0 ? s_cend[c - 1] : 0, p1 = s_cend[c];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        float acc = 0.0f;
+        for (int p = p0; p < p1; ++p) acc = acc + a.pts[3 * (int64_t)s_idx[p] + d];
+        acc = acc / (float)(p1 - p0);
+        a.pool_pts[3 * (int64_t)(off + c) + d] = acc;
+        bx[d] = fminf(bx[d], acc);
+        bx[3 + d] = fmaxf(bx[3 + d], acc);
+      }
+      a.pool_batch[off + c] = b;
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 6; ++d)
+    for (int o = 16; o > 0; o >>= 1) {
+      const float y = __shfl_xor_sync(0xffffffffu, bx[d], o);
+      bx[d] = d < 3 ? fminf(bx[d], y) : fmaxf(bx[d], y);
+    }
+  if (lane == 0)
+    for (int d = 0; d < 6; ++d) s_red[tid >> 5][d] = bx[d];
+  __syncthreads();
+  if (tid < 6) {
+    float r = s_red[0][tid];
+    for (int w = 1; w < THREADS / 32; ++w) r = tid < 3 ? fminf(r, s_red[w][tid]) : fmaxf(r, s_red[w][tid]);
+    if (tid < 3) a.pool_min[3 * b + tid] = r; else a.pool_max[3 * b + tid - 3] = r;
+  }
+}
+
+template <int THREADS, int ITEMS>
+static int launch_grid_level_cfg(const GridLevelArgs& a, cudaStream_t st) {
+  using Sort = cub::BlockRadixSort<uint64_t, THREADS, ITEMS, int>;
+  auto kern = k_grid_level<THREADS, ITEMS>;
+  size_t smem = sizeof(typename Sort::TempStorage);
+  if (smem < (size_t)3 * THREADS * ITEMS * sizeof(int)) smem = (size_t)3 * THREADS * ITEMS * sizeof(int);
+  SE3_SMEM_ONCE(kern, smem);
+  kern<<<a.n_batches, THREADS, smem, st>>>(a);
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
+}
+
 template <int THREADS, int ITEMS, int KIND>
 static int launch_seg_build_cfg(const SegBuildArgs& a, cudaStream_t st) {
   using Sort = cub::BlockRadixSort<uint64_t, THREADS, ITEMS, int>;
@@ -690,35 +890,33 @@ int se3::grid_cells_impl(const float* pts, const int32_t* batch_ids, int64_t n, 
   return SE3_OK;
 }
 
-// grid of a cloud whose batch items fit a CTA, straight from the raw boxes: extents + keys + sort in one launch
-// (k_seg_build), then the unique / rank pass.  Also writes the padded box and the grid extents.
-int se3::grid_cells_fused(const float* pts, const int32_t* batch_ids, int64_t n, const float* raw_min, const float* raw_max,
-                          float cell, float* min_pt_out, float* max_pt_out, int32_t* num_cells_out, void* workspace,
-                          size_t workspace_bytes, int64_t* cell_ids, int64_t* sorted_ids, int32_t* cell_ends,
-                          int64_t* m_out, int32_t n_batches, int32_t max_seg, int32_t* batch_cells, se3_stream_t stream) {
+// One pooling level in one launch (k_grid_level): grid of (pts, batch) with voxel `cell` from the raw boxes, and the
+// pooled cloud with ITS raw boxes.  state: [n_batches] ints of scratch.  Capacity of the pooled arrays: n points.
+int se3::grid_level_fused(const float* pts, const int32_t* batch_ids, int64_t n, const float* raw_min, const float* raw_max,
+                          float cell, float* min_pt_out, float* max_pt_out, int32_t* num_cells_out, int64_t* cell_ids,
+                          int64_t* sorted_ids, int32_t* cell_ends, int64_t* m_out, int32_t n_batches, int32_t max_seg,
+                          int32_t* batch_cells, int32_t* state, float* pool_pts, int32_t* pool_batch, float* pool_min,
+                          float* pool_max, se3_stream_t stream) {
   SE3_CHECK_ARG(n >= 1 && n < (1ll << 31) && cell > 0.0f && seg_build_possible(n_batches, max_seg), "bad arguments");
   cudaStream_t st = as_stream(stream);
-  CellsWorkspace w;
-  if (!cells_layout(workspace, workspace_bytes, n, w)) {
-    set_error("grid_cells_fused: workspace too small");
-    return SE3_EWORKSPACE;
-  }
-  SegBuildArgs a;
+  SE3_CUDA(cudaMemsetAsync(state, 0, (size_t)n_batches * sizeof(int32_t), st));
+  GridLevelArgs a;
   a.pts = pts; a.batch = batch_ids; a.n = (int)n; a.n_batches = n_batches;
-  a.raw_min = raw_min; a.raw_max = raw_max; a.cell = cell; a.max_pad = 1e-6f;
-  a.keys_sorted = reinterpret_cast<uint64_t*>(w.keys_sorted); a.idx_sorted = w.idx_sorted; a.pts_sorted = nullptr;
-  a.mn_out = min_pt_out; a.mx_out = max_pt_out; a.nc_out = num_cells_out; a.mm_out = nullptr;
-  a.zero = batch_cells; a.n_zero = batch_cells ? n_batches : 0;
-  if (int rc = launch_seg_build(0, a, max_seg, st)) return rc;
-  k_cell_flags<<<grid_for(n, 256), 256, 0, st>>>(w.keys_sorted, n, w.flags);
-  SE3_LAUNCH_CHECK();
-  size_t cb = w.cub_bytes;
-  SE3_CUDA(cub::DeviceScan::InclusiveSum(w.cub_tmp, cb, w.flags, w.rank1, (int)n, st));
-  count_launch(1);
-  k_cell_ranks<<<grid_for(n, 256), 256, 0, st>>>(w.rank1, w.idx_sorted, n, cell_ids, sorted_ids, cell_ends, m_out,
-                                                 batch_ids, batch_cells);
-  SE3_LAUNCH_CHECK();
-  return SE3_OK;
+  a.raw_min = raw_min; a.raw_max = raw_max; a.cell = cell;
+  a.mn_out = min_pt_out; a.mx_out = max_pt_out; a.nc_out = num_cells_out;
+  a.cell_ids = cell_ids; a.sorted_ids = sorted_ids; a.cell_ends = cell_ends; a.m_out = m_out;
+  a.batch_cells = batch_cells; a.state = state;
+  a.pool_pts = pool_pts; a.pool_batch = pool_batch; a.pool_min = pool_min; a.pool_max = pool_max;
+#define SE3_GL_CASE(T, I) \
+  if (max_seg <= (T) * (I)) return launch_grid_level_cfg<T, I>(a, st)
+  SE3_GL_CASE(64, 4);
+  SE3_GL_CASE(128, 8);
+  SE3_GL_CASE(256, 8);
+  SE3_GL_CASE(512, 8);
+  SE3_GL_CASE(1024, 7);
+#undef SE3_GL_CASE
+  set_error("grid_level_fused: batch item too large");
+  return SE3_EINVAL;
 }
 
 // pts / rec (optional): also packs the gather records (p, R) of the kept frames (se3_pack_records layout)

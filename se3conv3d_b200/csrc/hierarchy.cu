@@ -193,21 +193,29 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
   // grid on (p, b, n) with voxel `cell` from the cloud's raw box; fills g.cell_ids / sorted_ids / cell_ends.
   // grid_launch issues the kernels and the read of (m, per-item sizes); grid_finish blocks on it.  Whatever the
   // host issues in between (the side-stream work of the previous cloud) overlaps the grid chain on the GPU.
+  bool level_fused = false;  // the last grid_launch also produced the pooled cloud and its raw boxes
   auto grid_launch = [&](const float* p, const int32_t* b, int64_t n, int raw_slot, float cell, se3_hier_cloud& g,
-                         int max_seg) -> int {
+                         int max_seg, se3_hier_cloud& dst, int dst_raw_slot) -> int {
     g.cell_ids = ar.take((size_t)n * 8);
     g.sorted_ids = ar.take((size_t)n * 8);
     g.cell_ends = ar.take((size_t)n * 4);
-    const size_t wsb = se3_grid_cells_workspace_bytes(n);
-    const int64_t o_ws = ar.take(wsb);
-    HB_CHECK_ARENA("grid");
-    if (n > 0 && seg_build_possible(d->n_batches, max_seg)) {
-      // every batch item fits a CTA: extents + keys + sort in one launch, straight from the raw boxes
-      HB_TRY(grid_cells_fused(p, b, n, ar.at<float>(o_rawmin[raw_slot]), ar.at<float>(o_rawmax[raw_slot]), cell, min_pt,
-                              max_pt, num_cells, ar.at<char>(o_ws), wsb, ar.at<int64_t>(g.cell_ids),
-                              ar.at<int64_t>(g.sorted_ids), ar.at<int32_t>(g.cell_ends), d_m, d->n_batches, max_seg,
-                              track_items ? d_items : nullptr, stream));
+    level_fused = n > 0 && seg_build_possible(d->n_batches, max_seg);
+    if (level_fused) {
+      // every batch item fits a CTA: the whole level (extents, keys, sort, ranks, pooled cloud, its boxes) is one
+      // launch; the pooled arrays are taken at their upper bound (the source size), their length is read below
+      dst.pts = ar.take((size_t)n * 12);
+      dst.batch = ar.take((size_t)n * 4);
+      const int64_t o_state = ar.take((size_t)d->n_batches * 4);
+      HB_CHECK_ARENA("grid");
+      HB_TRY(grid_level_fused(p, b, n, ar.at<float>(o_rawmin[raw_slot]), ar.at<float>(o_rawmax[raw_slot]), cell, min_pt,
+                              max_pt, num_cells, ar.at<int64_t>(g.cell_ids), ar.at<int64_t>(g.sorted_ids),
+                              ar.at<int32_t>(g.cell_ends), d_m, d->n_batches, max_seg, track_items ? d_items : nullptr,
+                              ar.at<int32_t>(o_state), ar.at<float>(dst.pts), ar.at<int32_t>(dst.batch),
+                              ar.at<float>(o_rawmin[dst_raw_slot]), ar.at<float>(o_rawmax[dst_raw_slot]), stream));
     } else {
+      const size_t wsb = se3_grid_cells_workspace_bytes(n);
+      const int64_t o_ws = ar.take(wsb);
+      HB_CHECK_ARENA("grid");
       HB_TRY(se3_grid_extents(ar.at<float>(o_rawmin[raw_slot]), ar.at<float>(o_rawmax[raw_slot]), d->n_batches, cell,
                               1e-6f, min_pt, max_pt, num_cells, stream));
       HB_TRY(grid_cells_impl(p, b, n, min_pt, num_cells, cell, ar.at<char>(o_ws), wsb, ar.at<int64_t>(g.cell_ids),
@@ -262,6 +270,7 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
   // cloud `dst` = grid-average pooling of (p, b) over grid g
   auto pool_cloud = [&](const float* p, const int32_t* b, int64_t n, const se3_hier_cloud& g, se3_hier_cloud& dst) -> int {
     dst.n = g.m;
+    if (level_fused) return SE3_OK;  // pooled by the level kernel
     dst.pts = ar.take((size_t)g.m * 12);
     dst.batch = ar.take((size_t)g.m * 4);
     HB_CHECK_ARENA("pooled cloud");
@@ -404,8 +413,8 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
     return SE3_OK;
   };
   // cloud c is complete on the caller's stream (points, batch ids): raw box + the event the side streams wait on
-  auto cloud_mark = [&](int c, int raw_slot) -> int {
-    HB_TRY(cloud_bbox(out->clouds[c], raw_slot, stream));
+  auto cloud_mark = [&](int c, int raw_slot, bool have_box) -> int {
+    if (!have_box) HB_TRY(cloud_bbox(out->clouds[c], raw_slot, stream));
     SE3_CUDA(cudaEventRecord(ln->cloud[c], st));
     return SE3_OK;
   };
@@ -421,19 +430,20 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
 
   // ---- level 0 and the output cloud share the raw cloud's init_cell grid
   out->raw.n = d->n;
-  HB_TRY(grid_launch(pts, batch_ids, d->n, 0, d->init_cell, out->raw, seg_raw));
+  HB_TRY(grid_launch(pts, batch_ids, d->n, 0, d->init_cell, out->raw, seg_raw, out->clouds[0], 1));
   HB_TRY(grid_finish(d->n, out->raw));
   cloud_seg[0] = seg_next;
   if (d->out_cloud) cloud_seg[d->n_pool + 1] = seg_next;  // one point per raw cell, like level 0
   HB_TRY(pool_cloud(pts, batch_ids, d->n, out->raw, out->clouds[0]));
-  HB_TRY(cloud_mark(0, 1));
+  HB_TRY(cloud_mark(0, 1, level_fused));
   // ---- pooled levels.  Order per level: launch the grid of cloud l, THEN issue cloud l's side work (the host is the
   // bottleneck of this build: its launches now overlap the grid chain on the GPU), then block on the grid size.
   for (int l = 0; l <= d->n_pool; ++l) {
     se3_hier_cloud& src = out->clouds[l];
     if (l < d->n_pool) {
       SE3_CHECK_ARG(d->cells[l] > 0.0f, "cell sizes must be positive");
-      HB_TRY(grid_launch(ar.at<float>(src.pts), ar.at<int32_t>(src.batch), src.n, 1 + l, d->cells[l], src, cloud_seg[l]));
+      HB_TRY(grid_launch(ar.at<float>(src.pts), ar.at<int32_t>(src.batch), src.n, 1 + l, d->cells[l], src, cloud_seg[l],
+                         out->clouds[l + 1], 2 + l));
     }
     HB_TRY(cloud_side(l));
     if (l == 0 && d->out_cloud) {
@@ -450,7 +460,7 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
                               ar.at<int64_t>(out->out_picked), stream));
       const int64_t u_keep = u_off;
       u_off = (int64_t)(d->n_pool + 1) * d->n;
-      HB_TRY(cloud_mark(d->n_pool + 1, d->n_pool + 2));
+      HB_TRY(cloud_mark(d->n_pool + 1, d->n_pool + 2, false));
       HB_TRY(cloud_side(d->n_pool + 1));
       u_off = u_keep;
     }
@@ -458,7 +468,7 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
       HB_TRY(grid_finish(src.n, src));
       cloud_seg[l + 1] = seg_next;
       HB_TRY(pool_cloud(ar.at<float>(src.pts), ar.at<int32_t>(src.batch), src.n, src, out->clouds[l + 1]));
-      HB_TRY(cloud_mark(l + 1, 2 + l));
+      HB_TRY(cloud_mark(l + 1, 2 + l, level_fused));
     }
   }
 
