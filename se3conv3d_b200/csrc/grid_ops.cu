@@ -1495,6 +1495,20 @@ __device__ __forceinline__ void t_rows_finish_body(const int* __restrict__ t_row
     if (len <= 0) continue;
     int* row = t_edge + lo;
     int* alt = t_dst + lo;
+    if (len <= 32) {
+      // the common case (a row is a neighbourhood): one entry per lane, rank = number of smaller entries (distinct
+      // edge ids), everything in registers
+      const int v = lane < len ? row[lane] : INT_MAX;
+      int rank = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) rank += __shfl_sync(0xffffffffu, v, j) < v ? 1 : 0;
+      __syncwarp();
+      if (lane < len) {
+        row[rank] = v;
+        alt[rank] = edge_dst[v];
+      }
+      continue;
+    }
     for (int c0 = 0; c0 < len; c0 += T_CHUNK) {
       const int cn = min(T_CHUNK, len - c0);
       int P = 32;
