@@ -1475,7 +1475,7 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
   SE3_LAUNCH_CHECK();
   if (dW) {
     // dW[(c,k), o] = s * sum_r T[r,(c,k)] dy[r,o]
-    // tcgen05 (MN-major operands) when c_out is a whole number of 64-column atoms, mma.sync otherwise
+    // tcgen05 (MN-major operands); SE3_DW_IMPL=m / SE3_GEMM_IMPL=mma select the mma.sync kernel
     static const bool dw_mma = getenv("SE3_DW_IMPL") && getenv("SE3_DW_IMPL")[0] == 'm';  // A/B aid
     if (!dw_mma && gemm_impl_env() != 1 && tcgen05_gemm_mn_supported(ck, d->c_out, R, ck, d->c_out)) {
       if (int rc = launch_gemm_tcgen05_mn(ck, d->c_out, R, d->out_scale, T, ck, dyb, d->c_out, dW, d->c_out, splits, dWp, st))

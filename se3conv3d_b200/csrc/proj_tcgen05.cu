@@ -549,7 +549,8 @@ int launch_gemm_tcgen05(int64_t m, int64_t n, int64_t k, float alpha, const __nv
 
 // C[M,N] = alpha * A^T B, A stored [K][M], B stored [K][N] (bf16, fp32 output): the weight gradient on tcgen05.
 bool tcgen05_gemm_mn_supported(int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb) {
-  return m >= 1 && k >= 1 && n >= 64 && (n % 64) == 0 && (m % 8) == 0 && (lda % 8) == 0 && (ldb % 8) == 0;
+  // N need not fill its last 64-column atom: the missing columns are zero-filled in shared memory and never stored
+  return m >= 1 && k >= 1 && n >= 8 && (n % 8) == 0 && (m % 8) == 0 && (lda % 8) == 0 && (ldb % 8) == 0;
 }
 int launch_gemm_tcgen05_mn(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16* a, int64_t lda,
                            const __nv_bfloat16* b, int64_t ldb, float* c, int64_t ldc, int splits, float* partials,
