@@ -198,8 +198,11 @@ def main():
         barrier()
         return shard.max_over_ranks(tot, dev)
 
+    # rank 0 samples its GPU's clocks / throttle reasons during the timed region (one nvidia-smi poller, not one per
+    # rank: eight pollers on one box contend with the launch-bound hierarchy builders for the driver)
     clocks = ClockSampler(local_rank)
-    clocks.start()
+    if rank == 0:
+        clocks.start()
     launches0 = _lib.launch_count()
     # (1) device-resident: hierarchy + neighbourhoods + conv stack fwd+bwd
     ms_total = timed(lambda: hot_step(pts_d, batch_d), args.steps, args.warmup)
@@ -214,7 +217,7 @@ def main():
     ms_e2e = timed(e2e_step, args.steps, max(args.warmup, 3))
     # (3) convolutions only (hierarchy cached), and the dominant layer alone for the roofline
     ms_conv = timed(lambda: step.conv_fwd_bwd(pcs, neighs), args.steps, args.warmup)
-    clk = clocks.stop()
+    clk = clocks.stop() if rank == 0 else None
 
     sizes = [(pcs[lo].pts_.shape[0], nb.conv_geometry(pcs[li], pcs[lo]).n_edges, 2, cin, cout)
              for (_, li, lo, _, cin, cout), nb in zip(step.specs, neighs)]
