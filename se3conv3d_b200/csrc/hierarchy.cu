@@ -6,6 +6,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <chrono>
+#include <mutex>
 #include "common.cuh"
 
 namespace se3 {
@@ -34,14 +35,6 @@ struct Bump {
 
 constexpr size_t kPinnedBytes = 65536;  // edge totals (<= 32 x 8 B) or the per-batch input boxes (B x 24 B)
 
-int64_t* pinned_scalars() {
-  static int64_t* p = nullptr;
-  if (!p) {
-    if (cudaHostAlloc(reinterpret_cast<void**>(&p), kPinnedBytes, cudaHostAllocDefault) != cudaSuccess) p = nullptr;
-  }
-  return p;
-}
-
 // Side streams of the builder: the pooling chain (grid -> pooled cloud -> next grid) is the critical path and stays
 // on the caller's stream; frames (kNN + PCA), ball-query sources, counts, fills and transposes of different clouds /
 // neighbourhoods are independent and fan out over kSide streams, ordered by events and joined back into the
@@ -49,6 +42,8 @@ int64_t* pinned_scalars() {
 constexpr int kSide = 4;
 struct Lanes {
   bool ready = false;
+  std::mutex mu;            // one build per device at a time: the streams, events and the host buffer are shared
+  int64_t* host = nullptr;  // pinned buffer of the blocking size reads (kPinnedBytes)
   cudaStream_t s[kSide];
   cudaEvent_t fork, join[kSide], cloud[SE3_HIER_MAX_CLOUDS + 1], frames[SE3_HIER_MAX_CLOUDS + 1], src[SE3_HIER_MAX_NEIGH];
 };
@@ -57,9 +52,12 @@ Lanes* lanes_for_device() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   Lanes& l = all[dev];
+  static std::mutex init_mu;
+  std::lock_guard<std::mutex> init_lock(init_mu);
   if (!l.ready) {
     auto ev = [](cudaEvent_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
     bool ok = ev(&l.fork);
+    ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&l.host), kPinnedBytes, cudaHostAllocDefault) == cudaSuccess;
     for (int i = 0; i < kSide; ++i) ok = ok && cudaStreamCreateWithFlags(&l.s[i], cudaStreamNonBlocking) == cudaSuccess && ev(&l.join[i]);
     for (int i = 0; i <= SE3_HIER_MAX_CLOUDS; ++i) ok = ok && ev(&l.cloud[i]) && ev(&l.frames[i]);
     for (int i = 0; i < SE3_HIER_MAX_NEIGH; ++i) ok = ok && ev(&l.src[i]);
@@ -111,11 +109,14 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
       fprintf(stderr, "[se3_hierarchy_build] %-28s %8.1f us\n", what,
               std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count());
   };
-  int64_t* host = pinned_scalars();
-  if (!host) {
-    set_error("se3_hierarchy_build: cannot allocate pinned host scalars");
+  // per-device side streams, events and the pinned buffer of the size reads (see Lanes)
+  Lanes* ln = lanes_for_device();
+  if (!ln) {
+    set_error("se3_hierarchy_build: cannot create the side streams / pinned host buffer");
     return SE3_ECUDA;
   }
+  std::lock_guard<std::mutex> build_lock(ln->mu);
+  int64_t* host = ln->host;
   memset(out, 0, sizeof(*out));
   Bump ar(arena, arena_bytes);
   const int n_cand = d->fixed_axis > 0 ? 2 : 4;
@@ -282,11 +283,6 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
   };
 
   // ---- side streams (see Lanes): fork from the caller's stream
-  Lanes* ln = lanes_for_device();
-  if (!ln) {
-    set_error("se3_hierarchy_build: cannot create the side streams");
-    return SE3_ECUDA;
-  }
   float h_rad[SE3_HIER_MAX_NEIGH * 4];
   for (int i = 0; i < d->n_neigh; ++i) {
     SE3_CHECK_ARG(d->neigh_src[i] >= 0 && d->neigh_src[i] < n_clouds && d->neigh_dst[i] >= 0 && d->neigh_dst[i] < n_clouds,
