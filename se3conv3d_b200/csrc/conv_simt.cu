@@ -254,6 +254,13 @@ __global__ void __launch_bounds__(128) k_edge_grad_f32(const EdgeGradArgs a) {
     for (int fr = 0; fr < a.f_out; ++fr) {
       const float* Fo = a.frm_out + (rp * a.f_out + fr) * 9;
       const float* dTrow = a.dT + (rp * a.f_out + fr) * (int64_t)a.c * 32;
+      // up to 32 channels: this lane's column of the dT tile lives in registers for the whole row
+      float dTr[32];
+      const bool small_c = a.c <= 32;
+      if (small_c) {
+#pragma unroll
+        for (int cc = 0; cc < 32; ++cc) dTr[cc] = cc < a.c ? __ldg(dTrow + cc * 32 + lane) : 0.0f;
+      }
       for (int e = lo; e < hi; ++e) {
         const int64_t q = a.col_src[e];
         const float dx = (__ldg(a.pts_in + 3 * q) - prx) * a.norm;
@@ -269,11 +276,17 @@ __global__ void __launch_bounds__(128) k_edge_grad_f32(const EdgeGradArgs a) {
             pre = fmaf(gd[d], wk[d], pre);
           }
           const float* xrow = a.x + (q * a.f_in + fg) * a.c;
-          for (int cc = lane; cc < a.c; cc += 32) xs[cc] = __ldg(xrow + cc);
-          __syncwarp();
           float dH = 0.0f;
-          for (int cc = 0; cc < a.c; ++cc) dH = fmaf(__ldg(dTrow + cc * 32 + lane), xs[cc], dH);
-          __syncwarp();
+          if (small_c) {
+            const float xv = lane < a.c ? __ldg(xrow + lane) : 0.0f;
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc) dH = fmaf(dTr[cc], __shfl_sync(0xffffffffu, xv, cc), dH);
+          } else {
+            for (int cc = lane; cc < a.c; cc += 32) xs[cc] = __ldg(xrow + cc);
+            __syncwarp();
+            for (int cc = 0; cc < a.c; ++cc) dH = fmaf(__ldg(dTrow + cc * 32 + lane), xs[cc], dH);
+            __syncwarp();
+          }
           const float dpre = dH * pne_act_grad(pre, a.act);
 #pragma unroll
           for (int d = 0; d < 9; ++d) acc9[d] = fmaf(gd[d], dpre, acc9[d]);
@@ -288,16 +301,26 @@ __global__ void __launch_bounds__(128) k_edge_grad_f32(const EdgeGradArgs a) {
   p[9 * 32 + lane] = accb;
 }
 
-__global__ void k_edge_grad_reduce(const float* __restrict__ partials, int n_partials, float* __restrict__ d_axes,
-                                   float* __restrict__ d_bias) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= 320) return;
+// Ordered reduction of the per-warp partials [n_partials][320]: block b owns outputs 32b..32b+31; warp w sums
+// partials w, w+32, ... (lane = output, coalesced 128-byte rows), then the 32 warp sums are added in warp order.
+__global__ void __launch_bounds__(1024) k_edge_grad_reduce(const float* __restrict__ partials, int n_partials,
+                                                           float* __restrict__ d_axes, float* __restrict__ d_bias) {
+  __shared__ float sm[32][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int t = blockIdx.x * 32 + lane;
   float s = 0.0f;
-  for (int p = 0; p < n_partials; ++p) s += partials[(int64_t)p * 320 + t];
-  if (t < 288) {
-    if (d_axes) d_axes[t] = s;
-  } else if (d_bias) {
-    d_bias[t - 288] = s;
+  for (int p = w; p < n_partials; p += 32) s += partials[(int64_t)p * 320 + t];
+  sm[w][lane] = s;
+  __syncthreads();
+  if (w == 0) {
+    float tot = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) tot += sm[i][lane];
+    if (t < 288) {
+      if (d_axes) d_axes[t] = tot;
+    } else if (d_bias) {
+      d_bias[t - 288] = tot;
+    }
   }
 }
 
@@ -314,7 +337,7 @@ int launch_edge_grad_f32(const EdgeGradArgs& a, float* d_axes, float* d_bias, cu
   const size_t smem = (size_t)4 * a.c * sizeof(float);
   k_edge_grad_f32<<<blocks, 128, smem, st>>>(a);
   SE3_LAUNCH_CHECK();
-  k_edge_grad_reduce<<<2, 160, 0, st>>>(a.partials, a.n_partials, d_axes, d_bias);
+  k_edge_grad_reduce<<<10, 1024, 0, st>>>(a.partials, a.n_partials, d_axes, d_bias);
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }
