@@ -30,20 +30,23 @@ __global__ void __launch_bounds__(128) k_aggregate_f32(const AggArgs a, const in
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t total = a.n_rows * ncb;
+  // one warp per (row point, row frame, 32-channel block)
+  const int per_row = ncb * a.f_row;
+  const int64_t total = a.n_rows * per_row;
   float wk[9];
 #pragma unroll
   for (int d = 0; d < 9; ++d) wk[d] = a.w9[d * 32 + lane];
   const float bk = a.bias[lane];
   int it = 0;
   for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += nwarps) {
-    const int64_t rp = w / ncb;
-    const int cb = (int)(w - rp * ncb);
+    const int64_t rp = w / per_row;
+    const int sub = (int)(w - rp * per_row);
+    const int fr = sub / ncb, cb = sub - fr * ncb;
     const int lo = rp > 0 ? a.row_ends[rp - 1] : 0;
     const int hi = a.row_ends[rp];
     const float prx = a.pts_row[3 * rp], pry = a.pts_row[3 * rp + 1], prz = a.pts_row[3 * rp + 2];
     const int ch = cb * 32 + lane;
-    for (int fr = 0; fr < a.f_row; ++fr) {
+    {
       const float* Frow = a.frm_row + (rp * a.f_row + fr) * 9;
       float acc[32];
 #pragma unroll
@@ -88,7 +91,7 @@ __global__ void __launch_bounds__(128) k_aggregate_f32(const AggArgs a, const in
 int launch_aggregate_f32(const AggArgs& a, bool transposed, cudaStream_t st) {
   if (a.n_rows == 0) return SE3_OK;
   const int ncb = (a.c + 31) / 32;
-  const int64_t warps = a.n_rows * ncb;
+  const int64_t warps = a.n_rows * ncb * a.f_row;
   int64_t blocks = (warps + 3) / 4;
   const int64_t cap = (int64_t)num_sms() * 64;
   if (blocks > cap) blocks = cap;
