@@ -521,6 +521,96 @@ def test_fused_hierarchy_objects_release_their_arena_without_gc():
         gc.enable()
 
 
+def test_fused_hierarchy_against_cpu_oracle():
+    """The fused builder against the C oracle directly (no GPU code on the reference side): the level-0 grid
+    (oracle keys -> unique -> dense ranks, cell means in sorted order), the kNN table behind the PCA frames is not
+    exposed, so frames are checked as candidates elsewhere; every ball-query CSR row by row."""
+    from se3conv3d_b200 import workloads as wl
+    pts, b = wl.synthetic_bodies(3, 1800, seed=7)
+    step = wl.DfaustStep(DEV, precision=1)
+    pcs, neighs = step.build_hierarchy(pts.to(DEV), b.to(DEV), fused=True, n_batches=3)
+    h = step.hierarchy
+    # level 0 = grid average of the raw cloud at 0.04 (pc/Grid.py:26-58, pc/GridSubSample.py:59-73)
+    p_np, b_np = pts.numpy(), b.numpy()
+    cell = np.float32(wl.DFAUST_CFG["init_subsample"])
+    mn = np.stack([p_np[b_np == i].min(0) for i in range(3)]).astype(np.float32) - np.float32(1e-6)
+    mx = np.stack([p_np[b_np == i].max(0) for i in range(3)]).astype(np.float32) + np.float32(1e-6)
+    nc = (((mx - mn) * (np.float32(1.0) / cell)).astype(np.int32) + 1).max(0).astype(np.int32)
+    keys = io.compute_keys(p_np, b_np, mn, nc, np.full(3, cell, np.float32))
+    uniq, inv = np.unique(keys, return_inverse=True)
+    assert np.array_equal(h.init_cell_ids_.cpu().numpy(), inv)
+    assert pcs[0].pts_.shape[0] == uniq.shape[0]
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(h.init_sorted_ids_.cpu().numpy(), order)
+    ends = np.cumsum(np.bincount(inv, minlength=uniq.shape[0]))
+    assert np.array_equal(h.init_cell_ends_.cpu().numpy(), ends)
+    means = np.zeros((uniq.shape[0], 3), np.float32)
+    lo_ = 0
+    for c, hi_ in enumerate(ends):                     # sequential fp32 sums in sorted order, then one division
+        acc = np.zeros(3, np.float32)
+        for i in order[lo_:hi_]:
+            acc = (acc + p_np[i]).astype(np.float32)
+        means[c] = acc / np.float32(hi_ - lo_)
+        lo_ = hi_
+    assert np.array_equal(pcs[0].pts_.cpu().numpy(), means)
+    assert np.array_equal(pcs[0].batch_ids_.cpu().numpy(), b_np[order[ends - 1]])
+    # every neighbourhood against the oracle ball query on the same clouds
+    for nb in {id(n): n for n in neighs}.values():
+        s_np, d_np = nb.pc_src_.pts_.cpu().numpy(), nb.samples_.pts_.cpu().numpy()
+        bs, bd = nb.pc_src_.batch_ids_.cpu().numpy(), nb.samples_.batch_ids_.cpu().numpy()
+        mn_q, nc_q = io.grid_setup_ball_query(s_np, bs, nb.radius_)
+        ref_nb, ref_ends = io.ball_query(s_np, d_np, bs, bd, mn_q, nc_q, np.full(3, nb.radius_, np.float32))
+        assert np.array_equal(nb.start_ids_.cpu().numpy(), ref_ends)
+        assert np.array_equal(io.canonical_rows(nb.neighbors_.cpu().numpy(), None), io.canonical_rows(ref_nb, None))
+
+
+def test_full_size_hierarchy_invariants():
+    """BASELINE config 2 at full size (32 x 6890 points): properties that do not need a reference -- the dense cell
+    ranks are consistent with the sorted order, pooled sizes chain, every CSR is grouped by sample with sources of
+    the same batch item inside the radius, same-level neighbourhoods are symmetric, and every transposed CSR is the
+    permutation of its forward CSR with rows in ascending edge order."""
+    from se3conv3d_b200 import workloads as wl
+    pts, b = wl.synthetic_bodies(32, 6890, seed=0)
+    step = wl.DfaustStep(DEV, precision=1)
+    pcs, neighs = step.build_hierarchy(pts.to(DEV), b.to(DEV), fused=True, n_batches=32)
+    h = step.hierarchy
+    sizes = [int(pc.pts_.shape[0]) for pc in pcs]
+    assert sizes[0] == sizes[5] and all(a > c for a, c in zip(sizes[:5], sizes[1:5]))
+    for lvl, samp in enumerate(h.sub_sampled_objs_):
+        g = samp.grid_
+        n, m = sizes[lvl], sizes[lvl + 1]
+        ids, srt, ends = g.cell_ids_, g.sorted_ids_, g.cell_ends_.to(torch.int64)
+        assert int(ids.max()) == m - 1 and int(ends[-1]) == n and bool((ends[1:] > ends[:-1]).all())
+        assert torch.equal(torch.sort(srt)[0], torch.arange(n, device=DEV))          # a permutation
+        ranks_sorted = ids[srt]
+        assert bool((ranks_sorted[1:] >= ranks_sorted[:-1]).all())                    # ranks ascend in sorted order
+        assert torch.equal(torch.bincount(ids, minlength=m).cumsum(0), ends)
+        assert bool((pcs[lvl + 1].batch_ids_[1:] >= pcs[lvl + 1].batch_ids_[:-1]).all())
+    for nb in {id(n): n for n in neighs}.values():
+        geom = list(nb.conv_geometry_cache_.values())[0]
+        e = geom.n_edges
+        pairs, ends = nb.neighbors_, nb.start_ids_.to(torch.int64)
+        assert int(ends[-1]) == e == pairs.shape[0] and bool((ends[1:] >= ends[:-1]).all())
+        assert bool((pairs[1:, 0] >= pairs[:-1, 0]).all())
+        src, dst = nb.pc_src_, nb.samples_
+        assert torch.equal(src.batch_ids_[pairs[:, 1]], dst.batch_ids_[pairs[:, 0]])
+        d = (src.pts_[pairs[:, 1]] - dst.pts_[pairs[:, 0]]).norm(dim=1)
+        assert float(d.max()) < nb.radius_ * (1 + 1e-5)
+        if src is dst:                                                                # symmetric relation
+            n = src.pts_.shape[0]
+            fwd = pairs[:, 0] * n + pairs[:, 1]
+            rev = pairs[:, 1] * n + pairs[:, 0]
+            assert torch.equal(torch.sort(fwd)[0], torch.sort(rev)[0])
+        t_edge, t_dst = geom.t_edge[:e].to(torch.int64), geom.t_dst[:e].to(torch.int64)
+        t_ends = geom.t_row_ends[:geom.n_in].to(torch.int64)
+        assert torch.equal(torch.sort(t_edge)[0], torch.arange(e, device=DEV))         # a permutation of the edges
+        assert torch.equal(t_dst, pairs[t_edge, 0]) and int(t_ends[-1]) == e
+        rows = torch.repeat_interleave(torch.arange(geom.n_in, device=DEV), torch.diff(t_ends, prepend=t_ends.new_zeros(1)))
+        assert torch.equal(rows, pairs[t_edge, 1])                                     # entry t belongs to row src(edge)
+        same_row = rows[1:] == rows[:-1]
+        assert bool((t_edge[1:][same_row] > t_edge[:-1][same_row]).all())              # ascending edge order per row
+
+
 def wl_grid_of(pcs, lvl, step):
     """Grid of level `lvl` -> `lvl + 1` rebuilt with the per-object API (for comparison)."""
     from se3conv3d_b200 import workloads as wl
