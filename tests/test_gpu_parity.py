@@ -611,6 +611,43 @@ def test_full_size_hierarchy_invariants():
         assert bool((t_edge[1:][same_row] > t_edge[:-1][same_row]).all())              # ascending edge order per row
 
 
+def test_conv_stack_full_size_deterministic_and_bf16_vs_fp32():
+    """BASELINE config 2 at full size: the 21 convolutions forward + backward twice on the same hierarchy give
+    bit-identical outputs and gradients (atomic-free backward, ordered reductions, dependent launches that wait for
+    their predecessor); the largest layer (seg_head, E ~ 775 k) agrees between the bf16 and the fp32 path."""
+    from se3conv3d_b200 import workloads as wl
+    pts, b = wl.synthetic_bodies(32, 6890, seed=0)
+    step = wl.DfaustStep(DEV, precision=1)
+    pcs, neighs = step.build_hierarchy(pts.to(DEV), b.to(DEV), fused=True, n_batches=32)
+    step.calibrate(pcs, neighs)
+    xs, dys = step.make_inputs(pcs)
+    runs = []
+    for _ in range(2):
+        step.zero_grad()
+        ys = [layer(pcs[li], pcs[lo], x, nb)
+              for layer, nb, (_, li, lo, _, _, _), x in zip(step.layers, neighs, step.specs, xs)]
+        torch.autograd.backward(ys, list(dys))
+        runs.append([y.detach().clone() for y in ys] + [x.grad.clone() for x in xs] +
+                    [p.grad.clone() for layer in step.layers for p in layer.parameters()])
+    for a, c in zip(*runs):
+        assert torch.equal(a, c)
+    i = [sp[0] for sp in step.specs].index("seg_head")
+    layer, nb, (_, li, lo, _, _, _) = step.layers[i], neighs[i], step.specs[i]
+    res = []
+    for precision in (1, 0):
+        layer.precision = precision
+        layer.zero_grad()
+        xx = xs[i].detach().clone().requires_grad_(True)
+        y = layer(pcs[li], pcs[lo], xx, nb)
+        y.backward(dys[i])
+        res.append([t.detach().cpu().numpy() for t in (y, xx.grad, layer.conv_weights_.grad, layer.proj_axes_.grad,
+                                                       layer.proj_biases_.grad)])
+    for a, c, name in zip(res[0], res[1], ("y", "dx", "dW", "dA", "dB")):
+        err = rel_err(a, c)
+        print("seg_head full size", name, "bf16 vs fp32 rel err %.2e" % err)
+        assert err < 3e-2, name
+
+
 def wl_grid_of(pcs, lvl, step):
     """Grid of level `lvl` -> `lvl + 1` rebuilt with the per-object API (for comparison)."""
     from se3conv3d_b200 import workloads as wl
