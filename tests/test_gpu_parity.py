@@ -655,7 +655,8 @@ def wl_grid_of(pcs, lvl, step):
     return Grid(pcs[lvl], wl.DFAUST_CFG["grid_subsamples"][lvl])
 
 
-@pytest.mark.parametrize("cin,cout,frames", [(64, 64, 2), (128, 32, 2), (1, 32, 2), (16, 48, 1), (48, 64, 1), (256, 128, 2)])
+@pytest.mark.parametrize("cin,cout,frames", [(64, 64, 2), (128, 32, 2), (1, 32, 2), (16, 48, 1), (48, 64, 1), (256, 128, 2),
+                                              (512, 64, 1), (320, 256, 2), (40, 8, 2)])
 def test_layer_bf16_matches_fp32_path_channel_sweep(cin, cout, frames):
     """Every channel-block configuration of the tensor-core kernels (16 / 32 / 64-channel row items, multi-block
     items, padded odd channel counts) against the fp32 exactness path on the same inputs: 3e-2 relative."""
