@@ -648,7 +648,7 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_EDGE_MIN_BLOCKS) k_edge_tc
         const int i = i0 + lane;
         const int c = i >> 2, part = i & 3;
         const bool ok = cb * CB + c < a.c;
-        cp_async16_ca(wbase_s + SM::OFF_T + buf * SM::T_BYTES + (c * TS + part * 8) * 2, dTrow + (ok ? c * 32 + part * 8 : 0), ok);
+        cp_async16(wbase_s + SM::OFF_T + buf * SM::T_BYTES + (c * TS + part * 8) * 2, dTrow + (ok ? c * 32 + part * 8 : 0), ok);
       }
       if (with_row && lane < 3)
         cp_async16_ca(wbase_s + SM::OFF_RS + rb * SM::RS_BYTES + lane * 16,
@@ -849,7 +849,7 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, CB >= 64 ? 2 : SE3_EDGE_MIN_BL
         const int i = i0 + lane;
         const int c = i >> 2, part = i & 3;
         const bool ok = c < a.c;
-        cp_async16_ca(wbase_s + SM::OFF_T + f * SM::T_BYTES + (c * TS + part * 8) * 2, dTrow + (ok ? c * 32 + part * 8 : 0), ok);
+        cp_async16(wbase_s + SM::OFF_T + f * SM::T_BYTES + (c * TS + part * 8) * 2, dTrow + (ok ? c * 32 + part * 8 : 0), ok);
       }
     };
 
