@@ -1097,10 +1097,11 @@ struct BqScanArgs {
 constexpr int BQ_BATCH = kBqBatch;  // queries per batched launch (kernel parameter space)
 struct BqScanBatch {
   BqScanArgs q[BQ_BATCH];
+  int blk[BQ_BATCH + 1];  // first block of every query; unused entries repeat the total
 };
 
 template <bool FILL>
-__device__ __forceinline__ void bq_scan_body(const BqScanArgs& a) {
+__device__ __forceinline__ void bq_scan_body(const BqScanArgs& a, int block, int nblocks) {
   const float* __restrict__ pts_dst = a.pts_dst;
   const int* __restrict__ batch_dst = a.batch_dst;
   const int64_t n_dst = a.n_dst;
@@ -1124,8 +1125,8 @@ __device__ __forceinline__ void bq_scan_body(const BqScanArgs& a) {
   // advanced per hit, so it ends as the inclusive row ends; t_edge receives the edge ids in arrival order
   // (k_t_rows_finish orders every row afterwards, so the result does not depend on the arrival order).
   const int lane = threadIdx.x & 31;
-  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t warp = (block * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)nblocks * blockDim.x) >> 5;
   const float irx = __fdiv_rn(1.0f, radius[0]), iry = __fdiv_rn(1.0f, radius[1]), irz = __fdiv_rn(1.0f, radius[2]);
   for (int64_t s = warp; s < n_dst; s += nwarps) {
     const float sx = pts_dst[3 * s], sy = pts_dst[3 * s + 1], sz = pts_dst[3 * s + 2];
@@ -1182,13 +1183,16 @@ __device__ __forceinline__ void bq_scan_body(const BqScanArgs& a) {
 
 template <bool FILL>
 __global__ void __launch_bounds__(256) k_bq_scan(const BqScanArgs a) {
-  bq_scan_body<FILL>(a);
+  bq_scan_body<FILL>(a, (int)blockIdx.x, (int)gridDim.x);
 }
-// several queries in one launch: blockIdx.y selects the query (the fused builder batches the neighbourhoods that
-// become possible together; a launch costs the host more than most of these queries cost the GPU)
+// several queries in one launch (the fused builder batches the neighbourhoods that become possible together; a
+// launch costs the host more than most of these queries cost the GPU): query q owns blocks [blk[q], blk[q + 1]) of
+// the 1-D grid, as many as it would get on its own
 template <bool FILL>
 __global__ void __launch_bounds__(256) k_bq_scan_multi(const BqScanBatch b) {
-  bq_scan_body<FILL>(b.q[blockIdx.y]);
+  int q = 0;
+  while (q + 1 < BQ_BATCH && (int)blockIdx.x >= b.blk[q + 1]) ++q;
+  bq_scan_body<FILL>(b.q[q], (int)blockIdx.x - b.blk[q], b.blk[q + 1] - b.blk[q]);
 }
 
 __global__ void k_bq_total(const int* __restrict__ row_ends, int64_t n_dst, int64_t* __restrict__ total) {
@@ -1480,15 +1484,16 @@ struct FinishJob {
 };
 struct FinishBatch {
   FinishJob j[BQ_BATCH];
+  int blk[BQ_BATCH + 1];
 };
 __device__ __forceinline__ void t_rows_finish_body(const int* __restrict__ t_row_ends, int64_t n_src,
                                                    int* __restrict__ t_edge, const int* __restrict__ edge_dst,
-                                                   int* __restrict__ t_dst) {
+                                                   int* __restrict__ t_dst, int block, int nblocks) {
   __shared__ int s_buf[T_WARPS][T_CHUNK];
   const int lane = threadIdx.x & 31;
   int* sb = s_buf[threadIdx.x >> 5];
-  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t warp = (block * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)nblocks * blockDim.x) >> 5;
   for (int64_t j = warp; j < n_src; j += nwarps) {
     const int lo = j > 0 ? t_row_ends[j - 1] : 0, hi = t_row_ends[j];
     const int len = hi - lo;
@@ -1551,11 +1556,13 @@ __device__ __forceinline__ void t_rows_finish_body(const int* __restrict__ t_row
 __global__ void __launch_bounds__(T_WARPS * 32) k_t_rows_finish(const int* __restrict__ t_row_ends, int64_t n_src,
                                                                 int* __restrict__ t_edge, const int* __restrict__ edge_dst,
                                                                 int* __restrict__ t_dst) {
-  t_rows_finish_body(t_row_ends, n_src, t_edge, edge_dst, t_dst);
+  t_rows_finish_body(t_row_ends, n_src, t_edge, edge_dst, t_dst, (int)blockIdx.x, (int)gridDim.x);
 }
 __global__ void __launch_bounds__(T_WARPS * 32) k_t_rows_finish_multi(const FinishBatch b) {
-  const FinishJob& j = b.j[blockIdx.y];
-  t_rows_finish_body(j.t_row_ends, j.n_src, j.t_edge, j.edge_dst, j.t_dst);
+  int q = 0;
+  while (q + 1 < BQ_BATCH && (int)blockIdx.x >= b.blk[q + 1]) ++q;
+  const FinishJob& j = b.j[q];
+  t_rows_finish_body(j.t_row_ends, j.n_src, j.t_edge, j.edge_dst, j.t_dst, (int)blockIdx.x - b.blk[q], b.blk[q + 1] - b.blk[q]);
 }
 
 namespace se3 {
@@ -1631,7 +1638,7 @@ int bq_count_transposed_batch(const BqBatchItem* it, int n, void* t_row_block, s
   if (t_row_block_bytes) SE3_CUDA(cudaMemsetAsync(t_row_block, 0, t_row_block_bytes, st));
   BqScanBatch qb;
   ScanBatch sb;
-  int nq = 0, blocks = 1;
+  int nq = 0, blocks = 0;
   for (int i = 0; i < n; ++i) {
     const BqBatchItem& q = it[i];
     SE3_CHECK_ARG(q.n_src >= 0 && q.n_dst >= 0 && q.n_src < (1ll << 31) && q.n_dst < (1ll << 31) && q.total_out, "bad sizes");
@@ -1649,12 +1656,13 @@ int bq_count_transposed_batch(const BqBatchItem* it, int n, void* t_row_block, s
                           w.pts_sorted, w.idx_sorted, w.ranges, w.counts, nullptr, nullptr, nullptr, nullptr, q.t_row, nullptr};
     sb.j[2 * nq] = ScanJob{w.counts, q.row_ends, (int)q.n_dst, 0, q.total_out};
     sb.j[2 * nq + 1] = ScanJob{q.t_row, q.t_row, (int)q.n_src, 1, nullptr};
-    const int bx = grid_for(q.n_dst * 32, 256);
-    if (bx > blocks) blocks = bx;
+    qb.blk[nq] = blocks;
+    blocks += grid_for(q.n_dst * 32, 256);
     ++nq;
   }
   if (nq == 0) return SE3_OK;
-  k_bq_scan_multi<false><<<dim3(blocks, nq), 256, 0, st>>>(qb);
+  for (int i = nq; i <= BQ_BATCH; ++i) qb.blk[i] = blocks;
+  k_bq_scan_multi<false><<<blocks, 256, 0, st>>>(qb);
   SE3_LAUNCH_CHECK();
   k_scan_multi<<<2 * nq, 1024, 0, st>>>(sb);
   SE3_LAUNCH_CHECK();
@@ -1666,7 +1674,7 @@ int bq_fill_transposed_batch(const BqBatchItem* it, int n, se3_stream_t stream) 
   cudaStream_t st = as_stream(stream);
   BqScanBatch qb;
   FinishBatch fb;
-  int nq = 0, blocks = 1, fblocks = 1;
+  int nq = 0, blocks = 0, fblocks = 0;
   for (int i = 0; i < n; ++i) {
     const BqBatchItem& q = it[i];
     if (q.n_edges == 0 || q.n_dst == 0 || q.n_src == 0) continue;  // t_row is all zero already
@@ -1678,15 +1686,20 @@ int bq_fill_transposed_batch(const BqBatchItem* it, int n, se3_stream_t stream) 
     qb.q[nq] = BqScanArgs{q.pts_dst, nullptr, q.n_dst, (int)q.n_src, nullptr, nullptr, q.radius, w.keys_sorted, w.pts_sorted,
                           w.idx_sorted, w.ranges, w.counts, q.row_ends, nullptr, q.col_src, q.edge_dst, q.t_row, q.t_edge};
     fb.j[nq] = FinishJob{q.t_row, q.n_src, q.t_edge, q.edge_dst, q.t_dst};
-    const int bx = grid_for(q.n_dst * 32, 256), fx = grid_for(q.n_src * 32, T_WARPS * 32);
-    if (bx > blocks) blocks = bx;
-    if (fx > fblocks) fblocks = fx;
+    qb.blk[nq] = blocks;
+    fb.blk[nq] = fblocks;
+    blocks += grid_for(q.n_dst * 32, 256);
+    fblocks += grid_for(q.n_src * 32, T_WARPS * 32);
     ++nq;
   }
   if (nq == 0) return SE3_OK;
-  k_bq_scan_multi<true><<<dim3(blocks, nq), 256, 0, st>>>(qb);
+  for (int i = nq; i <= BQ_BATCH; ++i) {
+    qb.blk[i] = blocks;
+    fb.blk[i] = fblocks;
+  }
+  k_bq_scan_multi<true><<<blocks, 256, 0, st>>>(qb);
   SE3_LAUNCH_CHECK();
-  k_t_rows_finish_multi<<<dim3(fblocks, nq), T_WARPS * 32, 0, st>>>(fb);
+  k_t_rows_finish_multi<<<fblocks, T_WARPS * 32, 0, st>>>(fb);
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }
