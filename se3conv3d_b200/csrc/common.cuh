@@ -44,8 +44,6 @@ int bq_fill_transposed(const float* pts_dst, int64_t n_src, int64_t n_dst, int64
                        void* ws_src, size_t ws_src_bytes, void* ws_dst, size_t ws_dst_bytes, const int32_t* row_ends,
                        int64_t n_edges, int32_t* col_src_out, int32_t* edge_dst_out, int32_t* t_row, int32_t* t_edge,
                        int32_t* t_dst, se3_stream_t stream);
-int frames_select_pack(const float* cand, const float* u, int64_t n, int32_t n_cand, int32_t n_keep, float* out,
-                       const float* pts, float* rec, se3_stream_t stream);
 bool seg_build_possible(int n_batches, int max_seg);
 int grid_level_fused(const float* pts, const int32_t* batch_ids, int64_t n, const float* raw_min, const float* raw_max,
                      float cell, float* min_pt_out, float* max_pt_out, int32_t* num_cells_out, int64_t* cell_ids,
@@ -82,6 +80,8 @@ int bq_fill_transposed_batch(const BqBatchItem* items, int n, se3_stream_t strea
 int knn_sorted_fused(const float* pts, const int32_t* batch_ids, int64_t n, const float* raw_min, const float* raw_max,
                      int* idx_sorted, void* pts_sorted_f4, float* minmax, int32_t n_batches, int32_t max_seg,
                      se3_stream_t stream);
+int pca_frames_select_pack(const float* pts, const int32_t* knn, int64_t n, int32_t k, int32_t fixed_axis, const float* u,
+                           int32_t n_keep, float* frames_out, float* rec_out, se3_stream_t stream);
 int knn_query_impl(const float* pts, const int32_t* batch_ids, int64_t n, int32_t k, void* workspace,
                    size_t workspace_bytes, int32_t* out, int32_t n_batches, int32_t max_seg, se3_stream_t stream,
                    const float* raw_min = nullptr, const float* raw_max = nullptr);

@@ -919,10 +919,8 @@ int se3::grid_level_fused(const float* pts, const int32_t* batch_ids, int64_t n,
   return SE3_EINVAL;
 }
 
-// pts / rec (optional): also packs the gather records (p, R) of the kept frames (se3_pack_records layout)
 __global__ void k_frames_select(const float* __restrict__ cand, const float* __restrict__ u, int64_t n, int n_cand,
-                                int n_keep, float* __restrict__ out, const float* __restrict__ pts,
-                                float4* __restrict__ rec) {
+                                int n_keep, float* __restrict__ out) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int perm[4] = {0, 1, 2, 3};
     if (u) {
@@ -940,15 +938,8 @@ __global__ void k_frames_select(const float* __restrict__ cand, const float* __r
     for (int f = 0; f < n_keep; ++f) {
       const float* src = cand + (i * n_cand + perm[f]) * 9;
       float* dst = out + (i * n_keep + f) * 9;
-      float fr[9];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) { fr[k] = src[k]; dst[k] = fr[k]; }
-      if (rec) {
-        float4* r = rec + 3 * (i * n_keep + f);
-        r[0] = make_float4(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], fr[0]);
-        r[1] = make_float4(fr[1], fr[2], fr[3], fr[4]);
-        r[2] = make_float4(fr[5], fr[6], fr[7], fr[8]);
-      }
+      for (int k = 0; k < 9; ++k) dst[k] = src[k];
     }
   }
 }
@@ -958,18 +949,7 @@ extern "C" int se3_frames_select(const float* cand, const float* u, int64_t n, i
   SE3_CHECK_ARG(n >= 0 && n_cand >= 1 && n_cand <= 4 && n_keep >= 1 && n_keep <= n_cand, "bad arguments");
   if (n == 0) return SE3_OK;
   SE3_CHECK_ARG(cand && out, "null pointer");
-  k_frames_select<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(cand, u, n, n_cand, n_keep, out, nullptr, nullptr);
-  SE3_LAUNCH_CHECK();
-  return SE3_OK;
-}
-
-int se3::frames_select_pack(const float* cand, const float* u, int64_t n, int32_t n_cand, int32_t n_keep, float* out,
-                            const float* pts, float* rec, se3_stream_t stream) {
-  SE3_CHECK_ARG(n >= 0 && n_cand >= 1 && n_cand <= 4 && n_keep >= 1 && n_keep <= n_cand, "bad arguments");
-  if (n == 0) return SE3_OK;
-  SE3_CHECK_ARG(cand && out && pts && rec && (reinterpret_cast<uintptr_t>(rec) & 15) == 0, "bad pointer");
-  k_frames_select<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(cand, u, n, n_cand, n_keep, out, pts,
-                                                                   reinterpret_cast<float4*>(rec));
+  k_frames_select<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(cand, u, n, n_cand, n_keep, out);
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }

@@ -254,7 +254,6 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
       return se3_pack_records(ar.at<float>(c.pts), ar.at<float>(c.frames), n, F, ar.at<float>(c.rec), s);
     }
     const int64_t o_knn = ar.take((size_t)n * d->knn_k * 4);
-    const int64_t o_cand = ar.take((size_t)n * n_cand * 36);
     const size_t wsb = se3_knn_workspace_bytes(n);
     const int64_t o_ws = ar.take(wsb);
     HB_CHECK_ARENA("frames");
@@ -262,9 +261,8 @@ extern "C" int se3_hierarchy_build(const se3_hier_desc* d, const float* pts, con
     HB_TRY(knn_query_impl(ar.at<float>(c.pts), ar.at<int32_t>(c.batch), n, d->knn_k, ar.at<char>(o_ws), wsb,
                           ar.at<int32_t>(o_knn), d->n_batches, max_seg, s, ar.at<float>(o_rawmin[raw_slot]),
                           ar.at<float>(o_rawmax[raw_slot])));
-    HB_TRY(se3_pca_frames(ar.at<float>(c.pts), ar.at<int32_t>(o_knn), n, d->knn_k, d->fixed_axis, ar.at<float>(o_cand), s));
-    HB_TRY(frames_select_pack(ar.at<float>(o_cand), u_frames + u_off, n, n_cand, F, ar.at<float>(c.frames),
-                              ar.at<float>(c.pts), ar.at<float>(c.rec), s));
+    HB_TRY(pca_frames_select_pack(ar.at<float>(c.pts), ar.at<int32_t>(o_knn), n, d->knn_k, d->fixed_axis, u_frames + u_off, F,
+                                  ar.at<float>(c.frames), ar.at<float>(c.rec), s));
     u_off += n;
     return SE3_OK;
   };

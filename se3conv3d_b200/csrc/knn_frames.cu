@@ -208,8 +208,11 @@ __device__ void jacobi3(double a[3][3], double v[3][3], double w[3]) {
   w[2] = a[2][2];
 }
 
+// sel_u / sel_frames / sel_rec (optional, fused hierarchy builder): instead of all candidates, write the n_keep
+// candidates a uniform variate selects (the permutation decode of k_frames_select) and their gather records
 __global__ void k_pca_frames(const float* __restrict__ pts, const int* __restrict__ knn, int64_t n, int k,
-                             int fixed_axis, float* __restrict__ frames) {
+                             int fixed_axis, float* __restrict__ frames, const float* __restrict__ sel_u, int n_keep,
+                             float* __restrict__ sel_frames, float4* __restrict__ sel_rec) {
   const bool fixed = fixed_axis > 0;  // `not axis_fixed` makes axis 0 behave as "none" (RotationFunctions.py:323)
   const int nf = fixed ? 2 : 4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -250,19 +253,43 @@ __global__ void k_pca_frames(const float* __restrict__ pts, const int* __restric
     // proper sign flips of the columns, in itertools.product([1,-1],repeat=3) order
     const float sg4[4][3] = {{1, 1, 1}, {1, -1, -1}, {-1, 1, -1}, {-1, -1, 1}};
     const float sg2[2][3] = {{1, 1, 1}, {-1, -1, 1}};
-    for (int f = 0; f < nf; ++f) {
+    int perm[4] = {0, 1, 2, 3};
+    if (sel_frames && sel_u) {
+      // one uniform variate -> a permutation of the nf candidates (Fisher-Yates), as k_frames_select
+      int total = 1;
+      for (int q = 2; q <= nf; ++q) total *= q;
+      int code = min((int)(sel_u[i] * (float)total), total - 1);
+      for (int q = 0; q < nf - 1; ++q) {
+        const int span = nf - q;
+        const int pick = q + code % span;
+        code /= span;
+        const int tmp = perm[q]; perm[q] = perm[pick]; perm[pick] = tmp;
+      }
+    }
+    const int n_out = sel_frames ? n_keep : nf;
+    for (int fo = 0; fo < n_out; ++fo) {
+      const int f = sel_frames ? perm[fo] : fo;
       float o[3][3];
       for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) o[r][c] = (float)m[r][c] * (fixed ? sg2[f][c] : sg4[f][c]);
-      float* dst = frames + (i * nf + f) * 9;
+      float fr[9];
       for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) {
           int cc = c;
           if (fixed && fixed_axis == 1) cc = (c == 0) ? 0 : (c == 1 ? 2 : 1);  // columns [0,2,1]
           float val = o[r][cc];
           if (fixed && fabsf(val) < 1e-6f) val = 0.0f;
-          dst[r * 3 + c] = val;
+          fr[r * 3 + c] = val;
         }
+      float* dst = sel_frames ? sel_frames + (i * n_keep + fo) * 9 : frames + (i * nf + fo) * 9;
+#pragma unroll
+      for (int q = 0; q < 9; ++q) dst[q] = fr[q];
+      if (sel_frames) {
+        float4* rc = sel_rec + 3 * (i * n_keep + fo);
+        rc[0] = make_float4(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], fr[0]);
+        rc[1] = make_float4(fr[1], fr[2], fr[3], fr[4]);
+        rc[2] = make_float4(fr[5], fr[6], fr[7], fr[8]);
+      }
     }
   }
 }
@@ -362,7 +389,21 @@ extern "C" int se3_pca_frames(const float* pts, const int32_t* knn, int64_t n, i
   SE3_CHECK_ARG(n >= 0 && k >= 1 && fixed_axis >= -1 && fixed_axis <= 2, "bad arguments");
   if (n == 0) return SE3_OK;
   SE3_CHECK_ARG(pts && knn && frames_out, "null pointer");
-  k_pca_frames<<<grid_for(n, 128), 128, 0, as_stream(stream)>>>(pts, knn, n, k, fixed_axis, frames_out);
+  k_pca_frames<<<grid_for(n, 128), 128, 0, as_stream(stream)>>>(pts, knn, n, k, fixed_axis, frames_out, nullptr, 0, nullptr,
+                                                                nullptr);
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
+}
+
+// PCA frames + candidate selection + gather records in one launch (fused hierarchy builder)
+int se3::pca_frames_select_pack(const float* pts, const int32_t* knn, int64_t n, int32_t k, int32_t fixed_axis,
+                                const float* u, int32_t n_keep, float* frames_out, float* rec_out, se3_stream_t stream) {
+  SE3_CHECK_ARG(n >= 0 && k >= 1 && fixed_axis >= -1 && fixed_axis <= 2 && n_keep >= 1 && n_keep <= (fixed_axis > 0 ? 2 : 4),
+                "bad arguments");
+  if (n == 0) return SE3_OK;
+  SE3_CHECK_ARG(pts && knn && frames_out && rec_out && (reinterpret_cast<uintptr_t>(rec_out) & 15) == 0, "bad pointer");
+  k_pca_frames<<<grid_for(n, 128), 128, 0, as_stream(stream)>>>(pts, knn, n, k, fixed_axis, nullptr, u, n_keep, frames_out,
+                                                                reinterpret_cast<float4*>(rec_out));
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }
