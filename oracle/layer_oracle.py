@@ -121,3 +121,59 @@ def standard_conv_forward(x, proj_axes, proj_biases, conv_weights, pts_in, pts_o
     T = torch.zeros((pts_out.shape[0], cin, k), dtype=x.dtype)
     T.index_add_(0, i, x[j][:, :, None] * h[:, None, :])
     return torch.einsum("nik,iko->no", T, conv_weights) * norm_num_neighs
+
+
+def act_grad_fn(name):
+    return {"mlp_linear": lambda t: torch.ones_like(t), "mlp_relu": lambda t: (t > 0).to(t.dtype),
+            "mlp_gelu": lambda t: 0.5 * (1.0 + torch.erf(t / math.sqrt(2.0))) +
+            t * torch.exp(-0.5 * t * t) / math.sqrt(2.0 * math.pi),
+            "mlp_sin": torch.cos}[name]
+
+
+def conv_forward_backward(x, proj_axes, proj_biases, conv_weights, pts_in, pts_out, frames_in, frames_out, neighbors,
+                          norm_neigh_dist, norm_num_neighs, dy, pne_type="mlp_gelu", chunk=1 << 13):
+    """y and the four gradients (dx, dW, dA, dB) of sum(y * dy), WITHOUT autograd: the same sums as conv_forward and
+    its autograd graph (layers/PNEConvLayerRotEquiv.py:199-216; backward of FeatBasisProj,
+    custom_ops/feature_aggregation/feat_basis_proj_grads.cu:100-145: dBasis[e,k] = sum_c dT[r,c,k] x[src,c],
+    dX[src,c] = sum_k dT[r,c,k] basis[e,k]), evaluated chunk by chunk so that BASELINE-size layers
+    (E*C of a few million pairs) fit in host memory.  tests/test_oracle.py pins it to conv_forward + autograd."""
+    fo, fi = frames_out.shape[1], frames_in.shape[1]
+    m = pts_out.shape[0]
+    cin, k, cout = conv_weights.shape
+    act, dact = act_fn(pne_type), act_grad_fn(pne_type)
+    s = norm_num_neighs / fi
+    T = torch.zeros((m * fo, cin, k), dtype=x.dtype)
+    for c0 in range(0, neighbors.shape[0], chunk):
+        g, rows, cols = rot_tensors(pts_in, pts_out, frames_in, frames_out, neighbors[c0:c0 + chunk], norm_neigh_dist)
+        h = act(g.reshape(-1, 9) @ proj_axes + proj_biases)
+        T.index_add_(0, rows.reshape(-1), x[cols.reshape(-1)][:, :, None] * h[:, None, :])
+    W2 = conv_weights.reshape(cin * k, cout)
+    y = (T.reshape(m * fo, cin * k) @ W2) * s
+    dW = (T.reshape(m * fo, cin * k).t() @ dy).reshape(cin, k, cout) * s
+    dT = ((dy @ W2.t()) * s).reshape(m * fo, cin, k)
+    del T
+    dx = torch.zeros_like(x)
+    dA = torch.zeros_like(proj_axes)
+    dB = torch.zeros_like(proj_biases)
+    for c0 in range(0, neighbors.shape[0], chunk):
+        g, rows, cols = rot_tensors(pts_in, pts_out, frames_in, frames_out, neighbors[c0:c0 + chunk], norm_neigh_dist)
+        g = g.reshape(-1, 9)
+        rows, cols = rows.reshape(-1), cols.reshape(-1)
+        pre = g @ proj_axes + proj_biases
+        dTr = dT[rows]                                             # [n, cin, k]
+        dx.index_add_(0, cols, torch.einsum("nck,nk->nc", dTr, act(pre)))
+        dpre = torch.einsum("nck,nc->nk", dTr, x[cols]) * dact(pre)
+        dA += g.t() @ dpre
+        dB += dpre.sum(0)
+    return y, dx, dW, dA, dB
+
+
+def err_metrics(got, ref):
+    """(max-abs error / max-abs value, ||err||_2 / ||ref||_2, 99.9th percentile of |err| / (|ref| + rms(ref)))
+    -- the second and third cannot hide behind one large entry."""
+    import numpy as np
+    a, b = np.asarray(got, np.float64).ravel(), np.asarray(ref, np.float64).ravel()
+    d = np.abs(a - b)
+    rms = max(float(np.sqrt(np.mean(b * b))), 1e-300)
+    return (float(d.max() / max(np.abs(b).max(), 1e-300)), float(np.sqrt((d * d).sum()) / max(np.sqrt((b * b).sum()), 1e-300)),
+            float(np.percentile(d / (np.abs(b) + rms), 99.9)))

@@ -31,14 +31,50 @@ class SubSample(ABC):
         return "### Ids:\n{}\n".format(self.ids_)
 
 
-def segment_pool(p_tensor, grid, mode):
-    """mean (mode 0) / max (mode 1) of float rows per grid cell through se3_segment_pool_f32."""
-    squeeze = p_tensor.dim() == 1
-    x = p_tensor.reshape(p_tensor.shape[0], -1).to(torch.float32).contiguous()
+def _segment_pool_raw(x, grid, mode):
     m = grid.num_used_cells_
     out = torch.empty((m, x.shape[1]), dtype=torch.float32, device=x.device)
     check(lib().se3_segment_pool_f32(ptr(x), x.shape[0], x.shape[1], ptr(grid.sorted_ids_), ptr(grid.cell_ends_), m,
                                      mode, ptr(out), stream()), "se3_segment_pool_f32")
+    return out
+
+
+class _SegmentPool(torch.autograd.Function):
+    """Differentiable cell pooling (the reference pools features with torch_scatter's scatter_mean / scatter_max,
+    pc/GridSubSample.py:69-72, which are differentiable): mean -> grad[cell] / count; max -> the gradient goes to one
+    arg-max row per (cell, channel), the first in point order."""
+
+    @staticmethod
+    def forward(ctx, x, grid, mode):
+        out = _segment_pool_raw(x, grid, mode)
+        ctx.grid, ctx.mode = grid, mode
+        if mode == 1:
+            ctx.save_for_backward(x, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        grid, ids = ctx.grid, ctx.grid.cell_ids_
+        if ctx.mode == 0:
+            ends = grid.cell_ends_.to(torch.int64)
+            counts = torch.diff(ends, prepend=ends.new_zeros(1)).to(grad.dtype).clamp_min(1)
+            return (grad / counts[:, None])[ids], None, None
+        x, out = ctx.saved_tensors
+        n, c = x.shape
+        row = torch.arange(n, device=x.device, dtype=torch.int64)[:, None].expand(n, c)
+        cand = torch.where(x == out[ids], row, torch.full_like(row, n))
+        win = torch.full((out.shape[0], c), n, dtype=torch.int64, device=x.device)
+        win.scatter_reduce_(0, ids[:, None].expand(n, c), cand, reduce="amin", include_self=True)
+        gx = torch.zeros((n + 1, c), dtype=grad.dtype, device=x.device)
+        gx.scatter_(0, win, grad)
+        return gx[:n], None, None
+
+
+def segment_pool(p_tensor, grid, mode):
+    """mean (mode 0) / max (mode 1) of float rows per grid cell through se3_segment_pool_f32 (differentiable)."""
+    squeeze = p_tensor.dim() == 1
+    x = p_tensor.reshape(p_tensor.shape[0], -1).to(torch.float32).contiguous()
+    out = _SegmentPool.apply(x, grid, mode) if x.requires_grad else _segment_pool_raw(x, grid, mode)
     return out[:, 0] if squeeze else out
 
 

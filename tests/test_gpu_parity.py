@@ -944,3 +944,25 @@ def test_layer_ragged_rows_and_empty_neighbourhoods(precision, tol):
     y0.backward(dy)
     assert float(y0.abs().max()) == 0.0 and float(x2.grad.abs().max()) == 0.0
     assert float(layer.conv_weights_.grad.abs().max()) == 0.0 and float(layer.proj_axes_.grad.abs().max()) == 0.0
+
+
+def test_segment_pool_is_differentiable():
+    """Grid pooling of a feature tensor that requires grad (the reference uses torch_scatter's scatter_mean /
+    scatter_max, pc/GridSubSample.py:69-72): values and gradients against index_add / scatter_reduce."""
+    from se3conv3d_b200.pc import Pointcloud, GridSubSample
+    pts, b = cloud(4000, 3, 21)
+    pc = Pointcloud(pts.to(DEV), b.to(DEV))
+    samp = GridSubSample(pc, 0.12)
+    ids, m = samp.grid_.cell_ids_, samp.grid_.num_used_cells_
+    feats = torch.randn(4000, 7, generator=torch.Generator().manual_seed(1)).to(DEV)
+    w = torch.randn(m, 7, generator=torch.Generator().manual_seed(2)).to(DEV)
+    for method, red in (("avg", "mean"), ("max", "amax")):
+        x = feats.clone().requires_grad_(True)
+        out = samp.__subsample_tensor__(x, method)
+        assert out.requires_grad
+        (out * w).sum().backward()
+        x2 = feats.clone().requires_grad_(True)
+        ref = torch.zeros(m, 7, device=DEV).scatter_reduce(0, ids[:, None].expand(-1, 7), x2, reduce=red, include_self=False)
+        (ref * w).sum().backward()
+        assert rel_err(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) < 1e-6
+        assert rel_err(x.grad.cpu().numpy(), x2.grad.cpu().numpy()) < 1e-6, method

@@ -1,0 +1,184 @@
+"""GPU parity at BASELINE sizes against the ORACLE (not against the CUDA path itself).
+
+* config 1 (8192 points, F=2, 32->64, r=0.1, E=258754) and the config-2 `seg_head` layer (M=42234 output points,
+  E~775k, 32->32, F=2): the fp32 exactness mode AND the bf16 tensor-core mode against oracle/layer_oracle.py in
+  float64 (conv_forward_backward: the chunked restatement pinned to conv_forward + autograd, which is pinned to
+  the reference's own Python through tests/golden/layer_*.npz) -- y, dx, dW, dA, dB.
+* three error figures per tensor (layer_oracle.err_metrics): max-abs error / max-abs value, ||err||_2 / ||ref||_2
+  and the 99.9th percentile of |err| / (|ref| + rms(ref)); the last two cannot hide behind one large entry.
+  Tolerances: fp32 mode <= 1e-4 on all three; bf16 mode (stated tolerance) <= 1e-2 max/max and relL2, <= 2e-2 on the
+  99.9th percentile (3.3 sigma of the bf16 rounding noise of the [K*Cin] tile).
+* fused-hierarchy frames against oracle PCA frames on the oracle kNN table (eigengap guard).
+* INTEGRATION Level 1: the reference's __compute_convolution__ flow (layers/PNEConvLayerRotEquiv.py:199-216) over
+  the reference's own get_rot_tenors output stored in the goldens, with FeatBasisProj bound to this package's
+  legacy op (se3_feat_basis_proj / _grad), replayed on the GPU against the reference's forward / backward.
+"""
+import math
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, LAYER_CASES
+from oracle import int_oracle as io
+from oracle import layer_oracle as lo
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+FP32_TOL = (1e-4, 1e-4, 1e-4)
+BF16_TOL = (1e-2, 1e-2, 2e-2)
+
+
+def _check(tag, got, ref, tol):
+    worst = 0.0
+    for name, a, b in zip(("y", "dx", "dW", "dA", "dB"), got, ref):
+        m = lo.err_metrics(a, b)
+        print("%s %-2s max/max %.2e  relL2 %.2e  p99.9 %.2e" % (tag, name, *m))
+        for v, t, what in zip(m, tol, ("max/max", "relL2", "p99.9")):
+            assert v < t, "%s %s %s = %.3e (tolerance %.1e)" % (tag, name, what, v, t)
+        worst = max(worst, max(m))
+    return worst
+
+
+def _oracle(layer, pc_in, pc_out, neighbors, x, dy):
+    c = lambda t: t.detach().cpu().double()
+    with torch.no_grad():
+        return lo.conv_forward_backward(c(x), c(layer.proj_axes_), c(layer.proj_biases_), c(layer.conv_weights_),
+                                        c(pc_in.pts_), c(pc_out.pts_), c(pc_in.local_frames_), c(pc_out.local_frames_),
+                                        neighbors.cpu(), float(layer.norm_neigh_dist_), float(layer.norm_num_neighs_),
+                                        c(dy))
+
+
+def _run(layer, pc_in, pc_out, neigh, x, dy, precision):
+    layer.precision = precision
+    layer.zero_grad()
+    xx = x.detach().clone().requires_grad_(True)
+    y = layer(pc_in, pc_out, xx, neigh)
+    y.backward(dy)
+    return [t.detach().cpu().numpy() for t in (y, xx.grad, layer.conv_weights_.grad, layer.proj_axes_.grad,
+                                               layer.proj_biases_.grad)]
+
+
+def test_config1_both_precisions_against_fp64_oracle():
+    """BASELINE configs[0]: one 8192-point cloud, F=2 PCA frames, 32->64, r=0.1."""
+    from se3conv3d_b200.layers import PNEConvLayerRotEquiv
+    from test_gpu_parity import _synthetic_layer_problem
+    pc, neigh, x = _synthetic_layer_problem(8192, 0.1, 2, 32, 64)
+    assert neigh.neighbors_.shape[0] == 258754
+    torch.manual_seed(2)
+    layer = PNEConvLayerRotEquiv(9, 32, 64, 32, "mlp_gelu").to(DEV)
+    with torch.no_grad():
+        layer.proj_biases_.copy_(0.1 * torch.randn(32))
+    layer.norm_neigh_dist_.fill_(10.0)
+    layer.norm_num_neighs_.fill_(8192 / 258754)
+    dy = torch.randn(8192 * 2, 64, generator=torch.Generator().manual_seed(5)).to(DEV) / 8.0
+    ref = [t.numpy() for t in _oracle(layer, pc, pc, neigh.neighbors_, x, dy)]
+    _check("config1 fp32", _run(layer, pc, pc, neigh, x, dy, 0), ref, FP32_TOL)
+    _check("config1 bf16", _run(layer, pc, pc, neigh, x, dy, 1), ref, BF16_TOL)
+
+
+def test_config2_seg_head_both_precisions_against_fp64_oracle():
+    """BASELINE configs[1], the largest layer of the dfaust FPN (seg_head: level 0 -> output cloud, 32->32, F=2,
+    M = 42234 rows points, E ~ 775 k) on the full 32 x 6890 hierarchy."""
+    from se3conv3d_b200 import workloads as wl
+    pts, b = wl.synthetic_bodies(32, 6890, seed=0)
+    step = wl.DfaustStep(DEV, precision=1)
+    pcs, neighs = step.build_hierarchy(pts.to(DEV), b.to(DEV), fused=True, n_batches=32)
+    step.calibrate(pcs, neighs)
+    xs, dys = step.make_inputs(pcs)
+    i = [sp[0] for sp in step.specs].index("seg_head")
+    layer, nb, (_, li, lo_, _, _, _) = step.layers[i], neighs[i], step.specs[i]
+    with torch.no_grad():
+        layer.proj_biases_.copy_(0.1 * torch.randn(32))
+    assert nb.neighbors_.shape[0] > 700000 and pcs[lo_].pts_.shape[0] > 40000
+    ref = [t.numpy() for t in _oracle(layer, pcs[li], pcs[lo_], nb.neighbors_, xs[i], dys[i])]
+    _check("seg_head fp32", _run(layer, pcs[li], pcs[lo_], nb, xs[i], dys[i], 0), ref, FP32_TOL)
+    _check("seg_head bf16", _run(layer, pcs[li], pcs[lo_], nb, xs[i], dys[i], 1), ref, BF16_TOL)
+
+
+@pytest.mark.parametrize("name", ["enc1_block0", "enc2_down", "dec0", "patch_enc0"])
+def test_config2_other_layers_bf16_against_fp64_oracle(name):
+    """Wider / cross-level / single-channel layers of the same FPN (64->64 on level 2, 128->256 level 3->4,
+    256->128 level 4->3, 1->32 level 0->1) on an 8-cloud hierarchy: bf16 mode against the fp64 oracle."""
+    from se3conv3d_b200 import workloads as wl
+    pts, b = wl.synthetic_bodies(8, 6890, seed=1)
+    step = wl.DfaustStep(DEV, precision=1)
+    pcs, neighs = step.build_hierarchy(pts.to(DEV), b.to(DEV), fused=True, n_batches=8)
+    step.calibrate(pcs, neighs)
+    xs, dys = step.make_inputs(pcs)
+    i = [sp[0] for sp in step.specs].index(name)
+    layer, nb, (_, li, lo_, _, _, _) = step.layers[i], neighs[i], step.specs[i]
+    ref = [t.numpy() for t in _oracle(layer, pcs[li], pcs[lo_], nb.neighbors_, xs[i], dys[i])]
+    _check(name + " fp32", _run(layer, pcs[li], pcs[lo_], nb, xs[i], dys[i], 0), ref, FP32_TOL)
+    _check(name + " bf16", _run(layer, pcs[li], pcs[lo_], nb, xs[i], dys[i], 1), ref, BF16_TOL)
+
+
+def test_fused_hierarchy_frames_against_oracle_pca():
+    """Frames of every level of the fused builder against oracle PCA frames (layer_oracle.pca_frames, float64) on the
+    ORACLE's kNN table (int_oracle.knn_query): each kept frame must be one of the four sign candidates, and the two
+    kept frames must be different candidates.  Points whose covariance has a small eigengap (eigenvectors
+    ill-conditioned) or whose k-th / (k+1)-th neighbour distances tie (kNN set ambiguous) are excluded and counted."""
+    from se3conv3d_b200 import workloads as wl
+    pts, b = wl.synthetic_bodies(3, 2500, seed=11)
+    step = wl.DfaustStep(DEV, precision=1)
+    pcs, _ = step.build_hierarchy(pts.to(DEV), b.to(DEV), fused=True, n_batches=3)
+    checked = 0
+    for lvl in range(5):
+        pc = pcs[lvl]
+        P, B = pc.pts_.cpu().numpy(), pc.batch_ids_.cpu().numpy().astype(np.int32)
+        n = P.shape[0]
+        k = 16
+        idx, dist = io.knn_query(P, B, k + 1) if n > k + 1 else (None, None)
+        if idx is None:
+            continue
+        knn = torch.from_numpy(idx[:, :k].astype(np.int64))
+        P64 = torch.from_numpy(P).double()
+        cand = lo.pca_frames(P64, knn)                                        # [n,4,9]
+        # guards
+        ii = torch.where(knn < 0, torch.arange(n)[:, None].expand(n, k), knn)
+        X = P64[ii]
+        Xc = X - X.mean(1, keepdim=True)
+        ev = torch.linalg.eigvalsh(Xc.transpose(1, 2) @ Xc)
+        gap = torch.minimum(ev[:, 1] - ev[:, 0], ev[:, 2] - ev[:, 1]) / ev[:, 2].clamp_min(1e-30)
+        full = torch.from_numpy((idx >= 0).all(1))
+        tie = torch.from_numpy(np.abs(dist[:, k] - dist[:, k - 1]) <= 1e-6 * np.maximum(dist[:, k], 1e-12))
+        ok = (gap > 2e-2) & full & ~tie
+        fr = pc.local_frames_.cpu().double()                                   # [n,2,9]
+        d = (fr[:, :, None, :] - cand[:, None, :, :]).abs().amax(-1)           # [n,2,4]
+        best, which = d.min(-1)
+        assert float(best[ok].max()) < 2e-3, "level %d: frame is not a PCA candidate (%.2e)" % (lvl, float(best[ok].max()))
+        assert bool((which[ok][:, 0] != which[ok][:, 1]).all())
+        checked += int(ok.sum())
+        print("level %d: %d / %d points checked, worst distance to a candidate %.2e" % (lvl, int(ok.sum()), n,
+                                                                                        float(best[ok].max())))
+    assert checked > 2000
+
+
+@pytest.mark.parametrize("case", LAYER_CASES)
+def test_level1_reference_layer_flow_over_legacy_ops(case):
+    """INTEGRATION.md Level 1 on the GPU: the statement sequence of the reference's __compute_convolution__
+    (layers/PNEConvLayerRotEquiv.py:199-216) over the rot tensors the REFERENCE's get_rot_tenors produced (stored in
+    the golden), with `FeatBasisProj` bound to this package's legacy op; forward and all gradients against the
+    reference's own float64 run."""
+    from se3conv3d_b200.custom_ops import FeatBasisProj
+    g = dict(np.load(os.path.join(GOLDEN, "layer_%s.npz" % case)))
+    t = lambda k: torch.from_numpy(g[k]).to(DEV)
+    fi = g["frames_in"].shape[1]
+    geo = torch.from_numpy(g["g_sorted"]).float().to(DEV)                      # rel_pts_rel_orient [E*C, 9]
+    nbe = torch.from_numpy(g["nb_expanded"]).to(DEV)                           # neighbs [E*C, 2] int64
+    ends = torch.from_numpy(g["ends_expanded"]).to(DEV)                        # neighbs_start_ids
+    A, B, W = (t(k).clone().requires_grad_(True) for k in ("proj_axes", "proj_biases", "conv_weights"))
+    x = t("x").clone().requires_grad_(True)
+    act = {"mlp_gelu": torch.nn.GELU(), "mlp_relu": torch.nn.ReLU()}[str(g["pne"])]
+    pt_pne = torch.matmul(geo, A) + B.reshape(1, -1)                           # :199
+    pt_pne = act(pt_pne)                                                       # :202-203
+    w_feat = FeatBasisProj.apply(pt_pne, x, nbe, ends)                         # :206-207 (our op underneath)
+    y = torch.einsum("nik,iko->no", w_feat, W)                                 # :210
+    y = y / fi                                                                 # :213
+    y = y * float(g["norm_num_neighs"])                                        # :216
+    (y * t("dy")).sum().backward()
+    got = [v.detach().cpu().numpy() for v in (y, x.grad, W.grad, A.grad, B.grad)]
+    ref = [g[k + "_f64"] for k in ("y", "dx", "dW", "dA", "dB")]
+    _check("level1 " + case, got, ref, FP32_TOL)

@@ -127,3 +127,18 @@ def test_int_oracle_keys_and_knn():
     sb = np.concatenate([np.zeros(5, np.int32), np.ones(400, np.int32)])
     idx2, _ = io.knn_query(small, sb, k)
     assert np.all(idx2[:5, 5:] == -1) and np.all(idx2[:5, :5] >= 0)
+
+
+@pytest.mark.parametrize("case", LAYER_CASES)
+def test_chunked_forward_backward_matches_reference(case):
+    """conv_forward_backward (the no-autograd, chunked restatement used at BASELINE sizes) against the reference's
+    own float64 forward / backward, with a chunk size that splits the edge list."""
+    g = load("layer_%s.npz" % case)
+    t = lambda k: torch.from_numpy(g[k]).double()
+    out = lo.conv_forward_backward(t("x"), t("proj_axes"), t("proj_biases"), t("conv_weights"), t("pts_in"), t("pts_out"),
+                                   t("frames_in"), t("frames_out"), torch.from_numpy(g["neighbors"]),
+                                   float(g["norm_neigh_dist"]), float(g["norm_num_neighs"]), t("dy"), str(g["pne"]),
+                                   chunk=97)
+    for got, key in zip(out, ("y", "dx", "dW", "dA", "dB")):
+        np.testing.assert_allclose(got.numpy(), g[key + "_f64"], rtol=1e-9, atol=1e-10, err_msg=key)
+        assert max(lo.err_metrics(got.numpy(), g[key + "_f64"])) < 1e-9
