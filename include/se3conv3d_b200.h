@@ -324,6 +324,14 @@ int se3_conv_bwd(const se3_conv_desc* d, const float* x, const float* dy, const 
                  float* dx, float* d_conv_weights, float* d_proj_axes, float* d_proj_biases,
                  void* workspace, size_t workspace_bytes, se3_stream_t stream);
 
+/* Kernel selection of precision 1 for layers with 9..64 gathered channels and 1..2 row frames:
+ *   0 (default) aggregation kernel (mma.sync) + projection GEMM (tcgen05), T [R, Cin*K] through HBM;
+ *   1 warp-specialised tcgen05 aggregation kernel (conv_fused.cu) + projection GEMM;
+ *   2 aggregation AND projection in the fused tcgen05 kernel when the projection weights fit in shared memory (T stays
+ *     on chip; a bf16 copy is still written for the weight gradient).
+ * Returns the previous mode.  Byte counts of a descriptor (se3_conv_*_bytes) depend on the mode: query them after. */
+int se3_conv_set_fused(int32_t mode);
+
 /* The projection GEMM on its own: C[M,N] = alpha * A[M,K] . B[N,K]^T, bf16 operands stored K-major
  * (row-major [rows][K]), fp32 accumulation, C fp32 or bf16 row-major.  This is the [K*Cin] x Cout
  * contraction of the layer (layers/PNEConvLayerRotEquiv.py:210) and its data-gradient twins.

@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "se3_segment_pool_f32",
     "se3_feat_basis_proj", "se3_feat_basis_proj_grad",
     "se3_conv_fwd_workspace_bytes", "se3_conv_bwd_workspace_bytes", "se3_conv_saved_bytes",
-    "se3_conv_fwd", "se3_conv_bwd", "se3_gemm_bf16_tn", "se3_pack_records",
+    "se3_conv_fwd", "se3_conv_bwd", "se3_gemm_bf16_tn", "se3_pack_records", "se3_conv_set_fused",
     "se3_ball_query_fill_csr", "se3_csr_transpose_i32", "se3_segment_first_i32", "se3_segment_pick",
     "se3_hierarchy_build", "se3_bbox", "se3_grid_extents", "se3_ball_query_src_workspace_bytes",
     "se3_ball_query_dst_workspace_bytes", "se3_ball_query_prepare", "se3_ball_query_count_prepared",
@@ -140,6 +140,7 @@ def lib():
         getattr(L, n).argtypes = [dp]
         getattr(L, n).restype = sz
     L.se3_conv_fwd.argtypes = [dp, vp, vp, vp, vp, sz, vp]
+    L.se3_conv_set_fused.argtypes = [i32]
     L.se3_gemm_bf16_tn.argtypes = [vp, vp, i64, i64, i64, f32, vp, i32, i32, vp]
     L.se3_pack_records.argtypes = [vp, vp, i64, i32, vp, vp]
     L.se3_ball_query_fill_csr.argtypes = [vp, i64, i64, vp, vp, sz, vp, i64, vp, vp, vp]
@@ -254,6 +255,13 @@ def profile_kernels(fn, reps=1):
         L.se3_profile_enable(0)
     check(L.se3_profile_read(ms, cnt), "se3_profile_read")
     return [(PROF_KERNELS[i], (ms[i] / cnt[i]) if cnt[i] else 0.0, int(cnt[i])) for i in range(3)]
+
+
+def set_fused_mode(mode):
+    """Selects the precision-1 kernel family (see se3_conv_set_fused in the header); returns the previous mode.
+    Cached descriptor byte counts belong to the mode they were computed under: geometry objects created before
+    the switch must drop their `_desc_cache`."""
+    return int(lib().se3_conv_set_fused(int(mode)))
 
 
 def launch_count():

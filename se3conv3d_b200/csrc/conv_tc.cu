@@ -18,6 +18,7 @@
 #include <stdlib.h>
 #include <algorithm>
 #include "conv_simt.cuh"
+#include "conv_fused.cuh"
 #include "tc_common.cuh"
 
 namespace se3 {
@@ -1345,6 +1346,19 @@ __global__ void __launch_bounds__(256) k_fwd_prep(const float* __restrict__ w, i
   }
 }
 
+// dW[c][k][o] = dWkc[(k * cp + c)][o]: the weight gradient of a fused forward comes out in the (k, padded c) order of
+// the saved tile
+__global__ void k_dw_from_kc(const float* __restrict__ src, int c_in, int c_out, int cp, float* __restrict__ dw) {
+  pdl_wait();
+  const int64_t total = (int64_t)c_in * 32 * c_out;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int o = (int)(i % c_out);
+    const int k = (int)((i / c_out) & 31);
+    const int c = (int)(i / ((int64_t)32 * c_out));
+    dw[i] = src[((int64_t)k * cp + c) * c_out + o];
+  }
+}
+
 static inline int blocks_for(int64_t n) {
   int64_t b = (n + 255) / 256;
   const int64_t cap = (int64_t)num_sms() * 16;
@@ -1388,12 +1402,28 @@ struct TcSaved {
   __nv_bfloat16 *T, *xb, *Wt, *Wb, *Wp;
   size_t bytes;
 };
+// forward through the fused tcgen05 kernel (conv_fused.cu)?  Then the saved tile is [R][32 * CP] in (k,c) order.
+// 2 = aggregation and projection in the fused kernel, 1 = fused aggregation + stand-alone GEMM, 0 = k_agg_tc + GEMM
+static int fwd_fused(const se3_conv_desc* d) {
+  if (fused_supported(d->c_in, d->c_out, d->f_out, d->f_in, true)) return 2;
+  return fused_supported(d->c_in, d->c_out, d->f_out, d->f_in, false) ? 1 : 0;
+}
+static int dx_fused(const se3_conv_desc* d) {
+  if (fused_supported(d->c_out, d->c_in, d->f_in, d->f_out, true)) return 2;
+  return fused_supported(d->c_out, d->c_in, d->f_in, d->f_out, false) ? 1 : 0;
+}
+static int64_t saved_tile_cols(const se3_conv_desc* d) {
+  return fwd_fused(d) ? (int64_t)32 * fused_cp(d->c_in) : (int64_t)d->c_in * d->k;
+}
+static int64_t u_tile_cols(const se3_conv_desc* d) {
+  return dx_fused(d) ? (int64_t)32 * fused_cp(d->c_out) : (int64_t)d->c_out * d->k;
+}
 static TcSaved tc_saved_layout(const se3_conv_desc* d, void* base) {
   const size_t wbytes = align_up((size_t)d->c_in * d->k * d->c_out * 2);
   char* p = reinterpret_cast<char*>(base);
   size_t off = 0;
   TcSaved s;
-  s.T = reinterpret_cast<__nv_bfloat16*>(p + off); off += align_up((size_t)d->n_out * d->f_out * d->c_in * d->k * 2);
+  s.T = reinterpret_cast<__nv_bfloat16*>(p + off); off += align_up((size_t)d->n_out * d->f_out * saved_tile_cols(d) * 2);
   s.xb = reinterpret_cast<__nv_bfloat16*>(p + off); off += align_up((size_t)d->n_in * d->f_in * pad8(d->c_in) * 2);
   s.Wt = reinterpret_cast<__nv_bfloat16*>(p + off); off += wbytes;
   s.Wb = reinterpret_cast<__nv_bfloat16*>(p + off); off += wbytes;
@@ -1403,6 +1433,10 @@ static TcSaved tc_saved_layout(const se3_conv_desc* d, void* base) {
 }
 size_t conv_tc_saved_bytes(const se3_conv_desc* d) { return tc_saved_layout(d, nullptr).bytes; }
 size_t conv_tc_fwd_workspace_bytes(const se3_conv_desc* d) {
+  if (fwd_fused(d) == 2) return align_up(fused_w3_bytes(d->c_in, d->c_out)) + 256;
+  if (fwd_fused(d) == 1)
+    return align_up((size_t)d->c_out * saved_tile_cols(d) * 2) +
+           gemm_tn_partial_bytes(d->n_out * d->f_out, d->c_out, saved_tile_cols(d)) + 256;
   return gemm_tn_partial_bytes(d->n_out * d->f_out, d->c_out, (int64_t)d->c_in * d->k) + 256;
 }
 size_t conv_tc_bwd_workspace_bytes(const se3_conv_desc* d) {
@@ -1410,10 +1444,16 @@ size_t conv_tc_bwd_workspace_bytes(const se3_conv_desc* d) {
   size_t b = 0;
   b += align_up((size_t)R * d->c_out * 2);                                        // dy bf16
   b += align_up((size_t)R * ck * 2);                                              // dT bf16
-  b += align_up((size_t)Nf * d->c_out * d->k * 2);                                // U bf16
-  b += align_up((size_t)splits_for_tc(ck, d->c_out, R) * ck * d->c_out * 4);      // dW partials
+  b += dx_fused(d) == 2 ? 0 : align_up((size_t)Nf * u_tile_cols(d) * 2);         // U bf16
+  {
+    const int64_t tc = saved_tile_cols(d);                                        // dW partials (+ the (k,c)-ordered result)
+    b += align_up((size_t)splits_for_tc(tc, d->c_out, R) * tc * d->c_out * 4);
+    if (fwd_fused(d)) b += align_up((size_t)tc * d->c_out * 4);
+  }
+  if (dx_fused(d) == 2) b += align_up(fused_w3_bytes(d->c_out, d->c_in));        // transposed projection weights
+  if (dx_fused(d) == 1) b += align_up((size_t)d->c_in * u_tile_cols(d) * 2);      // ... as a plain (k,o)-ordered matrix
   b += align_up((size_t)edge_tc_warps(d->n_out * d->f_out, d->c_in, d->f_out) * 512 * 4);                       // basis-gradient partials
-  b += gemm_tn_partial_bytes(Nf, d->c_in, (int64_t)d->c_out * d->k);                         // dx split-K partials
+  b += gemm_tn_partial_bytes(Nf, d->c_in, u_tile_cols(d));                                   // dx split-K partials
   return b + 256;
 }
 
@@ -1422,12 +1462,15 @@ int conv_tc_fwd(const se3_conv_desc* d, const float* x, float* y, void* saved, v
   if (int rc = check_tc(d)) return rc;
   SE3_CHECK_ARG(saved, "precision 1 needs the saved buffer");
   const int64_t R = d->n_out * d->f_out, ck = (int64_t)d->c_in * d->k;
-  const size_t pbytes = gemm_tn_partial_bytes(R, d->c_out, ck);
-  if (pbytes && (!ws || ws_bytes < pbytes)) {
+  const int fmode = fwd_fused(d);
+  const int64_t tcols = saved_tile_cols(d);
+  const size_t wkc_bytes = fmode == 1 ? align_up((size_t)d->c_out * tcols * 2) : 0;
+  const size_t pbytes = fmode == 2 ? 0 : gemm_tn_partial_bytes(R, d->c_out, fmode ? tcols : ck);
+  if ((pbytes || wkc_bytes) && (!ws || ws_bytes < pbytes + wkc_bytes)) {
     set_error("conv_tc_fwd: workspace too small");
     return SE3_EWORKSPACE;
   }
-  float* partials = pbytes ? reinterpret_cast<float*>(ws) : nullptr;
+  float* partials = pbytes ? reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + wkc_bytes) : nullptr;
   const TcSaved sv = tc_saved_layout(d, saved);
   const int cs = pad8(d->c_in);
   const int64_t Nf = d->n_in * d->f_in;
@@ -1440,6 +1483,26 @@ int conv_tc_fwd(const se3_conv_desc* d, const float* x, float* y, void* saved, v
     SE3_CUDA(launch_pdl(k_fwd_prep, dim3(w_blocks + x_blocks), dim3(256), smem, st, d->conv_weights, d->c_in, d->k, d->c_out,
                         o_chunks, sv.Wt, sv.Wb, sv.Wp, w_blocks, x, Nf, d->c_in, cs, sv.xb));
     SE3_LAUNCH_CHECK();
+  }
+  if (fmode) {
+    // geometry -> basis -> aggregation (-> projection) in one tcgen05 kernel; with the projection inside, T only leaves
+    // the SM as the copy dW needs
+    const size_t w3b = fmode == 2 ? align_up(fused_w3_bytes(d->c_in, d->c_out)) : wkc_bytes;
+    if (!ws || ws_bytes < w3b) {
+      set_error("conv_tc_fwd: workspace too small");
+      return SE3_EWORKSPACE;
+    }
+    __nv_bfloat16* w3 = reinterpret_cast<__nv_bfloat16*>(ws);
+    if (int rc = launch_w3_image(d->conv_weights, d->c_in, d->c_out, false, fmode == 1, w3, st)) return rc;
+    FusedArgs f;
+    f.row_ends = d->row_ends; f.nbr = d->col_src; f.rec_row = d->rec_out; f.rec_g = d->rec_in; f.f_g = d->f_in;
+    f.feat = sv.xb; f.cs = cs; f.c = d->c_in; f.w9 = d->proj_axes; f.bias = d->proj_biases; f.norm = d->norm_neigh_dist;
+    f.act = d->act; f.out_scale = d->out_scale; f.w3img = fmode == 2 ? reinterpret_cast<const unsigned char*>(w3) : nullptr;
+    f.co = d->c_out; f.out = y; f.t_save = sv.T; f.n_rows = d->n_out; f.n_edges = d->n_edges;
+    if (int rc = launch_conv_fused(f, d->f_out, false, st)) return rc;
+    if (fmode == 2) return SE3_OK;
+    // y[r,o] = s * sum_(k,c) T[r,(k,c)] Wkc[o,(k,c)]
+    return gemm_tn(R, d->c_out, tcols, d->out_scale, sv.T, tcols, w3, tcols, y, d->c_out, false, 0, st, partials);
   }
   TcAggArgs a;
   a.row_ends = d->row_ends; a.nbr = d->col_src;
@@ -1461,12 +1524,19 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
   Arena ar(ws, ws_bytes);
   __nv_bfloat16* dyb = ar.take<__nv_bfloat16>(R * d->c_out);
   __nv_bfloat16* dTb = ar.take<__nv_bfloat16>(R * ck);
-  __nv_bfloat16* U = ar.take<__nv_bfloat16>(Nf * ok);
-  const int splits = splits_for_tc(ck, d->c_out, R);
-  float* dWp = ar.take<float>((size_t)splits * ck * d->c_out);
+  const int fdx = dx_fused(d);
+  const int64_t ucols = u_tile_cols(d);
+  __nv_bfloat16* U = fdx == 2 ? nullptr : ar.take<__nv_bfloat16>(Nf * ucols);
+  const bool ffwd = fwd_fused(d) != 0;
+  const int64_t tcols = saved_tile_cols(d);
+  const int splits = splits_for_tc(tcols, d->c_out, R);
+  float* dWp = ar.take<float>((size_t)splits * tcols * d->c_out);
+  float* dWkc = ffwd ? ar.take<float>((size_t)tcols * d->c_out) : nullptr;
+  __nv_bfloat16* w3t = fdx == 2 ? ar.take<__nv_bfloat16>(align_up(fused_w3_bytes(d->c_out, d->c_in)) / 2)
+                                : (fdx == 1 ? ar.take<__nv_bfloat16>((size_t)d->c_in * ucols) : nullptr);
   const int n_warps = edge_tc_warps(d->n_out * d->f_out, d->c_in, d->f_out);
   float* eg = ar.take<float>((size_t)n_warps * 512);
-  const size_t dx_pbytes = gemm_tn_partial_bytes(Nf, d->c_in, ok);
+  const size_t dx_pbytes = gemm_tn_partial_bytes(Nf, d->c_in, ucols);
   float* dx_partials = dx_pbytes ? ar.take<float>(dx_pbytes / 4) : nullptr;
   if (!ar.ok()) { set_error("conv_tc_bwd: workspace too small"); return SE3_EWORKSPACE; }
   const TcSaved sv = tc_saved_layout(d, const_cast<void*>(saved));
@@ -1477,12 +1547,20 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
     // dW[(c,k), o] = s * sum_r T[r,(c,k)] dy[r,o]
     // tcgen05 (MN-major operands); SE3_DW_IMPL=m / SE3_GEMM_IMPL=mma select the mma.sync kernel
     static const bool dw_mma = getenv("SE3_DW_IMPL") && getenv("SE3_DW_IMPL")[0] == 'm';  // A/B aid
-    if (!dw_mma && gemm_impl_env() != 1 && tcgen05_gemm_mn_supported(ck, d->c_out, R, ck, d->c_out)) {
-      if (int rc = launch_gemm_tcgen05_mn(ck, d->c_out, R, d->out_scale, T, ck, dyb, d->c_out, dW, d->c_out, splits, dWp, st))
+    // (fused forward: the saved rows are (k, c padded to CP) ordered -> the result is permuted afterwards)
+    float* dst = ffwd ? dWkc : dW;
+    if (!dw_mma && gemm_impl_env() != 1 && tcgen05_gemm_mn_supported(tcols, d->c_out, R, tcols, d->c_out)) {
+      if (int rc = launch_gemm_tcgen05_mn(tcols, d->c_out, R, d->out_scale, T, tcols, dyb, d->c_out, dst, d->c_out, splits, dWp, st))
         return rc;
-    } else if (int rc = launch_gemm_cfg<false, false, false>(ck, d->c_out, R, d->out_scale, T, ck, dyb, d->c_out, dW,
+    } else if (int rc = launch_gemm_cfg<false, false, false>(tcols, d->c_out, R, d->out_scale, T, tcols, dyb, d->c_out, dst,
                                                              d->c_out, splits, dWp, st)) {
       return rc;
+    }
+    if (ffwd) {
+      const int64_t n = ck * d->c_out;
+      SE3_CUDA(launch_pdl(k_dw_from_kc, dim3(blocks_for(n)), dim3(256), 0, st, (const float*)dWkc, d->c_in, d->c_out,
+                          fused_cp(d->c_in), dW));
+      SE3_LAUNCH_CHECK();
     }
   }
   if (dA || dB) {
@@ -1495,7 +1573,19 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
     g.act = d->act; g.dT = dTb; g.n_out = d->n_out; g.partials = eg;
     if (int rc = launch_edge_tc(g, d->f_out, d->n_in, n_warps, dA, dB, st)) return rc;
   }
-  if (dx) {
+  if (dx && fdx) {
+    // data gradient: the same fused kernel over the transposed CSR, gathered rows = dy, projection with W^T
+    if (int rc = launch_w3_image(d->conv_weights, d->c_in, d->c_out, true, fdx == 1, w3t, st)) return rc;
+    FusedArgs f;
+    f.row_ends = d->t_row_ends; f.nbr = d->t_dst; f.rec_row = d->rec_in; f.rec_g = d->rec_out; f.f_g = d->f_out;
+    f.feat = dyb; f.cs = d->c_out; f.c = d->c_out; f.w9 = d->proj_axes; f.bias = d->proj_biases; f.norm = d->norm_neigh_dist;
+    f.act = d->act; f.out_scale = d->out_scale; f.w3img = fdx == 2 ? reinterpret_cast<const unsigned char*>(w3t) : nullptr;
+    f.co = d->c_in; f.out = dx; f.t_save = fdx == 2 ? nullptr : U; f.n_rows = d->n_in; f.n_edges = d->n_edges;
+    if (int rc = launch_conv_fused(f, d->f_in, true, st)) return rc;
+    // dx[n,c] = s * sum_(k,o) U[n,(k,o)] Wp[c,(k,o)]
+    if (fdx == 1)
+      if (int rc = gemm_tn(Nf, d->c_in, ucols, d->out_scale, U, ucols, w3t, ucols, dx, d->c_in, false, 0, st, dx_partials)) return rc;
+  } else if (dx) {
     TcAggArgs a;
     a.row_ends = d->t_row_ends; a.nbr = d->t_dst;
     a.rec_row = d->rec_in; a.rec_g = d->rec_out; a.f_g = d->f_out;
@@ -1523,6 +1613,12 @@ __global__ void k_pack_records(const float* __restrict__ pts, const float* __res
   }
 }
 }  // namespace se3
+
+extern "C" int se3_conv_set_fused(int32_t mode) {
+  const int prev = se3::fused_mode();
+  se3::fused_set_mode(mode);
+  return prev;
+}
 
 extern "C" int se3_pack_records(const float* pts, const float* frames, int64_t n, int32_t f, float* rec,
                                 se3_stream_t stream) {

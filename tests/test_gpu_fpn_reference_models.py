@@ -116,7 +116,8 @@ def test_reference_fpn_forward_backward_on_this_package(precision):
         assert all(v < t for v, t in zip(mm, tol)), (n, mm)
     norms = np.array([float(grads[str(n)].double().norm()) for n in g["grad_names"]])
     ref = g["grad_norms_f64"]
-    rel = np.abs(norms - ref) / np.maximum(ref, 1e-12 * ref.max())
+    # (a Linear bias in front of a BatchNorm has an analytically zero gradient: norms below 1e-6 of the largest are noise)
+    rel = np.abs(norms - ref) / np.maximum(ref, 1e-6 * ref.max())
     worst = int(np.argmax(rel))
     print("  %d parameter-gradient norms, worst relative deviation %.2e (%s)" % (len(ref), rel[worst], g["grad_names"][worst]))
     assert rel.max() < (1e-4 if precision == 0 else 3e-2)

@@ -145,6 +145,8 @@ def test_fused_hierarchy_frames_against_oracle_pca():
         full = torch.from_numpy((idx >= 0).all(1))
         tie = torch.from_numpy(np.abs(dist[:, k] - dist[:, k - 1]) <= 1e-6 * np.maximum(dist[:, k], 1e-12))
         ok = (gap > 2e-2) & full & ~tie
+        if int(ok.sum()) == 0:                                                 # coarse levels: items smaller than k + 1
+            continue
         fr = pc.local_frames_.cpu().double()                                   # [n,2,9]
         d = (fr[:, :, None, :] - cand[:, None, :, :]).abs().amax(-1)           # [n,2,4]
         best, which = d.min(-1)
@@ -182,3 +184,30 @@ def test_level1_reference_layer_flow_over_legacy_ops(case):
     got = [v.detach().cpu().numpy() for v in (y, x.grad, W.grad, A.grad, B.grad)]
     ref = [g[k + "_f64"] for k in ("y", "dx", "dW", "dA", "dB")]
     _check("level1 " + case, got, ref, FP32_TOL)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("n,r,f,cin,cout", [(8192, 0.1, 2, 32, 32), (8192, 0.1, 2, 32, 64), (3000, 0.12, 1, 64, 64),
+                                             (3000, 0.12, 2, 16, 32), (333, 0.3, 2, 48, 24)])
+def test_fused_tcgen05_kernel_against_fp64_oracle(mode, n, r, f, cin, cout):
+    """The warp-specialised tcgen05 kernel (conv_fused.cu; opt-in through se3_conv_set_fused): aggregation-only mode
+    and aggregation + projection mode, forward and all gradients against the fp64 oracle at the bf16 tolerance --
+    includes config 1 (8192 points, 32->64), a single-frame 64-channel layer, 16 / 48 padded channels and a cloud
+    smaller than the grid (333 points, most CTAs idle)."""
+    from se3conv3d_b200 import _lib
+    from se3conv3d_b200.layers import PNEConvLayerRotEquiv
+    from test_gpu_parity import _synthetic_layer_problem
+    prev = _lib.set_fused_mode(mode)
+    try:
+        pc, neigh, x = _synthetic_layer_problem(n, r, f, cin, cout)
+        torch.manual_seed(2)
+        layer = PNEConvLayerRotEquiv(9, cin, cout, 32, "mlp_gelu").to(DEV)
+        with torch.no_grad():
+            layer.proj_biases_.copy_(0.1 * torch.randn(32))
+        layer.norm_neigh_dist_.fill_(1.0 / r)
+        layer.norm_num_neighs_.fill_(n / neigh.neighbors_.shape[0])
+        dy = torch.randn(n * f, cout, generator=torch.Generator().manual_seed(5)).to(DEV) / cout ** 0.5
+        ref = [t.numpy() for t in _oracle(layer, pc, pc, neigh.neighbors_, x, dy)]
+        _check("fused mode %d %d->%d f=%d" % (mode, cin, cout, f), _run(layer, pc, pc, neigh, x, dy, 1), ref, BF16_TOL)
+    finally:
+        _lib.set_fused_mode(prev)
