@@ -10,6 +10,7 @@ same classes with the same attributes, their tensors are views into one device a
 """
 import ctypes as C
 import os
+import weakref
 
 import torch
 
@@ -173,6 +174,9 @@ def build_point_hierarchy(p_pts, p_batch_ids, p_ref_frames_config, p_init_subsam
     base = v.base_addr
     for i, (s, t, r) in enumerate(neighborhoods):
         neighs.append(_make_neighborhood(v, base, res.neigh[i], clouds[s], clouds[t], r, n_frames))
+        # weak: the hierarchy owns the neighbourhoods; a strong entry would close a cloud -> neighbourhood -> cloud cycle
+        # and the arena would wait for the garbage collector instead of returning to the allocator at once
+        clouds[s].__dict__.setdefault("_fused_bq_", {})[(id(clouds[t]), float(r))] = weakref.ref(neighs[-1])
         if s <= n_pool and t <= n_pool:
             h.neigh_cache_[str(s) + "_" + str(t) + "_ball_query" + str(r)] = neighs[-1]
     h.fused_neighborhoods_ = neighs
@@ -193,6 +197,7 @@ def _make_neighborhood(v, base, nr, src, dst, r, n_frames):
     n_in, n_out = int(src.pts_.shape[0]), int(dst.pts_.shape[0])
     o_re, o_cs, o_ed, o_tre, o_te, o_td = nr.row_ends, nr.col_src, nr.edge_dst, nr.t_row_ends, nr.t_edge, nr.t_dst
     nb = BQNeighborhood.__new__(BQNeighborhood)
+    nb._prebuilt_ = True
     nb.radius_ = r
     nb.max_neighbors_ = 0
     nb.pc_src_, nb.samples_ = src, dst

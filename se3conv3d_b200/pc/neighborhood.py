@@ -102,7 +102,21 @@ class Neighborhood(LazyAttrs, ABC):
 class BQNeighborhood(Neighborhood):
     """Ball-query neighbourhood (pc/BQNeighborhood.py:12-64)."""
 
+    def __new__(cls, p_pc_src=None, p_samples=None, p_radius=None, p_max_neighbors=0):
+        # A ball query the fused hierarchy builder has already answered (pc.build_point_hierarchy registers its
+        # neighbourhoods on the source cloud): the models construct the seg-head neighbourhood directly
+        # (models/FPNSegUNet.py:171-175), outside the hierarchy's cache -- hand back the prebuilt object.
+        pre = getattr(p_pc_src, "_fused_bq_", None) if p_pc_src is not None else None
+        if pre and not p_max_neighbors:
+            ref = pre.get((id(p_samples), float(p_radius)))
+            hit = ref() if ref is not None else None
+            if hit is not None:
+                return hit
+        return super(BQNeighborhood, cls).__new__(cls)
+
     def __init__(self, p_pc_src, p_samples, p_radius, p_max_neighbors=0):
+        if self.__dict__.get("_prebuilt_"):
+            return
         self.radius_ = p_radius
         self.max_neighbors_ = p_max_neighbors
         super(BQNeighborhood, self).__init__(p_pc_src, p_samples)

@@ -47,3 +47,78 @@ def sum_over_ranks(value, device):
 
 def is_reporter(rank):
     return rank == 0
+
+
+class GradAllReducer(object):
+    """The one collective of the path: the per-step all-reduce (mean) of the parameter gradients of data-parallel
+    replicas (training loop tasks/SemSeg/train_dfaust_rot.py:262-275).
+
+    All gradients live in ONE flat fp32 buffer (every `p.grad` is a view into it, so backward accumulates in place and
+    nothing is copied); the buffer is cut into buckets in reverse parameter order (the order backward produces them),
+    and a post-accumulate hook launches the asynchronous all-reduce of a bucket as soon as its last gradient has landed
+    -- the transfer of the early buckets overlaps the rest of backward (NCCL runs on its own stream over NVLink /
+    NVSwitch).  `finish()` waits for the handles before the optimiser step.  With one process it is a no-op apart from
+    the flat buffer (which also makes clip_grad_norm_ / zero_grad single kernels)."""
+
+    def __init__(self, params, bucket_bytes=8 << 20):
+        self.params = [p for p in params if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.bytes = total * 4
+        # reverse registration order ~ the order in which backward finishes the gradients
+        order = list(reversed(self.params))
+        self.buckets, self._bucket_of, self._pending0 = [], {}, []
+        off, start, count = 0, 0, 0
+        for p in order:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            self._bucket_of[id(p)] = len(self.buckets)
+            off += n
+            count += 1
+            if (off - start) * 4 >= bucket_bytes:
+                self.buckets.append((start, off))
+                self._pending0.append(count)
+                start, count = off, 0
+        if off > start:
+            self.buckets.append((start, off))
+            self._pending0.append(count)
+        self._pending = list(self._pending0)
+        self._handles = []
+        self.world = dist.get_world_size() if _active() else 1
+        self._hooks = []
+        if self.world > 1:
+            for p in self.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    def _on_grad(self, p):
+        b = self._bucket_of[id(p)]
+        self._pending[b] -= 1
+        if self._pending[b] == 0:
+            s, e = self.buckets[b]
+            self._handles.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.AVG if self.flat.is_cuda else
+                                                 dist.ReduceOp.SUM, async_op=True))
+
+    def finish(self):
+        """Waits for every bucket (call after backward, before clipping / the optimiser step)."""
+        if self.world > 1:
+            # parameters that received no gradient this step never fired their hook: reduce their buckets now
+            for b, left in enumerate(self._pending):
+                if left > 0:
+                    s, e = self.buckets[b]
+                    self._handles.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.AVG if self.flat.is_cuda else
+                                                         dist.ReduceOp.SUM, async_op=True))
+            for h in self._handles:
+                h.wait()
+            if not self.flat.is_cuda:            # gloo has no AVG
+                self.flat.div_(self.world)
+        self._handles = []
+        self._pending = list(self._pending0)
+
+    def zero_grad(self):
+        self.flat.zero_()
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

@@ -152,7 +152,7 @@ class DfaustStep(object):
         self.inputs = (xs, dys)
         return xs, dys
 
-    def conv_fwd_bwd(self, pcs, neighs, xs=None, dys=None):
+    def conv_fwd_bwd(self, pcs, neighs, xs=None, dys=None, return_output=False):
         """Forward of the 21 convolutions, then ONE backward pass over all of them (as a training step does:
         every forward first, a single autograd sweep after), returns the checksum of the last output."""
         if xs is None:
@@ -160,7 +160,9 @@ class DfaustStep(object):
         ys = [layer(pcs[li], pcs[lo], x, nb)
               for layer, nb, (_, li, lo, _, _, _), x in zip(self.layers, neighs, self.specs, xs)]
         torch.autograd.backward(ys, list(dys))
-        return ys[-1].detach().sum()  # the seg-head output is the model's result: its checksum is read back
+        if return_output:
+            return ys[-1].detach()    # the seg-head output is the model's result
+        return ys[-1].detach().sum()
 
     def zero_grad(self):
         for layer in self.layers:
@@ -169,3 +171,87 @@ class DfaustStep(object):
         if self.inputs is not None:
             for x in self.inputs[0]:
                 x.grad = None
+
+
+class FpnStep(object):
+    """One full training step of the dfaust_I_rot_pca_2F configuration on synthetic clouds with the UNMODIFIED
+    reference model code (models/FPNSegUNet.py through tasks/SemSeg/seg_models.py, imported with `point_cloud_lib`
+    aliased to this package; tools/stage_reference_models.py):
+
+        create_hierarchy (train_dfaust_rot.py:108-158, here the fused builder) -> features repeated per frame (:249-251)
+        -> pred = model(hierarchy, features, lev_radii, out_pc) (:262) -> cross-entropy with label smoothing 0.2 (:263,
+        confs/dfaust/dfaust_I_rot_pca_2F.yaml) -> loss.backward() (:264) -> gradient all-reduce (data parallel replicas;
+        shard.GradAllReducer) -> clip_grad_norm_(100) (:267-270) -> AdamW step + zero_grad (:271-272).
+
+    max_drop_path 0.5 as in the config; the pre-process epoch is replaced by its fixed point (norm_neigh_dist_ = 1/r,
+    norm_num_neighs_ = M/E) taken from the first hierarchy."""
+
+    def __init__(self, device, seg_models, precision=1, n_classes=20, max_drop_path=0.5, lr=5e-4, seed=0):
+        from .layers import PNEConvLayerRotEquiv
+        from . import shard
+        self.device = device
+        torch.manual_seed(seed)
+        self.model = seg_models.FPNSegUNetMLPGeluRotEqFAUST(1, n_classes, max_drop_path).to(device)
+        self.model.train()
+        for m in self.model.modules():
+            if isinstance(m, PNEConvLayerRotEquiv):
+                m.precision = precision
+        self.convs = [m for m in self.model.modules() if isinstance(m, PNEConvLayerRotEquiv)]
+        self.reducer = shard.GradAllReducer(self.model.parameters())
+        self.optim = torch.optim.AdamW(self.model.parameters(), lr=lr, weight_decay=1e-4, foreach=True)
+        self.loss_fn = torch.nn.CrossEntropyLoss(label_smoothing=0.2)
+        self.n_classes = n_classes
+        self.cfg = DFAUST_CFG
+        self.radii = [self.cfg["init_subsample"]] + list(self.cfg["grid_subsamples"])
+        # every ball query the model will ask for (Encoder.py:134-154, Decoder.py:72-80, FPNDecoder.py:104-113,
+        # PatchEncoder/Decoder, seg head FPNSegUNet.py:171-175): (src level, dst level, 2 x cell of the radius level)
+        wanted = []
+        for (_, li, lo, lr_, _, _) in dfaust_conv_specs():
+            key = (li, lo, 2.0 * self.radii[lr_])
+            if key not in wanted:
+                wanted.append(key)
+        self.wanted = wanted
+        self.calibrated = False
+
+    def build(self, pts, batch_ids, n_batches):
+        from .pc import build_point_hierarchy
+        with torch.no_grad():
+            h, out_pc = build_point_hierarchy(pts, batch_ids, self.cfg["RefFrames"], self.cfg["init_subsample"],
+                                              self.cfg["grid_subsamples"], neighborhoods=self.wanted, output_cloud=True,
+                                              n_batches=n_batches)
+        return h, out_pc
+
+    def calibrate(self, h, out_pc, feats):
+        """Fixed point of the pre-process EMA (layers/IConvLayer.py:76-97): one no-grad forward with the switch on, then
+        the buffers are set to the values the EMA converges to."""
+        self.model.start_pre_process()
+        with torch.no_grad():
+            for _ in range(3):
+                self.model(h, feats, self.radii, out_pc)
+        self.model.end_pre_process()
+        for c in self.convs:
+            # after k EMA updates from 0 the buffer holds (1 - 0.9^k) of the fixed point
+            scale = 1.0 / (1.0 - 0.9 ** 3)
+            c.norm_neigh_dist_ = (c.norm_neigh_dist_ * scale).clone()
+            c.norm_num_neighs_ = (c.norm_num_neighs_ * scale).clone()
+        self.calibrated = True
+
+    def features(self, h):
+        n = h.pcs_[0].pts_.shape[0] * self.cfg["RefFrames"]["n_frames"]
+        return torch.ones((n, 1), dtype=torch.float32, device=self.device)
+
+    def step(self, pts, batch_ids, labels_raw, n_batches):
+        """hierarchy + forward + loss + backward + all-reduce + clip + AdamW; returns the loss (device scalar)."""
+        h, out_pc = self.build(pts, batch_ids, n_batches)
+        feats = self.features(h)
+        if not self.calibrated:
+            self.calibrate(h, out_pc, feats)
+        labels = labels_raw[out_pc.picked_ids_]                  # labels of the points the output cloud picked
+        pred = self.model(h, feats, self.radii, out_pc)
+        loss = self.loss_fn(pred, labels)
+        loss.backward()
+        self.reducer.finish()
+        torch.nn.utils.clip_grad_norm_(self.model.parameters(), 100.0, foreach=True)
+        self.optim.step()
+        self.reducer.zero_grad()
+        return loss.detach()

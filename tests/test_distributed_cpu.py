@@ -55,3 +55,61 @@ def test_single_process_helpers_do_not_need_a_process_group():
     assert shard.sum_over_ranks(7, device=torch.device("cpu")) == 7
     assert shard.cloud_ids(0, 1, 4) == [0, 1, 2, 3]
     shard.barrier(device=torch.device("cpu"))
+
+
+def _reducer_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from se3conv3d_b200 import shard
+    torch.manual_seed(0)                                   # identical replicas
+    model = torch.nn.Sequential(torch.nn.Linear(6, 40), torch.nn.GELU(), torch.nn.Linear(40, 40), torch.nn.GELU(),
+                                torch.nn.Linear(40, 3))
+    unused = torch.nn.Parameter(torch.ones(5))             # a parameter that never receives a gradient
+    params = list(model.parameters()) + [unused]
+    red = shard.GradAllReducer(params, bucket_bytes=4096)  # several buckets
+    assert len(red.buckets) >= 2 and all(p.grad.data_ptr() >= red.flat.data_ptr() for p in params)
+    g = torch.Generator().manual_seed(100 + rank)          # different data per rank
+    x, y = torch.randn(16, 6, generator=g), torch.randn(16, 3, generator=g)
+    res = []
+    for step in range(2):                                  # two steps: pending counters and handles reset
+        loss = (model(x * (step + 1)) - y).square().mean()
+        loss.backward()
+        red.finish()
+        res.append(red.flat.clone())
+        red.zero_grad()
+    # what a single process would compute for the mean of both ranks' losses
+    torch.manual_seed(0)
+    ref = torch.nn.Sequential(torch.nn.Linear(6, 40), torch.nn.GELU(), torch.nn.Linear(40, 40), torch.nn.GELU(),
+                              torch.nn.Linear(40, 3))
+    tot = 0.0
+    for r in range(world):
+        g = torch.Generator().manual_seed(100 + r)
+        xr, yr = torch.randn(16, 6, generator=g), torch.randn(16, 3, generator=g)
+        tot = tot + (ref(xr) - yr).square().mean() / world
+    tot.backward()
+    flat_ref = torch.cat([p.grad.reshape(-1) for p in reversed(list(ref.parameters()))])
+    n_unused = unused.numel()
+    err = float((res[0][n_unused:] - flat_ref).abs().max() / flat_ref.abs().max())
+    out.put((rank, err, float(res[0][:n_unused].abs().max()), float(res[0].sum()), float(res[1].abs().sum())))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_gradient_allreduce_buckets_gloo_world2():
+    """shard.GradAllReducer: flat gradient buffer, reverse-order buckets reduced asynchronously from post-accumulate
+    hooks; the averaged gradients equal those of the mean loss over both ranks' shards, on both ranks."""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29900 + (os.getpid() % 90)
+    procs = [ctx.Process(target=_reducer_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(out.get(timeout=100) for _ in range(2))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    (_, e0, u0, s0, t0), (_, e1, u1, s1, t1) = res
+    assert e0 < 1e-6 and e1 < 1e-6
+    assert u0 == 0.0 and u1 == 0.0                          # the never-used parameter keeps a zero gradient
+    assert s0 == s1 and t0 == t1 and t0 > 0                 # both ranks hold the same reduced buffer, also in step 2
