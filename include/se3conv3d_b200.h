@@ -158,12 +158,17 @@ int se3_csr_transpose_i32(const int32_t* col_src, const int32_t* edge_dst, int64
                           int32_t* t_row_ends, int32_t* t_edge, int32_t* t_dst, se3_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
- * k-NN (self included, within batch, k <= 32).  Replaces knn_query
+ * k-NN (self included, within batch, k <= 64 as in the reference).  Replaces knn_query
  * (custom_ops/knn_query/knn_query.cu:18-197; caller custom_ops/KNNQuery.py:30-33).
  * out [N,k] int32, ascending distance, -1 padded. */
 size_t se3_knn_workspace_bytes(int64_t n);
 int se3_knn_query(const float* pts, const int32_t* batch_ids, int64_t n, int32_t k,
                   void* workspace, size_t workspace_bytes, int32_t* out, se3_stream_t stream);
+/* k-NN of every sample among the sources of ITS batch item, two different clouds (pc/KnnNeighborhood.py:78-84, the
+ * torch_cluster.knn branch used by the global-pooling convolutions).  Sources are grouped by batch item:
+ * src_batch_ends [B] int32 = inclusive end of item b.  out [M,k] int32: source ids by ascending distance, -1 padded. */
+int se3_knn_cross(const float* pts_src, const int32_t* src_batch_ends, const float* pts_dst, const int32_t* batch_dst,
+                  int64_t m, int32_t k, int32_t* out, se3_stream_t stream);
 
 /* PCA reference frames from a k-NN table (pc/RotationFunctions.py:307-406).
  * knn [N,k] int32 (-1 => self loop).  fixed_axis: -1 none (4 frames) | 0,1,2 (2 frames; 0 behaves

@@ -18,7 +18,7 @@ ABI_SYMBOLS = [
     "se3_compute_keys", "se3_grid_setup", "se3_grid_cells_workspace_bytes", "se3_grid_cells", "se3_frames_select",
     "se3_ball_query_workspace_bytes", "se3_ball_query_count", "se3_ball_query_fill",
     "se3_csr_transpose_workspace_bytes", "se3_csr_transpose",
-    "se3_knn_workspace_bytes", "se3_knn_query", "se3_pca_frames", "se3_quat_frames",
+    "se3_knn_workspace_bytes", "se3_knn_query", "se3_knn_cross", "se3_pca_frames", "se3_quat_frames",
     "se3_segment_pool_f32",
     "se3_feat_basis_proj", "se3_feat_basis_proj_grad",
     "se3_conv_fwd_workspace_bytes", "se3_conv_bwd_workspace_bytes", "se3_conv_saved_bytes",
@@ -130,6 +130,7 @@ def lib():
     L.se3_knn_workspace_bytes.argtypes = [i64]
     L.se3_knn_workspace_bytes.restype = sz
     L.se3_knn_query.argtypes = [vp, vp, i64, i32, vp, sz, vp, vp]
+    L.se3_knn_cross.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp]
     L.se3_pca_frames.argtypes = [vp, vp, i64, i32, i32, vp, vp]
     L.se3_quat_frames.argtypes = [vp, i64, vp, vp]
     L.se3_segment_pool_f32.argtypes = [vp, i64, i32, vp, vp, i64, i32, vp, vp]

@@ -32,6 +32,9 @@ static int check_desc(const se3_conv_desc* d) {
   SE3_CHECK_ARG(d->n_in >= 0 && d->n_out >= 0 && d->n_edges >= 0, "bad sizes");
   SE3_CHECK_ARG(d->act >= 0 && d->act <= 3, "unknown activation");
   SE3_CHECK_ARG(d->precision == 0 || d->precision == 1, "unknown precision");
+  // shape limits of the tensor-core path are reported when the byte counts are queried, not in the middle of a call
+  SE3_CHECK_ARG(d->precision == 0 || d->c_out % 8 == 0, "precision 1 needs c_out to be a multiple of 8");
+  SE3_CHECK_ARG(d->precision == 0 || (d->rec_in && d->rec_out), "precision 1 needs the packed gather records (se3_pack_records)");
   return SE3_OK;
 }
 

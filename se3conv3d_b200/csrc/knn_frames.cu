@@ -7,7 +7,7 @@
 //   SO(3) frames   pc/RotationFunctions.py:176-216, 53-82
 // B200-first choices: a warp (not a thread) owns a query point, candidates are examined 32 at a
 // time with coalesced float4 loads of the axis-sorted cloud, the running top-k lives in registers
-// (one entry per lane, k <= 32) and is updated with ballot/shuffle insertions; the ordering key is
+// (one or two entries per lane, k <= 64) and is updated with ballot/shuffle insertions; the ordering key is
 // an exact (batch, float-bits) 64-bit integer instead of the reference's rounded float key.
 #include <cub/cub.cuh>
 #include "common.cuh"
@@ -109,7 +109,42 @@ __global__ void k_knn_gather(const float* __restrict__ pts, const int* __restric
 
 __device__ __forceinline__ float comp(const float4& p, int d) { return d == 0 ? p.x : (d == 1 ? p.y : p.z); }
 
-// One warp per query (in sorted order).  Lanes 0..k-1 hold the running top-k, ascending.
+// Running top-k of a warp, ascending: rank r lives in slot r / 32 of lane r % 32 (KS = 1: k <= 32, KS = 2: k <= 64, the
+// reference's limit, knn_query.cu:135-197).  Insertion of (d, id) = ballot for the position + a shuffle shift.
+template <int KS>
+struct WarpTopK {
+  float best[KS];
+  int idx[KS];
+  float tau;
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int s = 0; s < KS; ++s) { best[s] = 1e10f; idx[s] = -1; }   // knn_query.cu:38
+    tau = 1e10f;
+  }
+  // all lanes call with the same (d, id); strict d < tau: the first found wins ties
+  __device__ __forceinline__ void insert(float d, int id, int k, int lane) {
+    if (!(d < tau)) return;
+    int pos = 0;
+#pragma unroll
+    for (int s = 0; s < KS; ++s) pos += __popc(__ballot_sync(0xffffffffu, 32 * s + lane < k && best[s] <= d));
+    const float wrap = __shfl_sync(0xffffffffu, best[0], 31);
+    const int wrapi = __shfl_sync(0xffffffffu, idx[0], 31);
+#pragma unroll
+    for (int s = KS - 1; s >= 0; --s) {
+      float up = __shfl_up_sync(0xffffffffu, best[s], 1);
+      int upi = __shfl_up_sync(0xffffffffu, idx[s], 1);
+      if (s > 0 && lane == 0) { up = wrap; upi = wrapi; }
+      const int r = 32 * s + lane;
+      if (r > pos) { best[s] = up; idx[s] = upi; }
+      if (r == pos) { best[s] = d; idx[s] = id; }
+    }
+    const int last = k - 1;
+    tau = __shfl_sync(0xffffffffu, (KS == 2 && last >= 32) ? best[KS - 1] : best[0], last & 31);
+  }
+};
+
+// One warp per query (in sorted order).
+template <int KS>
 __global__ void __launch_bounds__(256) k_knn_sweep(const float4* __restrict__ ps, const int* __restrict__ idx_sorted,
                                                    int n, int k, const float* __restrict__ mm,
                                                    int* __restrict__ out) {
@@ -120,9 +155,8 @@ __global__ void __launch_bounds__(256) k_knn_sweep(const float4* __restrict__ ps
   for (int64_t p = warp; p < n; p += nwarps) {
     const float4 cur = ps[p];
     const int cur_b = __float_as_int(cur.w);
-    float best = 1e10f;  // knn_query.cu:38
-    int best_idx = -1;
-    float tau = 1e10f;
+    WarpTopK<KS> top;
+    top.init();
 #pragma unroll 1
     for (int dir = 0; dir < 2; ++dir) {
       // dir 0: q = p, p+1, ...   dir 1: q = p-1, p-2, ...
@@ -145,30 +179,59 @@ __global__ void __launch_bounds__(256) k_knn_sweep(const float4* __restrict__ ps
         const float dist = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
         const float sdist = comp(c, sd) - comp(cur, sd);
         const float sd2 = sdist * sdist;
-        unsigned cand = __ballot_sync(0xffffffffu, valid && dist < tau);
+        unsigned cand = __ballot_sync(0xffffffffu, valid && dist < top.tau);
         while (cand) {
           const int src = __ffs(cand) - 1;
           cand &= cand - 1;
           const float d = __shfl_sync(0xffffffffu, dist, src);
           const int64_t qi = dir == 0 ? p + base + src : p - 1 - base - src;
-          if (d < tau) {  // best[k-1] > d  (strict: first found wins)
-            const unsigned le = __ballot_sync(0xffffffffu, lane < k && best <= d);
-            const int pos = __popc(le);
-            const float up = __shfl_up_sync(0xffffffffu, best, 1);
-            const int upi = __shfl_up_sync(0xffffffffu, best_idx, 1);
-            if (lane > pos) { best = up; best_idx = upi; }
-            if (lane == pos) { best = d; best_idx = (int)qi; }
-            tau = __shfl_sync(0xffffffffu, best, k - 1);
-          }
+          top.insert(d, (int)qi, k, lane);
         }
         // stop once the axis distance alone exceeds the k-th best (knn_query.cu:84,121)
-        if (__ballot_sync(0xffffffffu, valid && tau < sd2)) stop = true;
+        if (__ballot_sync(0xffffffffu, valid && top.tau < sd2)) stop = true;
       }
     }
-    if (lane < k) {
-      const int self = idx_sorted[p];
-      out[(int64_t)self * k + lane] = best_idx >= 0 ? idx_sorted[best_idx] : -1;
+    const int self = idx_sorted[p];
+#pragma unroll
+    for (int s = 0; s < KS; ++s)
+      if (32 * s + lane < k) out[(int64_t)self * k + 32 * s + lane] = top.idx[s] >= 0 ? idx_sorted[top.idx[s]] : -1;
+  }
+}
+
+// Cross-cloud k-NN (pc/KnnNeighborhood.py:78-84, the torch_cluster.knn branch: global pooling convolutions between two
+// different clouds): one warp per sample scans every source point of the sample's batch item (sources are grouped by
+// batch item: src_ends[b] = inclusive end of item b).  out [M, k]: source ids by ascending distance, -1 padded.
+template <int KS>
+__global__ void __launch_bounds__(256) k_knn_cross(const float* __restrict__ src, const int* __restrict__ src_ends,
+                                                   const float* __restrict__ dst, const int* __restrict__ batch_dst, int m,
+                                                   int k, int* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p = warp; p < m; p += nwarps) {
+    const float cx = dst[3 * p], cy = dst[3 * p + 1], cz = dst[3 * p + 2];
+    const int b = batch_dst[p];
+    const int lo = b > 0 ? src_ends[b - 1] : 0, hi = src_ends[b];
+    WarpTopK<KS> top;
+    top.init();
+    for (int base = lo; base < hi; base += 32) {
+      const int q = base + lane;
+      const bool valid = q < hi;
+      float dist = 1e30f;
+      if (valid) {
+        const float dx = src[3 * (int64_t)q] - cx, dy = src[3 * (int64_t)q + 1] - cy, dz = src[3 * (int64_t)q + 2] - cz;
+        dist = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+      }
+      unsigned cand = __ballot_sync(0xffffffffu, valid && dist < top.tau);
+      while (cand) {
+        const int s = __ffs(cand) - 1;
+        cand &= cand - 1;
+        top.insert(__shfl_sync(0xffffffffu, dist, s), base + s, k, lane);
+      }
     }
+#pragma unroll
+    for (int s = 0; s < KS; ++s)
+      if (32 * s + lane < k) out[p * k + 32 * s + lane] = top.idx[s];
   }
 }
 
@@ -349,7 +412,7 @@ int se3::knn_query_impl(const float* pts, const int32_t* batch_ids, int64_t n, i
                         size_t workspace_bytes, int32_t* out, int32_t n_batches, int32_t max_seg, se3_stream_t stream,
                         const float* raw_min, const float* raw_max) {
   SE3_CHECK_ARG(n >= 0 && n < (1ll << 31), "bad n");
-  SE3_CHECK_ARG(k >= 1 && k <= 32, "k must be in 1..32");
+  SE3_CHECK_ARG(k >= 1 && k <= 64, "k must be in 1..64");
   if (n == 0) return SE3_OK;
   SE3_CHECK_ARG(pts && batch_ids && workspace && out, "null pointer");
   cudaStream_t st = as_stream(stream);
@@ -363,7 +426,8 @@ int se3::knn_query_impl(const float* pts, const int32_t* batch_ids, int64_t n, i
     if (int rc = knn_sorted_fused(pts, batch_ids, n, raw_min, raw_max, w.idx_sorted, w.pts_sorted, w.minmax, n_batches,
                                   max_seg, stream))
       return rc;
-    k_knn_sweep<<<grid_for(n * 32, 256), 256, 0, st>>>(w.pts_sorted, w.idx_sorted, (int)n, k, w.minmax, out);
+    if (k <= 32) k_knn_sweep<1><<<grid_for(n * 32, 256), 256, 0, st>>>(w.pts_sorted, w.idx_sorted, (int)n, k, w.minmax, out);
+    else k_knn_sweep<2><<<grid_for(n * 32, 256), 256, 0, st>>>(w.pts_sorted, w.idx_sorted, (int)n, k, w.minmax, out);
     SE3_LAUNCH_CHECK();
     return SE3_OK;
   }
@@ -379,7 +443,20 @@ int se3::knn_query_impl(const float* pts, const int32_t* batch_ids, int64_t n, i
     return rc;
   k_knn_gather<<<grid_for(n, 256), 256, 0, st>>>(pts, batch_ids, w.idx_sorted, n, w.pts_sorted);
   SE3_LAUNCH_CHECK();
-  k_knn_sweep<<<grid_for(n * 32, 256), 256, 0, st>>>(w.pts_sorted, w.idx_sorted, (int)n, k, w.minmax, out);
+  if (k <= 32) k_knn_sweep<1><<<grid_for(n * 32, 256), 256, 0, st>>>(w.pts_sorted, w.idx_sorted, (int)n, k, w.minmax, out);
+  else k_knn_sweep<2><<<grid_for(n * 32, 256), 256, 0, st>>>(w.pts_sorted, w.idx_sorted, (int)n, k, w.minmax, out);
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
+}
+
+extern "C" int se3_knn_cross(const float* pts_src, const int32_t* src_batch_ends, const float* pts_dst, const int32_t* batch_dst,
+                             int64_t m, int32_t k, int32_t* out, se3_stream_t stream) {
+  SE3_CHECK_ARG(m >= 0 && m < ((int64_t)1 << 31) && k >= 1 && k <= 64, "bad sizes (k must be in 1..64)");
+  if (m == 0) return SE3_OK;
+  SE3_CHECK_ARG(pts_src && src_batch_ends && pts_dst && batch_dst && out, "null pointer");
+  cudaStream_t st = as_stream(stream);
+  if (k <= 32) k_knn_cross<1><<<grid_for(m * 32, 256), 256, 0, st>>>(pts_src, src_batch_ends, pts_dst, batch_dst, (int)m, k, out);
+  else k_knn_cross<2><<<grid_for(m * 32, 256), 256, 0, st>>>(pts_src, src_batch_ends, pts_dst, batch_dst, (int)m, k, out);
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }

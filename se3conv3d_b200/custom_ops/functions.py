@@ -142,6 +142,7 @@ class RotEquivConv(torch.autograd.Function):
         return y
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
         x32, pa, pb, cw, saved = ctx.saved_tensors
         act, precision, nnd, osc, x_dtype = ctx.meta

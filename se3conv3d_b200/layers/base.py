@@ -51,7 +51,9 @@ class IConvLayer(PreProcessModule, ABC):
                self.norm_num_neighs_._version)
         cache = getattr(self, "_scalar_cache", None)
         if cache is None or cache[0] != key:
-            cache = (key, float(self.norm_neigh_dist_), float(self.norm_num_neighs_))
+            # (the buffers are held by the entry: their ids cannot be recycled while it is cached)
+            cache = (key, float(self.norm_neigh_dist_), float(self.norm_num_neighs_), self.norm_neigh_dist_,
+                     self.norm_num_neighs_)
             self._scalar_cache = cache
         return cache[1], cache[2]
 

@@ -20,7 +20,8 @@ def gather_records(p_pc):
     rec = torch.empty((max(n * f, 1), 12), dtype=torch.float32, device=p32.device)
     check(lib().se3_pack_records(ptr(p32), ptr(f32), n, f, ptr(rec), stream()), "se3_pack_records")
     try:
-        p_pc._se3_records = (key, rec)
+        # the keyed tensors are held by the entry: their ids cannot be recycled while the entry is alive
+        p_pc._se3_records = (key, rec, pts, frames)
     except AttributeError:
         pass
     return rec
@@ -49,6 +50,9 @@ class ConvGeometry(LazyAttrs):
         self.frames_out = p_pc_out.local_frames_.detach().to(torch.float32).contiguous()
         self.rec_in = gather_records(p_pc_in)
         self.rec_out = self.rec_in if p_pc_out is p_pc_in else gather_records(p_pc_out)
+        if getattr(p_neighborhood, "keep_empty_", False):
+            raise Se3Error("a keep_empty k-NN neighbourhood is padded with -1 sources (pc/KnnNeighborhood.py:100-135); "
+                           "it cannot feed a convolution -- build it with p_keep_empty=False")
         self.row_ends = p_neighborhood.start_ids_.to(torch.int32).contiguous()
         if self.row_ends.shape[0] != self.n_out:
             raise Se3Error("neighbourhood has %d rows but the output cloud has %d points" %
@@ -84,13 +88,30 @@ class Neighborhood(LazyAttrs, ABC):
     def conv_geometry(self, p_pc_in, p_pc_out):
         """Cached ConvGeometry; keyed on the identity of the clouds and their frame tensors, so a
         cloud whose frames were re-sampled gets a fresh record."""
-        key = (id(p_pc_in), id(p_pc_out), id(getattr(p_pc_in, "local_frames_", None)),
-               id(getattr(p_pc_out, "local_frames_", None)), self._neighbors_token())
-        geom = self.conv_geometry_cache_.get(key)
-        if geom is None:
-            geom = ConvGeometry(p_pc_in, p_pc_out, self)
-            self.conv_geometry_cache_ = {key: geom}
+        fi, fo = getattr(p_pc_in, "local_frames_", None), getattr(p_pc_out, "local_frames_", None)
+        key = (id(p_pc_in), id(p_pc_out), id(fi), id(fo), self._neighbors_token())
+        hit = self.conv_geometry_cache_.get(key)
+        if hit is not None:
+            geom = hit
+            ver = geom.__dict__.get("_versions")
+            if ver is None or ver == self._versions(p_pc_in, p_pc_out):
+                return geom
+        geom = ConvGeometry(p_pc_in, p_pc_out, self)
+        # in-place edits of the coordinates / frames invalidate the record (tensor versions); the keyed objects are
+        # held by the entry so that their ids cannot be recycled while it is cached
+        geom._versions = self._versions(p_pc_in, p_pc_out)
+        geom._keyed = (p_pc_in, p_pc_out, fi, fo)
+        self.conv_geometry_cache_ = {key: geom}
         return geom
+
+    @staticmethod
+    def _versions(p_pc_in, p_pc_out):
+        out = []
+        for pc in (p_pc_in, p_pc_out):
+            for name in ("pts_", "local_frames_"):
+                t = getattr(pc, name, None)
+                out.append(t._version if isinstance(t, torch.Tensor) else None)
+        return tuple(out)
 
     def _neighbors_token(self):
         return id(self.neighbors_)
@@ -148,9 +169,11 @@ class BQNeighborhood(Neighborhood):
 
 
 class KnnNeighborhood(Neighborhood):
-    """k-NN neighbourhood (pc/KnnNeighborhood.py:14-135).  The self-query branch (k <= 32) runs on
-    the sweep kernel; the cross-cloud / standard_knn branch of the reference delegates to
-    torch_cluster.knn, which is outside this path -- it raises here."""
+    """k-NN neighbourhood (pc/KnnNeighborhood.py:14-135), k <= 64 as in the reference.  The self-query branch runs on
+    the sweep kernel (se3_knn_query); between two different clouds (the reference's torch_cluster.knn branch, used by
+    the global-pooling convolutions, pc/KnnNeighborhood.py:78-84) every sample scans the sources of its batch item
+    (se3_knn_cross).  `p_standard_knn` (the reference's deterministic torch_cluster path for evaluation) maps onto the
+    same exact kernels: both are exact k-NN, ties broken by scan order."""
 
     def __init__(self, p_pc_src, p_samples, p_k, p_keep_empty=False, p_standard_knn=False):
         self.k_ = p_k
@@ -159,16 +182,29 @@ class KnnNeighborhood(Neighborhood):
         super(KnnNeighborhood, self).__init__(p_pc_src, p_samples)
 
     def __compute_neighborhood__(self):
-        if self.pc_src_ is not self.samples_:
-            raise Se3Error("KnnNeighborhood between two different clouds (torch_cluster.knn branch, "
-                           "pc/KnnNeighborhood.py:78-84) is not part of the B200 hot path")
-        if self.k_ > 32:
-            raise Se3Error("KnnNeighborhood: k <= 32 (all shipped configs use k = 16)")
-        # [N,k] int32 table straight from the sweep kernel; the [N*k,2] pair list and the row ends of
-        # the reference layout are materialised lazily (the frame construction only needs the table)
-        self.knn_table_ = KNNQuery.apply(self.pc_src_.pts_, self.pc_src_.batch_ids_, self.k_)
+        if not 1 <= int(self.k_) <= 64:
+            raise Se3Error("KnnNeighborhood: k must be in 1..64 (the reference's custom op has the same limit, "
+                           "custom_ops/knn_query/knn_query.cu:135-197)")
         self._pairs = None
         self._ends = None
+        if self.pc_src_ is self.samples_:
+            # [N,k] int32 table straight from the sweep kernel; the [N*k,2] pair list and the row ends of
+            # the reference layout are materialised lazily (the frame construction only needs the table)
+            self.knn_table_ = KNNQuery.apply(self.pc_src_.pts_, self.pc_src_.batch_ids_, self.k_)
+            return
+        src, dst = self.pc_src_, self.samples_
+        pts_s = src.pts_.detach().to(torch.float32).contiguous()
+        pts_d = dst.pts_.detach().to(torch.float32).contiguous()
+        b_s = src.batch_ids_.to(torch.int64)
+        b_d = dst.batch_ids_.to(torch.int32).contiguous()
+        nb = max(num_batches(src), num_batches(dst))
+        ends = torch.searchsorted(b_s.contiguous(), torch.arange(nb, device=b_s.device, dtype=torch.int64),
+                                  right=True).to(torch.int32).contiguous()
+        m = int(pts_d.shape[0])
+        out = torch.empty((m, int(self.k_)), dtype=torch.int32, device=pts_d.device)
+        check(lib().se3_knn_cross(ptr(pts_s), ptr(ends), ptr(pts_d), ptr(b_d), m, int(self.k_), ptr(out), stream()),
+              "se3_knn_cross")
+        self.knn_table_ = out
 
     def _materialise(self):
         if self._pairs is not None:

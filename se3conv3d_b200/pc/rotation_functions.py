@@ -94,8 +94,6 @@ def get_relative_rot(frames_A, frames_B, return_representation="matrix"):
     """R_A^T R_B for all frame pairs, pair index a*F_B + b (pc/RotationFunctions.py:549-600)."""
     if return_representation not in ("matrix", "6D", "quaternion"):
         raise ValueError("return_representation must be 'matrix', '6D' or 'quaternion'")
-    if return_representation == "quaternion":
-        raise Se3Error("the quaternion relative-rotation encoding is outside the B200 hot path ('6D' is the default)")
     n, fa = frames_A.shape[0], frames_A.shape[1]
     fb = frames_B.shape[1]
     A = frames_A.reshape(n, fa, 1, 3, 3)
@@ -103,7 +101,26 @@ def get_relative_rot(frames_A, frames_B, return_representation="matrix"):
     rel = torch.matmul(A.transpose(-1, -2), B).reshape(n, fa * fb, 3, 3)
     if return_representation == "matrix":
         return rel.reshape(n, fa * fb, 9)
+    if return_representation == "quaternion":
+        return matrix_to_quaternion(rel)
     return matrix_to_rotation_6d(rel)
+
+
+def matrix_to_quaternion(matrix):
+    """Rotation matrices [..., 3, 3] -> quaternions [..., 4], real part first; of the four algebraically equal
+    candidates the best conditioned one (largest |component|) is taken (pc/RotationFunctions.py:114-173)."""
+    batch = matrix.shape[:-2]
+    m = matrix.reshape(batch + (9,))
+    m00, m01, m02, m10, m11, m12, m20, m21, m22 = torch.unbind(m, dim=-1)
+    q_abs = torch.sqrt(torch.clamp(torch.stack((1.0 + m00 + m11 + m22, 1.0 + m00 - m11 - m22, 1.0 - m00 + m11 - m22,
+                                                1.0 - m00 - m11 + m22), dim=-1), min=0.0))
+    cand = torch.stack((torch.stack((q_abs[..., 0] ** 2, m21 - m12, m02 - m20, m10 - m01), dim=-1),
+                        torch.stack((m21 - m12, q_abs[..., 1] ** 2, m10 + m01, m02 + m20), dim=-1),
+                        torch.stack((m02 - m20, m10 + m01, q_abs[..., 2] ** 2, m12 + m21), dim=-1),
+                        torch.stack((m10 - m01, m20 + m02, m21 + m12, q_abs[..., 3] ** 2), dim=-1)), dim=-2)
+    cand = cand / (2.0 * q_abs[..., None].clamp_min(0.1))
+    pick = q_abs.argmax(dim=-1)
+    return torch.gather(cand, -2, pick[..., None, None].expand(batch + (1, 4))).squeeze(-2)
 
 
 def change_points_to_local_frame(points, origins, ref_frames):

@@ -966,3 +966,70 @@ def test_segment_pool_is_differentiable():
         (ref * w).sum().backward()
         assert rel_err(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) < 1e-6
         assert rel_err(x.grad.cpu().numpy(), x2.grad.cpu().numpy()) < 1e-6, method
+
+
+@pytest.mark.parametrize("case", ["matrix", "quaternion", "softmax", "basis16"])
+def test_layer_variants_match_reference_golden(case):
+    """The configurations outside the fused kernels -- 'matrix' / 'quaternion' relative rotations
+    (pc/RotationFunctions.py:593-600), the mlp_softmax basis (layers/PNEConvLayer.py:97), 16 basis functions -- through
+    the composed GPU path (reference statement sequence over this package's FeatBasisProj op) against the reference's
+    own float64 forward / backward (tests/golden/gen_variant_golden.py): <= 1e-4 on y and all four gradients."""
+    from se3conv3d_b200.layers import PNEConvLayerRotEquiv, PNEConvLayerRotEquivFactory
+    from se3conv3d_b200.pc import BQNeighborhood
+    g = dict(np.load(os.path.join(GOLDEN, "variant_%s.npz" % case)))
+    t = lambda k: torch.from_numpy(g[k]).to(DEV)
+    f = g["frames"].shape[1]
+    pc = types.SimpleNamespace(pts_=t("pts"), local_frames_=t("frames"), n_frames_=f)
+    neigh = BQNeighborhood.__new__(BQNeighborhood)
+    neigh.neighbors_, neigh.start_ids_, neigh.conv_geometry_cache_ = t("neighbors"), t("ends"), {}
+    cin, k, cout = g["conv_weights"].shape
+    fac = PNEConvLayerRotEquivFactory(int(g["dims"]), k, str(g["pne"]), p_rel_rot=str(g["rel"]))   # sets rel_rot_type
+    try:
+        layer = fac.create_conv_layer(cin, cout).to(DEV)
+        with torch.no_grad():
+            layer.proj_axes_.copy_(t("proj_axes"))
+            layer.proj_biases_.copy_(t("proj_biases"))
+            layer.conv_weights_.copy_(t("conv_weights"))
+            layer.norm_neigh_dist_.fill_(float(g["norm_neigh_dist"]))
+            layer.norm_num_neighs_.fill_(float(g["norm_num_neighs"]))
+        x = t("x").clone().requires_grad_(True)
+        y = layer(pc, pc, x, neigh)
+        (y * t("dy")).sum().backward()
+        got = (y, x.grad, layer.conv_weights_.grad, layer.proj_axes_.grad, layer.proj_biases_.grad)
+        for name, a, key in zip(("y", "dx", "dW", "dA", "dB"), got, ("y", "dx", "dW", "dA", "dB")):
+            m = lo.err_metrics(a.detach().cpu().numpy(), g[key])
+            print(case, name, "max/max %.2e relL2 %.2e p99.9 %.2e" % m)
+            assert max(m) < 1e-4, (case, name, m)
+    finally:
+        PNEConvLayerRotEquiv.rel_rot_type = "6D"
+
+
+@pytest.mark.parametrize("k", [16, 33, 48, 64])
+def test_knn_up_to_64_and_cross_cloud(k):
+    """k up to 64 (two ranks per lane; the reference op's limit, knn_query.cu:135-197) and the cross-cloud query
+    (pc/KnnNeighborhood.py:78-84) against exact brute-force distances; ties by distance excluded through the sorted
+    distance rows."""
+    from se3conv3d_b200.pc import Pointcloud, KnnNeighborhood
+    pts, b = cloud(3000, 3, 41, scale=(1.0, 0.7, 0.4))
+    pc = Pointcloud(pts.to(DEV), b.to(DEV))
+    nbh = KnnNeighborhood(pc, pc, k, p_keep_empty=True)
+    tab = nbh.knn_table_.cpu().numpy()
+    P, B = pts.numpy().astype(np.float64), b.numpy()
+    full = ((P[:, None, :] - P[None, :, :]) ** 2).sum(-1)
+    full[B[:, None] != B[None, :]] = np.inf
+    ref = np.sort(full, axis=1)[:, :k]
+    got = np.where(tab >= 0, full[np.arange(3000)[:, None], np.maximum(tab, 0)], np.inf)
+    np.testing.assert_allclose(np.sort(got, 1), ref, rtol=1e-5, atol=1e-12)
+    assert nbh.neighbors_.shape == (3000 * k, 2) and int(nbh.start_ids_[-1]) == 3000 * k
+    # cross-cloud: 500 samples against the 3000 sources of their batch item
+    spts, sb = cloud(500, 3, 43, scale=(1.0, 0.7, 0.4))
+    spc = Pointcloud(spts.to(DEV), sb.to(DEV))
+    x = KnnNeighborhood(pc, spc, k)
+    xt = x.knn_table_.cpu().numpy()
+    S = spts.numpy().astype(np.float64)
+    cross = ((S[:, None, :] - P[None, :, :]) ** 2).sum(-1)
+    cross[sb.numpy()[:, None] != B[None, :]] = np.inf
+    refx = np.sort(cross, axis=1)[:, :k]
+    gotx = np.where(xt >= 0, cross[np.arange(500)[:, None], np.maximum(xt, 0)], np.inf)
+    np.testing.assert_allclose(gotx, refx, rtol=1e-5, atol=1e-12)          # already in ascending order
+    assert x.neighbors_.shape[0] == int(x.start_ids_[-1]) and x.neighbors_.shape[1] == 2
