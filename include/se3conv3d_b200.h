@@ -329,6 +329,30 @@ int se3_conv_bwd(const se3_conv_desc* d, const float* x, const float* dy, const 
                  float* dx, float* d_conv_weights, float* d_proj_axes, float* d_proj_biases,
                  void* workspace, size_t workspace_bytes, se3_stream_t stream);
 
+/* ---- the glue around the convolution ---------------------------------------------------
+ * out = drop_path(x * gamma) + y: layers/SkipConnection.py:31-43 with layers/DropPathPC.py:23-50.  x, y, out [rows, c];
+ * gamma [c]; item_scale [B] = keep_mask / keep_prob per batch item (NULL = no drop path); point_item [rows / frames] =
+ * batch item of every POINT (rows are (point, frame), `frames` rows per point).  bwd: dx (may be NULL) and dgamma [c]
+ * (ordered two-stage reduction through `workspace`); the gradient of y is dy itself. */
+size_t se3_gamma_skip_workspace_bytes(int64_t rows, int32_t c);
+int se3_gamma_skip_fwd(const float* x, const float* y, const float* gamma, const float* item_scale,
+                       const int32_t* point_item, int32_t frames, int64_t rows, int32_t c, float* out, se3_stream_t stream);
+int se3_gamma_skip_bwd(const float* dy, const float* x, const float* gamma, const float* item_scale,
+                       const int32_t* point_item, int32_t frames, int64_t rows, int32_t c, float* dx, float* dgamma,
+                       void* workspace, size_t workspace_bytes, se3_stream_t stream);
+/* pooling of the f per-frame rows of every point (pc/PointcloudRotEquiv.py:224-251): x [n*f, c] -> out [n, c];
+ * mode 0 avg, 1 sum, 2 max, 3 min.  bwd needs x and out for max / min (first frame attaining the extremum). */
+int se3_frame_pool_fwd(const float* x, int64_t n, int32_t f, int32_t c, int32_t mode, float* out, se3_stream_t stream);
+int se3_frame_pool_bwd(const float* dout, const float* x, const float* out, int64_t n, int32_t f, int32_t c, int32_t mode,
+                       float* dx, se3_stream_t stream);
+/* pooling of the rows of every batch item (global_pooling*, pc/PointcloudRotEquiv.py:195-222, 253-275): rows are grouped
+ * by item, item_ends [B] int32 inclusive ends; modes as above.  bwd: mode 0 / 1, or 4 = plain gather of dout rows
+ * (global_upsample, :277-286); row_item [rows] = item of every row. */
+int se3_batch_pool_fwd(const float* x, const int32_t* item_ends, int32_t n_items, int32_t c, int32_t mode, float* out,
+                       se3_stream_t stream);
+int se3_batch_pool_bwd(const float* dout, const int32_t* item_ends, const int32_t* row_item, int64_t rows, int32_t c,
+                       int32_t mode, float* dx, se3_stream_t stream);
+
 /* Kernel selection of precision 1 for layers with 9..64 gathered channels and 1..2 row frames:
  *   0 (default) aggregation kernel (mma.sync) + projection GEMM (tcgen05), T [R, Cin*K] through HBM;
  *   1 warp-specialised tcgen05 aggregation kernel (conv_fused.cu) + projection GEMM;

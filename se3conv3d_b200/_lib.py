@@ -23,6 +23,8 @@ ABI_SYMBOLS = [
     "se3_feat_basis_proj", "se3_feat_basis_proj_grad",
     "se3_conv_fwd_workspace_bytes", "se3_conv_bwd_workspace_bytes", "se3_conv_saved_bytes",
     "se3_conv_fwd", "se3_conv_bwd", "se3_gemm_bf16_tn", "se3_pack_records", "se3_conv_set_fused",
+    "se3_gamma_skip_workspace_bytes", "se3_gamma_skip_fwd", "se3_gamma_skip_bwd", "se3_frame_pool_fwd", "se3_frame_pool_bwd",
+    "se3_batch_pool_fwd", "se3_batch_pool_bwd",
     "se3_ball_query_fill_csr", "se3_csr_transpose_i32", "se3_segment_first_i32", "se3_segment_pick",
     "se3_hierarchy_build", "se3_bbox", "se3_grid_extents", "se3_ball_query_src_workspace_bytes",
     "se3_ball_query_dst_workspace_bytes", "se3_ball_query_prepare", "se3_ball_query_count_prepared",
@@ -142,6 +144,14 @@ def lib():
         getattr(L, n).restype = sz
     L.se3_conv_fwd.argtypes = [dp, vp, vp, vp, vp, sz, vp]
     L.se3_conv_set_fused.argtypes = [i32]
+    L.se3_gamma_skip_workspace_bytes.argtypes = [i64, i32]
+    L.se3_gamma_skip_workspace_bytes.restype = sz
+    L.se3_gamma_skip_fwd.argtypes = [vp, vp, vp, vp, vp, i32, i64, i32, vp, vp]
+    L.se3_gamma_skip_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i64, i32, vp, vp, vp, sz, vp]
+    L.se3_frame_pool_fwd.argtypes = [vp, i64, i32, i32, i32, vp, vp]
+    L.se3_frame_pool_bwd.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp, vp]
+    L.se3_batch_pool_fwd.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    L.se3_batch_pool_bwd.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
     L.se3_gemm_bf16_tn.argtypes = [vp, vp, i64, i64, i64, f32, vp, i32, i32, vp]
     L.se3_pack_records.argtypes = [vp, vp, i64, i32, vp, vp]
     L.se3_ball_query_fill_csr.argtypes = [vp, i64, i64, vp, vp, sz, vp, i64, vp, vp, vp]

@@ -161,3 +161,99 @@ class RotEquivConv(torch.autograd.Function):
                              ws.data_ptr(), ws.numel(), stream()), "se3_conv_bwd")
         return (dx.to(x_dtype) if dx is not None else None, dA if need[1] else None, dB if need[2] else None, dW,
                 None, None, None, None, None)
+
+
+def _point_items(p_pc):
+    """int32 batch item of every POINT of a cloud (cached on the cloud)."""
+    t = p_pc.__dict__.get("_point_items_i32") if hasattr(p_pc, "__dict__") else None
+    if t is None or t.shape[0] != p_pc.batch_ids_.shape[0]:
+        t = p_pc.batch_ids_.to(torch.int32).contiguous()
+        try:
+            p_pc._point_items_i32 = t
+        except AttributeError:
+            pass
+    return t
+
+
+class GammaSkip(torch.autograd.Function):
+    """out = drop_path(x * gamma) + y in one kernel each way (layers/SkipConnection.py:31-43, DropPathPC.py:23-50)."""
+
+    @staticmethod
+    def forward(ctx, x, y, gamma, item_scale, point_item, frames):
+        x, y = _f32c(x), _f32c(y)
+        g = _f32c(gamma).reshape(-1)
+        rows, c = x.shape
+        out = torch.empty_like(x)
+        check(lib().se3_gamma_skip_fwd(ptr(x), ptr(y), ptr(g), ptr(item_scale), ptr(point_item), int(frames), rows, c,
+                                       ptr(out), stream()), "se3_gamma_skip_fwd")
+        ctx.save_for_backward(x, g, item_scale, point_item)
+        ctx.frames, ctx.gshape = int(frames), gamma.shape
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        x, g, item_scale, point_item = ctx.saved_tensors
+        dy = _f32c(dy)
+        rows, c = x.shape
+        L = lib()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dg = torch.empty(c, dtype=torch.float32, device=x.device)
+        ws = workspace(L.se3_gamma_skip_workspace_bytes(rows, c), x.device, "block")
+        check(L.se3_gamma_skip_bwd(ptr(dy), ptr(x), ptr(g), ptr(item_scale), ptr(point_item), ctx.frames, rows, c, ptr(dx),
+                                   ptr(dg), ptr(ws), ws.numel(), stream()), "se3_gamma_skip_bwd")
+        return dx, (dy if ctx.needs_input_grad[1] else None), dg.reshape(ctx.gshape), None, None, None
+
+
+POOL_MODES = {"avg": 0, "sum": 1, "max": 2, "min": 3}
+
+
+class FramePool(torch.autograd.Function):
+    """Pooling over the F per-frame rows of every point (pc/PointcloudRotEquiv.py:224-251)."""
+
+    @staticmethod
+    def forward(ctx, x, frames, mode):
+        x = _f32c(x)
+        n, c = x.shape[0] // int(frames), x.shape[1]
+        out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        check(lib().se3_frame_pool_fwd(ptr(x), n, int(frames), c, int(mode), ptr(out), stream()), "se3_frame_pool_fwd")
+        ctx.meta = (n, int(frames), c, int(mode))
+        if mode >= 2:
+            ctx.save_for_backward(x, out)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dout):
+        n, f, c, mode = ctx.meta
+        x, out = ctx.saved_tensors if mode >= 2 else (None, None)
+        dout = _f32c(dout)
+        dx = torch.empty((n * f, c), dtype=torch.float32, device=dout.device)
+        check(lib().se3_frame_pool_bwd(ptr(dout), ptr(x), ptr(out), n, f, c, mode, ptr(dx), stream()), "se3_frame_pool_bwd")
+        return dx, None, None
+
+
+class BatchPool(torch.autograd.Function):
+    """avg / sum pooling of the rows of every batch item (global_pooling*, pc/PointcloudRotEquiv.py:195-222, 253-275);
+    rows are grouped by item (item_ends inclusive, row_item per row)."""
+
+    @staticmethod
+    def forward(ctx, x, item_ends, row_item, mode):
+        x = _f32c(x)
+        b, c = item_ends.shape[0], x.shape[1]
+        out = torch.empty((b, c), dtype=torch.float32, device=x.device)
+        check(lib().se3_batch_pool_fwd(ptr(x), ptr(item_ends), b, c, int(mode), ptr(out), stream()), "se3_batch_pool_fwd")
+        ctx.save_for_backward(item_ends, row_item)
+        ctx.meta = (x.shape[0], c, int(mode))
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dout):
+        item_ends, row_item = ctx.saved_tensors
+        rows, c, mode = ctx.meta
+        dout = _f32c(dout)
+        dx = torch.empty((rows, c), dtype=torch.float32, device=dout.device)
+        check(lib().se3_batch_pool_bwd(ptr(dout), ptr(item_ends), ptr(row_item), rows, c, mode, ptr(dx), stream()),
+              "se3_batch_pool_bwd")
+        return dx, None, None, None

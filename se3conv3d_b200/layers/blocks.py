@@ -1,9 +1,8 @@
 """The block around the convolution: BatchNormPC, DropPathPC, SkipConnection, Block and
 ResNetFormer with the reference's constructors, attribute / parameter names (so checkpoints load) and forward
 signatures (layers/BatchNormPC.py:7-31, DropPathPC.py:5-49, SkipConnection.py:7-42, Block.py:5-50,
-ResNetFormer.py:5-90).  The convolution inside is the fused kernel; normalisation, the two Linear layers and the
-skips are still plain tensor ops -- folding BN-apply and the gamma-skip into the conv prologue / epilogue is the
-planned next step of this row."""
+ResNetFormer.py:5-90).  The convolution inside is the fused kernel; the gamma-skip with its drop path is one kernel each way
+(csrc/block_ops.cu); normalisation and the two Linear layers are library ops (cuDNN / cuBLAS through torch)."""
 import torch
 
 from .base import PreProcessModule
@@ -46,7 +45,9 @@ class DropPathPC(torch.nn.Module):
 
 
 class SkipConnection(torch.nn.Module):
-    """out = drop_path(x * gamma) + y with a learnable per-channel gamma initialised to 1e-6."""
+    """out = drop_path(x * gamma) + y with a learnable per-channel gamma initialised to 1e-6
+    (layers/SkipConnection.py:7-42).  On CUDA tensors the scale, the per-item drop-path mask, its 1 / keep rescale and
+    the skip add are ONE kernel forward (se3_gamma_skip_fwd) and one backward (+ an ordered reduction for d gamma)."""
 
     def __init__(self, p_drop_prob, p_num_features, p_init_gamma=1e-6):
         super(SkipConnection, self).__init__()
@@ -54,7 +55,20 @@ class SkipConnection(torch.nn.Module):
         self.gamma_ = torch.nn.Parameter(p_init_gamma * torch.ones((1, p_num_features)))
 
     def forward(self, p_x, p_y, p_pc):
-        return self.drop_path_(p_x * self.gamma_, p_pc) + p_y
+        if not (p_x.is_cuda and p_x.dtype == torch.float32 and p_y.dtype == torch.float32 and p_x.dim() == 2):
+            return self.drop_path_(p_x * self.gamma_, p_pc) + p_y
+        from ..custom_ops.functions import GammaSkip, _point_items
+        n_points = int(p_pc.batch_ids_.shape[0])
+        frames = max(int(p_x.shape[0]) // max(n_points, 1), 1)
+        scale, items = None, None
+        p = self.drop_path_.drop_prob_
+        if p != 0.0 and self.training:
+            keep = 1.0 - p
+            n_items = int(getattr(p_pc, "batch_size_host_", None) or p_pc.batch_size_)
+            # the same draw as DropPathPC: floor(keep + U[0,1)) per batch item, divided by keep
+            scale = torch.floor(keep + torch.rand((n_items,), dtype=torch.float32, device=p_x.device)) / keep
+            items = _point_items(p_pc)
+        return GammaSkip.apply(p_x, p_y, self.gamma_, scale, items, frames)
 
 
 class Block(PreProcessModule):

@@ -95,9 +95,15 @@ class PointcloudRotEquiv(Pointcloud):
         self.batch_ids_considering_frames_ = self.batch_ids_considering_frames_.to(p_device)
 
     def feature_pooling(self, p_in_tensor, p_pooling_method="avg"):
-        """Pools the F per-frame feature rows of every point (pc/PointcloudRotEquiv.py:224-251)."""
+        """Pools the F per-frame feature rows of every point (pc/PointcloudRotEquiv.py:224-251): one kernel each way
+        (se3_frame_pool_fwd / _bwd) on CUDA float32 matrices."""
         f = self.local_frames_config_["n_frames"]
         n = self.pts_.shape[0]
+        if p_pooling_method not in ("avg", "sum", "max", "min"):
+            raise ValueError("unknown pooling method " + str(p_pooling_method))
+        if p_in_tensor.is_cuda and p_in_tensor.dim() == 2 and p_in_tensor.dtype == torch.float32:
+            from ..custom_ops.functions import FramePool, POOL_MODES
+            return FramePool.apply(p_in_tensor, f, POOL_MODES[p_pooling_method])
         x = p_in_tensor.reshape(n, f, *p_in_tensor.shape[1:])
         if p_pooling_method == "avg":
             return x.mean(dim=1)
@@ -105,17 +111,36 @@ class PointcloudRotEquiv(Pointcloud):
             return x.sum(dim=1)
         if p_pooling_method == "max":
             return x.max(dim=1)[0]
-        if p_pooling_method == "min":
-            return x.min(dim=1)[0]
-        raise ValueError("unknown pooling method " + str(p_pooling_method))
+        return x.min(dim=1)[0]
+
+    def _item_rows(self, frames):
+        """(inclusive row ends per batch item int32 [B], item of every row int32) for rows = points x frames."""
+        key = "_item_rows_%d" % frames
+        hit = self.__dict__.get(key)
+        if hit is None:
+            b = self.batch_ids_.to(torch.int64)
+            nb = int(getattr(self, "batch_size_host_", None) or self.batch_size_)
+            ends = (torch.searchsorted(b.contiguous(), torch.arange(nb, device=b.device), right=True) * frames).to(torch.int32)
+            rows = torch.repeat_interleave(self.batch_ids_.to(torch.int32), frames) if frames > 1 else self.batch_ids_.to(torch.int32)
+            hit = (ends.contiguous(), rows.contiguous())
+            self.__dict__[key] = hit
+        return hit
+
+    def _batch_pool(self, x, frames, method):
+        if method in ("avg", "sum") and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32:
+            from ..custom_ops.functions import BatchPool, POOL_MODES
+            ends, rows = self._item_rows(frames)
+            return BatchPool.apply(x, ends, rows, POOL_MODES[method])
+        ids = (self.batch_ids_considering_frames_ if frames > 1 else self.batch_ids_).to(torch.int64)
+        return pool_by_index(x, ids, method)
 
     def global_pooling_specific_feature_pooling(self, p_in_tensor, p_global_pooling_method="avg",
                                                 p_feature_pooling_method="avg"):
         pooled = self.feature_pooling(p_in_tensor, p_pooling_method=p_feature_pooling_method)
-        return pool_by_index(pooled, self.batch_ids_.to(torch.int64), p_global_pooling_method)
+        return self._batch_pool(pooled, 1, p_global_pooling_method)
 
     def global_pooling(self, p_in_tensor, p_pooling_method="avg"):
-        return pool_by_index(p_in_tensor, self.batch_ids_considering_frames_.to(torch.int64), p_pooling_method)
+        return self._batch_pool(p_in_tensor, self.n_frames_, p_pooling_method)
 
     def global_upsample(self, p_in_tensor):
         return torch.index_select(p_in_tensor, 0, self.batch_ids_considering_frames_.to(torch.int64))
