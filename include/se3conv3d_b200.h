@@ -310,6 +310,14 @@ typedef struct se3_conv_desc {
   const float* proj_axes;    /* [9,K]   */
   const float* proj_biases;  /* [K]     */
   const float* conv_weights; /* [c_in,K,c_out] */
+  /* optional (precision 1): device buffer of se3_conv_weight_cache_bytes() for the bf16 operand layouts of
+   * conv_weights.  They depend on the weights only, i.e. they change once per optimiser step, not per call:
+   * weight_cache_state 1 = the forward (re)builds them into the buffer, 2 = the buffer is up to date and the forward
+   * skips the conversion (evaluation, gradient accumulation, several calls per step).  NULL / 0 = rebuilt on every
+   * forward inside the call's saved buffer.  The backward of a call reads the buffer the forward used. */
+  void* weight_cache;
+  int32_t weight_cache_state;
+  int32_t reserved2;
 } se3_conv_desc;
 
 /* rec [n*f,12] = (pts[i,0..2], frames[i,a,0..8]) -- the gather record of the tensor-core path. */
@@ -320,6 +328,8 @@ size_t se3_conv_fwd_workspace_bytes(const se3_conv_desc* d);
 size_t se3_conv_bwd_workspace_bytes(const se3_conv_desc* d);
 /* bytes of the per-call "saved" buffer written by fwd and consumed by bwd (may be 0) */
 size_t se3_conv_saved_bytes(const se3_conv_desc* d);
+/* bytes of the optional per-layer weight-layout cache (0 for precision 0) */
+size_t se3_conv_weight_cache_bytes(const se3_conv_desc* d);
 
 /* y [M*f_out, c_out] = conv(x [N*f_in, c_in]) */
 int se3_conv_fwd(const se3_conv_desc* d, const float* x, float* y, void* saved,

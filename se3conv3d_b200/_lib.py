@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "se3_knn_workspace_bytes", "se3_knn_query", "se3_knn_cross", "se3_pca_frames", "se3_quat_frames",
     "se3_segment_pool_f32",
     "se3_feat_basis_proj", "se3_feat_basis_proj_grad",
-    "se3_conv_fwd_workspace_bytes", "se3_conv_bwd_workspace_bytes", "se3_conv_saved_bytes",
+    "se3_conv_fwd_workspace_bytes", "se3_conv_bwd_workspace_bytes", "se3_conv_saved_bytes", "se3_conv_weight_cache_bytes",
     "se3_conv_fwd", "se3_conv_bwd", "se3_gemm_bf16_tn", "se3_pack_records", "se3_conv_set_fused",
     "se3_gamma_skip_workspace_bytes", "se3_gamma_skip_fwd", "se3_gamma_skip_bwd", "se3_frame_pool_fwd", "se3_frame_pool_bwd",
     "se3_batch_pool_fwd", "se3_batch_pool_bwd",
@@ -44,6 +44,7 @@ class ConvDesc(C.Structure):
         ("t_row_ends", C.c_void_p), ("t_edge", C.c_void_p), ("t_dst", C.c_void_p),
         ("rec_in", C.c_void_p), ("rec_out", C.c_void_p),
         ("proj_axes", C.c_void_p), ("proj_biases", C.c_void_p), ("conv_weights", C.c_void_p),
+        ("weight_cache", C.c_void_p), ("weight_cache_state", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 
@@ -139,7 +140,8 @@ def lib():
     L.se3_feat_basis_proj.argtypes = [vp, vp, vp, vp, i64, i64, i32, i32, vp, vp]
     L.se3_feat_basis_proj_grad.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, vp, vp, vp]
     dp = C.POINTER(ConvDesc)
-    for n in ("se3_conv_fwd_workspace_bytes", "se3_conv_bwd_workspace_bytes", "se3_conv_saved_bytes"):
+    for n in ("se3_conv_fwd_workspace_bytes", "se3_conv_bwd_workspace_bytes", "se3_conv_saved_bytes",
+              "se3_conv_weight_cache_bytes"):
         getattr(L, n).argtypes = [dp]
         getattr(L, n).restype = sz
     L.se3_conv_fwd.argtypes = [dp, vp, vp, vp, vp, sz, vp]

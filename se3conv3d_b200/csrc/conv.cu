@@ -16,6 +16,7 @@ namespace se3 {
 size_t conv_tc_fwd_workspace_bytes(const se3_conv_desc* d);
 size_t conv_tc_bwd_workspace_bytes(const se3_conv_desc* d);
 size_t conv_tc_saved_bytes(const se3_conv_desc* d);
+size_t conv_tc_weight_cache_bytes(const se3_conv_desc* d);
 int conv_tc_fwd(const se3_conv_desc* d, const float* x, float* y, void* saved, void* ws, size_t ws_bytes,
                 cudaStream_t st);
 int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const void* saved, float* dx, float* dW,
@@ -51,6 +52,11 @@ extern "C" size_t se3_conv_saved_bytes(const se3_conv_desc* d) {
   if (check_desc(d) != SE3_OK) return 0;
   if (d->precision == 1) return conv_tc_saved_bytes(d);
   return align_up((size_t)d->n_out * d->f_out * d->c_in * d->k * sizeof(float)) + 256;
+}
+
+extern "C" size_t se3_conv_weight_cache_bytes(const se3_conv_desc* d) {
+  if (check_desc(d) != SE3_OK || d->precision != 1) return 0;
+  return conv_tc_weight_cache_bytes(d);
 }
 
 extern "C" size_t se3_conv_fwd_workspace_bytes(const se3_conv_desc* d) {

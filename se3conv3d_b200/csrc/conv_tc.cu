@@ -1425,13 +1425,22 @@ static TcSaved tc_saved_layout(const se3_conv_desc* d, void* base) {
   TcSaved s;
   s.T = reinterpret_cast<__nv_bfloat16*>(p + off); off += align_up((size_t)d->n_out * d->f_out * saved_tile_cols(d) * 2);
   s.xb = reinterpret_cast<__nv_bfloat16*>(p + off); off += align_up((size_t)d->n_in * d->f_in * pad8(d->c_in) * 2);
-  s.Wt = reinterpret_cast<__nv_bfloat16*>(p + off); off += wbytes;
-  s.Wb = reinterpret_cast<__nv_bfloat16*>(p + off); off += wbytes;
-  s.Wp = reinterpret_cast<__nv_bfloat16*>(p + off); off += wbytes;
+  if (d->weight_cache) {
+    // the three operand layouts live in the caller's per-layer cache (valid across calls until the weights change)
+    char* w = reinterpret_cast<char*>(d->weight_cache);
+    s.Wt = reinterpret_cast<__nv_bfloat16*>(w);
+    s.Wb = reinterpret_cast<__nv_bfloat16*>(w + wbytes);
+    s.Wp = reinterpret_cast<__nv_bfloat16*>(w + 2 * wbytes);
+  } else {
+    s.Wt = reinterpret_cast<__nv_bfloat16*>(p + off); off += wbytes;
+    s.Wb = reinterpret_cast<__nv_bfloat16*>(p + off); off += wbytes;
+    s.Wp = reinterpret_cast<__nv_bfloat16*>(p + off); off += wbytes;
+  }
   s.bytes = off + 256;
   return s;
 }
 size_t conv_tc_saved_bytes(const se3_conv_desc* d) { return tc_saved_layout(d, nullptr).bytes; }
+size_t conv_tc_weight_cache_bytes(const se3_conv_desc* d) { return 3 * align_up((size_t)d->c_in * d->k * d->c_out * 2) + 256; }
 size_t conv_tc_fwd_workspace_bytes(const se3_conv_desc* d) {
   if (fwd_fused(d) == 2) return align_up(fused_w3_bytes(d->c_in, d->c_out)) + 256;
   if (fwd_fused(d) == 1)
@@ -1476,13 +1485,16 @@ int conv_tc_fwd(const se3_conv_desc* d, const float* x, float* y, void* saved, v
   const int64_t Nf = d->n_in * d->f_in;
   {
     const int o_chunks = (d->c_out + 255) / 256;
-    const int w_blocks = d->c_in * o_chunks;
+    // weight layouts: skipped when the caller's cache is up to date
+    const int w_blocks = (d->weight_cache && d->weight_cache_state == 2) ? 0 : d->c_in * o_chunks;
     const int64_t work = cs == d->c_in ? Nf * cs / 8 : Nf * cs;
     const int x_blocks = Nf > 0 ? blocks_for(work) : 0;
     const size_t smem = (size_t)d->k * (std::min(256, d->c_out) + 1) * sizeof(float);
-    SE3_CUDA(launch_pdl(k_fwd_prep, dim3(w_blocks + x_blocks), dim3(256), smem, st, d->conv_weights, d->c_in, d->k, d->c_out,
-                        o_chunks, sv.Wt, sv.Wb, sv.Wp, w_blocks, x, Nf, d->c_in, cs, sv.xb));
-    SE3_LAUNCH_CHECK();
+    if (w_blocks + x_blocks > 0) {
+      SE3_CUDA(launch_pdl(k_fwd_prep, dim3(w_blocks + x_blocks), dim3(256), smem, st, d->conv_weights, d->c_in, d->k, d->c_out,
+                          o_chunks, sv.Wt, sv.Wb, sv.Wp, w_blocks, x, Nf, d->c_in, cs, sv.xb));
+      SE3_LAUNCH_CHECK();
+    }
   }
   if (fmode) {
     // geometry -> basis -> aggregation (-> projection) in one tcgen05 kernel; with the projection inside, T only leaves

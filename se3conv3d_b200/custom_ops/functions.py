@@ -100,12 +100,35 @@ def make_conv_desc(geom, c_in, c_out, k, act, precision, norm_neigh_dist, out_sc
         L = lib()
         ref = C.byref(d)
         entry = (d, ref, int(L.se3_conv_saved_bytes(ref)), int(L.se3_conv_fwd_workspace_bytes(ref)),
-                 int(L.se3_conv_bwd_workspace_bytes(ref)))
+                 int(L.se3_conv_bwd_workspace_bytes(ref)), int(L.se3_conv_weight_cache_bytes(ref)))
         cache[key] = entry
     d = entry[0]
     d.norm_neigh_dist, d.out_scale = float(norm_neigh_dist), float(out_scale)
     d.proj_axes, d.proj_biases, d.conv_weights = ptr(proj_axes), ptr(proj_biases), ptr(conv_weights)
+    d.weight_cache, d.weight_cache_state = None, 0
     return entry
+
+
+class WeightLayoutCache(object):
+    """Per-layer device buffer for the bf16 operand layouts of conv_weights_ (precision 1).  They depend on the weights
+    only: the forward rebuilds them when the parameter tensor was replaced or written (optimiser step, load_state_dict),
+    and skips the conversion otherwise (evaluation, gradient accumulation, several calls per step)."""
+
+    def __init__(self):
+        self.key, self.buf, self.param = None, None, None
+
+    def attach(self, d, cw_param, cw32, nbytes):
+        """Sets the descriptor's cache fields; returns nothing.  `cw_param` is the nn.Parameter (identity + version are
+        the key; the entry holds it so that its id cannot be recycled), `cw32` the float32 tensor the kernels read."""
+        if nbytes <= 0:
+            return
+        key = (id(cw_param), cw_param._version, cw32.data_ptr(), nbytes, str(cw32.device))
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != cw32.device:
+            self.buf = torch.empty(nbytes, dtype=torch.uint8, device=cw32.device)
+            self.key = None
+        d.weight_cache = self.buf.data_ptr()
+        d.weight_cache_state = 2 if self.key == key else 1
+        self.key, self.param = key, cw_param
 
 
 def _f32c(t):
@@ -117,7 +140,7 @@ class RotEquivConv(torch.autograd.Function):
     (layers/PNEConvLayerRotEquiv.py:160-216) through se3_conv_fwd / se3_conv_bwd."""
 
     @staticmethod
-    def forward(ctx, x, proj_axes, proj_biases, conv_weights, geom, act, precision, norm_neigh_dist, out_scale):
+    def forward(ctx, x, proj_axes, proj_biases, conv_weights, geom, act, precision, norm_neigh_dist, out_scale, wcache=None):
         if not x.is_cuda:
             raise Se3Error("RotEquivConv needs CUDA tensors; there is no CPU fallback")
         x32 = _f32c(x)
@@ -129,14 +152,17 @@ class RotEquivConv(torch.autograd.Function):
         if pa.shape[0] != 9:
             raise Se3Error("RotEquivConv: proj_axes_ must be [9, K] (p_dims=9, '6D' relative rotation)")
         L = lib()
-        d, dref, saved_bytes, fwd_ws, _ = make_conv_desc(geom, c_in, c_out, k, act, precision, norm_neigh_dist, out_scale,
-                                                        pa, pb, cw)
+        d, dref, saved_bytes, fwd_ws, _, wc_bytes = make_conv_desc(geom, c_in, c_out, k, act, precision, norm_neigh_dist,
+                                                                  out_scale, pa, pb, cw)
+        if wcache is not None and precision == 1:
+            wcache.attach(d, conv_weights, cw, wc_bytes)
         y = torch.empty((geom.n_out * geom.f_out, c_out), dtype=torch.float32, device=x.device)
         saved = torch.empty(max(saved_bytes, 256), dtype=torch.uint8, device=x.device)
         ws = workspace(fwd_ws, x.device, 'conv')
         check(L.se3_conv_fwd(dref, x32.data_ptr(), y.data_ptr(), saved.data_ptr(), ws.data_ptr(), ws.numel(), stream()),
               "se3_conv_fwd")
         ctx.geom = geom
+        ctx.wcache = (d.weight_cache, wcache.buf) if (wcache is not None and d.weight_cache) else None
         ctx.meta = (act, precision, float(norm_neigh_dist), float(out_scale), x.dtype)
         ctx.save_for_backward(x32, pa, pb, cw, saved)
         return y
@@ -150,7 +176,9 @@ class RotEquivConv(torch.autograd.Function):
         c_in, k, c_out = cw.shape
         dy = _f32c(dy)
         L = lib()
-        d, dref, _, _, bwd_ws = make_conv_desc(geom, c_in, c_out, k, act, precision, nnd, osc, pa, pb, cw)
+        d, dref, _, _, bwd_ws, _ = make_conv_desc(geom, c_in, c_out, k, act, precision, nnd, osc, pa, pb, cw)
+        if ctx.wcache is not None:       # the layouts the forward of this call used
+            d.weight_cache, d.weight_cache_state = ctx.wcache[0], 2
         need = ctx.needs_input_grad
         dx = torch.empty_like(x32) if need[0] else None
         dA = torch.empty_like(pa) if (need[1] or need[2]) else None
@@ -160,7 +188,7 @@ class RotEquivConv(torch.autograd.Function):
         check(L.se3_conv_bwd(dref, x32.data_ptr(), dy.data_ptr(), saved.data_ptr(), ptr(dx), ptr(dW), ptr(dA), ptr(dB),
                              ws.data_ptr(), ws.numel(), stream()), "se3_conv_bwd")
         return (dx.to(x_dtype) if dx is not None else None, dA if need[1] else None, dB if need[2] else None, dW,
-                None, None, None, None, None)
+                None, None, None, None, None, None)
 
 
 def _point_items(p_pc):

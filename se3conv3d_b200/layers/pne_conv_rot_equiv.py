@@ -3,7 +3,7 @@ import math
 import torch
 
 from .base import IConvLayer, IConvLayerFactory
-from ..custom_ops.functions import RotEquivConv, ACT_CODES
+from ..custom_ops.functions import RotEquivConv, ACT_CODES, WeightLayoutCache
 from .._lib import Se3Error
 
 
@@ -77,8 +77,11 @@ class PNEConvLayerRotEquiv(IConvLayer):
             return self._composed_convolution(p_pc_in, p_pc_out, p_in_features, p_neighborhood)
         geom = p_neighborhood.conv_geometry(p_pc_in, p_pc_out)
         norm_dist, norm_num = self._host_scalars()
+        wc = self.__dict__.get("_wcache")
+        if wc is None:
+            wc = self.__dict__["_wcache"] = WeightLayoutCache()
         return RotEquivConv.apply(p_in_features, self.proj_axes_, self.proj_biases_, self.conv_weights_, geom,
-                                  ACT_CODES[self.pne_type_], int(self.precision), norm_dist, norm_num / geom.f_in)
+                                  ACT_CODES[self.pne_type_], int(self.precision), norm_dist, norm_num / geom.f_in, wc)
 
     def _composed_convolution(self, p_pc_in, p_pc_out, p_in_features, p_neighborhood):
         """The configurations outside the fused kernels ('matrix' / 'quaternion' relative rotations,

@@ -1033,3 +1033,37 @@ def test_knn_up_to_64_and_cross_cloud(k):
     gotx = np.where(xt >= 0, cross[np.arange(500)[:, None], np.maximum(xt, 0)], np.inf)
     np.testing.assert_allclose(gotx, refx, rtol=1e-5, atol=1e-12)          # already in ascending order
     assert x.neighbors_.shape[0] == int(x.start_ids_[-1]) and x.neighbors_.shape[1] == 2
+
+
+def test_weight_layout_cache_follows_the_parameter():
+    """The per-layer cache of the bf16 weight layouts (se3_conv_desc.weight_cache): a second call with unchanged weights
+    skips the conversion and is bit-identical; after an in-place update (optimiser step) or a replaced parameter tensor
+    the layouts are rebuilt -- results equal those of a fresh layer with the same weights."""
+    from se3conv3d_b200.layers import PNEConvLayerRotEquiv
+    pc, neigh, x = _synthetic_layer_problem(2048, 0.16, 2, 32, 64)
+    torch.manual_seed(2)
+    layer = PNEConvLayerRotEquiv(9, 32, 64, 32, "mlp_gelu").to(DEV)
+    layer.precision = 1
+    layer.norm_neigh_dist_.fill_(1 / 0.16)
+    layer.norm_num_neighs_.fill_(2048 / neigh.neighbors_.shape[0])
+
+    def run(l):
+        xx = x.clone().requires_grad_(True)
+        y = l(pc, pc, xx, neigh)
+        y.square().mean().backward()
+        return y.detach().clone(), xx.grad.clone(), l.conv_weights_.grad.clone()
+    a = run(layer)
+    assert layer._wcache.key is not None
+    layer.zero_grad()
+    b = run(layer)                                   # cached layouts
+    assert all(torch.equal(u, v) for u, v in zip(a, b))
+    with torch.no_grad():
+        layer.conv_weights_.mul_(1.5)                # in-place update: version bump
+    layer.zero_grad()
+    c = run(layer)
+    fresh = PNEConvLayerRotEquiv(9, 32, 64, 32, "mlp_gelu").to(DEV)
+    fresh.precision = 1
+    fresh.load_state_dict(layer.state_dict())
+    d = run(fresh)
+    assert all(torch.equal(u, v) for u, v in zip(c, d))
+    assert not torch.equal(a[0], c[0])
