@@ -374,7 +374,8 @@ int se3_conv_set_fused(int32_t mode);
 /* The projection GEMM on its own: C[M,N] = alpha * A[M,K] . B[N,K]^T, bf16 operands stored K-major
  * (row-major [rows][K]), fp32 accumulation, C fp32 or bf16 row-major.  This is the [K*Cin] x Cout
  * contraction of the layer (layers/PNEConvLayerRotEquiv.py:210) and its data-gradient twins.
- * impl: 0 = auto (tcgen05/TMEM when N % 16 == 0, else mma.sync), 1 = mma.sync, 2 = tcgen05. */
+ * impl: 0 = auto (the persistent TMA-fed tcgen05 kernel when N % 16 == 0, else mma.sync), 1 = mma.sync, 2 = tcgen05 with
+ * cp.async operand loads (round-1 kernel), 3 = tcgen05 with TMA operand loads. */
 int se3_gemm_bf16_tn(const void* a_bf16, const void* b_bf16, int64_t m, int64_t n, int64_t k, float alpha,
                      void* c, int32_t c_is_bf16, int32_t impl, se3_stream_t stream);
 

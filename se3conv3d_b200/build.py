@@ -12,7 +12,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libse3conv3d_b200.so")
-SOURCES = ["grid_ops.cu", "knn_frames.cu", "conv_simt.cu", "conv_tc.cu", "conv_fused.cu", "proj_tcgen05.cu", "conv.cu", "hierarchy.cu", "block_ops.cu"]
+SOURCES = ["grid_ops.cu", "knn_frames.cu", "conv_simt.cu", "conv_tc.cu", "conv_fused.cu", "proj_tcgen05.cu", "proj_tma.cu", "conv.cu", "hierarchy.cu", "block_ops.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

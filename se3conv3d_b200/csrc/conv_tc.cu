@@ -31,6 +31,11 @@ int launch_gemm_tcgen05(int64_t m, int64_t n, int64_t k, float alpha, const __nv
                         const __nv_bfloat16* b, int64_t ldb, void* c, int64_t ldc, bool out_bf16, int splits,
                         float* partials, cudaStream_t st);
 bool tcgen05_gemm_mn_supported(int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb);
+// proj_tma.cu
+bool tma_gemm_supported(int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb, int64_t ldc, bool out_bf16, const void* a,
+                        const void* b, const void* c);
+int launch_gemm_tma(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16* a, int64_t lda, const __nv_bfloat16* b,
+                    int64_t ldb, void* c, int64_t ldc, bool out_bf16, int splits, float* partials, cudaStream_t st);
 int launch_gemm_tcgen05_mn(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16* a, int64_t lda,
                            const __nv_bfloat16* b, int64_t ldb, float* c, int64_t ldc, int splits, float* partials,
                            cudaStream_t st);
@@ -1268,6 +1273,9 @@ int gemm_tn(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16* a
   }
   if (impl != 1 && can) {
     const int splits = (partials && !out_bf16) ? tcgen05_gemm_splits(m, n, k) : 1;
+    // impl 3 / auto: the persistent TMA-fed kernel (proj_tma.cu); impl 2 keeps the cp.async kernel (A/B runs)
+    if (impl != 2 && tma_gemm_supported(m, n, k, lda, ldb, ldc, out_bf16, a, b, c))
+      return launch_gemm_tma(m, n, k, alpha, a, lda, b, ldb, c, ldc, out_bf16, splits, partials, st);
     return launch_gemm_tcgen05(m, n, k, alpha, a, lda, b, ldb, c, ldc, out_bf16, splits, partials, st);
   }
   if (out_bf16) return launch_gemm_cfg<true, true, true>(m, n, k, alpha, a, lda, b, ldb, c, ldc, 1, nullptr, st);
@@ -1526,8 +1534,38 @@ int conv_tc_fwd(const se3_conv_desc* d, const float* x, float* y, void* saved, v
   return gemm_tn(R, d->c_out, ck, d->out_scale, sv.T, ck, sv.Wt, ck, y, d->c_out, false, 0, st, partials);
 }
 
+// The backward of a layer is three independent chains behind the bf16 conversion of dy -- (dW), (dT -> edge gradient),
+// (transposed aggregation -> dx).  They run concurrently: two chains on forked streams, joined before the call returns,
+// so the caller still sees plain stream order.  Measured on the dfaust stack (profiles/r02_experiments.md): 4.77 -> 4.40 ms
+// with the fork on the coarse levels only, 4.26 ms on every layer (the HBM-bound GEMMs fill the issue gaps of the
+// gather kernels).  SE3_BWD_STREAMS=0 keeps everything on the caller's stream, SE3_BWD_STREAMS_LIMIT bounds the layer
+// size (edges x channels / 32) that forks.
+struct SideStreams {
+  cudaStream_t s[2];
+  cudaEvent_t fork, join[2];
+  bool ok;
+};
+static SideStreams* side_streams() {
+  static SideStreams per_dev[16];
+  static bool init[16] = {};
+  static const bool off = getenv("SE3_BWD_STREAMS") && getenv("SE3_BWD_STREAMS")[0] == '0';
+  if (off) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  SideStreams& ss = per_dev[dev];
+  if (!init[dev]) {
+    init[dev] = true;
+    ss.ok = cudaStreamCreateWithFlags(&ss.s[0], cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ss.s[1], cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ss.join[0], cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ss.join[1], cudaEventDisableTiming) == cudaSuccess;
+  }
+  return ss.ok ? &ss : nullptr;
+}
+
 int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const void* saved, float* dx, float* dW,
-                float* dA, float* dB, void* ws, size_t ws_bytes, cudaStream_t st) {
+                float* dA, float* dB, void* ws, size_t ws_bytes, cudaStream_t st_main) {
   if (int rc = check_tc(d)) return rc;
   SE3_CHECK_ARG(saved && ws, "precision 1 backward needs the forward's saved buffer and a workspace");
   SE3_CHECK_ARG(!dx || (d->t_row_ends && d->t_edge && d->t_dst), "dx needs the transposed CSR");
@@ -1553,8 +1591,22 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
   if (!ar.ok()) { set_error("conv_tc_bwd: workspace too small"); return SE3_EWORKSPACE; }
   const TcSaved sv = tc_saved_layout(d, const_cast<void*>(saved));
   const __nv_bfloat16 *T = sv.T, *xb = sv.xb, *Wb = sv.Wb, *Wpb = sv.Wp;
+  cudaStream_t st = st_main;
   SE3_CUDA(launch_pdl(k_f32_to_bf16, dim3(blocks_for(R * d->c_out / 8)), dim3(256), 0, st, dy, R * d->c_out, dyb));
   SE3_LAUNCH_CHECK();
+  // fork
+  SideStreams* ss = nullptr;
+  {
+    const int chains = (dW ? 1 : 0) + ((dA || dB) ? 1 : 0) + (dx ? 1 : 0);
+    static const int64_t limit = getenv("SE3_BWD_STREAMS_LIMIT") ? atoll(getenv("SE3_BWD_STREAMS_LIMIT")) : ((int64_t)1 << 62);
+    if (chains >= 2 && d->n_edges * (int64_t)std::max(d->c_in, d->c_out) / 32 < limit) ss = side_streams();
+  }
+  if (ss) {
+    SE3_CUDA(cudaEventRecord(ss->fork, st_main));
+    SE3_CUDA(cudaStreamWaitEvent(ss->s[0], ss->fork, 0));
+    SE3_CUDA(cudaStreamWaitEvent(ss->s[1], ss->fork, 0));
+  }
+  st = ss ? ss->s[0] : st_main;     // chain 1: weight gradient
   if (dW) {
     // dW[(c,k), o] = s * sum_r T[r,(c,k)] dy[r,o]
     // tcgen05 (MN-major operands); SE3_DW_IMPL=m / SE3_GEMM_IMPL=mma select the mma.sync kernel
@@ -1575,6 +1627,7 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
       SE3_LAUNCH_CHECK();
     }
   }
+  st = st_main;                     // chain 2: basis gradient (stays on the caller's stream)
   if (dA || dB) {
     // dT[r,(c,k)] = s * sum_o dy[r,o] W[(c,k),o]
     if (int rc = gemm_tn(R, ck, d->c_out, d->out_scale, dyb, d->c_out, Wb, d->c_out, dTb, ck, true, 0, st)) return rc;
@@ -1585,6 +1638,7 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
     g.act = d->act; g.dT = dTb; g.n_out = d->n_out; g.partials = eg;
     if (int rc = launch_edge_tc(g, d->f_out, d->n_in, n_warps, dA, dB, st)) return rc;
   }
+  st = ss ? ss->s[1] : st_main;     // chain 3: data gradient
   if (dx && fdx) {
     // data gradient: the same fused kernel over the transposed CSR, gathered rows = dy, projection with W^T
     if (int rc = launch_w3_image(d->conv_weights, d->c_in, d->c_out, true, fdx == 1, w3t, st)) return rc;
@@ -1606,6 +1660,12 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
     if (int rc = launch_agg_tc<true>(a, d->f_in, d->n_out, st)) return rc;
     // dx[n,c] = s * sum_(o,k) U[n,(o,k)] Wp[c,(o,k)]
     if (int rc = gemm_tn(Nf, d->c_in, ok, d->out_scale, U, ok, Wpb, ok, dx, d->c_in, false, 0, st, dx_partials)) return rc;
+  }
+  if (ss) {   // join
+    SE3_CUDA(cudaEventRecord(ss->join[0], ss->s[0]));
+    SE3_CUDA(cudaEventRecord(ss->join[1], ss->s[1]));
+    SE3_CUDA(cudaStreamWaitEvent(st_main, ss->join[0], 0));
+    SE3_CUDA(cudaStreamWaitEvent(st_main, ss->join[1], 0));
   }
   return SE3_OK;
 }
@@ -1649,7 +1709,7 @@ extern "C" int se3_gemm_bf16_tn(const void* a, const void* b, int64_t m, int64_t
                                 int32_t c_is_bf16, int32_t impl, se3_stream_t stream) {
   using namespace se3;
   SE3_CHECK_ARG(m >= 0 && n >= 1 && k >= 8 && (k % 8) == 0, "bad sizes (k must be a multiple of 8)");
-  SE3_CHECK_ARG(impl >= 0 && impl <= 2, "impl must be 0, 1 or 2");
+  SE3_CHECK_ARG(impl >= 0 && impl <= 3, "impl must be 0 (auto), 1 (mma.sync), 2 (tcgen05, cp.async) or 3 (tcgen05, TMA)");
   if (m == 0) return SE3_OK;
   SE3_CHECK_ARG(a && b && c, "null pointer");
   return gemm_tn(m, n, k, alpha, reinterpret_cast<const __nv_bfloat16*>(a), k, reinterpret_cast<const __nv_bfloat16*>(b), k,

@@ -34,7 +34,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a pipeline bug must end as a trap (reported by the runtime as a launch failure) and never as a hung
 // GPU.  try_wait suspends in hardware for a while per call, so the bound is many seconds of wall time.
-__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
   printf("se3 mbar_wait timeout: block %d thread %d bar %u parity %u\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
   __trap();
 }
