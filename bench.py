@@ -37,6 +37,11 @@ def parse():
                     help="stack: hierarchy + the 21 convolutions fwd+bwd (BASELINE metric); fpn: the full FPN training step")
     ap.add_argument("--strong", action="store_true", help="fpn workload: 32 clouds in total (32/G per GPU) instead of 32 per GPU")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra measurements (other configs / precisions)")
+    ap.add_argument("--thread", action="store_true",
+                    help="pipelined mode: build the next hierarchy from a worker thread (measured slower: 5.37 vs 5.17 ms)")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="stack workload: build every hierarchy on the convolutions' stream (no overlap of the next batch's "
+                         "hierarchy with the current batch's convolutions)")
     return ap.parse_args()
 
 
@@ -341,9 +346,30 @@ def main():
     if rank == 0:
         clocks.start()
     launches0 = _lib.launch_count()
-    # (1) device-resident: hierarchy + neighbourhoods + conv stack fwd+bwd
-    ms_total = timed(lambda: hot_step(pts_d, batch_d), args.steps, args.warmup)
+    # (1) device-resident: hierarchy + neighbourhoods + conv stack fwd+bwd, every step on its own batch object.
+    #     sequential: each step builds its hierarchy, then runs its convolutions, on one stream (per-step events).
+    #     pipelined (default): the hierarchy of step i + 1 is built on a second stream while the convolutions of step i
+    #     run (K builds and K conv stacks inside ONE timed region; the L2 flush runs inside it, before every conv stack).
+    ms_seq = timed(lambda: hot_step(pts_d, batch_d), args.steps, args.warmup)
     launches = (_lib.launch_count() - launches0) // max(args.steps + args.warmup, 1) * args.steps
+    side = torch.cuda.Stream(dev)
+
+    def timed_pipeline(items, steps, warmup, after=None):
+        step.run_pipelined(items[:max(warmup, 1)], N_CLOUDS, side, threaded=args.thread)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step.run_pipelined(items[:steps], N_CLOUDS, side, before_conv=lambda: flush.fill_(1), after_conv=after,
+                           threaded=args.thread)
+        e1.record()
+        e1.synchronize()
+        side.synchronize()
+        barrier()
+        return shard.max_over_ranks(e0.elapsed_time(e1), dev)
+    if args.no_pipeline:
+        ms_total = ms_seq
+    else:
+        ms_total = timed_pipeline([(pts_d, batch_d)] * max(args.steps, args.warmup), args.steps, args.warmup)
 
     # (2) end to end: pinned host buffers -> H2D -> hot path -> D2H of the step's result, the seg-head output
     #     [42 k x 2, 32] fp32, into a pinned host buffer
@@ -359,7 +385,24 @@ def main():
         torch.cuda.current_stream().synchronize()
         return y.shape[0]
 
-    ms_e2e = timed(e2e_step, args.steps, max(args.warmup, 3))
+    if args.no_pipeline:
+        ms_e2e = timed(e2e_step, args.steps, max(args.warmup, 3))
+    else:
+        def h2d():
+            return pts_h.to(dev, non_blocking=True), batch_h.to(dev, non_blocking=True)
+
+        y_hosts = [y_host, torch.empty_like(y_host).pin_memory()]
+        d2h_ev = [None, None]
+
+        def d2h(y, i):
+            # the step's result goes to pinned host memory (double buffered); the host waits for the copy of step i - 1
+            # before it reuses that buffer, i.e. every result is on the host inside the timed region
+            if d2h_ev[i & 1] is not None:
+                d2h_ev[i & 1].synchronize()
+            y_hosts[i & 1][:y.shape[0]].copy_(y, non_blocking=True)
+            d2h_ev[i & 1] = torch.cuda.Event()
+            d2h_ev[i & 1].record()
+        ms_e2e = timed_pipeline([h2d] * max(args.steps, args.warmup, 3), args.steps, max(args.warmup, 3), after=d2h)
     d2h_bytes = int(y_probe.shape[0] * y_probe.shape[1] * 4)
     # (3) convolutions only (hierarchy cached), and the dominant layer alone for the roofline
     ms_conv = timed(lambda: step.conv_fwd_bwd(pcs, neighs), args.steps, args.warmup)
@@ -431,15 +474,20 @@ def main():
         "vs_baseline": None, "dtype": "f32" if args.precision == 0 else "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD,
                    "points_per_gpu": N_CLOUDS * N_POINTS, "precision": args.precision,
-                   "l2": "256 MB flush write between timed iterations",
+                   "l2": "256 MB flush write between timed iterations" if args.no_pipeline else
+                         "256 MB flush write before every conv stack, inside the timed region",
+                   "pipelined": (not args.no_pipeline),
+                   "pipeline": None if args.no_pipeline else
+                   "hierarchy of step i+1 built on a second CUDA stream while the convolutions of step i run; K hierarchy "
+                   "builds + K conv stacks inside one timed region (CUDA events on the conv stream, both streams drained)",
                    "level_points": [int(p.pts_.shape[0]) for p in pcs], "edges_total": int(sum(s[1] for s in sizes))},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(pts_h.numel() * 4 + batch_h.numel() * 4), "d2h_bytes_per_step": d2h_bytes,
                 "d2h": "the seg-head output y [rows, 32] fp32 (the result of the step) into pinned host memory"},
         "gpu_launches": int(launches),
-        "breakdown_ms": {"hierarchy_frames_neighbourhoods": (ms_total - ms_conv) / args.steps,
-                         "conv_fwd_bwd_x21": ms_conv / args.steps},
+        "breakdown_ms": {"hierarchy_frames_neighbourhoods": (ms_seq - ms_conv) / args.steps,
+                         "conv_fwd_bwd_x21": ms_conv / args.steps, "sequential_step": ms_seq / args.steps},
         "conv_only_points_per_s": n_pts_global * args.steps / (ms_conv * 1e-3),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic,

@@ -164,6 +164,51 @@ class DfaustStep(object):
             return ys[-1].detach()    # the seg-head output is the model's result
         return ys[-1].detach().sum()
 
+    def run_pipelined(self, batches, n_batches, side_stream, before_conv=None, after_conv=None, threaded=False):
+        """K hot-path steps with the hierarchy of batch i + 1 built on `side_stream` while the convolutions of batch i run
+        on the current stream (`threaded`: the build is issued by a worker thread -- measured slower, the launch calls
+        of the two threads serialise in the driver).  This is
+        what a training loop does with its input pipeline (the hierarchy is a no-grad function of the next batch only,
+        tasks/SemSeg/train_dfaust_rot.py:240-259).  Every step's hierarchy is built inside the call; nothing is cached
+        across steps.  `batches` yields (pts, batch_ids) already on the device or callables returning them (host ->
+        device copies then also run on the side stream).  Returns the last output."""
+        import concurrent.futures
+        cur = torch.cuda.current_stream()
+        dev = self.device
+
+        def build(item):
+            torch.cuda.set_device(dev)
+            with torch.cuda.stream(side_stream):
+                p, b = item() if callable(item) else item
+                pcs, neighs = self.build_hierarchy(p, b, n_batches=n_batches)
+                ev = torch.cuda.Event()
+                ev.record(side_stream)
+            return pcs, neighs, self.hierarchy, ev
+        pool = concurrent.futures.ThreadPoolExecutor(1) if threaded else None
+        submit = (lambda it: pool.submit(build, it)) if threaded else (lambda it: build(it))
+        get = (lambda f: f.result()) if threaded else (lambda f: f)
+        out = None
+        try:
+            nxt = submit(batches[0])
+            for i in range(len(batches)):
+                pcs, neighs, h, ev = get(nxt)
+                if threaded and i + 1 < len(batches):
+                    nxt = submit(batches[i + 1])        # the worker builds while this thread launches the convolutions
+                cur.wait_event(ev)
+                h.fused_arena_.record_stream(cur)       # allocated on the side stream, read by the convolutions here
+                if before_conv:
+                    before_conv()
+                out = self.conv_fwd_bwd(pcs, neighs, return_output=True)
+                if not threaded and i + 1 < len(batches):
+                    nxt = submit(batches[i + 1])
+                if after_conv:
+                    after_conv(out, i)
+                self.zero_grad()
+        finally:
+            if pool is not None:
+                pool.shutdown(wait=True)
+        return out
+
     def zero_grad(self):
         for layer in self.layers:
             for p in layer.parameters():
