@@ -11,6 +11,7 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
 // optional per-kernel timing (se3_profile_enable / se3_profile_read)
+bool profile_enabled();
 void profile_begin(int id, cudaStream_t st, void** handle);
 void profile_end(void* handle, cudaStream_t st);
 struct ProfScope {

@@ -93,6 +93,23 @@ __device__ __forceinline__ float act_grad_rt(float x, int act) {
   }
 }
 
+// pair forms: (z0, z1) -> bf16x2 of act(z), and bf16x2 of d * act'(z).  The compiled-in GELU runs packed
+// (tc_common.cuh), everything else in fp32 with one rounding at the end.
+template <int ACT>
+__device__ __forceinline__ uint32_t act_pair(float z0, float z1, int act) {
+#if SE3_PACKED_ACT
+  if (ACT == 2) return gelu_half_arg_bf2(pack_bf16(z0, z1));
+#endif
+  return pack_bf16(act_rt<ACT>(z0, act), act_rt<ACT>(z1, act));
+}
+template <int ACT>
+__device__ __forceinline__ uint32_t act_grad_pair(float d0, float d1, float z0, float z1, int act) {
+#if SE3_PACKED_ACT
+  if (ACT == 2) return bf2_mul(pack_bf16(d0, d1), gelu_grad_half_arg_bf2(pack_bf16(z0, z1)));
+#endif
+  return pack_bf16(d0 * act_grad_rt<ACT>(z0, act), d1 * act_grad_rt<ACT>(z1, act));
+}
+
 // n -> (edge, frame) for f frames per gathered point (f in 1..4, warp-uniform)
 __device__ __forceinline__ void split_nf(int n, int f, int& e, int& fg) {
   if (f == 1) {
@@ -159,48 +176,57 @@ __device__ __forceinline__ int chunk_gidx(const int* __restrict__ nbr, int lo, i
 }
 
 constexpr int AGG_WARPS = 4;  // warps per CTA of the aggregation / edge kernels
-constexpr int GSTR = 20;      // floats between geometry rows in shared memory (80 B: conflict-free 128-bit rows)
+constexpr int GROW = 32;      // bytes of a geometry row in shared memory: 16 f16 slots (9 components, 1, zeros)
 
-// A fragments of the basis affine on the tensor cores (tf32 m16n8k8): pre^T[k, n] = sum_d Wext[d, k] G[n, d]
-// with Wext = [proj_axes_ (9 rows); proj_biases_ (row 9); 0].  The 16 d-slots are permuted so that lane (g, t)
-// needs the four CONSECUTIVE components 4t..4t+3 of a geometry row (one 128-bit shared load):
-//   k-step s in {0,1}: slot t <-> component 4t + 2s, slot t+4 <-> component 4t + 2s + 1.
-// Components 12..15 are zero, so lanes t = 3 carry zero fragments and never touch shared memory.
-// `scale` (act_pre_scale) is folded into the fragments, so the tiles hold z = scale * pre.
+// A fragments of the basis affine on the tensor cores (f16 m16n8k16, fp32 accumulate):
+//   pre^T[k, n] = sum_d Wext[d, k] G[n, d],  Wext = [proj_axes_ (9 rows); proj_biases_ (row 9); 0].
+// f16 carries the 11 significant bits tf32 does (values are O(1): rotation entries, offsets scaled by 1 / radius,
+// trained axes), and one k = 16 instruction replaces a dependent pair of tf32 k = 8 ones.
+// The 16 k-slots are permuted so that lane (g, t) needs the four CONSECUTIVE components 4t..4t+3 of a geometry row
+// (one 64-bit shared load): slots (2t, 2t+1) <-> components (4t, 4t+1), slots (2t+8, 2t+9) <-> (4t+2, 4t+3).
+// Components 12..15 are zero, so lanes t = 3 carry zero fragments.  `scale` (act_pre_scale) is folded in.
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void mma_f16_zero(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.0f));
+}
 __device__ __forceinline__ void load_w9_frags(const float* __restrict__ w9, const float* __restrict__ bias, int g, int t,
-                                              float scale, uint32_t (&aw)[2][2][4]) {
+                                              float scale, uint32_t (&aw)[2][4]) {
   auto wext = [&](int d, int k) -> float {
     return scale * (d < 9 ? __ldg(w9 + d * 32 + k) : (d == 9 ? __ldg(bias + k) : 0.0f));
   };
 #pragma unroll
-  for (int m = 0; m < 2; ++m)
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const int d0 = 4 * t + 2 * s, k0 = 16 * m + g;
-      aw[m][s][0] = to_tf32(wext(d0, k0));
-      aw[m][s][1] = to_tf32(wext(d0, k0 + 8));
-      aw[m][s][2] = to_tf32(wext(d0 + 1, k0));
-      aw[m][s][3] = to_tf32(wext(d0 + 1, k0 + 8));
-    }
-}
-
-// pre^T tile of one 8-neighbour group: d[m][0..3] = pre[k = 16m+g (+8 for 2,3)][n = 2t (+1 for 1,3)]
-// (the geometry operand is fp32 whose low 13 mantissa bits the tf32 tensor core ignores)
-__device__ __forceinline__ void basis_pre(const uint32_t (&aw)[2][2][4], const float* grow, int t, float (&d)[2][4]) {
-  float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (t < 3) gv = *reinterpret_cast<const float4*>(grow + 4 * t);
-#pragma unroll
   for (int m = 0; m < 2; ++m) {
-    mma_tf32_zero(d[m], aw[m][0], __float_as_uint(gv.x), __float_as_uint(gv.y));
-    mma_tf32(d[m], aw[m][1], __float_as_uint(gv.z), __float_as_uint(gv.w));
+    const int d0 = 4 * t, k0 = 16 * m + g;
+    aw[m][0] = pack_f16(wext(d0, k0), wext(d0 + 1, k0));
+    aw[m][1] = pack_f16(wext(d0, k0 + 8), wext(d0 + 1, k0 + 8));
+    aw[m][2] = pack_f16(wext(d0 + 2, k0), wext(d0 + 3, k0));
+    aw[m][3] = pack_f16(wext(d0 + 2, k0 + 8), wext(d0 + 3, k0 + 8));
   }
 }
 
-__device__ __forceinline__ void store_geometry_row(float* row, const float (&gg)[9], float one) {
-  float4* gs = reinterpret_cast<float4*>(row);
-  gs[0] = make_float4(gg[0], gg[1], gg[2], gg[3]);
-  gs[1] = make_float4(gg[4], gg[5], gg[6], gg[7]);
-  gs[2] = make_float4(gg[8], one, 0.f, 0.f);
+// pre^T tile of one 8-neighbour group: d[m][0..3] = pre[k = 16m+g (+8 for 2,3)][n = 2t (+1 for 1,3)].
+// grow_s = shared-window address of the geometry row of neighbour g of the group, plus 8 * min(t, 2): lanes t = 3
+// own the slots of components 12..15, whose A fragments are zero -- they re-read the (finite) components 8..11 of
+// the lanes t = 2 (a broadcast) instead of branching around the load.
+__device__ __forceinline__ void basis_pre(const uint32_t (&aw)[2][4], uint32_t grow_s, float (&d)[2][4]) {
+  uint32_t b0, b1;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(grow_s) : "memory");
+#pragma unroll
+  for (int m = 0; m < 2; ++m) mma_f16_zero(d[m], aw[m], b0, b1);
+}
+
+// geometry row of this lane's neighbour: 9 components, the bias input, zeros (f16)
+__device__ __forceinline__ void store_geometry_row(uint32_t row_s, const float (&gg)[9], float one) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_s), "r"(pack_f16(gg[0], gg[1])), "r"(pack_f16(gg[2], gg[3])),
+               "r"(pack_f16(gg[4], gg[5])), "r"(pack_f16(gg[6], gg[7]))
+               : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %2, %2};" ::"r"(row_s + 16), "r"(pack_f16(gg[8], one)), "r"(0u) : "memory");
 }
 
 // This lane's gathered neighbour of a chunk from its staged record: scaled offset and frame.
@@ -227,8 +253,8 @@ __device__ __forceinline__ void load_row_frame(const float* Rs, int f, float (&F
 // basis h = act(pre) is produced directly as the B fragments of the aggregation mma -- n-tile j (k = 8j + g),
 // b0 = neighbours 2t,2t+1, b1 = neighbours 2t+8,2t+9 -- and T[c,k] += x[n,c] h[n,k].
 template <int CB, int FR, int NG, int ACT>
-__device__ __forceinline__ void agg_kstep(float (&acc)[FR][CB / 16][4][4], const uint32_t (&aw)[2][2][4], const float* Gs,
-                                          const __nv_bfloat16* Xs, int ks, int lane, int act) {
+__device__ __forceinline__ void agg_kstep(float (&acc)[FR][CB / 16][4][4], const uint32_t (&aw)[2][4], uint32_t gs_s,
+                                          int g_frame_bytes, const __nv_bfloat16* Xs, int ks, int lane, int act) {
   constexpr int XS = CB + 8, MT = CB / 16;
   const int g = lane >> 2, t = lane & 3, mid = lane >> 3, mr = lane & 7;
   // A fragments (x^T): [m = channel][k = neighbour], from Xs[n][c] through ldmatrix.trans
@@ -244,11 +270,11 @@ __device__ __forceinline__ void agg_kstep(float (&acc)[FR][CB / 16][4][4], const
     for (int hq = 0; hq < 2; ++hq) {
       if (hq < NG) {
         float d[2][4];
-        basis_pre(aw, Gs + (f * 32 + ks * 16 + hq * 8 + g) * GSTR, t, d);
+        basis_pre(aw, gs_s + f * g_frame_bytes + (ks * 16 + hq * 8 + g) * GROW + 8 * min(t, 2), d);
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
-          hb[2 * m][hq] = pack_bf16(act_rt<ACT>(d[m][0], act), act_rt<ACT>(d[m][1], act));
-          hb[2 * m + 1][hq] = pack_bf16(act_rt<ACT>(d[m][2], act), act_rt<ACT>(d[m][3], act));
+          hb[2 * m][hq] = act_pair<ACT>(d[m][0], d[m][1], act);
+          hb[2 * m + 1][hq] = act_pair<ACT>(d[m][2], d[m][3], act);
         }
       } else {
 #pragma unroll
@@ -267,8 +293,8 @@ struct AggSmem {
   static constexpr int XS = CB + 8;
   static constexpr int X_BYTES = 32 * XS * 2;         // one feature buffer (bf16)
   static constexpr int RG_BYTES = 32 * 48;            // one record buffer
-  // geometry rows [FR][32][GSTR]; reused as the T staging tiles ([CB][64 B] per frame), whichever is larger
-  static constexpr int G_FRAME_BYTES = (32 * GSTR * 4 > CB * 64) ? 32 * GSTR * 4 : CB * 64;
+  // per row frame: geometry rows [32][GROW B], reused as the T staging tile [CB][64 B], whichever is larger
+  static constexpr int G_FRAME_BYTES = (32 * GROW > CB * 64) ? 32 * GROW : CB * 64;
   static constexpr int G_BYTES = FR * G_FRAME_BYTES;
   static constexpr int RS_BYTES = ((FR * 48 + 63) / 64) * 64;  // one row-record buffer
   static constexpr int OFF_RG = 2 * X_BYTES;
@@ -294,14 +320,14 @@ struct AggSmem {
 // sits on the critical path after the first chunk.
 template <int CB, int FR, bool TR, int ACT>
 __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_AGG_MIN_BLOCKS) k_agg_tc(const TcAggArgs a, const int ncb) {
-  static_assert(FR == 1 || CB * 64 <= 32 * GSTR * 4, "the T staging tiles of consecutive frames would overlap");
   using SM = AggSmem<CB, FR>;
   constexpr int MT = CB / 16;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   unsigned char* wbase = smem_raw + wib * SM::WARP_BYTES;
   const uint32_t wbase_s = smem_u32(wbase);
-  float* Gs = reinterpret_cast<float*>(wbase + SM::OFF_G);  // [FR][32][GSTR]
+  unsigned char* Gs = wbase + SM::OFF_G;        // [FR][G_FRAME_BYTES]
+  const uint32_t gs_s = wbase_s + SM::OFF_G;
   const int g = lane >> 2, t = lane & 3;
   const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
   // an item = (row point, frame group, channel block); nfg = f_row / FR frame groups of FR row frames each.  The
@@ -313,7 +339,7 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_AGG_MIN_BLOCKS) k_agg_tc(c
   pdl_wait();
   pdl_trigger();
   if (item0 >= total) return;
-  uint32_t aw[2][2][4];
+  uint32_t aw[2][4];
   load_w9_frags(a.w9, a.bias, g, t, act_pre_scale(a.act), aw);
 
   // c0 carries the channel offset in its low 16 bits and the first row frame of the item above them
@@ -392,7 +418,7 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_AGG_MIN_BLOCKS) k_agg_tc(c
           float Frow[9], gg[9];
           load_row_frame(Rs, f, Frow);
           geometry9<TR>(Frow, Fq, dx, dy, dz, gg);
-          store_geometry_row(Gs + (f * 32 + lane) * GSTR, gg, 1.0f);
+          store_geometry_row(gs_s + f * SM::G_FRAME_BYTES + lane * GROW, gg, 1.0f);
         }
       }
       __syncwarp();
@@ -402,9 +428,9 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_AGG_MIN_BLOCKS) k_agg_tc(c
       for (int ks = 0; ks < 2; ++ks) {
         if (ks * 16 >= n_here) break;
         if (ks * 16 + 8 < n_here)
-          agg_kstep<CB, FR, 2, ACT>(acc, aw, Gs, Xs, ks, lane, a.act);
+          agg_kstep<CB, FR, 2, ACT>(acc, aw, gs_s, SM::G_FRAME_BYTES, Xs, ks, lane, a.act);
         else
-          agg_kstep<CB, FR, 1, ACT>(acc, aw, Gs, Xs, ks, lane, a.act);
+          agg_kstep<CB, FR, 1, ACT>(acc, aw, gs_s, SM::G_FRAME_BYTES, Xs, ks, lane, a.act);
       }
       __syncwarp();
       buf ^= 1;
@@ -414,7 +440,7 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_AGG_MIN_BLOCKS) k_agg_tc(c
     // row pair, conflict free both ways) -> 128-bit coalesced stores of the contiguous [CB x 32] block of T
 #pragma unroll
     for (int f = 0; f < FR; ++f) {
-      uint32_t* ts = reinterpret_cast<uint32_t*>(Gs + f * 32 * GSTR);  // [CB][16 words]
+      uint32_t* ts = reinterpret_cast<uint32_t*>(Gs + f * SM::G_FRAME_BYTES);  // [CB][16 words]
 #pragma unroll
       for (int m = 0; m < MT; ++m)
 #pragma unroll
@@ -427,7 +453,7 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_AGG_MIN_BLOCKS) k_agg_tc(c
     __syncwarp();
 #pragma unroll
     for (int f = 0; f < FR; ++f) {
-      const uint4* ts = reinterpret_cast<const uint4*>(Gs + f * 32 * GSTR);
+      const uint4* ts = reinterpret_cast<const uint4*>(Gs + f * SM::G_FRAME_BYTES);
       const int ch0 = c00 & 0xffff;
       __nv_bfloat16* o = a.out + ((int64_t)rp0 * a.f_row + (c00 >> 16) + f) * (int64_t)a.c * 32 + (int64_t)ch0 * 32;
 #pragma unroll
@@ -559,18 +585,20 @@ __device__ __forceinline__ void edge_dh(float (&dH)[2][4][4], const __nv_bfloat1
 // layout of dH: k in {g, g+8} + 16 m, n = 8 j + 2 t + {0,1} -- then accA[k, d] += dpre[k, n] G[n, d] with dpre
 // repacked as A fragments and G from Gb[n][16] (.trans).  Groups beyond the valid ones carry dH = 0.
 template <int NP, int ACT>
-__device__ __forceinline__ void edge_finish(float (&dH)[2][4][4], float (&accA)[2][2][4], const uint32_t (&aw)[2][2][4],
-                                            const float* Gs, const __nv_bfloat16* Gb, int lane, int act) {
+__device__ __forceinline__ void edge_finish(float (&dH)[2][4][4], float (&accA)[2][2][4], const uint32_t (&aw)[2][4],
+                                            uint32_t gs_s, const __nv_bfloat16* Gb, int lane, int act) {
   constexpr int GB = 16 + 8;
   const int g = lane >> 2, t = lane & 3, mid = lane >> 3, mr = lane & 7;
+  uint32_t dP[2][2 * NP][2];  // dpre as bf16 pairs: [m][jj][rows g / g+8]
 #pragma unroll
   for (int jj = 0; jj < 2 * NP; ++jj) {
     float d[2][4];
-    basis_pre(aw, Gs + (8 * jj + g) * GSTR, t, d);
+    basis_pre(aw, gs_s + (8 * jj + g) * GROW + 8 * min(t, 2), d);
 #pragma unroll
-    for (int m = 0; m < 2; ++m)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) dH[m][jj][i] *= act_grad_rt<ACT>(d[m][i], act);
+    for (int m = 0; m < 2; ++m) {
+      dP[m][jj][0] = act_grad_pair<ACT>(dH[m][jj][0], dH[m][jj][1], d[m][0], d[m][1], act);
+      dP[m][jj][1] = act_grad_pair<ACT>(dH[m][jj][2], dH[m][jj][3], d[m][2], d[m][3], act);
+    }
   }
 #pragma unroll
   for (int ks = 0; ks < NP; ++ks) {
@@ -578,11 +606,7 @@ __device__ __forceinline__ void edge_finish(float (&dH)[2][4][4], float (&accA)[
     ldmatrix_x4_trans(gb[0], gb[1], gb[2], gb[3], smem_u32(Gb + (ks * 16 + (mid & 1) * 8 + mr) * GB + (mid >> 1) * 8));
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
-      uint32_t afr[4];
-      afr[0] = pack_bf16(dH[m][2 * ks][0], dH[m][2 * ks][1]);
-      afr[1] = pack_bf16(dH[m][2 * ks][2], dH[m][2 * ks][3]);
-      afr[2] = pack_bf16(dH[m][2 * ks + 1][0], dH[m][2 * ks + 1][1]);
-      afr[3] = pack_bf16(dH[m][2 * ks + 1][2], dH[m][2 * ks + 1][3]);
+      const uint32_t afr[4] = {dP[m][2 * ks][0], dP[m][2 * ks][1], dP[m][2 * ks + 1][0], dP[m][2 * ks + 1][1]};
       mma_bf16(accA[m][0], afr, gb[0], gb[1]);
       mma_bf16(accA[m][1], afr, gb[2], gb[3]);
     }
@@ -597,7 +621,7 @@ struct EdgeSmem {
   static constexpr int X_BYTES = 32 * XS * 2;
   static constexpr int RG_BYTES = 32 * 48;
   static constexpr int T_BYTES = CB * TS * 2;
-  static constexpr int G_BYTES = 32 * GSTR * 4;
+  static constexpr int G_BYTES = 32 * GROW;
   static constexpr int GB_BYTES = 32 * GB * 2;
   static constexpr int RS_BYTES = 64;
   static constexpr int OFF_RG = 2 * X_BYTES;
@@ -623,7 +647,7 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_EDGE_MIN_BLOCKS) k_edge_tc
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   unsigned char* wbase = smem_raw + wib * SM::WARP_BYTES;
   const uint32_t wbase_s = smem_u32(wbase);
-  float* Gs = reinterpret_cast<float*>(wbase + SM::OFF_G);                    // [32][GSTR]
+  const uint32_t gs_s = wbase_s + SM::OFF_G;                                  // geometry rows [32][GROW B]
   __nv_bfloat16* Gb = reinterpret_cast<__nv_bfloat16*>(wbase + SM::OFF_GB);   // [32][GB]
   const int g = lane >> 2, t = lane & 3;
   float accA[2][2][4];  // [k m-tile][d n-tile]
@@ -640,7 +664,7 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_EDGE_MIN_BLOCKS) k_edge_tc
   pdl_wait();
   pdl_trigger();
   if (item0 < total) {
-    uint32_t aw[2][2][4];
+    uint32_t aw[2][4];
     load_w9_frags(a.w9, a.bias, g, t, act_pre_scale(a.act), aw);
     auto issue = [&](int item, int lo, int nt, int idx, int j, int buf, int rb, bool with_row) {
       const int jb = j / ncb, cb = j - jb * ncb;
@@ -712,7 +736,7 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_EDGE_MIN_BLOCKS) k_edge_tc
 #pragma unroll
             for (int i = 0; i < 9; ++i) gg[i] = 0.0f;
           }
-          store_geometry_row(Gs + lane * GSTR, gg, 1.0f);
+          store_geometry_row(gs_s + lane * GROW, gg, 1.0f);
           uint4 p0, p1;
           p0.x = pack_bf16(gg[0], gg[1]); p0.y = pack_bf16(gg[2], gg[3]);
           p0.z = pack_bf16(gg[4], gg[5]); p0.w = pack_bf16(gg[6], gg[7]);
@@ -740,9 +764,9 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_EDGE_MIN_BLOCKS) k_edge_tc
         }
         if (cb == ncb - 1) {
           if (nq > 2)
-            edge_finish<2, ACT>(dH, accA, aw, Gs, Gb, lane, a.act);
+            edge_finish<2, ACT>(dH, accA, aw, gs_s, Gb, lane, a.act);
           else if (nq > 0)
-            edge_finish<1, ACT>(dH, accA, aw, Gs, Gb, lane, a.act);
+            edge_finish<1, ACT>(dH, accA, aw, gs_s, Gb, lane, a.act);
         }
         __syncwarp();
         buf ^= 1;
@@ -802,7 +826,7 @@ struct EdgeRowSmem {
   static constexpr int X_BYTES = 32 * XS * 2;
   static constexpr int RG_BYTES = 32 * 48;
   static constexpr int T_BYTES = CB * TS * 2;  // one frame's dT tile
-  static constexpr int G_BYTES = 32 * GSTR * 4;
+  static constexpr int G_BYTES = 32 * GROW;
   static constexpr int GB_BYTES = 32 * GB * 2;
   static constexpr int RS_BYTES = ((FR * 48 + 63) / 64) * 64;
   static constexpr int OFF_RG = 2 * X_BYTES;
@@ -821,7 +845,7 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, CB >= 64 ? 2 : SE3_EDGE_MIN_BL
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   unsigned char* wbase = smem_raw + wib * SM::WARP_BYTES;
   const uint32_t wbase_s = smem_u32(wbase);
-  float* Gs = reinterpret_cast<float*>(wbase + SM::OFF_G);                    // [32][GSTR]
+  const uint32_t gs_s = wbase_s + SM::OFF_G;                                  // geometry rows [32][GROW B]
   __nv_bfloat16* Gb = reinterpret_cast<__nv_bfloat16*>(wbase + SM::OFF_GB);   // [32][GB]
   const int g = lane >> 2, t = lane & 3;
   float accA[2][2][4];  // [k m-tile][d n-tile]
@@ -837,7 +861,7 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, CB >= 64 ? 2 : SE3_EDGE_MIN_BL
   pdl_wait();
   pdl_trigger();
   if (rp0 < total) {
-    uint32_t aw[2][2][4];
+    uint32_t aw[2][4];
     load_w9_frags(a.w9, a.bias, g, t, act_pre_scale(a.act), aw);
     auto issue_gather = [&](int rp, int lo, int nt, int idx, int base, int buf, int rb, bool with_row) {
       const int gidx = chunk_gidx(a.col_src, lo, nt, idx, a.f_in, base, lane);
@@ -911,7 +935,7 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, CB >= 64 ? 2 : SE3_EDGE_MIN_BL
 #pragma unroll
               for (int i = 0; i < 9; ++i) gg[i] = 0.0f;
             }
-            store_geometry_row(Gs + lane * GSTR, gg, 1.0f);
+            store_geometry_row(gs_s + lane * GROW, gg, 1.0f);
             uint4 p0, p1;
             p0.x = pack_bf16(gg[0], gg[1]); p0.y = pack_bf16(gg[2], gg[3]);
             p0.z = pack_bf16(gg[4], gg[5]); p0.w = pack_bf16(gg[6], gg[7]);
@@ -939,9 +963,9 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, CB >= 64 ? 2 : SE3_EDGE_MIN_BL
             issue_tile(rp1, f);      // group B: the next row's tile streams in behind the rest of this chunk
           }
           if (nq > 2)
-            edge_finish<2, ACT>(dH, accA, aw, Gs, Gb, lane, a.act);
+            edge_finish<2, ACT>(dH, accA, aw, gs_s, Gb, lane, a.act);
           else if (nq > 0)
-            edge_finish<1, ACT>(dH, accA, aw, Gs, Gb, lane, a.act);
+            edge_finish<1, ACT>(dH, accA, aw, gs_s, Gb, lane, a.act);
           __syncwarp();
         }
         cp_async_commit();  // group B (possibly empty)
@@ -1599,7 +1623,9 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
   {
     const int chains = (dW ? 1 : 0) + ((dA || dB) ? 1 : 0) + (dx ? 1 : 0);
     static const int64_t limit = getenv("SE3_BWD_STREAMS_LIMIT") ? atoll(getenv("SE3_BWD_STREAMS_LIMIT")) : ((int64_t)1 << 62);
-    if (chains >= 2 && d->n_edges * (int64_t)std::max(d->c_in, d->c_out) / 32 < limit) ss = side_streams();
+    // per-kernel timing (se3_profile_enable) wants every kernel alone on the device: no fork while it is on
+    if (chains >= 2 && !profile_enabled() && d->n_edges * (int64_t)std::max(d->c_in, d->c_out) / 32 < limit)
+      ss = side_streams();
   }
   if (ss) {
     SE3_CUDA(cudaEventRecord(ss->fork, st_main));
