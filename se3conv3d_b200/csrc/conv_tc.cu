@@ -512,6 +512,238 @@ static int launch_agg_cfg(const TcAggArgs& a, int64_t n_g, cudaStream_t st) {
   return SE3_OK;
 }
 
+// --------------------------------------------------------------------------------------------
+// wide layers (more than 64 channels): one warp per (row point, row frame) walks ALL channel blocks of the item.
+// The basis of the item's (row frame, gathered entry) pairs is evaluated once, during the first channel block, and
+// its mma B fragments are kept in shared memory (the first STASH_KS k-steps = 16 * STASH_KS entries of the row;
+// longer rows re-evaluate the tail); the other channel blocks only gather their 64-channel slices and run the
+// aggregation mma.  k_agg_tc evaluates the basis once per channel block: 2x / 4x / 8x at 128 / 256 / 512 channels.
+// --------------------------------------------------------------------------------------------
+constexpr int WIDE_CB = 64;
+constexpr int STASH_KS = 8;
+struct WideSmem {
+  static constexpr int XS = WIDE_CB + 8;
+  static constexpr int X_BYTES = 32 * XS * 2;
+  static constexpr int RG_BYTES = 32 * 48;
+  static constexpr int G_BYTES = WIDE_CB * 64;  // T staging tile [64][64 B]; the geometry rows (32 * GROW) alias it
+  static constexpr int RS_BYTES = 64;
+  static constexpr int ST_BYTES = STASH_KS * 1024;  // per k-step: [2 halves][32 lanes][16 B]
+  static constexpr int OFF_RG = 2 * X_BYTES;
+  static constexpr int OFF_G = OFF_RG + 2 * RG_BYTES;
+  static constexpr int OFF_RS = OFF_G + G_BYTES;
+  static constexpr int OFF_ST = OFF_RS + 2 * RS_BYTES;
+  static constexpr int WARP_BYTES = OFF_ST + ST_BYTES;
+};
+
+// one k-step (16 entries) of a 64-channel block for one row frame.  MODE 0: evaluate the basis; 1: evaluate and keep
+// the fragments at st_s; 2: take them from st_s.
+template <int NG, int MODE, int ACT>
+__device__ __forceinline__ void wide_kstep(float (&acc)[WIDE_CB / 16][4][4], const uint32_t (&aw)[2][4], uint32_t gs_s,
+                                           uint32_t st_s, const __nv_bfloat16* Xs, int ks, int lane, int act) {
+  constexpr int XS = WideSmem::XS, MT = WIDE_CB / 16;
+  const int g = lane >> 2, t = lane & 3, mid = lane >> 3, mr = lane & 7;
+  uint32_t hb[4][2];
+  if (MODE == 2) {
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(hb[0][0]), "=r"(hb[1][0]), "=r"(hb[2][0]), "=r"(hb[3][0]) : "r"(st_s + lane * 16) : "memory");
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(hb[0][1]), "=r"(hb[1][1]), "=r"(hb[2][1]), "=r"(hb[3][1]) : "r"(st_s + 512 + lane * 16) : "memory");
+  } else {
+#pragma unroll
+    for (int hq = 0; hq < 2; ++hq) {
+      if (hq < NG) {
+        float d[2][4];
+        basis_pre(aw, gs_s + (ks * 16 + hq * 8 + g) * GROW + 8 * min(t, 2), d);
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          hb[2 * m][hq] = act_pair<ACT>(d[m][0], d[m][1], act);
+          hb[2 * m + 1][hq] = act_pair<ACT>(d[m][2], d[m][3], act);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hb[j][hq] = 0u;
+      }
+    }
+    if (MODE == 1) {
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_s + lane * 16), "r"(hb[0][0]), "r"(hb[1][0]),
+                   "r"(hb[2][0]), "r"(hb[3][0]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_s + 512 + lane * 16), "r"(hb[0][1]), "r"(hb[1][1]),
+                   "r"(hb[2][1]), "r"(hb[3][1]) : "memory");
+    }
+  }
+  uint32_t af[MT][4];
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+    ldmatrix_x4_trans(af[m][0], af[m][1], af[m][2], af[m][3],
+                      smem_u32(Xs + (ks * 16 + (mid >> 1) * 8 + mr) * XS + m * 16 + (mid & 1) * 8));
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int m = 0; m < MT; ++m) mma_bf16(acc[m][j], af[m], hb[j][0], hb[j][1]);
+}
+
+template <bool TR, int ACT>
+__global__ void __launch_bounds__(AGG_WARPS * 32, 2) k_agg_wide(const TcAggArgs a, const int ncb) {
+  using SM = WideSmem;
+  constexpr int CB = WIDE_CB, MT = CB / 16;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  unsigned char* wbase = smem_raw + wib * SM::WARP_BYTES;
+  const uint32_t wbase_s = smem_u32(wbase);
+  unsigned char* Gs = wbase + SM::OFF_G;
+  const uint32_t gs_s = wbase_s + SM::OFF_G, st_s = wbase_s + SM::OFF_ST;
+  const int g = lane >> 2, t = lane & 3;
+  const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+  const int total = (int)a.n_rows * a.f_row;
+  int item0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  pdl_wait();
+  pdl_trigger();
+  if (item0 >= total) return;
+  uint32_t aw[2][4];
+  load_w9_frags(a.w9, a.bias, g, t, act_pre_scale(a.act), aw);
+
+  auto issue = [&](int item, int cb, int lo, int nt, int idx, int base, int buf, int rb, bool with_row) {
+    const int gidx = chunk_gidx(a.nbr, lo, nt, idx, a.f_g, base, lane);
+    gather_chunk_async<CB>(a.rec_g, a.feat, a.cs, cb * CB, gidx, lane, wbase_s + SM::OFF_RG + buf * SM::RG_BYTES,
+                           wbase_s + buf * SM::X_BYTES);
+    if (with_row && lane < 3)
+      cp_async16_ca(wbase_s + SM::OFF_RS + rb * SM::RS_BYTES + lane * 16,
+                    reinterpret_cast<const float4*>(a.rec_row) + (int64_t)item * 3 + lane, true);
+  };
+  auto bounds = [&](int item, int& lo, int& ne) {
+    const int rp = item / a.f_row;
+    lo = rp > 0 ? __ldg(a.row_ends + rp - 1) : 0;
+    ne = __ldg(a.row_ends + rp) - lo;
+  };
+  int lo0, ne0;
+  bounds(item0, lo0, ne0);
+  int idx0 = lane < ne0 ? __ldg(a.nbr + lo0 + lane) : 0;
+  int item1 = item0 + nwarps, lo1 = 0, ne1 = 0, idx1 = 0;
+  if (item1 < total) {
+    bounds(item1, lo1, ne1);
+    idx1 = lane < ne1 ? __ldg(a.nbr + lo1 + lane) : 0;
+  }
+  int buf = 0, rb = 0;
+  issue(item0, 0, lo0, ne0 * a.f_g, idx0, 0, 0, 0, true);
+  cp_async_commit();
+
+  for (;;) {
+    const int nt0 = ne0 * a.f_g;
+    const int nch = max(1, (nt0 + 31) >> 5);
+    for (int cb = 0; cb < ncb; ++cb) {
+      float acc[MT][4][4];
+#pragma unroll
+      for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[m][j][i] = 0.0f;
+      for (int ch = 0; ch < nch; ++ch) {
+        const int base = ch * 32;
+        // ---- the next (channel block, chunk) of this item, or the first of the next item, in flight
+        if (ch + 1 < nch) {
+          issue(item0, cb, lo0, nt0, idx0, base + 32, buf ^ 1, rb, false);
+        } else if (cb + 1 < ncb) {
+          issue(item0, cb + 1, lo0, nt0, idx0, 0, buf ^ 1, rb, false);
+        } else if (item1 < total) {
+          issue(item1, 0, lo1, ne1 * a.f_g, idx1, 0, buf ^ 1, rb ^ 1, true);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        const bool stashed = 2 * ch + 1 < STASH_KS;          // both k-steps of this chunk fit the stash
+        const bool evaluate = cb == 0 || !stashed;
+        if (evaluate) {
+          const float* Rs = reinterpret_cast<const float*>(wbase + SM::OFF_RS + rb * SM::RS_BYTES);
+          const float* rg = reinterpret_cast<const float*>(wbase + SM::OFF_RG + buf * SM::RG_BYTES) + lane * 12;
+          float dx, dy, dz, Fq[9], Frow[9], gg[9];
+          unpack_neighbour<TR>(rg, Rs[0], Rs[1], Rs[2], a.norm, dx, dy, dz, Fq);
+          load_row_frame(Rs, 0, Frow);
+          geometry9<TR>(Frow, Fq, dx, dy, dz, gg);
+          store_geometry_row(gs_s + lane * GROW, gg, 1.0f);
+          __syncwarp();
+        }
+        const __nv_bfloat16* Xs = reinterpret_cast<const __nv_bfloat16*>(wbase + buf * SM::X_BYTES);
+        const int n_here = min(32, nt0 - base);
+#pragma unroll 1
+        for (int ks = 0; ks < 2; ++ks) {
+          if (ks * 16 >= n_here) break;
+          const uint32_t slot = st_s + (2 * ch + ks) * 1024;
+          if (!evaluate) {
+            wide_kstep<2, 2, ACT>(acc, aw, gs_s, slot, Xs, ks, lane, a.act);
+          } else if (ks * 16 + 8 < n_here) {
+            if (stashed) wide_kstep<2, 1, ACT>(acc, aw, gs_s, slot, Xs, ks, lane, a.act);
+            else wide_kstep<2, 0, ACT>(acc, aw, gs_s, slot, Xs, ks, lane, a.act);
+          } else {
+            if (stashed) wide_kstep<1, 1, ACT>(acc, aw, gs_s, slot, Xs, ks, lane, a.act);
+            else wide_kstep<1, 0, ACT>(acc, aw, gs_s, slot, Xs, ks, lane, a.act);
+          }
+        }
+        __syncwarp();
+        buf ^= 1;
+      }
+      // ---- epilogue of this channel block: [64][32] bf16 through the swizzled staging tile
+      {
+        uint32_t* ts = reinterpret_cast<uint32_t*>(Gs);
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int r0 = m * 16 + g, r1 = r0 + 8;
+            ts[r0 * 16 + ((j ^ ((r0 >> 1) & 3)) << 2) + t] = pack_bf16(acc[m][j][0], acc[m][j][1]);
+            ts[r1 * 16 + ((j ^ ((r1 >> 1) & 3)) << 2) + t] = pack_bf16(acc[m][j][2], acc[m][j][3]);
+          }
+        __syncwarp();
+        const uint4* tv = reinterpret_cast<const uint4*>(Gs);
+        const int ch0 = cb * CB;
+        __nv_bfloat16* o = a.out + (int64_t)item0 * (int64_t)a.c * 32 + (int64_t)ch0 * 32;
+#pragma unroll
+        for (int it = 0; it < CB / 8; ++it) {
+          const int row = it * 8 + (lane >> 2), part = lane & 3;
+          if (ch0 + row < a.c) reinterpret_cast<uint4*>(o + row * 32)[part] = tv[row * 4 + (part ^ ((row >> 1) & 3))];
+        }
+        __syncwarp();
+      }
+    }
+    if (item1 >= total) break;
+    item0 = item1; lo0 = lo1; ne0 = ne1; idx0 = idx1;
+    rb ^= 1;
+    item1 += nwarps;
+    if (item1 < total) {
+      bounds(item1, lo1, ne1);
+      idx1 = lane < ne1 ? __ldg(a.nbr + lo1 + lane) : 0;
+    }
+  }
+  cp_async_wait<0>();
+}
+
+template <bool TR>
+static int launch_agg_wide(const TcAggArgs& a, int64_t n_g, cudaStream_t st) {
+  const size_t smem = AGG_WARPS * WideSmem::WARP_BYTES;
+  const int ncb = (a.c + WIDE_CB - 1) / WIDE_CB;
+  const int64_t warps = a.n_rows * a.f_row;
+  if (warps >= (int64_t)1 << 30 || n_g * a.f_g * a.cs >= (int64_t)1 << 31 || (a.cs & 7) || a.cs < a.c) {
+    set_error("launch_agg_wide: problem too large for 32-bit row offsets");
+    return SE3_EINVAL;
+  }
+  int64_t blocks = (warps + AGG_WARPS - 1) / AGG_WARPS;
+  const int64_t cap = (int64_t)num_sms() * 2;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  ProfScope prof(TR ? 1 : 0, st);
+  if (a.act == 2) {
+    auto kern = k_agg_wide<TR, 2>;
+    SE3_SMEM_ONCE(kern, smem);
+    SE3_CUDA(launch_pdl(kern, dim3((unsigned)blocks), dim3(AGG_WARPS * 32), smem, st, a, ncb));
+  } else {
+    auto kern = k_agg_wide<TR, -1>;
+    SE3_SMEM_ONCE(kern, smem);
+    SE3_CUDA(launch_pdl(kern, dim3((unsigned)blocks), dim3(AGG_WARPS * 32), smem, st, a, ncb));
+  }
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
+}
+
 template <bool TR>
 static int launch_agg_tc(const TcAggArgs& a0, int f_row, int64_t n_g, cudaStream_t st) {
   if (a0.n_rows == 0) return SE3_OK;
@@ -523,6 +755,8 @@ static int launch_agg_tc(const TcAggArgs& a0, int f_row, int64_t n_g, cudaStream
   // frames x 32 channels, but half the basis evaluations (the dominant cost), since every channel block of an item
   // re-evaluates the basis of the item's frames
   static const bool no_cb64 = getenv("SE3_AGG_NO_CB64") != nullptr;  // tuning aid
+  static const bool no_wide = getenv("SE3_AGG_NO_WIDE") != nullptr;  // tuning aid
+  if (a.c > WIDE_CB && f_row >= 1 && f_row <= 4 && !no_wide) return launch_agg_wide<TR>(a, n_g, st);
   if (a.c > 32 && f_row >= 1 && f_row <= 4 && !no_cb64) return launch_agg_cfg<64, 1, TR>(a, n_g, st);
   switch (f_row) {
     case 1: return a.c > 16 ? launch_agg_cfg<32, 1, TR>(a, n_g, st) : launch_agg_cfg<16, 1, TR>(a, n_g, st);

@@ -10,7 +10,10 @@
 //   * warps 2..5: epilogue -- tcgen05.ld (32 columns at a time), scale, warp-private swizzled staging tile in shared
 //     memory, full 128-byte line stores;
 //   * persistent: one CTA per SM walks (m-tile, n-tile, k-split) work items in launch order; split-K (ordered reduction
-//     by k_splitk_reduce) when the output tiles alone cannot fill the GPU.
+//     by k_splitk_reduce) when the output tiles alone cannot fill the GPU.  Work items are ordered n-tile fastest, so
+//     the column tiles of one row tile run on neighbouring CTAs at the same time and the tall operand is read from HBM
+//     once (the repeat hits L2), and row tiles back to front: the tail of the operand the producing kernel has just
+//     written is still in L2.
 // Tensor maps are encoded on the host (cuTensorMapEncodeTiled through cudaGetDriverEntryPoint: the library links only
 // libcudart) and passed as __grid_constant__ kernel parameters; out-of-range rows / k are zero-filled by the hardware.
 #include <cuda.h>
@@ -87,7 +90,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_tma(const __grid_constant__ CU
       int s = 0;
       uint32_t ph = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const int mt = w % m_tiles, rest = w / m_tiles, nt = rest % n_tiles, sp = rest / n_tiles;
+        const int nt = w % n_tiles, rest = w / n_tiles, mt = m_tiles - 1 - rest % m_tiles, sp = rest / m_tiles;
         const int kb0 = sp * kb_per_split, nkb = min(kb_per_split, nkb_all - kb0);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(smem_addr(&empty[s]), ph ^ 1u);
@@ -105,7 +108,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_tma(const __grid_constant__ CU
       int s = 0, it = 0;
       uint32_t ph = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-        const int sp = (w / m_tiles) / n_tiles;
+        const int sp = (w / n_tiles) / m_tiles;
         const int kb0 = sp * kb_per_split, nkb = min(kb_per_split, nkb_all - kb0);
         const int ab = it & 1;
         mbar_wait(smem_addr(&acc_empty[ab]), (uint32_t)(((it >> 1) & 1) ^ 1));
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_tma(const __grid_constant__ CU
     unsigned char* stg = epi_gen + (warp - 2) * 4096;   // [32 rows][128 B], 16-byte chunks XOR-swizzled by the row
     int it = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-      const int mt = w % m_tiles, rest = w / m_tiles, nt = rest % n_tiles, sp = rest / n_tiles;
+      const int nt = w % n_tiles, rest = w / n_tiles, mt = m_tiles - 1 - rest % m_tiles, sp = rest / m_tiles;
       const int ab = it & 1;
       mbar_wait(smem_addr(&acc_full[ab]), (uint32_t)((it >> 1) & 1));
       tc_fence_after();

@@ -656,10 +656,12 @@ def wl_grid_of(pcs, lvl, step):
 
 
 @pytest.mark.parametrize("cin,cout,frames", [(64, 64, 2), (128, 32, 2), (1, 32, 2), (16, 48, 1), (48, 64, 1), (256, 128, 2),
-                                              (512, 64, 1), (320, 256, 2), (40, 8, 2)])
+                                              (512, 64, 1), (320, 256, 2), (40, 8, 2), (160, 72, 4), (128, 128, 3)])
 def test_layer_bf16_matches_fp32_path_channel_sweep(cin, cout, frames):
     """Every channel-block configuration of the tensor-core kernels (16 / 32 / 64-channel row items, multi-block
-    items, padded odd channel counts) against the fp32 exactness path on the same inputs: 3e-2 relative."""
+    items, padded odd channel counts, the wide-layer kernel that keeps the basis fragments of a row in shared memory --
+    rows inside and beyond its 128-entry stash, partial last channel block) against the fp32 exactness path on the same
+    inputs: 3e-2 relative."""
     from se3conv3d_b200.layers import PNEConvLayerRotEquiv
     pc, neigh, x = _synthetic_layer_problem(1500, 0.2, frames, cin, cout, seed=5, batches=2)
     torch.manual_seed(7)
