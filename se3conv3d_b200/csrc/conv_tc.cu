@@ -791,7 +791,8 @@ struct TcEdgeArgs {
 
 // dH^T[k, n] += sum_c dT[c, k] x[n, c] for the first NP pairs of 8-neighbour groups (straight-line code).
 //   A = dT^T: [m = k][kk = c] from dTs[c][k] (.trans); B = x^T: [kk = c][nn = n] from Xs[n][c]
-template <int CB, int NP>
+// FIRST: the accumulators are written, not accumulated into, by the first channel k-step (nothing to clear beforehand)
+template <int CB, int NP, bool FIRST = false>
 __device__ __forceinline__ void edge_dh(float (&dH)[2][4][4], const __nv_bfloat16* dTs, const __nv_bfloat16* Xs, int lane) {
   constexpr int XS = CB + 8, TS = 32 + 8;
   const int mid = lane >> 3, mr = lane & 7;
@@ -808,8 +809,13 @@ __device__ __forceinline__ void edge_dh(float (&dH)[2][4][4], const __nv_bfloat1
       ldmatrix_x4(b[0], b[1], b[2], b[3], smem_u32(Xs + (jp * 16 + (mid >> 1) * 8 + mr) * XS + ks * 16 + (mid & 1) * 8));
 #pragma unroll
       for (int m = 0; m < 2; ++m) {
-        mma_bf16(dH[m][2 * jp], af[m], b[0], b[1]);
-        mma_bf16(dH[m][2 * jp + 1], af[m], b[2], b[3]);
+        if (FIRST && ks == 0) {
+          mma_bf16_zero(dH[m][2 * jp], af[m], b[0], b[1]);
+          mma_bf16_zero(dH[m][2 * jp + 1], af[m], b[2], b[3]);
+        } else {
+          mma_bf16(dH[m][2 * jp], af[m], b[0], b[1]);
+          mma_bf16(dH[m][2 * jp + 1], af[m], b[2], b[3]);
+        }
       }
     }
   }
@@ -1152,7 +1158,6 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, CB >= 64 ? 2 : SE3_EDGE_MIN_BL
         cp_async_commit();
         cp_async_wait<1>();  // everything but group A: this chunk's gather and this row's dT tiles have landed
         __syncwarp();
-        const bool valid = base + lane < nt0;
         const int nq = (min(32, nt0 - base) + 7) >> 3;  // valid 8-neighbour groups (warp-uniform)
         const float* Rs = reinterpret_cast<const float*>(wbase + SM::OFF_RS + rb * SM::RS_BYTES);
         const float* rg = reinterpret_cast<const float*>(wbase + SM::OFF_RG + buf * SM::RG_BYTES) + lane * 12;
@@ -1163,35 +1168,27 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, CB >= 64 ? 2 : SE3_EDGE_MIN_BL
         for (int f = 0; f < FR; ++f) {
           {
             float Frow[9], gg[9];
+            // padding lanes (beyond the row) need no masking: their feature rows are zero-filled, so dH and with it
+            // dpre are exactly zero there, and their geometry is finite (a zero record against a finite row point)
             load_row_frame(Rs, f, Frow);
             geometry9<false>(Frow, Fq, dx, dy, dz, gg);
-            if (!valid) {
-#pragma unroll
-              for (int i = 0; i < 9; ++i) gg[i] = 0.0f;
-            }
             store_geometry_row(gs_s + lane * GROW, gg, 1.0f);
             uint4 p0, p1;
             p0.x = pack_bf16(gg[0], gg[1]); p0.y = pack_bf16(gg[2], gg[3]);
             p0.z = pack_bf16(gg[4], gg[5]); p0.w = pack_bf16(gg[6], gg[7]);
-            p1.x = pack_bf16(gg[8], valid ? 1.0f : 0.0f);  // column 9 = 1 -> bias gradient
+            p1.x = pack_bf16(gg[8], 1.0f);  // column 9 = 1 -> bias gradient
             p1.y = 0u; p1.z = 0u; p1.w = 0u;
             uint4* gb = reinterpret_cast<uint4*>(Gb + lane * GB);
             gb[0] = p0;
             gb[1] = p1;
           }
-          float dH[2][4][4];
-#pragma unroll
-          for (int m = 0; m < 2; ++m)
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-              for (int i = 0; i < 4; ++i) dH[m][jj][i] = 0.0f;
+          float dH[2][4][4];   // written by the first k-step of edge_dh (the tiles of 8-neighbour groups >= nq stay unused)
           __syncwarp();
           const __nv_bfloat16* dTs = reinterpret_cast<const __nv_bfloat16*>(wbase + SM::OFF_T + f * SM::T_BYTES);
           if (nq > 2)
-            edge_dh<CB, 2>(dH, dTs, Xs, lane);
+            edge_dh<CB, 2, true>(dH, dTs, Xs, lane);
           else if (nq > 0)
-            edge_dh<CB, 1>(dH, dTs, Xs, lane);
+            edge_dh<CB, 1, true>(dH, dTs, Xs, lane);
           if (last_chunk && rp1 < total) {
             __syncwarp();            // every lane is done reading this frame's tile
             issue_tile(rp1, f);      // group B: the next row's tile streams in behind the rest of this chunk

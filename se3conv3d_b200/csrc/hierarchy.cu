@@ -58,7 +58,12 @@ Lanes* lanes_for_device() {
     auto ev = [](cudaEvent_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
     bool ok = ev(&l.fork);
     ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&l.host), kPinnedBytes, cudaHostAllocDefault) == cudaSuccess;
-    for (int i = 0; i < kSide; ++i) ok = ok && cudaStreamCreateWithFlags(&l.s[i], cudaStreamNonBlocking) == cudaSuccess && ev(&l.join[i]);
+    // the builder's kernels are tiny and latency-bound: on the highest stream priority they are dispatched ahead of queued
+    // convolution kernels whenever the build overlaps a conv stack (input pipeline on a second stream)
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    for (int i = 0; i < kSide; ++i)
+      ok = ok && cudaStreamCreateWithPriority(&l.s[i], cudaStreamNonBlocking, prio_hi) == cudaSuccess && ev(&l.join[i]);
     for (int i = 0; i <= SE3_HIER_MAX_CLOUDS; ++i) ok = ok && ev(&l.cloud[i]) && ev(&l.frames[i]);
     for (int i = 0; i < SE3_HIER_MAX_NEIGH; ++i) ok = ok && ev(&l.src[i]);
     if (!ok) return nullptr;
