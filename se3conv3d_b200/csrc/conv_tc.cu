@@ -36,6 +36,10 @@ bool tma_gemm_supported(int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ld
                         const void* b, const void* c);
 int launch_gemm_tma(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16* a, int64_t lda, const __nv_bfloat16* b,
                     int64_t ldb, void* c, int64_t ldc, bool out_bf16, int splits, float* partials, cudaStream_t st);
+bool tma_gemm_mn_supported(int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb, int64_t ldc, const void* a, const void* b,
+                           const void* c);
+int launch_gemm_tma_mn(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16* a, int64_t lda, const __nv_bfloat16* b,
+                       int64_t ldb, float* c, int64_t ldc, int splits, float* partials, cudaStream_t st);
 int launch_gemm_tcgen05_mn(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16* a, int64_t lda,
                            const __nv_bfloat16* b, int64_t ldb, float* c, int64_t ldc, int splits, float* partials,
                            cudaStream_t st);
@@ -1870,7 +1874,11 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
     static const bool dw_mma = getenv("SE3_DW_IMPL") && getenv("SE3_DW_IMPL")[0] == 'm';  // A/B aid
     // (fused forward: the saved rows are (k, c padded to CP) ordered -> the result is permuted afterwards)
     float* dst = ffwd ? dWkc : dW;
-    if (!dw_mma && gemm_impl_env() != 1 && tcgen05_gemm_mn_supported(tcols, d->c_out, R, tcols, d->c_out)) {
+    if (!dw_mma && gemm_impl_env() != 1 && tma_gemm_mn_supported(tcols, d->c_out, R, tcols, d->c_out, d->c_out, T, dyb, dst)) {
+      // persistent TMA-fed kernel (producer / MMA / epilogue warps, double-buffered TMEM accumulator)
+      if (int rc = launch_gemm_tma_mn(tcols, d->c_out, R, d->out_scale, T, tcols, dyb, d->c_out, dst, d->c_out, splits, dWp, st))
+        return rc;
+    } else if (!dw_mma && gemm_impl_env() != 1 && tcgen05_gemm_mn_supported(tcols, d->c_out, R, tcols, d->c_out)) {
       if (int rc = launch_gemm_tcgen05_mn(tcols, d->c_out, R, d->out_scale, T, tcols, dyb, d->c_out, dst, d->c_out, splits, dWp, st))
         return rc;
     } else if (int rc = launch_gemm_cfg<false, false, false>(tcols, d->c_out, R, d->out_scale, T, tcols, dyb, d->c_out, dst,

@@ -44,7 +44,10 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
-template <int BN, bool OUT_BF16>
+// MN = false: A [M][K], B [N][K] (K-major operands).  MN = true: A stored [K][M], B stored [K][N] -- the contraction index
+// is the ROW index of both operands (dW = T^T dy): every [64 k-rows x 64 columns] TMA box lands as one canonical UMMA
+// MN-major SWIZZLE_128B atom (128-byte lines of 64 consecutive columns, one line per k), 64-column atoms 8 KB apart.
+template <int BN, bool OUT_BF16, bool MN = false>
 __global__ void __launch_bounds__(NTHR, 1) k_gemm_tma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                                                       int M, int N, int K, float alpha, void* __restrict__ Cout, int64_t ldc,
                                                       int m_tiles, int n_tiles, int splits, int kb_per_split,
@@ -96,15 +99,24 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_tma(const __grid_constant__ CU
           mbar_wait(smem_addr(&empty[s]), ph ^ 1u);
           const uint32_t a = ring + s * stage_bytes, b = a + A_BYTES;
           mbar_arrive_expect_tx(smem_addr(&full[s]), stage_bytes);
-          tma_load_2d(a, &map_a, (kb0 + kb) * TBK, mt * TBM, smem_addr(&full[s]));
-          tma_load_2d(b, &map_b, (kb0 + kb) * TBK, nt * BN, smem_addr(&full[s]));
+          if (MN) {
+#pragma unroll
+            for (int at = 0; at < TBM / 64; ++at)
+              tma_load_2d(a + at * 8192, &map_a, mt * TBM + at * 64, (kb0 + kb) * TBK, smem_addr(&full[s]));
+#pragma unroll
+            for (int at = 0; at < BN / 64; ++at)
+              tma_load_2d(b + at * 8192, &map_b, nt * BN + at * 64, (kb0 + kb) * TBK, smem_addr(&full[s]));
+          } else {
+            tma_load_2d(a, &map_a, (kb0 + kb) * TBK, mt * TBM, smem_addr(&full[s]));
+            tma_load_2d(b, &map_b, (kb0 + kb) * TBK, nt * BN, smem_addr(&full[s]));
+          }
           if (++s == nstages) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t ID = idesc(FMT_BF16, FMT_BF16, TBM, BN, false, false);
+      constexpr uint32_t ID = idesc(FMT_BF16, FMT_BF16, TBM, BN, MN, MN);
       int s = 0, it = 0;
       uint32_t ph = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
@@ -117,9 +129,16 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_tma(const __grid_constant__ CU
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(smem_addr(&full[s]), ph);
           tc_fence_after();
-          const uint64_t ad = desc_kmajor_sw128(ring + s * stage_bytes), bd = desc_kmajor_sw128(ring + s * stage_bytes + A_BYTES);
+          if (MN) {
+            // advancing K by 16 = two 8-line k-groups = 2048 bytes (128 descriptor units)
+            const uint64_t ad = desc_mnmajor_sw128(ring + s * stage_bytes, 8192), bd = desc_mnmajor_sw128(ring + s * stage_bytes + A_BYTES, 8192);
 #pragma unroll
-          for (int k4 = 0; k4 < TBK / 16; ++k4) mma_f16(d, ad + (uint64_t)(2 * k4), bd + (uint64_t)(2 * k4), ID, (kb | k4) ? 1u : 0u);
+            for (int k4 = 0; k4 < TBK / 16; ++k4) mma_f16(d, ad + (uint64_t)(128 * k4), bd + (uint64_t)(128 * k4), ID, (kb | k4) ? 1u : 0u);
+          } else {
+            const uint64_t ad = desc_kmajor_sw128(ring + s * stage_bytes), bd = desc_kmajor_sw128(ring + s * stage_bytes + A_BYTES);
+#pragma unroll
+            for (int k4 = 0; k4 < TBK / 16; ++k4) mma_f16(d, ad + (uint64_t)(2 * k4), bd + (uint64_t)(2 * k4), ID, (kb | k4) ? 1u : 0u);
+          }
           commit(smem_addr(&empty[s]));
           if (++s == nstages) { s = 0; ph ^= 1u; }
         }
@@ -220,6 +239,55 @@ bool make_map(CUtensorMap* m, const __nv_bfloat16* base, int64_t rows, int64_t k
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// operand stored [k_rows][cols] bf16 row-major -> tensor map with a [64 k-rows x 64 columns] SWIZZLE_128B box
+bool make_map_mn(CUtensorMap* m, const __nv_bfloat16* base, int64_t k_rows, int64_t cols, int64_t ld) {
+  EncodeFn fn = encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)k_rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {64u, (cuuint32_t)TBK};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// C[M,N] = alpha * A^T B, A stored [K][M], B stored [K][N], fp32 output; split-K over the rows with ordered reduction
+template <int BN>
+int launch_tma_mn_cfg(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16* a, int64_t lda, const __nv_bfloat16* b,
+                      int64_t ldb, float* c, int64_t ldc, int splits, float* partials, cudaStream_t st) {
+  CUtensorMap ma, mb;
+  if (!make_map_mn(&ma, a, k, m, lda) || !make_map_mn(&mb, b, k, n, ldb)) {
+    set_error("launch_gemm_tma_mn: cuTensorMapEncodeTiled failed");
+    return SE3_ECUDA;
+  }
+  auto kern = k_gemm_tma<BN, false, true>;
+  const int nkb = (int)((k + TBK - 1) / TBK);
+  if (partials == nullptr || splits < 1 || ldc != n) splits = 1;
+  int per = (nkb + splits - 1) / splits;
+  splits = (nkb + per - 1) / per;
+  const int m_tiles = (int)((m + TBM - 1) / TBM), n_tiles = (int)((n + BN - 1) / BN);
+  const size_t stage = (size_t)TBM * 128 + (size_t)BN * 128;
+  int nstages = (int)std::min<size_t>(8, (200 * 1024) / stage);
+  if (nstages < 2) nstages = 2;
+  const size_t smem = (size_t)nstages * stage + 4 * 4096 + 1024;
+  SE3_SMEM_ONCE(kern, smem);
+  const int64_t work = (int64_t)m_tiles * n_tiles * splits;
+  const int grid = (int)std::min<int64_t>(work, num_sms());
+  if (splits > 1) {
+    SE3_CUDA(launch_pdl(kern, dim3(grid), dim3(NTHR), smem, st, ma, mb, (int)m, (int)n, (int)k, 1.0f, (void*)partials, n, m_tiles,
+                        n_tiles, splits, per, m * n, nstages));
+    SE3_LAUNCH_CHECK();
+    splitk_reduce_launch(partials, splits, m * n, alpha, c, st);
+    SE3_LAUNCH_CHECK();
+  } else {
+    SE3_CUDA(launch_pdl(kern, dim3(grid), dim3(NTHR), smem, st, ma, mb, (int)m, (int)n, (int)k, alpha, (void*)c, ldc, m_tiles,
+                        n_tiles, 1, nkb, (int64_t)0, nstages));
+    SE3_LAUNCH_CHECK();
+  }
+  return SE3_OK;
+}
+
 template <int BN, bool OB>
 int launch_tma_cfg(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16* a, int64_t lda, const __nv_bfloat16* b,
                    int64_t ldb, void* c, int64_t ldc, int splits, float* partials, cudaStream_t st) {
@@ -284,6 +352,23 @@ int launch_gemm_tma(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfl
   }
 #undef SE3_TMA_CASE
   return SE3_EINVAL;
+}
+
+// dW = T^T dy on the TMA kernel: 16-byte aligned operand rows, whole 16-byte chunks per output row
+bool tma_gemm_mn_supported(int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb, int64_t ldc, const void* a, const void* b,
+                           const void* c) {
+  static const bool off = getenv("SE3_GEMM_TMA") && getenv("SE3_GEMM_TMA")[0] == '0';
+  if (off || encode_fn() == nullptr) return false;
+  return m >= 1 && n >= 8 && (n % 8) == 0 && (m % 8) == 0 && (lda % 8) == 0 && (ldb % 8) == 0 && (ldc % 4) == 0 && k >= 1 &&
+         (reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(c) & 15) == 0 && m < ((int64_t)1 << 31) && k < ((int64_t)1 << 31);
+}
+
+int launch_gemm_tma_mn(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bfloat16* a, int64_t lda, const __nv_bfloat16* b,
+                       int64_t ldb, float* c, int64_t ldc, int splits, float* partials, cudaStream_t st) {
+  if (n <= 64) return launch_tma_mn_cfg<64>(m, n, k, alpha, a, lda, b, ldb, c, ldc, splits, partials, st);
+  if (n <= 128) return launch_tma_mn_cfg<128>(m, n, k, alpha, a, lda, b, ldb, c, ldc, splits, partials, st);
+  return launch_tma_mn_cfg<256>(m, n, k, alpha, a, lda, b, ldb, c, ldc, splits, partials, st);
 }
 
 }  // namespace se3
