@@ -194,6 +194,9 @@ def measure_fpn(torch, dist, shard, wl, dev, rank, world, precision, steps, warm
     pts_h, batch_h = wl.synthetic_bodies(n_clouds, N_POINTS, seed=1000 + rank)
     labels_h = torch.randint(0, 20, (pts_h.shape[0],), generator=torch.Generator().manual_seed(7 + rank))
     pts_h, batch_h, labels_h = pts_h.pin_memory(), batch_h.pin_memory(), labels_h.pin_memory()
+    if precision == 1:
+        # bf16 mode: the blocks' Linear layers (torch matmuls) run on tf32 tensor cores instead of SIMT fp32
+        torch.backends.cuda.matmul.allow_tf32 = True
     step = wl.FpnStep(dev, seg, precision=precision)
     pts_d, batch_d, labels_d = pts_h.to(dev), batch_h.to(dev), labels_h.to(dev)
     from se3conv3d_b200 import _lib
@@ -219,9 +222,11 @@ def measure_fpn(torch, dist, shard, wl, dev, rank, world, precision, steps, warm
                     "h2d_bytes_per_step": int(pts_h.numel() * 4 + batch_h.numel() * 4 + labels_h.numel() * 8),
                     "d2h_bytes_per_step": 4},
             "scaling": "strong" if strong else "weak", "clouds_per_gpu": n_clouds, "precision": precision,
+            "linear_layers": "tf32 (torch.backends.cuda.matmul.allow_tf32)" if precision == 1 else "fp32",
             "model_parameters": int(sum(p.numel() for p in step.model.parameters())),
-            "allreduce": {"collective": "NCCL all-reduce (AVG) of one flat fp32 gradient buffer, %d buckets launched from "
-                                        "post-accumulate hooks during backward" % len(step.reducer.buckets),
+            "allreduce": {"collective": ("NCCL all-reduce (AVG) of one flat fp32 gradient buffer, %d buckets launched from "
+                                         "post-accumulate hooks during backward" % len(step.reducer.buckets)) if g > 1 else
+                                        "none (one replica; gradients are not flattened)",
                           "bytes_per_step": int(step.reducer.bytes),
                           "nvlink_bytes_per_gpu_per_step": int(2 * (g - 1) / g * step.reducer.bytes) if g > 1 else 0},
             "own_kernel_launches_per_step": int(launches)}

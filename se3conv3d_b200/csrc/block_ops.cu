@@ -10,7 +10,7 @@
 namespace se3 {
 namespace {
 
-constexpr int kRowsPerBlock = 256;
+constexpr int kRowsPerBlock = 64;   // rows per block of the gamma-skip backward: ~1 wave of blocks at dfaust sizes
 
 // out[r,c] = x[r,c] * gamma[c] * s(r) + y[r,c],  s(r) = row_scale[row_batch[r] / rows_per_id] (1 when row_scale is null)
 __global__ void __launch_bounds__(256) k_gamma_skip_fwd(const float* __restrict__ x, const float* __restrict__ y,
@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(256) k_gamma_skip_bwd(const float* __restrict_
     float acc = 0.0f;
     if (g < groups) {
       const float gm = gamma[ch];
+#pragma unroll 4
       for (int64_t r = r0 + g; r < r1; r += groups) {
         const float s = row_scale ? row_scale[row_batch[r / frames]] : 1.0f;
         const float d = dy[r * c + ch];
@@ -61,12 +62,23 @@ __global__ void __launch_bounds__(256) k_gamma_skip_bwd(const float* __restrict_
     }
   }
 }
-__global__ void __launch_bounds__(256) k_partial_reduce(const float* __restrict__ partial, int nb, int c, float* __restrict__ out) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
+// ordered two-level sum of the per-block partials: block = 32 channels, warp w adds partials w, w + 32, ... (128-byte rows),
+// then the 32 warp sums are added in warp order
+__global__ void __launch_bounds__(1024) k_partial_reduce(const float* __restrict__ partial, int nb, int c, float* __restrict__ out) {
+  __shared__ float sm[32][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + lane;
   float t = 0.0f;
-  for (int b = 0; b < nb; ++b) t += partial[(int64_t)b * c + ch];
-  out[ch] = t;
+  if (ch < c)
+    for (int b = w; b < nb; b += 32) t += partial[(int64_t)b * c + ch];
+  sm[w][lane] = t;
+  __syncthreads();
+  if (w == 0 && ch < c) {
+    float tot = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) tot += sm[i][lane];
+    out[ch] = tot;
+  }
 }
 
 // mode: 0 avg, 1 sum, 2 max, 3 min over the f consecutive rows of a point
@@ -196,7 +208,7 @@ extern "C" int se3_gamma_skip_bwd(const float* dy, const float* x, const float* 
   const size_t smem = c <= 256 ? (size_t)(256 / c) * c * sizeof(float) : 0;
   k_gamma_skip_bwd<<<nb, 256, smem, st>>>(dy, x, gamma, item_scale, point_item, frames, rows, c, dx, partial);
   SE3_LAUNCH_CHECK();
-  k_partial_reduce<<<(c + 255) / 256, 256, 0, st>>>(partial, nb, c, dgamma);
+  k_partial_reduce<<<(c + 31) / 32, 1024, 0, st>>>(partial, nb, c, dgamma);
   SE3_LAUNCH_CHECK();
   return SE3_OK;
 }

@@ -62,6 +62,13 @@ class GradAllReducer(object):
 
     def __init__(self, params, bucket_bytes=8 << 20):
         self.params = [p for p in params if p.requires_grad]
+        self.world = dist.get_world_size() if _active() else 1
+        if self.world == 1:
+            # one replica: nothing to reduce.  No flat buffer either -- with `p.grad = None` autograd hands every
+            # gradient over without a kernel, while a pre-set view costs one in-place add per parameter per step
+            self.flat, self.buckets, self._handles, self._hooks = None, [], [], []
+            self.bytes = 4 * sum(p.numel() for p in self.params)
+            return
         total = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -85,11 +92,9 @@ class GradAllReducer(object):
             self._pending0.append(count)
         self._pending = list(self._pending0)
         self._handles = []
-        self.world = dist.get_world_size() if _active() else 1
         self._hooks = []
-        if self.world > 1:
-            for p in self.params:
-                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        for p in self.params:
+            self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
 
     def _on_grad(self, p):
         b = self._bucket_of[id(p)]
@@ -101,6 +106,8 @@ class GradAllReducer(object):
 
     def finish(self):
         """Waits for every bucket (call after backward, before clipping / the optimiser step)."""
+        if self.world == 1:
+            return
         if self.world > 1:
             # parameters that received no gradient this step never fired their hook: reduce their buckets now
             for b, left in enumerate(self._pending):
@@ -116,7 +123,11 @@ class GradAllReducer(object):
         self._pending = list(self._pending0)
 
     def zero_grad(self):
-        self.flat.zero_()
+        if self.flat is None:
+            for p in self.params:
+                p.grad = None
+        else:
+            self.flat.zero_()
 
     def remove(self):
         for h in self._hooks:
