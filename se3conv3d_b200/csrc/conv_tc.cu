@@ -1859,8 +1859,9 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
     const int chains = (dW ? 1 : 0) + ((dA || dB) ? 1 : 0) + (dx ? 1 : 0);
     static const int64_t limit = getenv("SE3_BWD_STREAMS_LIMIT") ? atoll(getenv("SE3_BWD_STREAMS_LIMIT")) : ((int64_t)1 << 62);
     // per-kernel timing (se3_profile_enable) wants every kernel alone on the device: no fork while it is on
-    if (chains >= 2 && !profile_enabled() && d->n_edges * (int64_t)std::max(d->c_in, d->c_out) / 32 < limit)
-      ss = side_streams();
+    static const int64_t floor_ = getenv("SE3_BWD_STREAMS_MIN") ? atoll(getenv("SE3_BWD_STREAMS_MIN")) : 0;
+    const int64_t size = d->n_edges * (int64_t)std::max(d->c_in, d->c_out) / 32;
+    if (chains >= 2 && !profile_enabled() && size < limit && size >= floor_) ss = side_streams();
   }
   if (ss) {
     SE3_CUDA(cudaEventRecord(ss->fork, st_main));
