@@ -28,8 +28,8 @@ WORKLOAD = ("dfaust_I_rot_pca_2F hot path: grid hierarchy (0.04;0.05,0.1,0.2,0.4
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", type=int, default=int(os.environ.get("SE3_PRECISION", "1")))
     ap.add_argument("--no-cpu-baseline", action="store_true")

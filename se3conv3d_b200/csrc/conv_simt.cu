@@ -190,11 +190,32 @@ __global__ void k_splitk_reduce(const float* __restrict__ partials, int splits, 
     c[i] = alpha * s;
   }
 }
+// eight split loads in flight per thread; the sums stay in split order (same bits as the plain loop)
+__global__ void __launch_bounds__(256) k_splitk_reduce8(const float* __restrict__ partials, int splits, int64_t mn, float alpha,
+                                                        float* __restrict__ c) {
+  pdl_wait();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < mn; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.0f;
+    int z = 0;
+    for (; z + 8 <= splits; z += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcs(partials + (int64_t)(z + u) * mn + i);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; z < splits; ++z) s += __ldcs(partials + (int64_t)z * mn + i);
+    c[i] = alpha * s;
+  }
+}
 
 void splitk_reduce_launch(const float* partials, int splits, int64_t mn, float alpha, float* c, cudaStream_t st) {
   int64_t blocks = (mn + 255) / 256;
   if (blocks > (int64_t)num_sms() * 8) blocks = (int64_t)num_sms() * 8;
-  launch_pdl(k_splitk_reduce, dim3((unsigned)blocks), dim3(256), 0, st, partials, splits, mn, alpha, c);
+  if (splits >= 8)
+    launch_pdl(k_splitk_reduce8, dim3((unsigned)blocks), dim3(256), 0, st, partials, splits, mn, alpha, c);
+  else
+    launch_pdl(k_splitk_reduce, dim3((unsigned)blocks), dim3(256), 0, st, partials, splits, mn, alpha, c);
 }
 
 int launch_sgemm(bool at, bool bt, int64_t m, int64_t n, int64_t k, float alpha, const float* a, int64_t lda,
