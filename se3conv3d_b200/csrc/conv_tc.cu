@@ -114,6 +114,20 @@ __device__ __forceinline__ uint32_t act_grad_pair(float d0, float d1, float z0, 
   return pack_bf16(d0 * act_grad_rt<ACT>(z0, act), d1 * act_grad_rt<ACT>(z1, act));
 }
 
+// d * act'(z) as above, and act(z) for the same pair (merged backward pass): one tanh serves both
+template <int ACT>
+__device__ __forceinline__ uint32_t act_both_pair(float d0, float d1, float z0, float z1, int act, uint32_t& h) {
+#if SE3_PACKED_ACT
+  if (ACT == 2) {
+    uint32_t g;
+    gelu_both_half_arg_bf2(pack_bf16(z0, z1), h, g);
+    return bf2_mul(pack_bf16(d0, d1), g);
+  }
+#endif
+  h = pack_bf16(act_rt<ACT>(z0, act), act_rt<ACT>(z1, act));
+  return pack_bf16(d0 * act_grad_rt<ACT>(z0, act), d1 * act_grad_rt<ACT>(z1, act));
+}
+
 // n -> (edge, frame) for f frames per gathered point (f in 1..4, warp-uniform)
 __device__ __forceinline__ void split_nf(int n, int f, int& e, int& fg) {
   if (f == 1) {
@@ -791,6 +805,8 @@ struct TcEdgeArgs {
   const __nv_bfloat16* dT;  // [n_out*f_out, c, 32]
   int64_t n_out;
   float* partials;          // [n_ctas, 16, 32]
+  __nv_bfloat16* dxe;       // merged pass: per-entry data-gradient contributions [f_out][E * f_in][cs] + one spare row
+  uint32_t dxe_frame;       // elements between the row-frame blocks of dxe (E * f_in * cs); the spare row starts at f_out * it
 };
 
 // dH^T[k, n] += sum_c dT[c, k] x[n, c] for the first NP pairs of 8-neighbour groups (straight-line code).
@@ -828,9 +844,10 @@ __device__ __forceinline__ void edge_dh(float (&dH)[2][4][4], const __nv_bfloat1
 // dpre = dH * act'(pre) for 2 NP groups -- the pre^T tiles from the tensor cores (tf32) land in the accumulator
 // layout of dH: k in {g, g+8} + 16 m, n = 8 j + 2 t + {0,1} -- then accA[k, d] += dpre[k, n] G[n, d] with dpre
 // repacked as A fragments and G from Gb[n][16] (.trans).  Groups beyond the valid ones carry dH = 0.
-template <int NP, int ACT>
+template <int NP, int ACT, bool WITH_H = false>
 __device__ __forceinline__ void edge_finish(float (&dH)[2][4][4], float (&accA)[2][2][4], const uint32_t (&aw)[2][4],
-                                            uint32_t gs_s, const __nv_bfloat16* Gb, int lane, int act) {
+                                            uint32_t gs_s, const __nv_bfloat16* Gb, int lane, int act,
+                                            uint32_t (*hP)[4][2] = nullptr) {
   constexpr int GB = 16 + 8;
   const int g = lane >> 2, t = lane & 3, mid = lane >> 3, mr = lane & 7;
   uint32_t dP[2][2 * NP][2];  // dpre as bf16 pairs: [m][jj][rows g / g+8]
@@ -840,8 +857,13 @@ __device__ __forceinline__ void edge_finish(float (&dH)[2][4][4], float (&accA)[
     basis_pre(aw, gs_s + (8 * jj + g) * GROW + 8 * min(t, 2), d);
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
-      dP[m][jj][0] = act_grad_pair<ACT>(dH[m][jj][0], dH[m][jj][1], d[m][0], d[m][1], act);
-      dP[m][jj][1] = act_grad_pair<ACT>(dH[m][jj][2], dH[m][jj][3], d[m][2], d[m][3], act);
+      if (WITH_H) {   // basis values h^T (k = 16 m + g (+8), entries 8 jj + 2t, +1) for the data-gradient product
+        dP[m][jj][0] = act_both_pair<ACT>(dH[m][jj][0], dH[m][jj][1], d[m][0], d[m][1], act, hP[m][jj][0]);
+        dP[m][jj][1] = act_both_pair<ACT>(dH[m][jj][2], dH[m][jj][3], d[m][2], d[m][3], act, hP[m][jj][1]);
+      } else {
+        dP[m][jj][0] = act_grad_pair<ACT>(dH[m][jj][0], dH[m][jj][1], d[m][0], d[m][1], act);
+        dP[m][jj][1] = act_grad_pair<ACT>(dH[m][jj][2], dH[m][jj][3], d[m][2], d[m][3], act);
+      }
     }
   }
 #pragma unroll
@@ -853,6 +875,52 @@ __device__ __forceinline__ void edge_finish(float (&dH)[2][4][4], float (&accA)[
       const uint32_t afr[4] = {dP[m][2 * ks][0], dP[m][2 * ks][1], dP[m][2 * ks + 1][0], dP[m][2 * ks + 1][1]};
       mma_bf16(accA[m][0], afr, gb[0], gb[1]);
       mma_bf16(accA[m][1], afr, gb[2], gb[3]);
+    }
+  }
+}
+
+// Merged backward pass: the data-gradient contribution of every entry of the chunk for ONE row frame a,
+//   dXe[n, c] = sum_k h[n, k] dT_a[c, k]   (n = (edge, in-frame b) entry, dT_a already carries out_scale),
+// from the basis values the basis-gradient step has just produced.  h^T sits in the accumulator layout (rows k, pairs
+// along n); the product contracts over k, so it takes one trip through shared memory: Hs[k][n] (padded rows) -> A
+// fragments [m = n][kk = k] by ldmatrix.trans; B = dT^T [kk = k][nn = c] straight from the staged tile dTs[c][k].
+// The first k-step writes the accumulators.
+template <int CB, int NP>
+__device__ __forceinline__ void edge_dx(float (&dX)[2][CB / 8][4], const uint32_t (*hP)[4][2], __nv_bfloat16* Hs,
+                                        const __nv_bfloat16* dTs, int lane) {
+  constexpr int HS = 40, TS = 32 + 8;
+  const int g = lane >> 2, t = lane & 3, mid = lane >> 3, mr = lane & 7;
+  uint32_t* hw = reinterpret_cast<uint32_t*>(Hs);
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int jj = 0; jj < 2 * NP; ++jj) {
+      const int k0 = 16 * m + g, n = 8 * jj + 2 * t;
+      hw[(k0 * HS + n) >> 1] = hP[m][jj][0];
+      hw[((k0 + 8) * HS + n) >> 1] = hP[m][jj][1];
+    }
+  __syncwarp();
+#pragma unroll
+  for (int ki = 0; ki < 2; ++ki) {
+    uint32_t af[NP][4];
+#pragma unroll
+    for (int mi = 0; mi < NP; ++mi)
+      ldmatrix_x4_trans(af[mi][0], af[mi][1], af[mi][2], af[mi][3],
+                        smem_u32(Hs + (ki * 16 + (mid >> 1) * 8 + mr) * HS + mi * 16 + (mid & 1) * 8));
+#pragma unroll
+    for (int jp = 0; jp < CB / 16; ++jp) {
+      uint32_t b[4];
+      ldmatrix_x4(b[0], b[1], b[2], b[3], smem_u32(dTs + (jp * 16 + (mid >> 1) * 8 + mr) * TS + ki * 16 + (mid & 1) * 8));
+#pragma unroll
+      for (int mi = 0; mi < NP; ++mi) {
+        if (ki == 0) {
+          mma_bf16_zero(dX[mi][2 * jp], af[mi], b[0], b[1]);
+          mma_bf16_zero(dX[mi][2 * jp + 1], af[mi], b[2], b[3]);
+        } else {
+          mma_bf16(dX[mi][2 * jp], af[mi], b[0], b[1]);
+          mma_bf16(dX[mi][2 * jp + 1], af[mi], b[2], b[3]);
+        }
+      }
     }
   }
 }
@@ -1081,7 +1149,10 @@ struct EdgeRowSmem {
   static constexpr int WARP_BYTES = OFF_RS + 2 * RS_BYTES;
 };
 
-template <int CB, int FR, int ACT>
+// DX: the merged backward pass -- the kernel also writes, per (entry, row frame), the data-gradient contribution
+// dXe = h . dT (edge_dx) to a.dxe; k_dx_segsum adds them over the transposed CSR.  The transposed aggregation pass, its
+// [N F, Cout K] tile and the dx GEMM disappear, and the basis is evaluated twice per layer instead of three times.
+template <int CB, int FR, int ACT, bool DX = false>
 __global__ void __launch_bounds__(AGG_WARPS * 32, CB >= 64 ? 2 : SE3_EDGE_MIN_BLOCKS) k_edge_row_tc(const TcEdgeArgs a) {
   using SM = EdgeRowSmem<CB, FR>;
   constexpr int TS = SM::TS, GB = SM::GB;
@@ -1193,14 +1264,47 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, CB >= 64 ? 2 : SE3_EDGE_MIN_BL
             edge_dh<CB, 2, true>(dH, dTs, Xs, lane);
           else if (nq > 0)
             edge_dh<CB, 1, true>(dH, dTs, Xs, lane);
-          if (last_chunk && rp1 < total) {
+          if (!DX && last_chunk && rp1 < total) {
             __syncwarp();            // every lane is done reading this frame's tile
             issue_tile(rp1, f);      // group B: the next row's tile streams in behind the rest of this chunk
           }
+          uint32_t hP[DX ? 2 : 1][4][2];
           if (nq > 2)
-            edge_finish<2, ACT>(dH, accA, aw, gs_s, Gb, lane, a.act);
+            edge_finish<2, ACT, DX>(dH, accA, aw, gs_s, Gb, lane, a.act, hP);
           else if (nq > 0)
-            edge_finish<1, ACT>(dH, accA, aw, gs_s, Gb, lane, a.act);
+            edge_finish<1, ACT, DX>(dH, accA, aw, gs_s, Gb, lane, a.act, hP);
+          if (DX) {
+            __syncwarp();            // the geometry tiles (Gs | Gb) are free: they become the h^T tile
+            float dX[2][CB / 8][4];
+            __nv_bfloat16* Hs = reinterpret_cast<__nv_bfloat16*>(wbase + SM::OFF_G);
+            if (nq > 2)
+              edge_dx<CB, 2>(dX, hP, Hs, dTs, lane);
+            else if (nq > 0)
+              edge_dx<CB, 1>(dX, hP, Hs, dTs, lane);
+            // rows of dXe are (row frame, entry) ordered: the entries of this chunk are consecutive rows.  Lanes whose
+            // entry lies beyond the row write to the spare row instead of branching around the stores.
+            const int nmi = nq > 2 ? 2 : (nq > 0 ? 1 : 0);
+            const uint32_t spare = (uint32_t)FR * a.dxe_frame;
+            const uint32_t row0 = (uint32_t)f * a.dxe_frame + (uint32_t)(lo0 * a.f_in + base + g) * (uint32_t)a.cs + 2 * t;
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi) {
+              if (mi < nmi) {
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                  const int nl = 16 * mi + 8 * hf;               // entry of the chunk owned by lanes g = 0
+                  const uint32_t off = base + nl + g < nt0 ? row0 + (uint32_t)nl * (uint32_t)a.cs : spare + 2 * t;
+                  uint32_t* o = reinterpret_cast<uint32_t*>(a.dxe + off);
+#pragma unroll
+                  for (int jn = 0; jn < CB / 8; ++jn)
+                    if (8 * jn < a.cs) o[4 * jn] = pack_bf16(dX[mi][jn][2 * hf], dX[mi][jn][2 * hf + 1]);
+                }
+              }
+            }
+            if (last_chunk && rp1 < total) {
+              __syncwarp();          // every lane is done reading this frame's tile
+              issue_tile(rp1, f);
+            }
+          }
           __syncwarp();
         }
         cp_async_commit();  // group B (possibly empty)
@@ -1255,9 +1359,24 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, CB >= 64 ? 2 : SE3_EDGE_MIN_BL
 template <int CB, int FR>
 static int launch_edge_row_cfg(const TcEdgeArgs& a, int n_warps, cudaStream_t st) {
   static_assert(AGG_WARPS * EdgeRowSmem<CB, FR>::WARP_BYTES >= AGG_WARPS * 512 * 4, "partials must fit the staging area");
+  static_assert(EdgeRowSmem<CB, FR>::G_BYTES + EdgeRowSmem<CB, FR>::GB_BYTES >= 32 * 40 * 2, "the h^T tile aliases Gs | Gb");
   const size_t smem = AGG_WARPS * EdgeRowSmem<CB, FR>::WARP_BYTES;
   ProfScope prof(2, st);
-  if (a.act == 2) {
+  if (a.dxe) {
+    if (CB > 32) {
+      set_error("launch_edge_row_cfg: the merged pass covers at most 32 channels");
+      return SE3_EINVAL;
+    }
+    if (a.act == 2) {
+      auto kern = k_edge_row_tc<(CB > 32 ? 32 : CB), FR, 2, true>;
+      SE3_SMEM_ONCE(kern, smem);
+      SE3_CUDA(launch_pdl(kern, dim3((unsigned)(n_warps / AGG_WARPS)), dim3(AGG_WARPS * 32), smem, st, a));
+    } else {
+      auto kern = k_edge_row_tc<(CB > 32 ? 32 : CB), FR, -1, true>;
+      SE3_SMEM_ONCE(kern, smem);
+      SE3_CUDA(launch_pdl(kern, dim3((unsigned)(n_warps / AGG_WARPS)), dim3(AGG_WARPS * 32), smem, st, a));
+    }
+  } else if (a.act == 2) {
     auto kern = k_edge_row_tc<CB, FR, 2>;
     SE3_SMEM_ONCE(kern, smem);
     SE3_CUDA(launch_pdl(kern, dim3((unsigned)(n_warps / AGG_WARPS)), dim3(AGG_WARPS * 32), smem, st, a));
@@ -1292,6 +1411,76 @@ __global__ void __launch_bounds__(1024) k_edge_tc_reduce(const float* __restrict
       d_bias[out - 288] = tot;
     }
   }
+}
+
+// Merged backward pass, second half: dx[(j f_in + b), c] = sum over the transposed row of input point j (ascending edge id --
+// deterministic) and over the row frames a of dXe[edge, a, b, c].  One warp per input point; a lane owns the bf16 pairs
+// lane, lane + 32 of the [f_in, cs] block, so every edge is one (or two) fully coalesced 128-byte reads per row frame.
+template <int MAXW>
+__global__ void __launch_bounds__(256) k_dx_segsum(const int* __restrict__ t_row_ends, const int* __restrict__ t_edge,
+                                                   const uint32_t* __restrict__ dxe, int64_t frame_words, int f_out, int f_in,
+                                                   int cs, int c, int64_t n_in, float* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int cs2 = cs >> 1, wpa = f_in * cs2;      // words (bf16 pairs) per row frame of an edge
+  pdl_wait();
+  for (int64_t j = gw; j < n_in; j += nw) {
+    const int lo = j > 0 ? __ldg(t_row_ends + j - 1) : 0, hi = __ldg(t_row_ends + j);
+    float2 acc[MAXW];
+#pragma unroll
+    for (int w = 0; w < MAXW; ++w) acc[w] = make_float2(0.f, 0.f);
+    for (int t0 = lo; t0 < hi; t0 += 32) {
+      const int mine = t0 + lane < hi ? __ldg(t_edge + t0 + lane) : 0;
+      const int cnt = min(32, hi - t0);
+#pragma unroll 4
+      for (int i = 0; i < cnt; ++i) {
+        const uint32_t* row = dxe + (int64_t)__shfl_sync(0xffffffffu, mine, i) * wpa;
+        for (int a = 0; a < f_out; ++a) {
+#pragma unroll
+          for (int w = 0; w < MAXW; ++w) {
+            const int wi = lane + 32 * w;
+            if (wi < wpa) {
+              const uint32_t v = __ldcs(row + a * frame_words + wi);
+              acc[w].x += __uint_as_float(v << 16);
+              acc[w].y += __uint_as_float(v & 0xffff0000u);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int w = 0; w < MAXW; ++w) {
+      const int wi = lane + 32 * w;
+      if (wi < wpa) {
+        const int b = wi / cs2, cc = 2 * (wi - b * cs2);
+        float* o = dx + (j * f_in + b) * (int64_t)c + cc;
+        if (cc < c) o[0] = acc[w].x;
+        if (cc + 1 < c) o[1] = acc[w].y;
+      }
+    }
+  }
+}
+
+static int launch_dx_segsum(const int* t_row_ends, const int* t_edge, const __nv_bfloat16* dxe, int64_t frame_elems, int f_out,
+                            int f_in, int cs, int c, int64_t n_in, float* dx, cudaStream_t st) {
+  if (n_in == 0) return SE3_OK;
+  const int wpa = f_in * (cs >> 1);
+  if (wpa > 64) {
+    set_error("launch_dx_segsum: more than 64 bf16 pairs per row frame");
+    return SE3_EINVAL;
+  }
+  int64_t blocks = (n_in + 7) / 8;
+  if (blocks > (int64_t)num_sms() * 8) blocks = (int64_t)num_sms() * 8;
+  ProfScope prof(1, st);   // the data-gradient gather of the merged pass (counted where the transposed aggregation was)
+  if (wpa <= 32) {
+    SE3_CUDA(launch_pdl(k_dx_segsum<1>, dim3((unsigned)blocks), dim3(256), 0, st, t_row_ends, t_edge,
+                        reinterpret_cast<const uint32_t*>(dxe), frame_elems / 2, f_out, f_in, cs, c, n_in, dx));
+  } else {
+    SE3_CUDA(launch_pdl(k_dx_segsum<2>, dim3((unsigned)blocks), dim3(256), 0, st, t_row_ends, t_edge,
+                        reinterpret_cast<const uint32_t*>(dxe), frame_elems / 2, f_out, f_in, cs, c, n_in, dx));
+  }
+  SE3_LAUNCH_CHECK();
+  return SE3_OK;
 }
 
 // CTAs per SM of the edge-gradient kernel that launch_edge_tc picks: the 64-channel row kernel runs two (at three
@@ -1685,6 +1874,19 @@ static int64_t saved_tile_cols(const se3_conv_desc* d) {
 static int64_t u_tile_cols(const se3_conv_desc* d) {
   return dx_fused(d) ? (int64_t)32 * fused_cp(d->c_out) : (int64_t)d->c_out * d->k;
 }
+// merged backward pass (edge gradient + per-entry data-gradient contributions in one gather pass, then a segmented sum
+// over the transposed CSR): layers of at most 32 input channels and two output frames.  OPT-IN (SE3_BWD_MERGED=1): parity
+// green, but measured slower than the transposed aggregation pass it replaces (seg_head: 322 + 196 us against
+// 118 + 89 + 34 us; profiles/r02_experiments.md) -- the 198 MB of per-entry contributions leave as scattered 4-byte
+// stores and the next row's dT tile can no longer be prefetched behind the basis-gradient step.
+static bool merged_shape(const se3_conv_desc* d) {
+  static const bool off = !(getenv("SE3_BWD_MERGED") && getenv("SE3_BWD_MERGED")[0] == '1');
+  const int64_t elems = d->n_edges * d->f_out * d->f_in * (int64_t)((d->c_in + 7) & ~7);   // 32-bit element offsets
+  return !off && d->c_in <= 32 && d->f_out <= 2 && d->f_in <= 4 && !fused_mode() && elems < ((int64_t)1 << 31) - 64;
+}
+static size_t merged_dxe_bytes(const se3_conv_desc* d) {   // [f_out][E f_in][cs] bf16 + one spare row
+  return merged_shape(d) ? ((size_t)d->n_edges * d->f_out * d->f_in + 1) * (size_t)((d->c_in + 7) & ~7) * 2 : 0;
+}
 static TcSaved tc_saved_layout(const se3_conv_desc* d, void* base) {
   const size_t wbytes = align_up((size_t)d->c_in * d->k * d->c_out * 2);
   char* p = reinterpret_cast<char*>(base);
@@ -1720,7 +1922,7 @@ size_t conv_tc_bwd_workspace_bytes(const se3_conv_desc* d) {
   size_t b = 0;
   b += align_up((size_t)R * d->c_out * 2);                                        // dy bf16
   b += align_up((size_t)R * ck * 2);                                              // dT bf16
-  b += dx_fused(d) == 2 ? 0 : align_up((size_t)Nf * u_tile_cols(d) * 2);         // U bf16
+  b += dx_fused(d) == 2 ? 0 : align_up(std::max((size_t)Nf * u_tile_cols(d) * 2, merged_dxe_bytes(d)));   // U bf16 / dXe
   {
     const int64_t tc = saved_tile_cols(d);                                        // dW partials (+ the (k,c)-ordered result)
     b += align_up((size_t)splits_for_tc(tc, d->c_out, R) * tc * d->c_out * 4);
@@ -1835,7 +2037,8 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
   __nv_bfloat16* dTb = ar.take<__nv_bfloat16>(R * ck);
   const int fdx = dx_fused(d);
   const int64_t ucols = u_tile_cols(d);
-  __nv_bfloat16* U = fdx == 2 ? nullptr : ar.take<__nv_bfloat16>(Nf * ucols);
+  const bool merged = merged_shape(d) && dx && (dA || dB) && !fdx;
+  __nv_bfloat16* U = fdx == 2 ? nullptr : ar.take<__nv_bfloat16>(std::max((size_t)(Nf * ucols), merged_dxe_bytes(d) / 2));
   const bool ffwd = fwd_fused(d) != 0;
   const int64_t tcols = saved_tile_cols(d);
   const int splits = splits_for_tc(tcols, d->c_out, R);
@@ -1856,7 +2059,7 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
   // fork
   SideStreams* ss = nullptr;
   {
-    const int chains = (dW ? 1 : 0) + ((dA || dB) ? 1 : 0) + (dx ? 1 : 0);
+    const int chains = (dW ? 1 : 0) + ((dA || dB) ? 1 : 0) + ((dx && !merged) ? 1 : 0);
     static const int64_t limit = getenv("SE3_BWD_STREAMS_LIMIT") ? atoll(getenv("SE3_BWD_STREAMS_LIMIT")) : ((int64_t)1 << 62);
     // per-kernel timing (se3_profile_enable) wants every kernel alone on the device: no fork while it is on
     static const int64_t floor_ = getenv("SE3_BWD_STREAMS_MIN") ? atoll(getenv("SE3_BWD_STREAMS_MIN")) : 0;
@@ -1902,10 +2105,18 @@ int conv_tc_bwd(const se3_conv_desc* d, const float* x, const float* dy, const v
     g.rec_out = d->rec_out; g.rec_in = d->rec_in; g.f_in = d->f_in;
     g.x = xb; g.c = d->c_in; g.cs = pad8(d->c_in); g.w9 = d->proj_axes; g.bias = d->proj_biases; g.norm = d->norm_neigh_dist;
     g.act = d->act; g.dT = dTb; g.n_out = d->n_out; g.partials = eg;
+    g.dxe = merged ? U : nullptr;
+    g.dxe_frame = merged ? (uint32_t)(d->n_edges * d->f_in * pad8(d->c_in)) : 0u;
     if (int rc = launch_edge_tc(g, d->f_out, d->n_in, n_warps, dA, dB, st)) return rc;
+    if (merged)
+      if (int rc = launch_dx_segsum(d->t_row_ends, d->t_edge, U, (int64_t)g.dxe_frame, d->f_out, d->f_in, pad8(d->c_in), d->c_in,
+                                    d->n_in, dx, st))
+        return rc;
   }
   st = ss ? ss->s[1] : st_main;     // chain 3: data gradient
-  if (dx && fdx) {
+  if (merged) {
+    // dx came out of the basis-gradient chain
+  } else if (dx && fdx) {
     // data gradient: the same fused kernel over the transposed CSR, gathered rows = dy, projection with W^T
     if (int rc = launch_w3_image(d->conv_weights, d->c_in, d->c_out, true, fdx == 1, w3t, st)) return rc;
     FusedArgs f;

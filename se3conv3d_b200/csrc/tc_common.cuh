@@ -147,6 +147,18 @@ __device__ __forceinline__ uint32_t gelu_grad_half_arg_bf2(uint32_t y) {
   return bf2_fma(bf2_mul(y, s), dp, cdf);
 }
 
+// gelu(pre) and gelu'(pre) from ONE tanh (the merged backward pass needs both for the same basis entry)
+__device__ __forceinline__ void gelu_both_half_arg_bf2(uint32_t y, uint32_t& h, uint32_t& g) {
+  const uint32_t y2 = bf2_mul(y, y);
+  const uint32_t p = bf2_fma(BF2_GELU_B, y2, BF2_GELU_A);
+  const uint32_t dp = bf2_fma(BF2_GELU_DB, y2, BF2_GELU_DA);
+  const uint32_t th = bf2_tanh(bf2_mul(y, p));
+  const uint32_t s = bf2_fma(th ^ BF2_NEG, th, BF2_ONE);
+  const uint32_t cdf = bf2_fma(BF2_HALF, th, BF2_HALF);
+  g = bf2_fma(bf2_mul(y, s), dp, cdf);
+  h = bf2_fma(y, th, y);
+}
+
 // Activations of the tensor-core path take z = act_pre_scale(ACT) * pre (z = pre / 2 for GELU, pre otherwise).
 __host__ __device__ __forceinline__ float act_pre_scale(int act) { return act == 2 ? GELU_PRE_SCALE : 1.0f; }
 
