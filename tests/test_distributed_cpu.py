@@ -113,3 +113,24 @@ def test_gradient_allreduce_buckets_gloo_world2():
     assert e0 < 1e-6 and e1 < 1e-6
     assert u0 == 0.0 and u1 == 0.0                          # the never-used parameter keeps a zero gradient
     assert s0 == s1 and t0 == t1 and t0 > 0                 # both ranks hold the same reduced buffer, also in step 2
+
+
+def test_gradient_allreducer_single_replica_is_transparent():
+    """One replica: no flat buffer, no hooks -- gradients are the plain autograd tensors (autograd hands them over without
+    an accumulate kernel), zero_grad drops them, finish is a no-op, and the byte count of a step's gradients is still reported."""
+    from se3conv3d_b200 import shard
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 10), torch.nn.GELU(), torch.nn.Linear(10, 3))
+    params = list(model.parameters())
+    red = shard.GradAllReducer(params)
+    assert red.world == 1 and red.flat is None and red.buckets == [] and all(p.grad is None for p in params)
+    assert red.bytes == 4 * sum(p.numel() for p in params)
+    x = torch.randn(8, 6)
+    model(x).square().mean().backward()
+    red.finish()
+    got = [p.grad.clone() for p in params]
+    red.zero_grad()
+    assert all(p.grad is None for p in params)
+    model(x).square().mean().backward()
+    for a, p in zip(got, params):
+        assert torch.equal(a, p.grad)
