@@ -33,9 +33,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", type=int, default=int(os.environ.get("SE3_PRECISION", "1")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="stack", choices=["stack", "fpn"],
+    ap.add_argument("--workload", default="stack", choices=["stack", "fpn", "sweep"],
                     help="stack: hierarchy + the 21 convolutions fwd+bwd (BASELINE metric); fpn: the full FPN training step")
-    ap.add_argument("--strong", action="store_true", help="fpn workload: 32 clouds in total (32/G per GPU) instead of 32 per GPU")
+    ap.add_argument("--strong", action="store_true", help="32 clouds in total (32/G per GPU) instead of 32 per GPU")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra measurements (other configs / precisions)")
     ap.add_argument("--thread", action="store_true",
                     help="pipelined mode: build the next hierarchy from a worker thread (measured slower: 5.37 vs 5.17 ms)")
@@ -232,6 +232,49 @@ def measure_fpn(torch, dist, shard, wl, dev, rank, world, precision, steps, warm
             "own_kernel_launches_per_step": int(launches)}
 
 
+def measure_sweep(torch, shard, dev, world, precision, flush):
+    """BASELINE configs[4]: N in {64 k, 256 k, 1 M, 4 M} x F in {1, 2, 4} x (Cin, Cout) in {32, 64, 128, 256}, restricted to
+    the cases whose [N F, Cin K] tile fits comfortably (4 M points only at 32 channels, 1 M up to 64, F = 4 up to 64 channels);
+    every rank runs every case on its own replica, times are the max over ranks, points/s is the whole job's."""
+    from se3conv3d_b200.layers import PNEConvLayerRotEquiv
+    from se3conv3d_b200.pc import PointcloudRotEquiv, BQNeighborhood
+    rows = []
+    for n in (65536, 262144, 1048576, 4194304):
+        side = (n / 8192) ** (1.0 / 3.0)
+        pts = torch.rand(n, 3, generator=torch.Generator().manual_seed(0)) * side
+        for f in (1, 2, 4):
+            chans = [c for c in (32, 64, 128, 256)
+                     if n * f * c * 32 * 2 * 4 <= 40e9 and not (f == 4 and c > 64) and not (n > 1048576 and f > 2)]
+            if not chans:
+                continue
+            cfg = {"pca": True, "neigh_method": "knn", "neigh_kwargs": {"neigh_k": 16}, "fixed_axis": False, "n_frames": f}
+            pc = PointcloudRotEquiv(pts.to(dev), torch.zeros(n, dtype=torch.int32, device=dev), cfg)
+            nb = BQNeighborhood(pc, pc, 0.1)
+            e = int(nb.neighbors_.shape[0])
+            for c in chans:
+                torch.manual_seed(2)
+                layer = PNEConvLayerRotEquiv(9, c, c, 32, "mlp_gelu").to(dev)
+                layer.precision = precision
+                layer.norm_neigh_dist_.fill_(10.0)
+                layer.norm_num_neighs_.fill_(n / max(e, 1))
+                x = torch.randn(n * f, c, device=dev, requires_grad=True)
+                dy = torch.randn(n * f, c, device=dev) / c ** 0.5
+
+                def one():
+                    y = layer(pc, pc, x, nb)
+                    y.backward(dy)
+                shard.barrier(dev)
+                ms = shard.max_over_ranks(cuda_timed(torch, one, 3, 2, flush) / 3, dev)
+                fb, bb = algorithmic_bytes([(n, e, f, c, c)])
+                rows.append({"n": n, "edges": e, "f": f, "c_in": c, "c_out": c, "ms_fwd_bwd": ms,
+                             "points_per_s": n * world / (ms * 1e-3), "alg_gbs_s4_per_gpu": (fb + bb) / (ms * 1e-3) / 1e9})
+                layer = x = dy = one = None
+                torch.cuda.empty_cache()
+            pc = nb = None
+            torch.cuda.empty_cache()
+    return rows
+
+
 def measure_extras(torch, wl, dev, precision, flush):
     """Other BASELINE configs / precisions on the same kernels (a few iterations each; not the headline)."""
     from se3conv3d_b200.layers import PNEConvLayerRotEquiv
@@ -298,6 +341,27 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
 
+    if args.workload == "sweep":
+        # BASELINE configs[4]: single same-level layer, constant density (k ~ 34), every rank its own replica of the cloud
+        # (weak scaling, no collective); one JSON line with the whole table, `value` = the 1 M-point F = 2 32 -> 32 case
+        if rank == 0:
+            clocks.start()
+        table = measure_sweep(torch, shard, dev, world, args.precision, flush)
+        clk = clocks.stop() if rank == 0 else None
+        if rank == 0:
+            head = [t for t in table if t["n"] == 1048576 and t["f"] == 2 and t["c_in"] == 32][0]
+            print(json.dumps({"metric": "points/sec PNEConvLayerRotEquiv fwd+bwd, single layer sweep (BASELINE configs[4])",
+                              "value": head["points_per_s"], "unit": "points/s", "n_gpus": world, "steps": 3, "warmup": 2,
+                              "ms_per_step": head["ms_fwd_bwd"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                              "dtype": "f32" if args.precision == 0 else "bf16", "data": "synthetic",
+                              "config": {"workload": "layer sweep: N x F x C at constant density (r = 0.1, cube side ~ N^(1/3)), one replica "
+                                                     "of every cloud per GPU; value = N 1 M, F 2, 32 -> 32; L2 flushed between iterations",
+                                         "precision": args.precision},
+                              "clocks": clk, "extra": {"sweep": table}}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     if args.workload == "fpn":
         if rank == 0:
             clocks.start()
@@ -322,16 +386,17 @@ def main():
         return
 
     # ---- workload: 32 clouds x 6890 points per GPU (weak scaling: clouds are independent, no collective)
-    pts_h, batch_h = wl.synthetic_bodies(N_CLOUDS, N_POINTS, seed=shard.shard_seed(rank))
+    n_clouds = max(N_CLOUDS // world, 1) if args.strong else N_CLOUDS   # strong scaling: the 32 clouds are split over the ranks
+    pts_h, batch_h = wl.synthetic_bodies(n_clouds, N_POINTS, seed=shard.shard_seed(rank))
     pts_h, batch_h = pts_h.pin_memory(), batch_h.pin_memory()
     step = wl.DfaustStep(dev, precision=args.precision, seed=0)
     pts_d, batch_d = pts_h.to(dev), batch_h.to(dev)
-    pcs, neighs = step.build_hierarchy(pts_d, batch_d, n_batches=N_CLOUDS)
+    pcs, neighs = step.build_hierarchy(pts_d, batch_d, n_batches=n_clouds)
     step.calibrate(pcs, neighs)
     step.make_inputs(pcs)
 
     def hot_step(p, b):
-        pcs_, neighs_ = step.build_hierarchy(p, b, n_batches=N_CLOUDS)
+        pcs_, neighs_ = step.build_hierarchy(p, b, n_batches=n_clouds)
         return step.conv_fwd_bwd(pcs_, neighs_, return_output=True)
 
     def barrier():
@@ -360,11 +425,11 @@ def main():
     side = torch.cuda.Stream(dev, priority=-1)   # the hierarchy builder's tiny kernels go ahead of queued conv kernels
 
     def timed_pipeline(items, steps, warmup, after=None, drain=None):
-        step.run_pipelined(items[:max(warmup, 1)], N_CLOUDS, side, threaded=args.thread)
+        step.run_pipelined(items[:max(warmup, 1)], n_clouds, side, threaded=args.thread)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        step.run_pipelined(items[:steps], N_CLOUDS, side, before_conv=lambda: flush.fill_(1), after_conv=after,
+        step.run_pipelined(items[:steps], n_clouds, side, before_conv=lambda: flush.fill_(1), after_conv=after,
                            threaded=args.thread)
         if drain is not None:      # every result copy has landed on the host before the clock stops
             drain()
@@ -480,15 +545,17 @@ def main():
         pass
     dom = max(per_layer, key=lambda d: d["ms"])
 
-    n_pts_global = N_CLOUDS * N_POINTS * world
+    n_pts_global = n_clouds * N_POINTS * world
     value = n_pts_global * args.steps / (ms_total * 1e-3)
     e2e_value = n_pts_global * args.steps / (ms_e2e * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.strong else "weak",
         "vs_baseline": None, "dtype": "f32" if args.precision == 0 else "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "points_per_gpu": N_CLOUDS * N_POINTS, "precision": args.precision,
+        "config": {"workload": WORKLOAD if not args.strong else WORKLOAD.replace("32 clouds x 6890 points per GPU",
+                                                                               "%d clouds x 6890 points per GPU (32 in total)" % n_clouds),
+                   "points_per_gpu": n_clouds * N_POINTS, "precision": args.precision,
                    "l2": "256 MB flush write between timed iterations" if args.no_pipeline else
                          "256 MB flush write before every conv stack, inside the timed region",
                    "pipelined": (not args.no_pipeline),
@@ -545,7 +612,7 @@ def main():
                 step0.calibrate(pcs, neighs)
                 step0.make_inputs(pcs)
                 ms0 = cuda_timed(torch, lambda: step0.conv_fwd_bwd(pcs, neighs), 3, 1, flush, step0.zero_grad) / 3
-                extra["precision0_conv_stack"] = {"ms": ms0, "points_per_s": N_CLOUDS * N_POINTS / (ms0 * 1e-3)}
+                extra["precision0_conv_stack"] = {"ms": ms0, "points_per_s": n_clouds * N_POINTS / (ms0 * 1e-3)}
                 del step0
                 extra.update(measure_extras(torch, wl, dev, args.precision, flush))
             except Exception as e:
