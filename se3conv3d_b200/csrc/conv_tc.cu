@@ -336,12 +336,14 @@ struct AggSmem {
 // are in flight as cp.async copies into the other shared-memory buffer; the neighbour ids of the next row
 // and the CSR bounds of the row after it are register prefetches issued one row earlier.  No gather latency
 // sits on the critical path after the first chunk.
-template <int CB, int FR, bool TR, int ACT>
+// FG: gathered frames per point known at compile time (2: the entry -> (edge, frame) split is a shift / mask), 0: a.f_g
+template <int CB, int FR, bool TR, int ACT, int FG = 0>
 __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_AGG_MIN_BLOCKS) k_agg_tc(const TcAggArgs a, const int ncb) {
   using SM = AggSmem<CB, FR>;
   constexpr int MT = CB / 16;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int f_g = FG ? FG : a.f_g;
   unsigned char* wbase = smem_raw + wib * SM::WARP_BYTES;
   const uint32_t wbase_s = smem_u32(wbase);
   unsigned char* Gs = wbase + SM::OFF_G;        // [FR][G_FRAME_BYTES]
@@ -371,7 +373,7 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_AGG_MIN_BLOCKS) k_agg_tc(c
     }
   };
   auto issue = [&](int rp, int c0, int lo, int nt, int idx, int base, int buf, int rb, bool with_row) {
-    const int gidx = chunk_gidx(a.nbr, lo, nt, idx, a.f_g, base, lane);
+    const int gidx = chunk_gidx(a.nbr, lo, nt, idx, f_g, base, lane);
     gather_chunk_async<CB>(a.rec_g, a.feat, a.cs, c0 & 0xffff, gidx, lane, wbase_s + SM::OFF_RG + buf * SM::RG_BYTES,
                            wbase_s + buf * SM::X_BYTES);
     if (with_row && lane < FR * 3)
@@ -401,11 +403,11 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_AGG_MIN_BLOCKS) k_agg_tc(c
     e2b = __ldg(a.row_ends + rp2);
   }
   int buf = 0, rb = 0;
-  issue(rp0, c00, lo0, ne0 * a.f_g, idx0, 0, 0, 0, true);
+  issue(rp0, c00, lo0, ne0 * f_g, idx0, 0, 0, 0, true);
   cp_async_commit();
 
   for (;;) {
-    const int nt0 = ne0 * a.f_g;
+    const int nt0 = ne0 * f_g;
     float acc[FR][MT][4][4];
 #pragma unroll
     for (int f = 0; f < FR; ++f)
@@ -421,7 +423,7 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_AGG_MIN_BLOCKS) k_agg_tc(c
       if (base + 32 < nt0) {
         issue(rp0, c00, lo0, nt0, idx0, base + 32, buf ^ 1, rb, false);
       } else if (item1 < total) {
-        issue(rp1, c01, lo1, ne1 * a.f_g, idx1, 0, buf ^ 1, rb ^ 1, true);
+        issue(rp1, c01, lo1, ne1 * f_g, idx1, 0, buf ^ 1, rb ^ 1, true);
       }
       cp_async_commit();
       cp_async_wait<1>();  // chunk i has landed
@@ -517,7 +519,11 @@ static int launch_agg_cfg(const TcAggArgs& a, int64_t n_g, cudaStream_t st) {
   if (blocks > cap) blocks = cap;                                               // needs many rows per warp
   if (blocks < 1) blocks = 1;
   ProfScope prof(TR ? 1 : 0, st);
-  if (a.act == 2) {
+  if (a.act == 2 && a.f_g == 2) {
+    auto kern = k_agg_tc<CB, FR, TR, 2, 2>;
+    SE3_SMEM_ONCE(kern, smem);
+    SE3_CUDA(launch_pdl(kern, dim3((unsigned)blocks), dim3(AGG_WARPS * 32), smem, st, a, ncb));
+  } else if (a.act == 2) {
     auto kern = k_agg_tc<CB, FR, TR, 2>;
     SE3_SMEM_ONCE(kern, smem);
     SE3_CUDA(launch_pdl(kern, dim3((unsigned)blocks), dim3(AGG_WARPS * 32), smem, st, a, ncb));
@@ -1152,12 +1158,13 @@ struct EdgeRowSmem {
 // DX: the merged backward pass -- the kernel also writes, per (entry, row frame), the data-gradient contribution
 // dXe = h . dT (edge_dx) to a.dxe; k_dx_segsum adds them over the transposed CSR.  The transposed aggregation pass, its
 // [N F, Cout K] tile and the dx GEMM disappear, and the basis is evaluated twice per layer instead of three times.
-template <int CB, int FR, int ACT, bool DX = false>
+template <int CB, int FR, int ACT, bool DX = false, int FG = 0>
 __global__ void __launch_bounds__(AGG_WARPS * 32, CB >= 64 ? 2 : SE3_EDGE_MIN_BLOCKS) k_edge_row_tc(const TcEdgeArgs a) {
   using SM = EdgeRowSmem<CB, FR>;
   constexpr int TS = SM::TS, GB = SM::GB;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int f_in = FG ? FG : a.f_in;
   unsigned char* wbase = smem_raw + wib * SM::WARP_BYTES;
   const uint32_t wbase_s = smem_u32(wbase);
   const uint32_t gs_s = wbase_s + SM::OFF_G;                                  // geometry rows [32][GROW B]
@@ -1179,7 +1186,7 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, CB >= 64 ? 2 : SE3_EDGE_MIN_BL
     uint32_t aw[2][4];
     load_w9_frags(a.w9, a.bias, g, t, act_pre_scale(a.act), aw);
     auto issue_gather = [&](int rp, int lo, int nt, int idx, int base, int buf, int rb, bool with_row) {
-      const int gidx = chunk_gidx(a.col_src, lo, nt, idx, a.f_in, base, lane);
+      const int gidx = chunk_gidx(a.col_src, lo, nt, idx, f_in, base, lane);
       gather_chunk_async<CB>(a.rec_in, a.x, a.cs, 0, gidx, lane, wbase_s + SM::OFF_RG + buf * SM::RG_BYTES,
                              wbase_s + buf * SM::X_BYTES);
       if (with_row && lane < FR * 3)
@@ -1213,14 +1220,14 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, CB >= 64 ? 2 : SE3_EDGE_MIN_BL
       e2b = __ldg(a.row_ends + rp2);
     }
     int buf = 0, rb = 0;
-    issue_gather(rp0, lo0, ne0 * a.f_in, idx0, 0, 0, 0, true);
+    issue_gather(rp0, lo0, ne0 * f_in, idx0, 0, 0, 0, true);
 #pragma unroll
     for (int f = 0; f < FR; ++f) issue_tile(rp0, f);
     cp_async_commit();
     cp_async_commit();  // keeps the two-groups-per-iteration cadence (see the wait below)
 
     for (;;) {
-      const int nt0 = ne0 * a.f_in;
+      const int nt0 = ne0 * f_in;
       int base = 0;
       do {
         const bool last_chunk = base + 32 >= nt0;
@@ -1228,7 +1235,7 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, CB >= 64 ? 2 : SE3_EDGE_MIN_BL
         if (!last_chunk) {
           issue_gather(rp0, lo0, nt0, idx0, base + 32, buf ^ 1, rb, false);
         } else if (rp1 < total) {
-          issue_gather(rp1, lo1, ne1 * a.f_in, idx1, 0, buf ^ 1, rb ^ 1, true);
+          issue_gather(rp1, lo1, ne1 * f_in, idx1, 0, buf ^ 1, rb ^ 1, true);
         }
         cp_async_commit();
         cp_async_wait<1>();  // everything but group A: this chunk's gather and this row's dT tiles have landed
@@ -1285,7 +1292,7 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, CB >= 64 ? 2 : SE3_EDGE_MIN_BL
             // entry lies beyond the row write to the spare row instead of branching around the stores.
             const int nmi = nq > 2 ? 2 : (nq > 0 ? 1 : 0);
             const uint32_t spare = (uint32_t)FR * a.dxe_frame;
-            const uint32_t row0 = (uint32_t)f * a.dxe_frame + (uint32_t)(lo0 * a.f_in + base + g) * (uint32_t)a.cs + 2 * t;
+            const uint32_t row0 = (uint32_t)f * a.dxe_frame + (uint32_t)(lo0 * f_in + base + g) * (uint32_t)a.cs + 2 * t;
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi) {
               if (mi < nmi) {
@@ -1376,6 +1383,10 @@ static int launch_edge_row_cfg(const TcEdgeArgs& a, int n_warps, cudaStream_t st
       SE3_SMEM_ONCE(kern, smem);
       SE3_CUDA(launch_pdl(kern, dim3((unsigned)(n_warps / AGG_WARPS)), dim3(AGG_WARPS * 32), smem, st, a));
     }
+  } else if (a.act == 2 && a.f_in == 2) {
+    auto kern = k_edge_row_tc<CB, FR, 2, false, 2>;
+    SE3_SMEM_ONCE(kern, smem);
+    SE3_CUDA(launch_pdl(kern, dim3((unsigned)(n_warps / AGG_WARPS)), dim3(AGG_WARPS * 32), smem, st, a));
   } else if (a.act == 2) {
     auto kern = k_edge_row_tc<CB, FR, 2>;
     SE3_SMEM_ONCE(kern, smem);
