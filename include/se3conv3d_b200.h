@@ -379,6 +379,14 @@ int se3_conv_set_fused(int32_t mode);
 int se3_gemm_bf16_tn(const void* a_bf16, const void* b_bf16, int64_t m, int64_t n, int64_t k, float alpha,
                      void* c, int32_t c_is_bf16, int32_t impl, se3_stream_t stream);
 
+/* The weight-gradient GEMM on its own: C[M,N] = alpha * A^T . B with A stored [K][M] and B stored [K][N] (bf16,
+ * row-major: the contraction index is the row index of both operands), fp32 accumulation and output.  This is
+ * dW = T^T dy of the layer's backward (the autograd twin of layers/PNEConvLayerRotEquiv.py:210).  M and N multiples of 8.
+ * impl: 0 = auto (the persistent TMA-fed tcgen05 kernel when the operands are 16-byte aligned), 1 = mma.sync,
+ * 2 = tcgen05 with cp.async operand loads (round-1 kernel), 3 = tcgen05 with TMA operand loads. */
+int se3_gemm_bf16_mn(const void* a_bf16, const void* b_bf16, int64_t m, int64_t n, int64_t k, float alpha, float* c,
+                     int32_t impl, se3_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "se3_segment_pool_f32",
     "se3_feat_basis_proj", "se3_feat_basis_proj_grad",
     "se3_conv_fwd_workspace_bytes", "se3_conv_bwd_workspace_bytes", "se3_conv_saved_bytes", "se3_conv_weight_cache_bytes",
-    "se3_conv_fwd", "se3_conv_bwd", "se3_gemm_bf16_tn", "se3_pack_records", "se3_conv_set_fused",
+    "se3_conv_fwd", "se3_conv_bwd", "se3_gemm_bf16_tn", "se3_gemm_bf16_mn", "se3_pack_records", "se3_conv_set_fused",
     "se3_gamma_skip_workspace_bytes", "se3_gamma_skip_fwd", "se3_gamma_skip_bwd", "se3_frame_pool_fwd", "se3_frame_pool_bwd",
     "se3_batch_pool_fwd", "se3_batch_pool_bwd",
     "se3_ball_query_fill_csr", "se3_csr_transpose_i32", "se3_segment_first_i32", "se3_segment_pick",
@@ -155,6 +155,7 @@ def lib():
     L.se3_batch_pool_fwd.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     L.se3_batch_pool_bwd.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
     L.se3_gemm_bf16_tn.argtypes = [vp, vp, i64, i64, i64, f32, vp, i32, i32, vp]
+    L.se3_gemm_bf16_mn.argtypes = [vp, vp, i64, i64, i64, f32, vp, i32, vp]
     L.se3_pack_records.argtypes = [vp, vp, i64, i32, vp, vp]
     L.se3_ball_query_fill_csr.argtypes = [vp, i64, i64, vp, vp, sz, vp, i64, vp, vp, vp]
     L.se3_csr_transpose_i32.argtypes = [vp, vp, i64, i64, vp, sz, vp, vp, vp, vp]

@@ -2203,3 +2203,23 @@ extern "C" int se3_gemm_bf16_tn(const void* a, const void* b, int64_t m, int64_t
   return gemm_tn(m, n, k, alpha, reinterpret_cast<const __nv_bfloat16*>(a), k, reinterpret_cast<const __nv_bfloat16*>(b), k,
                  c, n, c_is_bf16 != 0, impl, as_stream(stream));
 }
+
+// C[M,N] = alpha * A^T B, A stored [K][M], B stored [K][N] (bf16), fp32 output.  impl as in the header.
+extern "C" int se3_gemm_bf16_mn(const void* a, const void* b, int64_t m, int64_t n, int64_t k, float alpha, float* c,
+                                int32_t impl, se3_stream_t stream) {
+  using namespace se3;
+  SE3_CHECK_ARG(m >= 0 && n >= 8 && (n % 8) == 0 && (m % 8) == 0 && k >= 1, "bad sizes (m and n must be multiples of 8)");
+  SE3_CHECK_ARG(impl >= 0 && impl <= 3, "impl must be 0 (auto), 1 (mma.sync), 2 (tcgen05, cp.async) or 3 (tcgen05, TMA)");
+  if (m == 0) return SE3_OK;
+  SE3_CHECK_ARG(a && b && c, "null pointer");
+  const __nv_bfloat16 *A = reinterpret_cast<const __nv_bfloat16*>(a), *B = reinterpret_cast<const __nv_bfloat16*>(b);
+  cudaStream_t st = as_stream(stream);
+  const bool tma_ok = tma_gemm_mn_supported(m, n, k, m, n, n, a, b, c);
+  if (impl == 3 && !tma_ok) {
+    set_error("se3_gemm_bf16_mn: shape / alignment not supported by the TMA kernel");
+    return SE3_EINVAL;
+  }
+  if ((impl == 0 || impl == 3) && tma_ok) return launch_gemm_tma_mn(m, n, k, alpha, A, m, B, n, c, n, 1, nullptr, st);
+  if (impl != 1 && tcgen05_gemm_mn_supported(m, n, k, m, n)) return launch_gemm_tcgen05_mn(m, n, k, alpha, A, m, B, n, c, n, 1, nullptr, st);
+  return launch_gemm_cfg<false, false, false>(m, n, k, alpha, A, m, B, n, c, n, 1, nullptr, st);
+}

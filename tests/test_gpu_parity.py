@@ -401,12 +401,13 @@ def test_grid_subsample_and_hierarchy():
 
 
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3])
 @pytest.mark.parametrize("m,n,k", [(128, 64, 64), (300, 32, 1024), (1000, 16, 8), (257, 256, 2048), (5000, 48, 520),
                                    (4096, 1024, 64)])
 def test_projection_gemm_matches_fp64(impl, m, n, k):
-    """The [K*Cin] x Cout projection on its own (tcgen05/TMEM = impl 2, mma.sync = impl 1): bf16 operands,
-    fp32 accumulation; tolerance 2e-5 relative for fp32 output (accumulation order only), 1.5e-2 for bf16 output."""
+    """The [K*Cin] x Cout projection on its own (auto = impl 0, mma.sync = 1, tcgen05 with cp.async loads = 2, the
+    persistent TMA-fed tcgen05 kernel = 3): bf16 operands, fp32 accumulation; tolerance 2e-5 relative for fp32 output
+    (accumulation order only), 1.5e-2 for bf16 output."""
     from se3conv3d_b200 import _lib
     L = _lib.lib()
     g = torch.Generator(device=DEV).manual_seed(m + n + k)
@@ -419,6 +420,28 @@ def test_projection_gemm_matches_fp64(impl, m, n, k):
                                       _lib.stream()), "se3_gemm_bf16_tn")
         torch.cuda.synchronize()
         assert rel_err(c.double().cpu(), ref.cpu()) < tol
+
+
+@pytest.mark.parametrize("impl", [0, 1, 2, 3])
+@pytest.mark.parametrize("m,n,k", [(1024, 32, 84468), (128, 64, 64), (1024, 72, 1), (2048, 64, 63), (512, 512, 3000),
+                                   (8, 8, 100), (16384, 256, 777), (1000, 40, 5001)])
+def test_weight_gradient_gemm_matches_fp64(impl, m, n, k):
+    """dW = T^T dy on its own (se3_gemm_bf16_mn: operands stored [K][M] / [K][N], the contraction index is the row index):
+    auto, mma.sync, the cp.async tcgen05 kernel and the persistent TMA-fed one (MN-major SWIZZLE_128B boxes) against
+    fp64 -- seg_head's shape, single and partial k-blocks, N below one 64-column atom, partial row tiles, N = 512."""
+    from se3conv3d_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device=DEV).manual_seed(m + n + k)
+    a = torch.randn(k, m, device=DEV, generator=g).to(torch.bfloat16)
+    b = torch.randn(k, n, device=DEV, generator=g).to(torch.bfloat16)
+    ref = 0.5 * (a.double().t() @ b.double())
+    c = torch.full((m, n), float("nan"), device=DEV, dtype=torch.float32)
+    _lib.check(L.se3_gemm_bf16_mn(_lib.ptr(a), _lib.ptr(b), m, n, k, 0.5, _lib.ptr(c), impl, _lib.stream()), "se3_gemm_bf16_mn")
+    torch.cuda.synchronize()
+    err = rel_err(c.double().cpu(), ref.cpu())
+    print("dW gemm", m, n, k, "impl", impl, "rel err %.2e" % err)
+    # fp32 accumulation of k terms in one chain (the layer splits long k over CTAs): the bound grows with sqrt(k)
+    assert err < 2e-5 * max(1.0, (k / 2048.0) ** 0.5)
 
 
 @pytest.mark.parametrize("n_clouds,n_points,n_batches", [(4, 3000, 4), (2, 6890, 2), (3, 900, 5), (2, 8000, 2)])
