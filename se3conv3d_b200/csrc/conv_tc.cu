@@ -165,7 +165,9 @@ __device__ __forceinline__ void gather_chunk_async(const float* __restrict__ rec
   }
   constexpr int LPR = CB / 8;    // lanes per row (16 B = 8 bf16 each)
   constexpr int RPI = 32 / LPR;  // rows per iteration
-  const int col = lane % LPR, r0 = lane / LPR;
+  // CB = 32 (80-byte rows, four lanes each): a quarter-warp takes rows q and q + 4 of the eight rows of an iteration --
+  // their 16-byte chunks fall into eight different bank groups (rows q, q + 1 collide in one: 5 chunks apart)
+  const int col = lane % LPR, r0 = CB == 32 ? (lane >> 3) + 4 * ((lane >> 2) & 1) : lane / LPR;
   const int ch = c0 + col * 8;
   const bool chok = ch < cs;
 #pragma unroll
@@ -240,11 +242,20 @@ __device__ __forceinline__ void basis_pre(const uint32_t (&aw)[2][4], uint32_t g
 }
 
 // geometry row of this lane's neighbour: 9 components, the bias input, zeros (f16)
-__device__ __forceinline__ void store_geometry_row(uint32_t row_s, const float (&gg)[9], float one) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_s), "r"(pack_f16(gg[0], gg[1])), "r"(pack_f16(gg[2], gg[3])),
-               "r"(pack_f16(gg[4], gg[5])), "r"(pack_f16(gg[6], gg[7]))
+__device__ __forceinline__ void store_geometry_row(uint32_t row_s, int row, const float (&gg)[9], float one) {
+  // rows are 32 bytes, one row per lane: the two 16-byte halves of rows 4..7 (mod 8) are swapped, so that the eight rows
+  // of a quarter-warp land in eight different 16-byte bank groups (plain 32-byte rows: a two-way conflict per store)
+  const uint32_t sw = ((uint32_t)row & 4u) << 2;   // 16 for rows 4..7 (mod 8)
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_s + sw), "r"(pack_f16(gg[0], gg[1])),
+               "r"(pack_f16(gg[2], gg[3])), "r"(pack_f16(gg[4], gg[5])), "r"(pack_f16(gg[6], gg[7]))
                : "memory");
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %2, %2};" ::"r"(row_s + 16), "r"(pack_f16(gg[8], one)), "r"(0u) : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %2, %2};" ::"r"(row_s + 16u - sw), "r"(pack_f16(gg[8], one)), "r"(0u) : "memory");
+}
+// byte offset, inside its group of eight geometry rows, of the 8 bytes lane (g, t) feeds to the basis mma: components
+// 4 min(t, 2) .. + 3 of row g, with the half swap of store_geometry_row
+__device__ __forceinline__ uint32_t geom_lane_off(int g, int t) {
+  const int tt = min(t, 2);
+  return (uint32_t)(g * GROW + ((((tt >> 1) ^ (g >> 2)) & 1) << 4) + ((tt & 1) << 3));
 }
 
 // This lane's gathered neighbour of a chunk from its staged record: scaled offset and frame.
@@ -288,7 +299,7 @@ __device__ __forceinline__ void agg_kstep(float (&acc)[FR][CB / 16][4][4], const
     for (int hq = 0; hq < 2; ++hq) {
       if (hq < NG) {
         float d[2][4];
-        basis_pre(aw, gs_s + f * g_frame_bytes + (ks * 16 + hq * 8 + g) * GROW + 8 * min(t, 2), d);
+        basis_pre(aw, gs_s + f * g_frame_bytes + (ks * 16 + hq * 8) * GROW + geom_lane_off(g, t), d);
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
           hb[2 * m][hq] = act_pair<ACT>(d[m][0], d[m][1], act);
@@ -438,7 +449,7 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_AGG_MIN_BLOCKS) k_agg_tc(c
           float Frow[9], gg[9];
           load_row_frame(Rs, f, Frow);
           geometry9<TR>(Frow, Fq, dx, dy, dz, gg);
-          store_geometry_row(gs_s + f * SM::G_FRAME_BYTES + lane * GROW, gg, 1.0f);
+          store_geometry_row(gs_s + f * SM::G_FRAME_BYTES + lane * GROW, lane, gg, 1.0f);
         }
       }
       __syncwarp();
@@ -577,7 +588,7 @@ __device__ __forceinline__ void wide_kstep(float (&acc)[WIDE_CB / 16][4][4], con
     for (int hq = 0; hq < 2; ++hq) {
       if (hq < NG) {
         float d[2][4];
-        basis_pre(aw, gs_s + (ks * 16 + hq * 8 + g) * GROW + 8 * min(t, 2), d);
+        basis_pre(aw, gs_s + (ks * 16 + hq * 8) * GROW + geom_lane_off(g, t), d);
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
           hb[2 * m][hq] = act_pair<ACT>(d[m][0], d[m][1], act);
@@ -684,7 +695,7 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, 2) k_agg_wide(const TcAggArgs 
           unpack_neighbour<TR>(rg, Rs[0], Rs[1], Rs[2], a.norm, dx, dy, dz, Fq);
           load_row_frame(Rs, 0, Frow);
           geometry9<TR>(Frow, Fq, dx, dy, dz, gg);
-          store_geometry_row(gs_s + lane * GROW, gg, 1.0f);
+          store_geometry_row(gs_s + lane * GROW, lane, gg, 1.0f);
           __syncwarp();
         }
         const __nv_bfloat16* Xs = reinterpret_cast<const __nv_bfloat16*>(wbase + buf * SM::X_BYTES);
@@ -860,7 +871,7 @@ __device__ __forceinline__ void edge_finish(float (&dH)[2][4][4], float (&accA)[
 #pragma unroll
   for (int jj = 0; jj < 2 * NP; ++jj) {
     float d[2][4];
-    basis_pre(aw, gs_s + (8 * jj + g) * GROW + 8 * min(t, 2), d);
+    basis_pre(aw, gs_s + 8 * jj * GROW + geom_lane_off(g, t), d);
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
       if (WITH_H) {   // basis values h^T (k = 16 m + g (+8), entries 8 jj + 2t, +1) for the data-gradient product
@@ -1054,7 +1065,7 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, SE3_EDGE_MIN_BLOCKS) k_edge_tc
 #pragma unroll
             for (int i = 0; i < 9; ++i) gg[i] = 0.0f;
           }
-          store_geometry_row(gs_s + lane * GROW, gg, 1.0f);
+          store_geometry_row(gs_s + lane * GROW, lane, gg, 1.0f);
           uint4 p0, p1;
           p0.x = pack_bf16(gg[0], gg[1]); p0.y = pack_bf16(gg[2], gg[3]);
           p0.z = pack_bf16(gg[4], gg[5]); p0.w = pack_bf16(gg[6], gg[7]);
@@ -1254,7 +1265,7 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, CB >= 64 ? 2 : SE3_EDGE_MIN_BL
             // dpre are exactly zero there, and their geometry is finite (a zero record against a finite row point)
             load_row_frame(Rs, f, Frow);
             geometry9<false>(Frow, Fq, dx, dy, dz, gg);
-            store_geometry_row(gs_s + lane * GROW, gg, 1.0f);
+            store_geometry_row(gs_s + lane * GROW, lane, gg, 1.0f);
             uint4 p0, p1;
             p0.x = pack_bf16(gg[0], gg[1]); p0.y = pack_bf16(gg[2], gg[3]);
             p0.z = pack_bf16(gg[4], gg[5]); p0.w = pack_bf16(gg[6], gg[7]);
