@@ -707,6 +707,61 @@ def test_layer_bf16_matches_fp32_path_channel_sweep(cin, cout, frames):
         assert err < 3e-2, name
 
 
+@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("cin,cout,frames", [(32, 32, 2), (1, 32, 2), (160, 72, 4), (64, 128, 1), (40, 8, 3)])
+def test_conv_calls_stay_inside_their_buffers(precision, cin, cout, frames):
+    """se3_conv_fwd / se3_conv_bwd called directly through the C ABI with every output, saved and workspace buffer
+    embedded between 4 KB guard zones: the guards are untouched afterwards (the library only writes what its *_bytes
+    functions announce), and the outputs equal those of the layer's own call.  Covers the row-item, one-channel,
+    wide-layer (basis stash) and multi-block kernels of both precisions."""
+    from se3conv3d_b200 import _lib
+    from se3conv3d_b200.custom_ops.functions import make_conv_desc
+    from se3conv3d_b200.layers import PNEConvLayerRotEquiv
+    pc, neigh, x = _synthetic_layer_problem(1200, 0.2, frames, cin, cout, seed=21, batches=2)
+    torch.manual_seed(22)
+    layer = PNEConvLayerRotEquiv(9, cin, cout, 32, "mlp_gelu").to(DEV)
+    layer.precision = precision
+    layer.norm_neigh_dist_.fill_(5.0)
+    layer.norm_num_neighs_.fill_(1200 / neigh.neighbors_.shape[0])
+    dy = torch.randn(1200 * frames, cout, generator=torch.Generator().manual_seed(23)).to(DEV)
+    xx = x.clone().requires_grad_(True)
+    y_ref = layer(pc, pc, xx, neigh)
+    y_ref.backward(dy)
+    want = [y_ref.detach(), xx.grad, layer.conv_weights_.grad, layer.proj_axes_.grad, layer.proj_biases_.grad]
+
+    G = 4096
+
+    def guarded(nbytes):
+        nbytes = max(int(nbytes), 16)
+        buf = torch.full((nbytes + 2 * G,), 0xA5, dtype=torch.uint8, device=DEV)
+        return buf, buf[G:G + nbytes]
+
+    def intact(buf):
+        return bool((buf[:G] == 0xA5).all()) and bool((buf[-G:] == 0xA5).all())
+    geom = neigh.conv_geometry(pc, pc)
+    pa, pb, cw = layer.proj_axes_.detach(), layer.proj_biases_.detach(), layer.conv_weights_.detach()
+    d, dref, saved_b, fwd_b, bwd_b, _ = make_conv_desc(geom, cin, cout, 32, 2, precision, float(layer.norm_neigh_dist_),
+                                                        float(layer.norm_num_neighs_) / frames, pa, pb, cw)
+    L = _lib.lib()
+    R = 1200 * frames
+    bufs = {name: guarded(nb) for name, nb in (("y", R * cout * 4), ("saved", saved_b), ("fws", fwd_b), ("bws", bwd_b),
+                                               ("dx", R * cin * 4), ("dW", cin * 32 * cout * 4), ("dA", 9 * 32 * 4),
+                                               ("dB", 32 * 4))}
+    p = lambda n: bufs[n][1].data_ptr()
+    _lib.check(L.se3_conv_fwd(dref, x.data_ptr(), p("y"), p("saved"), p("fws"), bufs["fws"][1].numel(), _lib.stream()),
+               "se3_conv_fwd")
+    _lib.check(L.se3_conv_bwd(dref, x.data_ptr(), dy.data_ptr(), p("saved"), p("dx"), p("dW"), p("dA"), p("dB"), p("bws"),
+                              bufs["bws"][1].numel(), _lib.stream()), "se3_conv_bwd")
+    torch.cuda.synchronize()
+    for name, (buf, _) in bufs.items():
+        assert intact(buf), "guard zone of %s was written" % name
+    got = [bufs["y"][1].view(torch.float32).reshape(R, cout), bufs["dx"][1].view(torch.float32).reshape(R, cin),
+           bufs["dW"][1].view(torch.float32).reshape(cin, 32, cout), bufs["dA"][1].view(torch.float32).reshape(9, 32),
+           bufs["dB"][1].view(torch.float32).reshape(32)]
+    for a, b, name in zip(got, want, ("y", "dx", "dW", "dA", "dB")):
+        assert torch.equal(a, b), name
+
+
 @pytest.mark.parametrize("precision,tol", [(0, 1e-4), (1, 3e-2)])
 def test_standard_pne_conv_layer_matches_oracle(precision, tol):
     """the non-equivariant PNEConvLayer (layers/PNEConvLayer.py:161-229) on the fused kernels
