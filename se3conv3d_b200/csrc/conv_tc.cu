@@ -1,20 +1,23 @@
 // bf16 tensor-core path (precision 1) of the fused PNEConvLayerRotEquiv.
 //
-//   k_agg_tc   : one warp per output row-point.  Per chunk of 32 expanded neighbours (edge x in-frame):
-//                lanes gather coordinates / frames / feature rows (128-bit loads, bf16 staging in
-//                shared memory), build the 9-vector g per (neighbour, out-frame), evaluate the basis
-//                h = act(g.W9 + b) DIRECTLY in the mma B-fragment layout (no shared-memory round trip
-//                for h) and accumulate T[c,k] += x[n,c] h[n,k] with mma.sync m16n8k16 (bf16 in, fp32
-//                accumulate).  g, h and the expanded neighbour list never reach HBM.
-//                TR=false: rows = output points (forward).  TR=true: rows = input points over the
-//                transposed CSR with dy as the gathered feature (atomic-free data gradient).
-//   k_edge_tc  : by output row, gradient of proj_axes_/proj_biases_: dH^T = dT^T X^T (mma), times
-//                act'(pre) recomputed in the accumulator layout, then [k x n].[n x 10] (mma) against
-//                the bf16 geometry (+ a ones column for the bias); per-warp partials, ordered reduce.
-//   k_gemm_bf16: generic bf16 tensor-core GEMM (cp.async 3-stage pipeline, ldmatrix, mma.sync) for the
+//   k_agg_tc   : one warp per (row point, frame group, channel block) item, persistent grid.  Per chunk of 32 expanded
+//                neighbours (edge x in-frame): records and bf16 feature rows arrive by cp.async (double buffered), lanes
+//                build the 9-vector g per (neighbour, row frame) into 32-byte f16 rows, the basis affine runs as ONE f16
+//                mma.m16n8k16 per 8 neighbours x 16 basis functions and h = act(g.W9 + b) lands DIRECTLY in the B-fragment
+//                layout of the aggregation mma (GELU in packed bf16x2), T[c,k] += x[n,c] h[n,k] with mma.sync m16n8k16
+//                (bf16 in, fp32 accumulate).  g, h and the expanded neighbour list never reach HBM.
+//                TR=false: rows = output points (forward).  TR=true: rows = input points over the transposed CSR with dy
+//                as the gathered feature (atomic-free data gradient).
+//   k_agg_wide : more than 64 channels: one warp per (row point, row frame) walks all 64-channel blocks, the basis
+//                fragments of the row stay in shared memory after the first block.
+//   k_edge_row_tc / k_edge_tc : by output row, gradient of proj_axes_ / proj_biases_: dH^T = dT^T X^T (mma), times
+//                act'(pre) with pre recomputed in the accumulator layout (f16 mma, packed bf16x2 GELU'), then
+//                [k x n].[n x 10] (mma) against the bf16 geometry (+ a ones column for the bias); per-CTA partials,
+//                ordered reduce.  DX variant + k_dx_segsum: the opt-in merged backward pass (SE3_BWD_MERGED=1).
+//   k_gemm_bf16: generic bf16 tensor-core GEMM (cp.async 3-stage pipeline, ldmatrix, mma.sync), the fallback of the
 //                projection and its three backward products; deterministic split-K.
-// The tcgen05/TMEM projection kernel lives in proj_tcgen05.cu and replaces k_gemm_bf16 for the
-// K-major x K-major products when it is enabled.
+// The tcgen05 / TMEM GEMMs live in proj_tma.cu (persistent, TMA-fed, warp-specialised: the default) and
+// proj_tcgen05.cu (cp.async operand loads); conv_tc_fwd / conv_tc_bwd at the end of this file orchestrate a layer call.
 #include <stdlib.h>
 #include <algorithm>
 #include "conv_simt.cuh"
@@ -858,7 +861,7 @@ __device__ __forceinline__ void edge_dh(float (&dH)[2][4][4], const __nv_bfloat1
   }
 }
 
-// dpre = dH * act'(pre) for 2 NP groups -- the pre^T tiles from the tensor cores (tf32) land in the accumulator
+// dpre = dH * act'(pre) for 2 NP groups -- the pre^T tiles from the tensor cores (f16 operands) land in the accumulator
 // layout of dH: k in {g, g+8} + 16 m, n = 8 j + 2 t + {0,1} -- then accA[k, d] += dpre[k, n] G[n, d] with dpre
 // repacked as A fragments and G from Gb[n][16] (.trans).  Groups beyond the valid ones carry dH = 0.
 template <int NP, int ACT, bool WITH_H = false>
