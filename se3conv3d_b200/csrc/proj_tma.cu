@@ -33,7 +33,11 @@ using namespace umma;
 namespace {
 
 constexpr int TBM = 128, TBK = 64;
-constexpr int NTHR = 192;   // warp 0: TMA, warp 1: MMA, warps 2-5: epilogue
+// warp 0: TMA, warp 1: MMA, then one or two groups of four epilogue warps (one warp per TMEM lane quadrant and group; with two
+// groups -- tiles of at least 128 columns -- each group drains half of the accumulator's columns: the bf16-output products
+// of the layer (dT = dy W^T, K = Cout) are all epilogue)
+constexpr int epi_groups(int bn) { return bn >= 128 ? 2 : 1; }
+constexpr int nthr(int bn) { return 64 + 128 * epi_groups(bn); }
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
@@ -48,7 +52,7 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
 // is the ROW index of both operands (dW = T^T dy): every [64 k-rows x 64 columns] TMA box lands as one canonical UMMA
 // MN-major SWIZZLE_128B atom (128-byte lines of 64 consecutive columns, one line per k), 64-column atoms 8 KB apart.
 template <int BN, bool OUT_BF16, bool MN = false>
-__global__ void __launch_bounds__(NTHR, 1) k_gemm_tma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+__global__ void __launch_bounds__(nthr(BN), 1) k_gemm_tma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                                                       int M, int N, int K, float alpha, void* __restrict__ Cout, int64_t ldc,
                                                       int m_tiles, int n_tiles, int splits, int kb_per_split,
                                                       int64_t split_stride, int nstages) {
@@ -77,7 +81,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_tma(const __grid_constant__ CU
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_addr(&acc_full[i]), 1);
-      mbar_init(smem_addr(&acc_empty[i]), 4);
+      mbar_init(smem_addr(&acc_empty[i]), 4 * epi_groups(BN));
     }
     mbar_init_fence();
   }
@@ -148,6 +152,8 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_tma(const __grid_constant__ CU
   } else {
     const int q = warp & 3;                     // TMEM lane quadrant of this warp
     unsigned char* stg = epi_gen + (warp - 2) * 4096;   // [32 rows][128 B], 16-byte chunks XOR-swizzled by the row
+    constexpr int CPG = BN / epi_groups(BN);            // accumulator columns of one epilogue group
+    const int cbeg = ((warp - 2) >> 2) * CPG;
     int it = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
       const int nt = w % n_tiles, rest = w / n_tiles, mt = m_tiles - 1 - rest % m_tiles, sp = rest / m_tiles;
@@ -158,7 +164,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_tma(const __grid_constant__ CU
       const float sc = split_stride ? 1.0f : alpha;
       constexpr int CW = OUT_BF16 ? 64 : 32;    // columns per staging pass (128 bytes per row)
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += CW) {
+      for (int c0 = cbeg; c0 < cbeg + CPG; c0 += CW) {
         uint32_t r[32], r2[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * ACC_COLS + c0), r);
         if (OUT_BF16 && c0 + 32 < BN) tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * ACC_COLS + c0 + 32), r2);
@@ -268,20 +274,20 @@ int launch_tma_mn_cfg(int64_t m, int64_t n, int64_t k, float alpha, const __nv_b
   splits = (nkb + per - 1) / per;
   const int m_tiles = (int)((m + TBM - 1) / TBM), n_tiles = (int)((n + BN - 1) / BN);
   const size_t stage = (size_t)TBM * 128 + (size_t)BN * 128;
-  int nstages = (int)std::min<size_t>(8, (200 * 1024) / stage);
+  int nstages = (int)std::min<size_t>(8, (226 * 1024 - 4 * epi_groups(BN) * 4096) / stage);   // 227 KB per CTA: ring + staging + barriers
   if (nstages < 2) nstages = 2;
-  const size_t smem = (size_t)nstages * stage + 4 * 4096 + 1024;
+  const size_t smem = (size_t)nstages * stage + 4 * epi_groups(BN) * 4096 + 1024;
   SE3_SMEM_ONCE(kern, smem);
   const int64_t work = (int64_t)m_tiles * n_tiles * splits;
   const int grid = (int)std::min<int64_t>(work, num_sms());
   if (splits > 1) {
-    SE3_CUDA(launch_pdl(kern, dim3(grid), dim3(NTHR), smem, st, ma, mb, (int)m, (int)n, (int)k, 1.0f, (void*)partials, n, m_tiles,
+    SE3_CUDA(launch_pdl(kern, dim3(grid), dim3(nthr(BN)), smem, st, ma, mb, (int)m, (int)n, (int)k, 1.0f, (void*)partials, n, m_tiles,
                         n_tiles, splits, per, m * n, nstages));
     SE3_LAUNCH_CHECK();
     splitk_reduce_launch(partials, splits, m * n, alpha, c, st);
     SE3_LAUNCH_CHECK();
   } else {
-    SE3_CUDA(launch_pdl(kern, dim3(grid), dim3(NTHR), smem, st, ma, mb, (int)m, (int)n, (int)k, alpha, (void*)c, ldc, m_tiles,
+    SE3_CUDA(launch_pdl(kern, dim3(grid), dim3(nthr(BN)), smem, st, ma, mb, (int)m, (int)n, (int)k, alpha, (void*)c, ldc, m_tiles,
                         n_tiles, 1, nkb, (int64_t)0, nstages));
     SE3_LAUNCH_CHECK();
   }
@@ -303,20 +309,20 @@ int launch_tma_cfg(int64_t m, int64_t n, int64_t k, float alpha, const __nv_bflo
   splits = (nkb + per - 1) / per;
   const int m_tiles = (int)((m + TBM - 1) / TBM), n_tiles = (int)((n + BN - 1) / BN);
   const size_t stage = (size_t)TBM * 128 + (size_t)BN * 128;
-  int nstages = (int)std::min<size_t>(8, (200 * 1024) / stage);
+  int nstages = (int)std::min<size_t>(8, (226 * 1024 - 4 * epi_groups(BN) * 4096) / stage);   // 227 KB per CTA: ring + staging + barriers
   if (nstages < 2) nstages = 2;
-  const size_t smem = (size_t)nstages * stage + 4 * 4096 + 1024;
+  const size_t smem = (size_t)nstages * stage + 4 * epi_groups(BN) * 4096 + 1024;
   SE3_SMEM_ONCE(kern, smem);
   const int64_t work = (int64_t)m_tiles * n_tiles * splits;
   const int grid = (int)std::min<int64_t>(work, num_sms());
   if (splits > 1) {
-    SE3_CUDA(launch_pdl(kern, dim3(grid), dim3(NTHR), smem, st, ma, mb, (int)m, (int)n, (int)k, 1.0f, (void*)partials, n, m_tiles,
+    SE3_CUDA(launch_pdl(kern, dim3(grid), dim3(nthr(BN)), smem, st, ma, mb, (int)m, (int)n, (int)k, 1.0f, (void*)partials, n, m_tiles,
                         n_tiles, splits, per, m * n, nstages));
     SE3_LAUNCH_CHECK();
     splitk_reduce_launch(partials, splits, m * n, alpha, reinterpret_cast<float*>(c), st);
     SE3_LAUNCH_CHECK();
   } else {
-    SE3_CUDA(launch_pdl(kern, dim3(grid), dim3(NTHR), smem, st, ma, mb, (int)m, (int)n, (int)k, alpha, c, ldc, m_tiles, n_tiles,
+    SE3_CUDA(launch_pdl(kern, dim3(grid), dim3(nthr(BN)), smem, st, ma, mb, (int)m, (int)n, (int)k, alpha, c, ldc, m_tiles, n_tiles,
                         1, nkb, (int64_t)0, nstages));
     SE3_LAUNCH_CHECK();
   }
