@@ -762,6 +762,45 @@ def test_conv_calls_stay_inside_their_buffers(precision, cin, cout, frames):
         assert torch.equal(a, b), name
 
 
+def test_merged_backward_pass_opt_in_matches_fp32_path():
+    """The opt-in merged backward pass (SE3_BWD_MERGED=1: basis gradient + per-entry data-gradient contributions in one
+    gather pass, k_dx_segsum over the transposed CSR) in a fresh process -- the switch is read once per process --
+    against the fp32 exactness path: every gradient within the bf16 tolerance, for 32 / 1 / 24 input channels and
+    F_in in {1, 2, 3}."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, torch
+sys.path.insert(0, %r)
+sys.path.insert(0, %r)
+import test_gpu_parity as tp
+from se3conv3d_b200.layers import PNEConvLayerRotEquiv
+for cin, cout, frames in ((32, 32, 2), (1, 32, 2), (24, 64, 1), (16, 16, 3)):
+    pc, neigh, x = tp._synthetic_layer_problem(1500, 0.2, frames, cin, cout, seed=5, batches=2)
+    torch.manual_seed(7)
+    layer = PNEConvLayerRotEquiv(9, cin, cout, 32, "mlp_gelu").to("cuda:0")
+    layer.norm_neigh_dist_.fill_(5.0)
+    layer.norm_num_neighs_.fill_(1500 / neigh.neighbors_.shape[0])
+    dy = torch.randn(1500 * frames, cout, generator=torch.Generator().manual_seed(9)).to("cuda:0")
+    res = []
+    for precision in (0, 1):
+        layer.precision = precision
+        layer.zero_grad()
+        xx = x.clone().requires_grad_(True)
+        layer(pc, pc, xx, neigh).backward(dy)
+        res.append([t.detach().cpu().numpy() for t in (xx.grad, layer.conv_weights_.grad, layer.proj_axes_.grad, layer.proj_biases_.grad)])
+    for a, b, name in zip(res[1], res[0], ("dx", "dW", "dA", "dB")):
+        err = tp.rel_err(a, b)
+        print(cin, cout, frames, name, "%%.2e" %% err)
+        assert err < 1e-2, (cin, cout, frames, name, err)
+print("MERGED-OK")
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SE3_BWD_MERGED="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "MERGED-OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 @pytest.mark.parametrize("precision,tol", [(0, 1e-4), (1, 3e-2)])
 def test_standard_pne_conv_layer_matches_oracle(precision, tol):
     """the non-equivariant PNEConvLayer (layers/PNEConvLayer.py:161-229) on the fused kernels
